@@ -1,0 +1,146 @@
+"""Generate the golden fixtures in this directory by RUNNING THE REFERENCE (read-only import from
+/root/reference, CPU, torch fp32).  Run in the build container only:
+
+    python tests/golden/make_golden.py
+
+The GPU box has no /root/reference; tests only read the committed .npz files.
+Import recipe: SURVEY.md Appendix C (stub modules for librosa/soundfile/matplotlib, which
+audiozen/acoustics/audio_feature.py:4-7 imports at module top but the path never uses).
+"""
+import json
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("GSN_REFERENCE_ROOT", "/root/reference")
+sys.path.insert(0, ROOT)
+
+for n in ["librosa", "soundfile", "matplotlib", "matplotlib.pyplot"]:
+    sys.modules.setdefault(n, types.ModuleType(n))
+sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+sys.path.insert(0, REF)
+
+from audiozen.models.spiking_fullsubnet import modeling_spiking_fullsubnet as MSF  # noqa: E402
+from audiozen.models.spiking_fullsubnet.efficient_spiking_neuron import GSUCell  # noqa: E402
+from audiozen.models.cirm_gsn import modeling_cirm_gsn as CGN  # noqa: E402
+from audiozen.models.cirm_gsn.efficient_spiking_neuron import GSUCell as GSUCellC  # noqa: E402
+
+from oracle import synth  # noqa: E402
+
+
+def pack(h):
+    """[T,R,H] {0,1} float -> packed bits along H."""
+    a = h.detach().numpy()
+    assert ((a == 0) | (a == 1)).all()
+    return np.packbits(a.astype(np.uint8), axis=-1)
+
+
+def load_params(model, params):
+    sd = {k: torch.from_numpy(np.array(v)) for k, v in params.items()}
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+
+
+def hook_cells(model, cell_cls):
+    """Collect c_t per step for every GSUCell, keyed by module name."""
+    traces = {}
+
+    def mk(name):
+        def hook(_m, _inp, out):
+            traces.setdefault(name, []).append(out[1][1].detach().numpy().copy())
+        return hook
+
+    hs = [m.register_forward_hook(mk(n)) for n, m in model.named_modules() if isinstance(m, cell_cls)]
+    return traces, hs
+
+
+def run_surface_a(name, cfg, seed, batch, num_samples, with_c):
+    torch.manual_seed(0)
+    model = MSF.SpikingFullSubNet(**cfg)
+    params = synth.make_params(cfg, seed)
+    load_params(model, params)
+    wave = synth.make_wave(batch, num_samples, seed + 1)
+    traces, hooks = hook_cells(model, GSUCell) if with_c else ({}, [])
+    x = torch.from_numpy(wave)
+    with torch.no_grad():
+        mag = model.stft(x)[0]
+        out = model(x)
+    for h in hooks:
+        h.remove()
+    d = {"cfg": json.dumps(cfg), "seed": seed, "wave": wave, "mag": mag.numpy()}
+    if cfg.get("num_spks", 1) > 1:
+        enh_y, fb_all, sb_all = out
+    else:
+        enh_y, enh_mag, fb_all, sb_all = out
+        d["enh_mag"] = enh_mag.numpy()
+    d["enh_y"] = enh_y.numpy()
+    # coefficient tensors (the "cIRM" of BASELINE.json): re-run the network part to fetch them
+    with torch.no_grad():
+        cm = (mag.unsqueeze(1) ** cfg["fdrc"])[..., :-1, :]
+        fb_in = cm[..., : cfg["fb_input_size"], :].squeeze(1)
+        fb_out, _ = model.fb_model(fb_in)
+        fb_out = fb_out.unsqueeze(1).repeat(1, 1, (cfg["n_fft"] // 2 + 1) // cfg["fb_input_size"], 1)
+        coefs, _ = model.sb_model(cm, fb_out)
+    for i, c in enumerate(coefs):
+        d[f"coef{i}"] = c.numpy()
+    L = cfg["fb_num_layers"]
+    d["fb_xnorm"] = fb_all[0].numpy()
+    for l in range(L):
+        d[f"fb_h{l}"] = pack(fb_all[1 + l])
+    d["fb_proj"] = fb_all[-1].numpy()
+    for i, al in enumerate(sb_all):
+        d[f"sb{i}_xnorm"] = al[0].numpy()
+        for l in range(cfg["sb_num_layers"]):
+            d[f"sb{i}_h{l}"] = pack(al[1 + l])
+        if with_c:
+            d[f"sb{i}_proj"] = al[-1].numpy()
+    if with_c:
+        for k, v in traces.items():  # hooks were removed before the second (network-only) pass
+            d["c__" + k] = np.stack(v)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
+    print(name, {k: (v.shape if hasattr(v, "shape") else v) for k, v in d.items() if k != "cfg"})
+
+
+def run_cirm(name, cfg, seed, batch, num_samples):
+    torch.manual_seed(0)
+    model = CGN.Model(**cfg)
+    params = synth.make_params_cirm(cfg, seed)
+    load_params(model, params)
+    wave = synth.make_wave(batch, num_samples, seed + 1)
+    traces, hooks = hook_cells(model, GSUCellC)
+    x = torch.from_numpy(wave)
+    with torch.no_grad():
+        mag = model.stft(x)[0]
+        enh_y, enh_mag = model(x)
+        fb_out, all_out = model.fb_model(mag ** cfg["fdrc"])
+    for h in hooks:
+        h.remove()
+    d = {"cfg": json.dumps(cfg), "seed": seed, "wave": wave, "mag": mag.numpy(), "enh_y": enh_y.numpy(),
+         "enh_mag": enh_mag.numpy(), "fb_out": fb_out.numpy(), "fb_xnorm": all_out[0].numpy()}
+    for l in range(cfg["num_layers"]):
+        d[f"fb_h{l}"] = pack(all_out[1 + l])
+    for k, v in traces.items():  # hooks fired twice (full forward, then fb_model alone): keep pass 1
+        T = len(v) // 2
+        d["c__" + k] = np.stack(v[:T])
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
+    print(name, {k: (v.shape if hasattr(v, "shape") else v) for k, v in d.items() if k != "cfg"})
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(4)
+    # tiny structural variants with per-step membrane traces (teacher-forced protocol P1)
+    run_surface_a("tiny_shared_bn", synth.tiny_cfg(), 101, 2, 16 * 39, True)
+    run_surface_a("tiny_unshared_nobn", synth.tiny_cfg(shared_weights=False, bn=False,
+                                                       use_pre_layer_norm_fb=False,
+                                                       use_pre_layer_norm_sb=False), 102, 3, 16 * 24, True)
+    run_surface_a("tiny_spk2_tanh", synth.tiny_cfg(num_spks=2, fb_output_activate_function="tanh",
+                                                   sb_num_layers=1, fb_num_layers=3), 103, 2, 16 * 20, True)
+    run_cirm("tiny_cirm", dict(synth.CFG_CIRM, n_fft=64, hop_length=16, win_length=64, input_size=33,
+                               hidden_size=40, num_layers=3, proj_size=33, df_order=2), 104, 2, 16 * 30)
+    # config 1 of BASELINE.json: single 1 s clip, baseline_m, CPU forward (protocol P2)
+    run_surface_a("cfg1_baseline_m_1s", synth.CFG_M, 20220815, 1, 16000, False)
