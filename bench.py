@@ -1,0 +1,266 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of the GSN hot path (BASELINE.json metric) on N B200s, plus the CPU reference arm.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--size S|M|L|XL]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path (STFT magnitude in -> deep-filter coefficients out, SURVEY.md 8a
+a9) over one batch of synthetic spectrograms.  Default workload = BASELINE.json configs[1]:
+spiking_fullsubnet-S inference, batch 32 x 4 s clips (T = 501 frames of a 512-pt / 257-bin STFT) per GPU.
+Weak scaling: every rank processes its own batch of 32 clips (utterance-batch sharding, no collective
+on the data path).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", default="S", choices=["S", "M", "L", "XL"])
+    ap.add_argument("--batch", type=int, default=32, help="clips per GPU")
+    ap.add_argument("--seconds", type=float, default=4.0)
+    ap.add_argument("--backend", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload(args):
+    from oracle import synth  # synthetic weights/inputs only (test infrastructure, not on the timed path)
+    cfg = synth.CONFIGS[args.size]
+    L = int(round(args.seconds * 16000))
+    T = 1 + L // cfg["hop_length"]
+    return synth, cfg, L, T
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", d.get("bf16_tflops")), d.get("hbm_gbs"), "measured (MEASURED_PEAKS.json, sustained bf16)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.01)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def time_cpu_port(synth, cfg, batch, T, steps, warmup, seed=11):
+    """The reference's CPU implementation of the path (torch-CPU port, oracle/gsn_oracle_torch.py)."""
+    from oracle import gsn_oracle_torch as OT
+    torch.set_num_threads(os.cpu_count() or 1)
+    params = OT.to_torch(synth.make_params(cfg, 5))
+    mag = torch.from_numpy(synth.make_mag(batch, cfg["n_fft"] // 2 + 1, T, seed))
+    for _ in range(warmup):
+        OT.spiking_fullsubnet_network(mag[:, :, : max(8, T // 8)], params, cfg)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        OT.spiking_fullsubnet_network(mag, params, cfg)
+        times.append(time.perf_counter() - t0)
+    return times, torch.get_num_threads()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    synth, cfg, L, T = workload(args)
+    B = args.batch
+    wl = {"workload": f"intel_ndns spiking_fullsubnet-{args.size} inference (surface A args), batch {B} x "
+                      f"{args.seconds:g} s synthetic clips per GPU, T={T} frames, 257-bin STFT; hot path = "
+                      f"magnitude in -> deep-filter coefficients out",
+          "size": args.size, "batch_per_gpu": B, "frames_per_clip": T, "sharding": f"utterance batch x{world}",
+          "weights": "random-init (synthetic, seed 5), eval-mode BatchNorm"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        times, cores = time_cpu_port(synth, cfg, B, T, args.steps, args.warmup)
+        sec = float(np.mean(times))
+        val = B * T / sec
+        line = {"impl": "reference", "metric": "frames/sec", "value": val, "unit": "frames/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": wl,
+                "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": "port",
+                                 "sample": f"full batch {B} x T={T} per step, torch-CPU port of the reference "
+                                           f"path (oracle/gsn_oracle_torch.py), network part only"},
+                "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ B200 arm
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from spiking_fullsubnet_b200 import SpikingFullSubNet, ops
+
+    params = synth.make_params(cfg, 5)
+    model = SpikingFullSubNet(**cfg)
+    model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in params.items()}, strict=True)
+    model = model.eval().to(dev).set_backend(args.backend)
+    mag = torch.from_numpy(synth.make_mag(B, 257, T, 11 + rank)).to(dev)
+    wave_host = torch.from_numpy(synth.make_wave(B, L, 21 + rank)).pin_memory()
+    out_host = torch.empty((B, L), dtype=torch.float32).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        with torch.no_grad():
+            return model.network(mag)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ops.LAUNCHES[0] = 0
+    evs = []
+    for _ in range(args.steps):
+        flush.fill_(1.0)  # L2 flush between timed iterations (untimed)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step()
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    launches = ops.LAUNCHES[0]
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+
+    # end to end through the public API: pinned host waveform -> H2D -> forward() -> D2H enhanced waveform
+    def e2e_step():
+        w = wave_host.to(dev, non_blocking=True)
+        with torch.no_grad():
+            y = model(w)[0]
+        out_host.copy_(y, non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    sampler.stop_flag = True
+    sampler.join()
+
+    # per-kernel timing of the dominant kernel (the recurrence), live, with CUDA events on its stream
+    ops.PROFILE = []
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    rec = ops.PROFILE
+    ops.PROFILE = None
+    rec_ms = sum(a.elapsed_time(b) for (_, a, b) in rec) / 3.0
+    rec_flops = sum(f for (f, _, _) in rec) / 3.0
+
+    t = torch.tensor([dev_ms, e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_s = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    frames = world * B * T * args.steps
+    value = frames / (dev_ms * 1e-3)
+    tf_peak, hbm_peak, peak_src = peaks()
+    achieved = rec_flops / (rec_ms * 1e-3) / 1e12 if rec_ms > 0 else 0.0
+    backends = sorted({ops.pick_backend(r, h, cfg["shared_weights"]) if args.backend == "auto" else args.backend
+                       for (r, h) in [(B, cfg["fb_hidden_size"])] +
+                       [(B * ((cfg["freq_cutoffs"][i + 1] - cfg["freq_cutoffs"][i]) // c), cfg["sb_hidden_size"])
+                        for i, c in enumerate(cfg["center_freq_sizes"])]})
+    line = {
+        "metric": "frames/sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (recurrent weights as exact bf16x3 planes on tcgen05 where that backend runs)",
+        "data": "synthetic",
+        "config": dict(wl, l2="flushed between timed iterations (256 MiB write)",
+                       recurrence_backends=backends),
+        "clocks": sampler.summary(),
+        "e2e": {"value": world * B * T * args.steps / e2e_s, "unit": "frames/s",
+                "h2d_bytes_per_step": int(wave_host.numel() * 4), "d2h_bytes_per_step": int(out_host.numel() * 4),
+                "what": "model.forward(wave): pinned host waveform -> STFT -> network -> deep filter -> iSTFT -> host"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
+                     "frac": achieved / tf_peak if tf_peak else None, "traffic": None,
+                     "kernel": "GSN recurrence (all layers of all sequence models of one step)",
+                     "algorithmic_flops_per_step": rec_flops, "kernel_ms_per_step": rec_ms,
+                     "share_of_step": rec_ms / (dev_ms / args.steps), "peak_source": peak_src},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        times, cores = time_cpu_port(synth, cfg, B, T, 3, 1)
+        line["cpu_baseline"] = {"value": B * T / min(times), "unit": "frames/s", "cores": cores, "kind": "port",
+                                "sample": f"full batch {B} x T={T}, best of 3, torch-CPU port of the reference "
+                                          f"path (network part only)"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,114 @@
+/*
+ * gsn_b200.h -- C ABI of libgsn_b200.so: the B200 (sm_100a) implementation of the GSN hot path of
+ * Spiking-FullSubNet.  Plain device pointers, sizes and a CUDA stream; no torch types.
+ *
+ * Reference interfaces replaced (paths relative to the reference root):
+ *   ESN = audiozen/models/spiking_fullsubnet/efficient_spiking_neuron.py
+ *   MSF = audiozen/models/spiking_fullsubnet/modeling_spiking_fullsubnet.py
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous fp32 unless stated otherwise;
+ *   - nothing is allocated inside: outputs and workspaces are caller-owned, sizes come from the
+ *     *_workspace_bytes() queries;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); calls are asynchronous;
+ *   - return value 0 = success, otherwise a GSN_E* code; gsn_last_error() gives the message of the
+ *     last failure on the calling thread (mirrors the Python exceptions of the reference);
+ *   - "rows" R are the independent recurrences of one sequence model: R = batch (full-band model) or
+ *     batch * num_subbands (sub-band model), row index r = b * N + n  (MSF:155).
+ */
+#ifndef GSN_B200_H_
+#define GSN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSN_ABI_VERSION 1
+
+#define GSN_OK 0
+#define GSN_EINVAL 1   /* bad argument (ValueError / AssertionError in the reference) */
+#define GSN_ECUDA 2    /* CUDA runtime error (RuntimeError) */
+#define GSN_ENOSUP 3   /* shape not supported by the requested backend (NotImplementedError) */
+
+/* recurrence back ends */
+#define GSN_BACKEND_AUTO 0
+#define GSN_BACKEND_SIMT 1     /* fp32 CUDA-core kernel: any H <= 512, the on-device fp32 arbiter */
+#define GSN_BACKEND_TCGEN05 2  /* tcgen05/TMEM kernel, recurrent weights split in exact bf16 planes */
+
+typedef void* gsn_stream_t;
+
+#if defined(__GNUC__)
+#define GSN_API __attribute__((visibility("default")))
+#else
+#define GSN_API
+#endif
+
+GSN_API int gsn_abi_version(void);
+GSN_API const char* gsn_last_error(void);
+/* cudaSetDevice for the library's runtime instance (call when the caller switches device). */
+GSN_API int gsn_bind_device(int device);
+/* sm count, compute capability and max opt-in shared memory of the bound device. */
+GSN_API int gsn_device_info(int* sm_count, int* cc_major, int* cc_minor, int* smem_optin_bytes);
+
+/* ---- front end ------------------------------------------------------------------------------
+ * MSF:434-436 + the 'b f t -> t b f' of MSF:108:  cm[t, b, f] = mag[b, f, t] ** fdrc  for f < f_keep.
+ * mag [B, F, T] (STFT magnitude), cm [T, B, f_keep].  fdrc == 0.5 is evaluated as sqrt (as torch
+ * does), fdrc == 1 as a copy.                                                                    */
+GSN_API int gsn_compress_mag(const float* mag, float* cm, int B, int F, int f_keep, int T, float fdrc,
+                     gsn_stream_t stream);
+
+/* MSF:241-258 (+ _freq_unfold MSF:265-312, concat with the tiled full-band output MSF:443) and the
+ * pre-LayerNorm MSF:111-112, as ONE gather:
+ *   x[t, b*N + n, j] = LN_j( j <  ctr+2*nbr : cm[t, b, reflect(lo + n*ctr - nbr + j)]
+ *                            j >= ctr+2*nbr : fb[t, b, (lo + n*ctr + j - (ctr+2*nbr)) mod f_fb] )
+ * reflect(q) = -q for q < 0, 2*(f_cm-1) - q for q > f_cm-1.   K = ctr + 2*nbr + (fb ? ctr : 0).
+ * fb == NULL drops the second part (full-band model input: N = 1, lo = 0, ctr = K, nbr = 0).
+ * ln_weight == NULL skips the LayerNorm (use_pre_layer_norm = False).  K <= 1024.               */
+GSN_API int gsn_subband_features(const float* cm, int f_cm, const float* fb, int f_fb, float* x, int T, int B,
+                         int N, int lo, int ctr, int nbr, const float* ln_weight, const float* ln_bias,
+                         float ln_eps, gsn_stream_t stream);
+
+/* ---- dense fp32 linear (input-to-hidden product ESN:141, proj MSF:118) -------------------------
+ * out[M, N] = a[M, K] @ w[N, K]^T + bias[N]   (bias may be NULL).  fp32 FMA, k ascending.
+ * act: 0 none, 1 tanh, 2 sigmoid, 3 relu applied to a SECOND output out_act (may be NULL) so that
+ * both the pre-activation trace entry (MSF:119) and the activated output (MSF:122) are produced.  */
+GSN_API int gsn_linear_f32(const float* a, const float* w, const float* bias, float* out, float* out_act,
+                   int act, int64_t M, int K, int N, gsn_stream_t stream);
+
+/* ---- the recurrence: GSULayer.forward ESN:75-81 over GSUCell.forward ESN:132-153 ----------------
+ * For t = 0..T-1, rows r, neurons j:
+ *   z      = xproj[t, r, :] + h_{t-1}[r, :] @ w_hh^T            (xproj = x @ w_ih^T, no bias)
+ *   f      = sigmoid(z_f + bias[j]);  g = z_g + bias[H + j]     (shared: z_f = z_g = z[j]; else
+ *                                                                z_f = z[j], z_g = z[H + j])
+ *   c_t    = (f * c_{t-1} + (1 - f) * g) * bn_scale[j] + bn_shift[j]   (eval BatchNorm folded the way
+ *                                                                torch's CPU kernel folds it; NULL = no BN)
+ *   h_t    = c_t >= 0
+ * xproj [T, R, gH], w_hh [gH, H] (g = 1 shared, 2 unshared), bias [2H].
+ * h0 / c0 [R, H] may be NULL (zeros, MSF:100-106).  h_out [T, R, H] fp32 {0,1} (the trace entry of
+ * all_layer_outputs, ESN:60); c_out [T, R, H] optional (NULL) membrane trace; hT / cT [R, H] optional.
+ * workspace: gsn_layer_recurrence_workspace_bytes(R, H, shared, backend) bytes, 256-byte aligned.   */
+GSN_API size_t gsn_layer_recurrence_workspace_bytes(int R, int H, int shared, int backend);
+GSN_API int gsn_layer_recurrence(const float* xproj, const float* w_hh, const float* bias,
+                         const float* bn_scale, const float* bn_shift, const float* h0,
+                         const float* c0, float* h_out, float* c_out, float* hT, float* cT, int T,
+                         int R, int H, int shared, int backend, void* workspace,
+                         gsn_stream_t stream);
+/* which backend GSN_BACKEND_AUTO resolves to for this shape (GSN_BACKEND_SIMT / _TCGEN05). */
+GSN_API int gsn_layer_recurrence_pick_backend(int R, int H, int shared);
+
+/* ---- back end: deep filter (MSF:315-346) -- "next" row f1 ----------------------
+ * Applies the coefficients straight from the sub-band proj output, skipping the 6-D rearrangement:
+ *   proj [T, B*N, P] with p = ((c2*ctr + fc)*df + d)*S + s   (MSF:160-167)
+ *   spec_re/spec_im [B, F, T] noisy STFT;  out_re/out_im [B, S, F_out, T]
+ *   out[b, s, lo + n*ctr + fc, t] = sum_d spec[b, lo + n*ctr + fc, t - (df-1) + d] * coef[d]      */
+GSN_API int gsn_deepfilter_band(const float* proj, const float* spec_re, const float* spec_im, float* out_re,
+                        float* out_im, int T, int B, int N, int ctr, int df, int S, int lo, int F,
+                        int F_out, gsn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSN_B200_H_ */

@@ -1,0 +1,92 @@
+// C-ABI glue of libgsn_b200: error reporting, device binding, recurrence back-end dispatch.
+#include <stdarg.h>
+
+#include "gsn_common.cuh"
+
+namespace gsn {
+
+char* err_buf() {
+  static thread_local char buf[512] = "";
+  return buf;
+}
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(err_buf(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+// gsn_recurrence_simt.cu
+int launch_recurrence_simt(const float*, const float*, const float*, const float*, const float*,
+                           const float*, const float*, float*, float*, float*, float*, int, int, int,
+                           int, void*, cudaStream_t);
+size_t recurrence_simt_workspace(int H, int shared);
+// gsn_recurrence_tc.cu
+int launch_recurrence_tc(const float*, const float*, const float*, const float*, const float*,
+                         const float*, const float*, float*, float*, float*, float*, int, int, int, int,
+                         void*, cudaStream_t);
+size_t recurrence_tc_workspace(int R, int H, int shared);
+bool recurrence_tc_supported(int R, int H, int shared);
+
+}  // namespace gsn
+
+extern "C" int gsn_abi_version(void) { return GSN_ABI_VERSION; }
+
+extern "C" const char* gsn_last_error(void) { return gsn::err_buf(); }
+
+extern "C" int gsn_bind_device(int device) {
+  GSN_CUDA(cudaSetDevice(device));
+  return GSN_OK;
+}
+
+extern "C" int gsn_device_info(int* sm_count, int* cc_major, int* cc_minor, int* smem_optin_bytes) {
+  int dev = 0;
+  GSN_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  GSN_CUDA(cudaGetDeviceProperties(&p, dev));
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  if (smem_optin_bytes) *smem_optin_bytes = (int)p.sharedMemPerBlockOptin;
+  return GSN_OK;
+}
+
+extern "C" int gsn_layer_recurrence_pick_backend(int R, int H, int shared) {
+  return gsn::recurrence_tc_supported(R, H, shared) ? GSN_BACKEND_TCGEN05 : GSN_BACKEND_SIMT;
+}
+
+extern "C" size_t gsn_layer_recurrence_workspace_bytes(int R, int H, int shared, int backend) {
+  if (R <= 0 || H <= 0) return 0;
+  size_t a = gsn::recurrence_simt_workspace(H, shared);
+  size_t b = gsn::recurrence_tc_supported(R, H, shared) ? gsn::recurrence_tc_workspace(R, H, shared) : 0;
+  if (backend == GSN_BACKEND_SIMT) return a;
+  if (backend == GSN_BACKEND_TCGEN05) return b;
+  return a > b ? a : b;
+}
+
+extern "C" int gsn_layer_recurrence(const float* xproj, const float* w_hh, const float* bias,
+                                    const float* bn_scale, const float* bn_shift, const float* h0,
+                                    const float* c0, float* h_out, float* c_out, float* hT, float* cT,
+                                    int T, int R, int H, int shared, int backend, void* workspace,
+                                    gsn_stream_t stream) {
+  GSN_REQUIRE(xproj && w_hh && bias && h_out && workspace, "gsn_layer_recurrence: null pointer");
+  GSN_REQUIRE(T > 0 && R > 0 && H > 0, "gsn_layer_recurrence: bad shape T=%d R=%d H=%d", T, R, H);
+  GSN_REQUIRE((bn_scale == nullptr) == (bn_shift == nullptr), "gsn_layer_recurrence: bn params");
+  GSN_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+              "gsn_layer_recurrence: workspace must be 256-byte aligned");
+  if (backend == GSN_BACKEND_AUTO) backend = gsn_layer_recurrence_pick_backend(R, H, shared);
+  cudaStream_t st = gsn::as_stream(stream);
+  if (backend == GSN_BACKEND_SIMT)
+    return gsn::launch_recurrence_simt(xproj, w_hh, bias, bn_scale, bn_shift, h0, c0, h_out, c_out, hT,
+                                       cT, T, R, H, shared, workspace, st);
+  if (backend == GSN_BACKEND_TCGEN05) {
+    if (!gsn::recurrence_tc_supported(R, H, shared))
+      return gsn::fail(GSN_ENOSUP, "gsn_layer_recurrence(TCGEN05): shape R=%d H=%d shared=%d not supported",
+                       R, H, shared);
+    return gsn::launch_recurrence_tc(xproj, w_hh, bias, bn_scale, bn_shift, h0, c0, h_out, c_out, hT,
+                                     cT, T, R, H, shared, workspace, st);
+  }
+  return gsn::fail(GSN_EINVAL, "gsn_layer_recurrence: unknown backend %d", backend);
+}

@@ -1,0 +1,53 @@
+// Shared helpers for libgsn_b200 (sm_100a).  Internal header -- the public ABI is include/gsn_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "gsn_b200.h"
+
+namespace gsn {
+
+// thread-local last-error message (gsn_last_error)
+char* err_buf();
+int fail(int code, const char* fmt, ...);
+
+#define GSN_REQUIRE(cond, ...)                          \
+  do {                                                  \
+    if (!(cond)) return gsn::fail(GSN_EINVAL, __VA_ARGS__); \
+  } while (0)
+
+#define GSN_CUDA(call)                                                                      \
+  do {                                                                                      \
+    cudaError_t e__ = (call);                                                               \
+    if (e__ != cudaSuccess)                                                                 \
+      return gsn::fail(GSN_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),  \
+                       __FILE__, __LINE__);                                                 \
+  } while (0)
+
+#define GSN_LAUNCH_CHECK(name)                                                               \
+  do {                                                                                       \
+    cudaError_t e__ = cudaGetLastError();                                                    \
+    if (e__ != cudaSuccess)                                                                  \
+      return gsn::fail(GSN_ECUDA, "launch of %s failed: %s", name, cudaGetErrorString(e__)); \
+  } while (0)
+
+static inline cudaStream_t as_stream(gsn_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+__device__ __forceinline__ float sigmoid_f32(float x) {
+  // same formula as the reference's torch.sigmoid: 1 / (1 + exp(-x)), full-precision expf and division
+  return 1.0f / (1.0f + expf(-x));
+}
+
+// c_t and h_t of one neuron from the gate pre-activations (ESN:146-151)
+__device__ __forceinline__ float gsu_membrane(float f_hat, float g_hat, float c_prev, float bn_scale,
+                                              float bn_shift) {
+  const float f = sigmoid_f32(f_hat);
+  // written exactly as the reference evaluates it: f*c + (1-f)*g, then the folded BN affine
+  float c = __fadd_rn(__fmul_rn(f, c_prev), __fmul_rn(__fsub_rn(1.0f, f), g_hat));
+  c = __fadd_rn(__fmul_rn(c, bn_scale), bn_shift);
+  return c;
+}
+
+}  // namespace gsn

@@ -1,0 +1,409 @@
+"""Drop-in nn.Module facades for the GSN hot path.
+
+Same constructor arguments, forward() return tuples, parameter / buffer names and shapes as the
+reference modules, so `audiozen/trainer.py` and the model-zoo `pytorch_model.bin` files work
+unchanged; the arithmetic between "magnitude in" and "coefficients out" runs in libgsn_b200.so.
+
+Reference modules mirrored (paths relative to the reference root):
+  ESN = audiozen/models/spiking_fullsubnet/efficient_spiking_neuron.py  (GSUCell :104, GSULayer :70,
+        StackedGSU :43, efficient_spiking_neuron :12)
+  MSF = audiozen/models/spiking_fullsubnet/modeling_spiking_fullsubnet.py (SequenceModel :12,
+        SubBandSequenceModel :128, SubbandModel :172, SpikingFullSubNet :349)
+  CGN = audiozen/models/cirm_gsn/modeling_cirm_gsn.py (Model :162)
+
+The modules hold parameters only; there is no per-frame Python loop and no CPU / eager fallback:
+CPU tensors raise.  Training-mode BatchNorm statistics and the backward pass are not implemented yet
+(forward raises in train mode when bn=True), see DESIGN.md.
+"""
+from __future__ import annotations
+
+import math
+from collections import namedtuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+MemoryState = namedtuple("MemoryState", ["hx", "cx"])
+
+__all__ = ["MemoryState", "efficient_spiking_neuron", "GSUCell", "GSULayer", "StackedGSU",
+           "SequenceModel", "SubBandSequenceModel", "SubbandModel", "SpikingFullSubNet", "CirmGSN"]
+
+
+# ------------------------------------------------------------------------------------------------
+# neuron stack (ESN)
+# ------------------------------------------------------------------------------------------------
+class GSUCell(nn.Module):
+    """Parameter holder of one gated spiking layer: weight_ih [gH,K], weight_hh [gH,H], bias_ih [2H],
+    optional batchnorm (ESN:105-130).  All three parameters start U(+-1/sqrt(H)) like the reference
+    (whose reset_parameters also overwrites the zero bias)."""
+
+    def __init__(self, input_size, hidden_size, shared_weights=False, bn=False):
+        super().__init__()
+        self.input_size, self.hidden_size = input_size, hidden_size
+        self.shared_weights, self.use_bn = shared_weights, bn
+        g = 1 if shared_weights else 2
+        self.weight_ih = nn.Parameter(torch.empty(g * hidden_size, input_size))
+        self.weight_hh = nn.Parameter(torch.empty(g * hidden_size, hidden_size))
+        self.bias_ih = nn.Parameter(torch.empty(2 * hidden_size))
+        bound = 1.0 / math.sqrt(hidden_size) if hidden_size > 0 else 0.0
+        for p in (self.weight_ih, self.weight_hh, self.bias_ih):
+            nn.init.uniform_(p, -bound, bound)
+        if bn:
+            self.batchnorm = nn.BatchNorm1d(hidden_size)
+        self._bn_cache = None
+
+    def folded_bn(self):
+        """Eval-mode BatchNorm as the per-channel affine torch's own CPU kernel applies:
+        alpha = weight / sqrt(running_var + eps), beta = bias - running_mean * alpha."""
+        if not self.use_bn:
+            return None, None
+        bn = self.batchnorm
+        key = (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version,
+               bn.weight.data_ptr(), bn.running_var.data_ptr())
+        if self._bn_cache is None or self._bn_cache[0] != key:
+            with torch.no_grad():
+                invstd = 1.0 / torch.sqrt(bn.running_var + bn.eps)
+                alpha = (invstd * bn.weight).contiguous()
+                beta = (bn.bias - bn.running_mean * alpha).contiguous()
+            self._bn_cache = (key, alpha, beta)
+        return self._bn_cache[1], self._bn_cache[2]
+
+    def forward(self, input, state):
+        """One frame (ESN:132-153): input [R,K], state (h [R,H], c [R,H]) -> (h, (h, c))."""
+        h, c, (hT, cT) = _run_layer(self, input.unsqueeze(0).contiguous(), state, want_c=False,
+                                    backend="auto")
+        return hT, MemoryState(hT, cT)
+
+
+class GSULayer(nn.Module):
+    def __init__(self, cell, *cell_args):
+        super().__init__()
+        self.cell = cell(*cell_args)
+
+    def forward(self, input, state):
+        """input [T,R,K] -> (h [T,R,H], final state) (ESN:75-81) -- one kernel, no Python time loop."""
+        h, _, (hT, cT) = _run_layer(self.cell, input, state, want_c=False, backend="auto")
+        return h, MemoryState(hT, cT)
+
+
+def _run_layer(cell, x, state, want_c, backend):
+    if cell.use_bn and cell.batchnorm.training:
+        raise NotImplementedError("training-mode BatchNorm inside the GSN recurrence is not implemented "
+                                  "yet; call model.eval()")
+    if not x.is_cuda:
+        raise RuntimeError("spiking_fullsubnet_b200 has no CPU path: move the model and input to CUDA")
+    x = x.contiguous()
+    xproj = ops.linear(x, cell.weight_ih.detach())  # bias joins in the recurrence, in reference order
+    a, b = cell.folded_bn()
+    h0 = c0 = None
+    if state is not None:
+        h0, c0 = state[0].contiguous(), state[1].contiguous()
+    return ops.layer_recurrence(xproj, cell.weight_hh.detach(), cell.bias_ih.detach(), a, b,
+                                shared=cell.shared_weights, want_c=want_c, h0=h0, c0=c0,
+                                want_state=True, backend=backend)
+
+
+class StackedGSU(nn.Module):
+    def __init__(self, num_layers, layer, first_layer_args, other_layer_args):
+        super().__init__()
+        self.layers = nn.ModuleList([layer(*first_layer_args)] +
+                                    [layer(*other_layer_args) for _ in range(num_layers - 1)])
+        self.backend = "auto"
+
+    def forward(self, input, states=None, want_c=False):
+        """(ESN:50-62) input [T,R,K], states list of (h,c) or None (zeros) ->
+        (output [T,R,H], output_states, all_layer_output = [input, h1..hL])."""
+        out = input
+        out_states, trace = [], [input]
+        self.last_c = []
+        for i, layer in enumerate(self.layers):
+            st = None if states is None else states[i]
+            h, c, (hT, cT) = _run_layer(layer.cell, out, st, want_c, self.backend)
+            out_states.append(MemoryState(hT, cT))
+            trace.append(h)
+            self.last_c.append(c)
+            out = h
+        return out, out_states, trace
+
+
+def efficient_spiking_neuron(input_size, hidden_size, num_layers, shared_weights=False, bn=False,
+                             batch_first=False):
+    """Factory with the reference's signature (ESN:12-40)."""
+    assert not batch_first
+    return StackedGSU(num_layers, GSULayer,
+                      first_layer_args=[GSUCell, input_size, hidden_size, shared_weights, bn],
+                      other_layer_args=[GSUCell, hidden_size, hidden_size, shared_weights, bn])
+
+
+# ------------------------------------------------------------------------------------------------
+# sequence models (MSF)
+# ------------------------------------------------------------------------------------------------
+_ACTS = ("tanh", "sigmoid", "relu")
+
+
+class SequenceModel(nn.Module):
+    def __init__(self, input_size, hidden_size, num_layers, sequence_model="GSN", proj_size=0,
+                 shared_weights=False, output_activate_function=None, bn=False, use_pre_layer_norm=True):
+        super().__init__()
+        if use_pre_layer_norm:
+            self.pre_layer_norm = nn.LayerNorm(input_size)
+        if sequence_model == "GSN":
+            self.sequence_model = efficient_spiking_neuron(input_size, hidden_size, num_layers,
+                                                           shared_weights=shared_weights, bn=bn)
+        elif sequence_model == "LSTM":
+            raise NotImplementedError("sequence_model='LSTM' is outside the GSN hot path (SURVEY 8a, a6); "
+                                      "use the reference implementation for LSTM models")
+        else:
+            raise NotImplementedError(f"Sequence model {sequence_model} not implemented.")
+        self.proj = nn.Linear(hidden_size, proj_size) if proj_size > 0 else nn.Identity()
+        self.output_activate_function = {"tanh": nn.Tanh, "sigmoid": nn.Sigmoid, "relu": nn.ReLU}.get(
+            output_activate_function, nn.Identity)()
+        self._act = output_activate_function if output_activate_function in _ACTS else None
+        self.input_size, self.hidden_size, self.num_layers = input_size, hidden_size, num_layers
+        self.proj_size = proj_size
+        self.use_pre_layer_norm = use_pre_layer_norm
+        self.sequence_model_name = sequence_model
+
+    # --- time-major core used by every facade -----------------------------------------------------
+    def run_time_major(self, x):
+        """x [T,R,K] already normalised -> (proj_out [T,R,P], activated [T,R,P], all_layer_outputs)."""
+        out, _, trace = self.sequence_model(x, None)
+        if isinstance(self.proj, nn.Linear):
+            res = ops.linear(out, self.proj.weight.detach(), self.proj.bias.detach(), act=self._act)
+            proj, act = res if self._act else (res, res)
+        else:
+            proj = out
+            act = self.output_activate_function(out)
+        return proj, act, trace + [proj]
+
+    def forward(self, input):
+        """input [R,K,T] -> (output [R,P,T], all_layer_outputs) (MSF:81-125)."""
+        assert input.ndim == 3, f"Input tensor must be 3D, but got {input.ndim}D."
+        if not input.is_cuda:
+            raise RuntimeError("spiking_fullsubnet_b200 has no CPU path: move the model and input to CUDA")
+        R, K, T = input.shape
+        cm = input.permute(2, 0, 1).contiguous()  # 'b f t -> t b f'
+        lnw = self.pre_layer_norm.weight.detach() if self.use_pre_layer_norm else None
+        lnb = self.pre_layer_norm.bias.detach() if self.use_pre_layer_norm else None
+        eps = self.pre_layer_norm.eps if self.use_pre_layer_norm else 1e-5
+        x = ops.subband_features(cm, None, 1, 0, K, 0, lnw, lnb, eps)
+        _, act, all_out = self.run_time_major(x)
+        return act.permute(1, 2, 0), all_out
+
+
+class SubBandSequenceModel(SequenceModel):
+    def __init__(self, df_order, num_spks, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.df_order, self.num_spks = df_order, num_spks
+
+    def forward(self, input_features):
+        """[B,N,1,fs,T] -> ([B,df,S,N*fc,T,2], all_layer_outputs) (MSF:134-169)."""
+        B, N, C, fs, T = input_features.shape
+        assert C == 1, "Only mono audio is supported."
+        out, all_out = super().forward(input_features.reshape(B * N, fs, T))
+        return coef_layout(out.permute(2, 0, 1), B, N, self.df_order, self.num_spks), all_out
+
+
+def coef_layout(proj, B, N, df, S):
+    """proj [T, B*N, P] -> [B, df, S, N*fc, T, 2]: '(b n) (c fc df s) t -> b df s (n fc) t c'
+    (MSF:160-167); pure index arithmetic (a strided view + one copy)."""
+    T, _, P = proj.shape
+    fc = P // (2 * df * S)
+    v = proj.reshape(T, B, N, 2, fc, df, S)
+    return v.permute(1, 5, 6, 2, 4, 0, 3).reshape(B, df, S, N * fc, T, 2)
+
+
+class SubbandModel(nn.Module):
+    def __init__(self, freq_cutoffs, center_freq_sizes, neighbor_freq_sizes, df_orders, num_spks, **kwargs):
+        super().__init__()
+        assert len(freq_cutoffs) - 1 == len(center_freq_sizes), "Number of subbands must be equal to len(cutoffs)."
+        self.sb_models = nn.ModuleList([
+            SubBandSequenceModel(input_size=(c + n * 2) + c, proj_size=2 * c * d * num_spks, df_order=d,
+                                 num_spks=num_spks, **kwargs)
+            for c, n, d in zip(center_freq_sizes, neighbor_freq_sizes, df_orders)])
+        self.freq_cutoffs = freq_cutoffs
+        self.center_freq_sizes = center_freq_sizes
+        self.neighbor_freq_sizes = neighbor_freq_sizes
+        self.df_orders = df_orders
+        self.num_spks = num_spks
+
+    def run_time_major(self, cm, fb):
+        """cm [T,B,F] compressed magnitude, fb [T,B,f_fb] full-band output (tiled by index) ->
+        list of proj outputs [T, B*N_i, P_i] and the per-band all_layer_outputs (MSF:216-263)."""
+        T, B, F = cm.shape
+        projs, all_outs = [], []
+        for i, m in enumerate(self.sb_models):
+            lo, hi = self.freq_cutoffs[i], self.freq_cutoffs[i + 1]
+            ctr, nbr = self.center_freq_sizes[i], self.neighbor_freq_sizes[i]
+            if (hi - lo) % ctr != 0:
+                raise ValueError(f"Number of frequency bins must be divisible by the center frequency."
+                                 f"GOT: ctr_freq={ctr}, upper_cutoff_freq={hi}, lower_cutoff_freq={lo}")
+            lnw = m.pre_layer_norm.weight.detach() if m.use_pre_layer_norm else None
+            lnb = m.pre_layer_norm.bias.detach() if m.use_pre_layer_norm else None
+            eps = m.pre_layer_norm.eps if m.use_pre_layer_norm else 1e-5
+            x = ops.subband_features(cm, fb, (hi - lo) // ctr, lo, ctr, nbr, lnw, lnb, eps)
+            proj, _, all_out = m.run_time_major(x)
+            projs.append(proj)
+            all_outs.append(all_out)
+        return projs, all_outs
+
+    def forward(self, noisy_input, fb_output):
+        """noisy_input [B,1,F,T], fb_output [B,1,F,T] (already tiled) -> (coef list, all_layer_outputs)."""
+        B, C, F, T = noisy_input.shape
+        assert C == 1, "Only mono audio is supported."
+        cm = noisy_input[:, 0].permute(2, 0, 1).contiguous()
+        fb = fb_output[:, 0].permute(2, 0, 1).contiguous()
+        projs, all_outs = self.run_time_major(cm, fb)
+        coefs = [coef_layout(p, B, p.shape[1] // B, d, self.num_spks) for p, d in zip(projs, self.df_orders)]
+        return coefs, all_outs
+
+
+def _stft(y, n_fft, hop, win):
+    # audiozen/acoustics/audio_feature.py:236-294 (hann window, center=True, pad_mode="constant")
+    window = torch.hann_window(n_fft, device=y.device)
+    return torch.stft(y, n_fft, hop, win, window=window, return_complex=True, pad_mode="constant")
+
+
+def _istft(spec, n_fft, hop, win, length):
+    # audiozen/acoustics/audio_feature.py:297-347
+    window = torch.hann_window(n_fft, device=spec.device)
+    return torch.istft(spec, n_fft, hop, win, window=window, length=length)
+
+
+class SpikingFullSubNet(nn.Module):
+    """Surface A (MSF:349-474).  forward(wave [B,L]) ->
+    (enh_y [B,L], enh_mag [B,F,T], fb_all_layer_outputs, sb_all_layer_outputs), or for num_spks > 1
+    (enh_y [B,S,L], fb_all_layer_outputs, sb_all_layer_outputs)."""
+
+    def __init__(self, n_fft, hop_length, win_length, fdrc, fb_input_size, fb_hidden_size, fb_num_layers,
+                 fb_proj_size, fb_output_activate_function, sb_hidden_size, sb_num_layers, freq_cutoffs,
+                 df_orders, center_freq_sizes, neighbor_freq_sizes, use_pre_layer_norm_fb=True,
+                 use_pre_layer_norm_sb=True, bn=False, shared_weights=False, sequence_model="GSN", num_spks=1):
+        super().__init__()
+        self.fb_model = SequenceModel(input_size=fb_input_size, hidden_size=fb_hidden_size,
+                                      num_layers=fb_num_layers, shared_weights=shared_weights,
+                                      sequence_model=sequence_model, proj_size=fb_proj_size,
+                                      output_activate_function=fb_output_activate_function, bn=bn,
+                                      use_pre_layer_norm=use_pre_layer_norm_fb)
+        self.sb_model = SubbandModel(freq_cutoffs=freq_cutoffs, center_freq_sizes=center_freq_sizes,
+                                     neighbor_freq_sizes=neighbor_freq_sizes, df_orders=df_orders,
+                                     num_spks=num_spks, hidden_size=sb_hidden_size, num_layers=sb_num_layers,
+                                     shared_weights=shared_weights, sequence_model=sequence_model, bn=bn,
+                                     use_pre_layer_norm=use_pre_layer_norm_sb)
+        self.subband_model = None
+        self.fb_input_size, self.n_fft, self.hop_length, self.win_length = fb_input_size, n_fft, hop_length, win_length
+        self.fdrc, self.df_orders, self.num_spks = fdrc, df_orders, num_spks
+
+    def set_backend(self, backend):
+        """'auto' | 'simt' | 'tcgen05' for every recurrence of the model."""
+        for m in self.modules():
+            if isinstance(m, StackedGSU):
+                m.backend = backend
+        return self
+
+    # the hot path: magnitude in -> sub-band proj outputs (the coefficients) out  (MSF:434-447)
+    def network(self, mag):
+        """mag [B, n_fft//2+1, T] -> (projs: list of [T, B*N_i, P_i], fb_all, sb_all)."""
+        if not mag.is_cuda:
+            raise RuntimeError("spiking_fullsubnet_b200 has no CPU path: move the model and input to CUDA")
+        F = mag.shape[1]
+        cm = ops.compress_mag(mag.contiguous(), F - 1, self.fdrc)  # drops the last bin, MSF:436
+        fbm = self.fb_model
+        lnw = fbm.pre_layer_norm.weight.detach() if fbm.use_pre_layer_norm else None
+        lnb = fbm.pre_layer_norm.bias.detach() if fbm.use_pre_layer_norm else None
+        eps = fbm.pre_layer_norm.eps if fbm.use_pre_layer_norm else 1e-5
+        x = ops.subband_features(cm, None, 1, 0, self.fb_input_size, 0, lnw, lnb, eps)
+        _, fb_act, fb_all = fbm.run_time_major(x)
+        # the reference tiles the full-band output (n_fft//2+1)//fb_input_size times (MSF:443); the
+        # gather indexes it modulo its width instead, which needs the tiling to cover all bins
+        rep = (self.n_fft // 2 + 1) // self.fb_input_size
+        if rep * fb_act.shape[2] < F - 1:
+            raise ValueError(f"full-band output ({fb_act.shape[2]} bins x {rep}) does not cover {F - 1} bins")
+        projs, sb_all = self.sb_model.run_time_major(cm, fb_act)
+        return projs, fb_all, sb_all
+
+    def coefficients(self, mag):
+        """Deep-filter coefficient tensors [B, df_i, S, F_i, T, 2] in the reference layout."""
+        projs, fb_all, sb_all = self.network(mag)
+        B = mag.shape[0]
+        return [coef_layout(p, B, p.shape[1] // B, d, self.num_spks)
+                for p, d in zip(projs, self.df_orders)], fb_all, sb_all
+
+    def forward(self, input):
+        assert input.ndim == 2, f"Input tensor must be 2D, but got {input.ndim}D."
+        B, L = input.shape
+        cmp = _stft(input, self.n_fft, self.hop_length, self.win_length)  # [B,F,T] complex
+        mag = cmp.abs().contiguous()
+        projs, fb_all, sb_all = self.network(mag)
+        F, T = cmp.shape[1], cmp.shape[2]
+        S = self.num_spks
+        sre, sim = cmp.real.contiguous(), cmp.imag.contiguous()
+        # start from the noisy spectrum so un-filtered bins (Nyquist) pass through (MSF:461-468)
+        ore = sre.unsqueeze(1).repeat(1, S, 1, 1)
+        oim = sim.unsqueeze(1).repeat(1, S, 1, 1)
+        cuts, ctrs = self.sb_model.freq_cutoffs, self.sb_model.center_freq_sizes
+        lo = 0
+        for i, p in enumerate(projs):
+            n = (cuts[i + 1] - cuts[i]) // ctrs[i]
+            ops.deepfilter_band(p, sre, sim, ore, oim, n, ctrs[i], self.df_orders[i], S, lo)
+            lo += n * ctrs[i]
+        enh = torch.complex(ore, oim)
+        if S > 1:
+            y = _istft(enh.reshape(B * S, F, T), self.n_fft, self.hop_length, self.win_length, L)
+            return y.reshape(B, S, L), fb_all, sb_all
+        enh = enh[:, 0]
+        return _istft(enh, self.n_fft, self.hop_length, self.win_length, L), enh.abs(), fb_all, sb_all
+
+
+class CirmGSN(nn.Module):
+    """cirm_gsn `Model` (CGN:162-244): one full-band GSN over all bins emitting deep-filter coefficients."""
+
+    def __init__(self, n_fft, hop_length, win_length, fdrc, input_size, hidden_size, num_layers, proj_size,
+                 output_activate_function, df_order, use_pre_layer_norm_fb=True, bn=False,
+                 shared_weights=False, sequence_model="LSTM", num_spks=2):
+        super().__init__()
+        self.fb_model = SequenceModel(input_size=input_size, hidden_size=hidden_size, num_layers=num_layers,
+                                      shared_weights=shared_weights, sequence_model=sequence_model,
+                                      proj_size=proj_size * num_spks * df_order * 2,
+                                      output_activate_function=output_activate_function, bn=bn,
+                                      use_pre_layer_norm=use_pre_layer_norm_fb)
+        self.fb_input_size, self.n_fft, self.hop_length, self.win_length = input_size, n_fft, hop_length, win_length
+        self.fdrc, self.df_order, self.num_spks = fdrc, df_order, num_spks
+
+    def network(self, mag):
+        """mag [B,F,T] -> (activated proj [T,B,P], all_layer_outputs)."""
+        fbm = self.fb_model
+        cm = ops.compress_mag(mag.contiguous(), mag.shape[1], self.fdrc)
+        lnw = fbm.pre_layer_norm.weight.detach() if fbm.use_pre_layer_norm else None
+        lnb = fbm.pre_layer_norm.bias.detach() if fbm.use_pre_layer_norm else None
+        x = ops.subband_features(cm, None, 1, 0, self.fb_input_size, 0, lnw, lnb,
+                                 fbm.pre_layer_norm.eps if fbm.use_pre_layer_norm else 1e-5)
+        _, act, all_out = fbm.run_time_major(x)
+        return act, all_out
+
+    def coefficients(self, mag):
+        """'b (c d s f) t -> b d s f t c' (CGN:230)."""
+        act, all_out = self.network(mag)
+        T, B, P = act.shape
+        d, S = self.df_order, self.num_spks
+        v = act.reshape(T, B, 2, d, S, P // (2 * d * S))
+        return v.permute(1, 3, 4, 5, 0, 2).contiguous(), all_out
+
+    def forward(self, input):
+        assert input.ndim == 2, f"Input tensor must be 2D, but got {input.ndim}D."
+        B, L = input.shape
+        cmp = _stft(input, self.n_fft, self.hop_length, self.win_length)
+        coef, all_out = self.coefficients(cmp.abs().contiguous())  # [B,d,S,F,T,2]
+        cc = torch.complex(coef[..., 0], coef[..., 1])
+        d = self.df_order
+        pad = torch.nn.functional.pad(cmp, (d - 1, 0))
+        T = cmp.shape[2]
+        enh = sum(pad[:, None, :, k:k + T] * cc[:, k] for k in range(d))  # [B,S,F,T]
+        if self.num_spks > 1:
+            y = _istft(enh.reshape(B * self.num_spks, *enh.shape[2:]), self.n_fft, self.hop_length,
+                       self.win_length, L)
+            return y.reshape(B, self.num_spks, L), all_out
+        enh = enh[:, 0]
+        return _istft(enh, self.n_fft, self.hop_length, self.win_length, L), enh.abs()

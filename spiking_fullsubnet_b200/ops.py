@@ -1,0 +1,125 @@
+"""Tensor-level wrappers over the C ABI (include/gsn_b200.h).  PyTorch is used only for device
+memory and streams: every function takes CUDA fp32 tensors, allocates outputs with torch, and
+enqueues the library's kernels on torch's current stream."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+_ACT = {None: 0, False: 0, "tanh": 1, "sigmoid": 2, "relu": 3}
+_bound_device = [None]
+LAUNCHES = [0]   # number of libgsn_b200 kernels enqueued so far (bench.py reports it)
+PROFILE = None   # bench.py sets a list: (algorithmic flops, start event, stop event) per recurrence call
+
+
+def _prep(*tensors):
+    """Validate device/dtype/contiguity; bind the library to the tensors' device; return stream."""
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("spiking_fullsubnet_b200 ops need CUDA tensors (there is no CPU path)")
+        if t.dtype != torch.float32:
+            raise TypeError(f"expected float32, got {t.dtype}")
+        if not t.is_contiguous():
+            raise ValueError("expected a contiguous tensor")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise ValueError("tensors on different devices")
+    lib = _lib.load()
+    if _bound_device[0] != dev.index:
+        _lib.check(lib.gsn_bind_device(dev.index))
+        _bound_device[0] = dev.index
+    return lib, torch.cuda.current_stream(dev).cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def compress_mag(mag, f_keep, fdrc):
+    """mag [B,F,T] -> cm [T,B,f_keep] = mag**fdrc (MSF:434-436, time-major)."""
+    lib, st = _prep(mag)
+    B, F, T = mag.shape
+    cm = torch.empty((T, B, f_keep), device=mag.device, dtype=torch.float32)
+    _lib.check(lib.gsn_compress_mag(_ptr(mag), _ptr(cm), B, F, f_keep, T, float(fdrc), st))
+    LAUNCHES[0] += 1
+    return cm
+
+
+def subband_features(cm, fb, N, lo, ctr, nbr, ln_weight=None, ln_bias=None, eps=1e-5):
+    """Gather (+reflect, + tiled full-band output) + LayerNorm -> x [T, B*N, K] (MSF:241-312, 111-112)."""
+    lib, st = _prep(cm, fb, ln_weight, ln_bias)
+    T, B, f_cm = cm.shape
+    K = ctr + 2 * nbr + (ctr if fb is not None else 0)
+    f_fb = fb.shape[2] if fb is not None else 0
+    x = torch.empty((T, B * N, K), device=cm.device, dtype=torch.float32)
+    _lib.check(lib.gsn_subband_features(_ptr(cm), f_cm, _ptr(fb), f_fb, _ptr(x), T, B, N, lo, ctr, nbr,
+                                        _ptr(ln_weight), _ptr(ln_bias), float(eps), st))
+    LAUNCHES[0] += 1
+    return x
+
+
+def linear(a, w, bias=None, act=None):
+    """out[..., N] = a[..., K] @ w[N,K]^T + bias (fp32 FMA).  Returns out, or (out, act(out)) if act."""
+    lib, st = _prep(a, w, bias)
+    K = a.shape[-1]
+    N = w.shape[0]
+    if w.shape[1] != K:
+        raise ValueError(f"linear: a[..., {K}] vs w{tuple(w.shape)}")
+    M = a.numel() // K
+    out = torch.empty(a.shape[:-1] + (N,), device=a.device, dtype=torch.float32)
+    code = _ACT[act]
+    out_act = torch.empty_like(out) if code else None
+    _lib.check(lib.gsn_linear_f32(_ptr(a), _ptr(w), _ptr(bias), _ptr(out), _ptr(out_act), code, M, K, N, st))
+    LAUNCHES[0] += 1
+    return (out, out_act) if code else out
+
+
+def layer_recurrence(xproj, w_hh, bias, bn_scale=None, bn_shift=None, shared=True, want_c=False,
+                     h0=None, c0=None, want_state=False, backend="auto"):
+    """One GSULayer over all frames (ESN:75-81 / 132-153).  xproj [T,R,gH] -> h [T,R,H] (and c, (hT,cT))."""
+    lib, st = _prep(xproj, w_hh, bias, bn_scale, bn_shift, h0, c0)
+    T, R, gH = xproj.shape
+    H = w_hh.shape[1]
+    if gH != (H if shared else 2 * H) or w_hh.shape[0] != gH or bias.numel() != 2 * H:
+        raise ValueError(f"layer_recurrence: inconsistent shapes xproj{tuple(xproj.shape)} "
+                         f"w_hh{tuple(w_hh.shape)} bias{tuple(bias.shape)} shared={shared}")
+    be = _lib.BACKENDS[backend]
+    dev = xproj.device
+    h = torch.empty((T, R, H), device=dev, dtype=torch.float32)
+    c = torch.empty((T, R, H), device=dev, dtype=torch.float32) if want_c else None
+    hT = torch.empty((R, H), device=dev, dtype=torch.float32) if want_state else None
+    cT = torch.empty((R, H), device=dev, dtype=torch.float32) if want_state else None
+    nbytes = lib.gsn_layer_recurrence_workspace_bytes(R, H, int(shared), be)
+    ws = torch.empty((max(nbytes, 256) + 255) // 4 + 1, device=dev, dtype=torch.float32)
+    off = (-ws.data_ptr()) % 256
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    _lib.check(lib.gsn_layer_recurrence(_ptr(xproj), _ptr(w_hh), _ptr(bias), _ptr(bn_scale), _ptr(bn_shift),
+                                        _ptr(h0), _ptr(c0), _ptr(h), _ptr(c), _ptr(hT), _ptr(cT), T, R, H,
+                                        int(shared), be, ws.data_ptr() + off, st))
+    LAUNCHES[0] += 2  # weight preparation + the recurrence kernel
+    if PROFILE is not None:
+        e1.record()
+        PROFILE.append((2.0 * T * R * gH * H, e0, e1))
+    return h, c, (hT, cT)
+
+
+def pick_backend(R, H, shared):
+    return {1: "simt", 2: "tcgen05"}[_lib.load().gsn_layer_recurrence_pick_backend(R, H, int(shared))]
+
+
+def deepfilter_band(proj, spec_re, spec_im, out_re, out_im, N, ctr, df, S, lo):
+    """Deep filter of one band straight from its proj output (MSF:315-346, layout MSF:160-167)."""
+    lib, st = _prep(proj, spec_re, spec_im, out_re, out_im)
+    T = proj.shape[0]
+    B, F, _ = spec_re.shape
+    F_out = out_re.shape[2]
+    _lib.check(lib.gsn_deepfilter_band(_ptr(proj), _ptr(spec_re), _ptr(spec_im), _ptr(out_re), _ptr(out_im),
+                                       T, B, N, ctr, df, S, lo, F, F_out, st))
+    LAUNCHES[0] += 1

@@ -1,0 +1,87 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/gsn_b200.h declares,
+the facade keeps the reference's state_dict contract, and the product refuses to run without CUDA."""
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import synth
+from spiking_fullsubnet_b200 import CirmGSN, SpikingFullSubNet, _lib
+from spiking_fullsubnet_b200.modeling import coef_layout
+from tests.helpers import load_golden
+
+
+def test_header_symbols_all_exported_and_bound():
+    text = open(_lib.HEADER_PATH).read()
+    declared = set(re.findall(r"GSN_API\s+[\w\s\*]+?\b(gsn_\w+)\s*\(", text))
+    assert declared, "no GSN_API declarations found"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.gsn_abi_version() == 1
+
+
+def test_argument_validation_without_gpu():
+    lib = _lib.load()
+    rc = lib.gsn_compress_mag(None, None, 1, 1, 1, 1, 0.5, None)
+    assert rc == _lib.GSN_EINVAL and b"null" in lib.gsn_last_error()
+    with pytest.raises(ValueError):
+        _lib.check(rc)
+    assert lib.gsn_layer_recurrence_workspace_bytes(8, 64, 1, _lib.BACKEND_SIMT) == 64 * 64 * 4
+    assert lib.gsn_layer_recurrence_workspace_bytes(8, 64, 0, _lib.BACKEND_SIMT) == 64 * 128 * 4
+
+
+@pytest.mark.parametrize("name", ["S", "M", "L", "XL"])
+def test_state_dict_contract(name):
+    """Same parameter/buffer names and shapes as the reference (so zoo checkpoints load strict=True);
+    parameter counts of SURVEY.md section 6 (S 520 920 ... are surface B; surface A M = 954 412)."""
+    cfg = synth.CONFIGS[name]
+    model = SpikingFullSubNet(**cfg)
+    params = synth.make_params(cfg, 1)
+    sd = model.state_dict()
+    assert set(sd) == set(params)
+    for k, v in params.items():
+        assert tuple(sd[k].shape) == tuple(np.shape(v)), k
+    model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in params.items()}, strict=True)
+    if name == "M":
+        assert sum(p.numel() for p in model.parameters()) == 954412
+
+
+def test_golden_state_dict_loads():
+    g = load_golden("cfg1_baseline_m_1s")
+    m = SpikingFullSubNet(**g["cfg"])
+    m.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in synth.make_params(g["cfg"], g["seed"]).items()})
+    c = CirmGSN(**synth.CFG_CIRM)
+    assert set(c.state_dict()) == set(synth.make_params_cirm(synth.CFG_CIRM, 0))
+
+
+def test_init_distribution_matches_reference_rule():
+    m = SpikingFullSubNet(**synth.CFG_S)
+    cell = m.fb_model.sequence_model.layers[0].cell
+    bound = 1.0 / np.sqrt(240)
+    for p in (cell.weight_ih, cell.weight_hh, cell.bias_ih):
+        assert p.abs().max() <= bound and p.abs().max() > 0.9 * bound
+    assert cell.weight_ih.shape == (240, 64) and cell.bias_ih.shape == (480,)
+
+
+def test_no_cpu_fallback():
+    m = SpikingFullSubNet(**synth.tiny_cfg()).eval()
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(torch.zeros(1, 320))
+    with pytest.raises(NotImplementedError):
+        SpikingFullSubNet(**dict(synth.tiny_cfg(), sequence_model="LSTM"))
+    with pytest.raises(NotImplementedError):
+        SpikingFullSubNet(**dict(synth.tiny_cfg(), sequence_model="GRU"))
+
+
+def test_coef_layout_matches_oracle_index_map():
+    from oracle import gsn_oracle as O
+    rs = np.random.RandomState(0)
+    B, N, ctr, df, S, T = 2, 3, 4, 3, 2, 5
+    P = 2 * ctr * df * S
+    proj = rs.standard_normal((T, B * N, P)).astype(np.float32)
+    want = O.subband_coef_layout(np.transpose(proj, (1, 2, 0)), B, ctr, df, S)
+    got = coef_layout(torch.from_numpy(proj), B, N, df, S).numpy()
+    assert np.array_equal(got, want)

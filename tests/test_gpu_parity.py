@@ -1,0 +1,205 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the golden fixtures and the CPU oracle.
+
+Tolerances: north_star asks for outputs within 1e-3 relative fp32 of the reference CPU path; real-valued
+tensors are checked at 1e-3 * max|ref| (they agree to ~1e-5 when no spike flips) and spikes must be
+IDENTICAL on the golden fixtures (protocol P2).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gsn_oracle as O
+from oracle import synth
+from spiking_fullsubnet_b200 import CirmGSN, SpikingFullSubNet, ops
+from tests.helpers import SURFACE_A, golden_params, load_golden, spike_flip_stats, unpack
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+BACKENDS = ["simt", "auto"]
+
+
+def _rel(a, b):
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+def _model(cfg, params, backend="auto"):
+    m = SpikingFullSubNet(**cfg)
+    m.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in params.items()}, strict=True)
+    return m.eval().to(DEV).set_backend(backend)
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("name", SURFACE_A)
+def test_network_vs_golden(name, backend):
+    g = load_golden(name)
+    cfg = g["cfg"]
+    m = _model(cfg, golden_params(g), backend)
+    with torch.no_grad():
+        coefs, fb_all, sb_all = m.coefficients(_t(g["mag"]))
+    Hf, Hs = cfg["fb_hidden_size"], cfg["sb_hidden_size"]
+    assert _rel(fb_all[0].cpu().numpy(), g["fb_xnorm"]) < 1e-4
+    for l in range(cfg["fb_num_layers"]):
+        frac, first = spike_flip_stats(fb_all[1 + l].cpu().numpy(), unpack(g[f"fb_h{l}"], Hf))
+        assert frac == 0, f"fb layer {l}: {frac:.2e} spikes flipped, first at frame {first}"
+    assert _rel(fb_all[-1].cpu().numpy(), g["fb_proj"]) < 1e-3
+    for i in range(len(cfg["center_freq_sizes"])):
+        assert _rel(sb_all[i][0].cpu().numpy(), g[f"sb{i}_xnorm"]) < 1e-4
+        for l in range(cfg["sb_num_layers"]):
+            frac, first = spike_flip_stats(sb_all[i][1 + l].cpu().numpy(), unpack(g[f"sb{i}_h{l}"], Hs))
+            assert frac == 0, f"sb{i} layer {l}: {frac:.2e} spikes flipped, first at frame {first}"
+        assert coefs[i].shape == g[f"coef{i}"].shape
+        assert _rel(coefs[i].cpu().numpy(), g[f"coef{i}"]) < 1e-3  # the "cIRM max|delta|" bar
+
+
+@pytest.mark.parametrize("name", SURFACE_A)
+def test_full_forward_vs_golden(name):
+    """forward(wave) end to end: STFT -> network -> deep filter -> iSTFT, same return tuple."""
+    g = load_golden(name)
+    cfg = g["cfg"]
+    m = _model(cfg, golden_params(g))
+    with torch.no_grad():
+        out = m(_t(g["wave"]))
+    if cfg["num_spks"] > 1:
+        assert len(out) == 3
+        enh_y = out[0]
+    else:
+        assert len(out) == 4
+        enh_y, enh_mag = out[0], out[1]
+        assert _rel(enh_mag.cpu().numpy(), g["enh_mag"]) < 1e-3
+    assert enh_y.shape == g["enh_y"].shape
+    assert _rel(enh_y.cpu().numpy(), g["enh_y"]) < 1e-3
+    L = cfg["fb_num_layers"]
+    assert len(out[-2]) == L + 2 and len(out[-1]) == len(cfg["center_freq_sizes"])
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("name", ["tiny_shared_bn", "tiny_unshared_nobn", "tiny_spk2_tanh"])
+def test_recurrence_teacher_forced(name, backend):
+    """Protocol P1 per layer: one frame at a time from the reference's own (x_t, h_{t-1}, c_{t-1})."""
+    g = load_golden(name)
+    cfg = g["cfg"]
+    params = golden_params(g)
+    shared = cfg["shared_weights"]
+    models = [("fb_model.", cfg["fb_num_layers"], cfg["fb_hidden_size"], "fb")]
+    models += [(f"sb_model.sb_models.{i}.", cfg["sb_num_layers"], cfg["sb_hidden_size"], f"sb{i}")
+               for i in range(len(cfg["center_freq_sizes"]))]
+    for prefix, L, H, tag in models:
+        inp = g[f"{tag}_xnorm"]
+        for l in range(L):
+            q = f"{prefix}sequence_model.layers.{l}.cell."
+            cref = g["c__" + q[:-1]]
+            href = unpack(g[f"{tag}_h{l}"], H)
+            T, R, _ = cref.shape
+            w_ih, w_hh, bias = _t(params[q + "weight_ih"]), _t(params[q + "weight_hh"]), _t(params[q + "bias_ih"])
+            a = b = None
+            if cfg["bn"]:
+                inv = 1.0 / np.sqrt(params[q + "batchnorm.running_var"] + np.float32(1e-5))
+                al = (inv * params[q + "batchnorm.weight"]).astype(np.float32)
+                a, b = _t(al), _t((params[q + "batchnorm.bias"] - params[q + "batchnorm.running_mean"] * al).astype(np.float32))
+            # all T single-frame problems at once: fold time into rows (each row is independent)
+            hprev = np.concatenate([np.zeros_like(href[:1]), href[:-1]]).reshape(1, T * R, H)
+            cprev = np.concatenate([np.zeros_like(cref[:1]), cref[:-1]]).reshape(1, T * R, H)
+            xproj = ops.linear(_t(inp.reshape(1, T * R, -1)), w_ih)
+            h, c, _ = ops.layer_recurrence(xproj, w_hh, bias, a, b, shared=shared, want_c=True,
+                                           h0=_t(hprev[0]), c0=_t(cprev[0]), backend=backend)
+            c = c.cpu().numpy().reshape(T, R, H)
+            h = h.cpu().numpy().reshape(T, R, H)
+            assert np.abs(c - cref).max() <= 1e-5 * max(1.0, np.abs(cref).max()), (tag, l)
+            safe = np.abs(cref) > 1e-5
+            assert np.array_equal(h[safe], href[safe]), (tag, l)
+            inp = href
+
+
+def test_cirm_gsn_vs_golden():
+    g = load_golden("tiny_cirm")
+    cfg = g["cfg"]
+    params = synth.make_params_cirm(cfg, g["seed"])
+    m = CirmGSN(**cfg)
+    m.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in params.items()}, strict=True)
+    m = m.eval().to(DEV)
+    with torch.no_grad():
+        act, all_out = m.network(_t(g["mag"]))
+        enh_y, enh_mag = m(_t(g["wave"]))
+    for l in range(cfg["num_layers"]):
+        assert np.array_equal(all_out[1 + l].cpu().numpy(), unpack(g[f"fb_h{l}"], cfg["hidden_size"]))
+    assert _rel(act.permute(1, 2, 0).cpu().numpy(), g["fb_out"]) < 1e-3
+    assert _rel(enh_y.cpu().numpy(), g["enh_y"]) < 1e-3
+    assert _rel(enh_mag.cpu().numpy(), g["enh_mag"]) < 1e-3
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("R,K,H,L,shared,bn", [
+    (1, 5, 16, 1, True, False),      # single row, tiny
+    (3, 38, 160, 2, True, True),     # S sub-band shape, ragged row tile
+    (130, 64, 240, 2, True, True),   # S full-band width, rows spill over one 128-row tile
+    (37, 94, 224, 2, False, True),   # XL-style unshared gates
+    (9, 33, 268, 3, True, True),     # cirm_gsn hidden size (not a multiple of 16)
+    (70, 20, 320, 2, True, False),   # M/L full-band width
+])
+def test_stack_vs_oracle_shapes(R, K, H, L, shared, bn, backend):
+    """StackedGSU.forward (the reference's operator API) on ragged / edge shapes vs the oracle."""
+    from spiking_fullsubnet_b200 import efficient_spiking_neuron
+    rs = np.random.RandomState(R * 1000 + H)
+    T = 24
+    p = synth._seq_model_params(rs, "m.", K, H, L, 0, shared, bn, False)
+    stack = efficient_spiking_neuron(K, H, L, shared_weights=shared, bn=bn)
+    stack.load_state_dict({k[len("m.sequence_model."):]: torch.from_numpy(np.array(v)) for k, v in p.items()})
+    stack = stack.eval().to(DEV)
+    stack.backend = backend
+    x = rs.standard_normal((T, R, K)).astype(np.float32)
+    with torch.no_grad():
+        out, states, trace = stack(_t(x), None, want_c=True)
+    ref_out, ref_trace, ref_c = O.gsn_stack_forward(x, p, "m.sequence_model.", L, shared, return_c=True)
+    assert len(trace) == L + 1 and len(states) == L
+    for l in range(L):
+        c = stack.last_c[l].cpu().numpy()
+        frac, first = spike_flip_stats(trace[1 + l].cpu().numpy(), ref_trace[1 + l])
+        if frac == 0:
+            assert np.abs(c - ref_c[l]).max() < 1e-4
+        else:  # a flip is only legitimate where the oracle's membrane potential is at the threshold
+            assert np.abs(ref_c[l][first]).min() < 1e-5, f"layer {l}: flip at frame {first} away from threshold"
+            break
+    assert np.array_equal(states[-1].hx.cpu().numpy(), trace[-1][-1].cpu().numpy())
+
+
+def test_initial_state_and_chunked_equivalence():
+    """Carrying (h,c) across two calls equals one call over the concatenated frames (streaming use)."""
+    rs = np.random.RandomState(3)
+    T, R, K, H = 20, 5, 12, 64
+    from spiking_fullsubnet_b200 import efficient_spiking_neuron
+    stack = efficient_spiking_neuron(K, H, 2, shared_weights=True, bn=False).eval().to(DEV)
+    x = _t(rs.standard_normal((T, R, K)).astype(np.float32))
+    with torch.no_grad():
+        full, st_full, _ = stack(x, None)
+        a, st_a, _ = stack(x[:9].contiguous(), None)
+        b, st_b, _ = stack(x[9:].contiguous(), st_a)
+    assert torch.equal(torch.cat([a, b]), full)
+    assert torch.equal(st_b[1].cx, st_full[1].cx)
+
+
+def test_properties_at_full_size_S():
+    """BASELINE config 2 size (S, batch 32 x 4 s): size-independent properties.
+    (1) batch-composition independence (SURVEY 8c determinism fact): clip 0 alone == clip 0 in the batch;
+    (2) spikes are exactly {0,1}; (3) the two recurrence back ends agree on every spike."""
+    cfg = synth.CFG_S
+    params = synth.make_params(cfg, 5)
+    m = _model(cfg, params, "auto")
+    mag = _t(synth.make_mag(32, 257, 501, 11))
+    with torch.no_grad():
+        projs, fb_all, sb_all = m.network(mag)
+        projs1, fb1, sb1 = m.network(mag[:1].contiguous())
+    assert torch.equal(fb_all[1][:, :1], fb1[1])
+    n0 = projs1[0].shape[1]
+    assert torch.equal(projs[0][:, :n0], projs1[0])
+    for t in fb_all[1:-1] + [x for al in sb_all for x in al[1:-1]]:
+        assert bool(((t == 0) | (t == 1)).all())
+    m.set_backend("simt")
+    with torch.no_grad():
+        projs_s, fb_s, sb_s = m.network(mag)
+    flips = sum(float((a != b).float().sum()) for a, b in zip(fb_all[1:-1], fb_s[1:-1]))
+    total = sum(a.numel() for a in fb_all[1:-1])
+    assert flips / total < 1e-4, f"back ends disagree on {flips / total:.2e} of full-band spikes"
