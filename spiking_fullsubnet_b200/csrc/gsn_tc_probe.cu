@@ -1,0 +1,111 @@
+// gsn_tc_selftest: one [128 x N] = A[128 x K] * B[N x K]^T product on tcgen05 with the exact operand
+// layouts the recurrence kernel uses (K-major no-swizzle shared-memory operands; A optionally resident
+// in TMEM).  tests/test_gpu_tc_selftest.py checks it against a CPU product; it pins the descriptor
+// encodings independently of the recurrence logic.
+#include "gsn_common.cuh"
+#include "gsn_tc.cuh"
+
+namespace gsn {
+
+__global__ void __launch_bounds__(128)
+    k_tc_probe(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ d,
+               int* __restrict__ status, int N, int K, int a_in_tmem, int swap_lbo_sbo, int use_fp16) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t lbo = 128, sbo = 16u * K;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 128 * K * 2;
+
+  auto cvt = [&](float v) -> uint16_t {
+    if (use_fp16) return __half_as_ushort(__float2half_rn(v));
+    return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+  };
+  for (int i = tid; i < 128 * K; i += 128) {
+    const int r = i / K, k = i % K;
+    *reinterpret_cast<uint16_t*>(sA + (r / 8) * sbo + (k / 8) * lbo + (r % 8) * 16 + (k % 8) * 2) = cvt(a[i]);
+  }
+  for (int i = tid; i < N * K; i += 128) {
+    const int r = i / K, k = i % K;
+    *reinterpret_cast<uint16_t*>(sB + (r / 8) * sbo + (k / 8) * lbo + (r % 8) * 16 + (k % 8) * 2) = cvt(b[i]);
+  }
+  if (tid == 0) {
+    tc::mbar_init(&bar, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc<512>(&tmem_base_slot);
+  tc::tc_fence_before();
+  tc::fence_proxy_async_smem();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+  const uint32_t tmem_d = tmem;            // columns [0, N)
+  const uint32_t tmem_a = tmem + 256;      // columns [256, 256 + K/2)
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+
+  if (a_in_tmem) {
+    // thread m owns TMEM lane m: pack two consecutive k per 32-bit column
+    for (int c0 = 0; c0 < K / 2; c0 += 8) {
+      uint32_t v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = 2 * (c0 + j);
+        v[j] = (uint32_t)cvt(a[tid * K + k]) | ((uint32_t)cvt(a[tid * K + k + 1]) << 16);
+      }
+      tc::tmem_st8(tmem_a + lane_base + c0, v);
+    }
+    tc::tmem_wait_st();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+  }
+
+  if (tid == 0) {
+    const uint32_t idesc = tc::make_idesc_f16(128, N, !use_fp16);
+    const uint32_t l = swap_lbo_sbo ? sbo : lbo, s = swap_lbo_sbo ? lbo : sbo;
+    for (int ks = 0; ks < K / 16; ++ks) {
+      const uint64_t db = tc::make_smem_desc(tc::smem_u32(sB) + ks * 2 * lbo, l, s);
+      if (a_in_tmem) {
+        tc::mma_ts(tmem_d, tmem_a + ks * 8, db, idesc, ks > 0);
+      } else {
+        const uint64_t da = tc::make_smem_desc(tc::smem_u32(sA) + ks * 2 * lbo, l, s);
+        tc::mma_ss(tmem_d, da, db, idesc, ks > 0);
+      }
+    }
+    tc::mma_commit(&bar);
+  }
+  const bool ok = tc::mbar_wait(&bar, 0);
+  tc::tc_fence_after();
+  if (!ok) {
+    if (tid == 0) *status = 1;
+  } else {
+    for (int c0 = 0; c0 < N; c0 += 16) {
+      uint32_t v[16];
+      tc::tmem_ld16(tmem_d + lane_base + c0, v);
+      tc::tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) d[tid * N + c0 + j] = __uint_as_float(v[j]);
+    }
+    if (tid == 0) *status = 0;
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<512>(tmem);
+}
+
+}  // namespace gsn
+
+extern "C" int gsn_tc_selftest(const float* a, const float* b, float* d, int* status, int N, int K,
+                               int a_in_tmem, int swap_lbo_sbo, int use_fp16, gsn_stream_t stream) {
+  GSN_REQUIRE(a && b && d && status, "gsn_tc_selftest: null pointer");
+  GSN_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0, "gsn_tc_selftest: N=%d must be a multiple of 16 in [16,256]", N);
+  GSN_REQUIRE(K >= 16 && K <= 512 && K % 16 == 0, "gsn_tc_selftest: K=%d must be a multiple of 16 in [16,512]", K);
+  const size_t smem = (size_t)(128 + N) * K * 2;
+  GSN_REQUIRE(smem <= 200 * 1024, "gsn_tc_selftest: operands do not fit shared memory");
+  GSN_CUDA(cudaFuncSetAttribute(gsn::k_tc_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gsn::k_tc_probe<<<1, 128, smem, gsn::as_stream(stream)>>>(a, b, d, status, N, K, a_in_tmem, swap_lbo_sbo,
+                                                          use_fp16);
+  GSN_LAUNCH_CHECK("k_tc_probe");
+  return GSN_OK;
+}
