@@ -35,6 +35,8 @@ def parse():
     ap.add_argument("--seconds", type=float, default=4.0)
     ap.add_argument("--backend", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of "
+                    "replaying the captured CUDA graph")
     return ap.parse_args()
 
 
@@ -170,12 +172,15 @@ def main():
         with torch.no_grad():
             return model.network(mag)
 
+    ops.LAUNCHES[0] = 0
+    step()  # eager pass: counts the kernels one step launches
+    launches_per_step = ops.LAUNCHES[0]
+    model.enable_cuda_graph(not args.no_graph)
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    ops.LAUNCHES[0] = 0
     evs = []
     for _ in range(args.steps):
         flush.fill_(1.0)  # L2 flush between timed iterations (untimed)
@@ -185,7 +190,7 @@ def main():
         e1.record()
         evs.append((e0, e1))
     barrier()
-    launches = ops.LAUNCHES[0]
+    launches = launches_per_step * args.steps
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
 
     # end to end through the public API: pinned host waveform -> H2D -> forward() -> D2H enhanced waveform
@@ -207,12 +212,23 @@ def main():
     sampler.join()
 
     # per-kernel timing of the dominant kernel (the recurrence), live, with CUDA events on its stream
+    # (sub-band streams serialised for this pass so each launch is timed alone; `share_of_step` is the
+    # kernel's share of that serial step)
+    model.enable_cuda_graph(False)
+    model.sb_model.concurrent_bands = False
+    step()
+    torch.cuda.synchronize()
     ops.PROFILE = []
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
     for _ in range(3):
         step()
+    s1.record()
     torch.cuda.synchronize()
     rec = ops.PROFILE
     ops.PROFILE = None
+    model.sb_model.concurrent_bands = True
+    serial_ms = s0.elapsed_time(s1) / 3.0
     rec_ms = sum(a.elapsed_time(b) for (_, a, b) in rec) / 3.0
     rec_flops = sum(f for (f, _, _) in rec) / 3.0
 
@@ -240,7 +256,9 @@ def main():
         "dtype": "f32 (recurrent weights as exact bf16x3 planes on tcgen05 where that backend runs)",
         "data": "synthetic",
         "config": dict(wl, l2="flushed between timed iterations (256 MiB write)",
-                       recurrence_backends=backends),
+                       recurrence_backends=backends,
+                       launch="CUDA graph replay of the step (captured once per shape)" if not args.no_graph
+                       else "eager enqueue from Python"),
         "clocks": sampler.summary(),
         "e2e": {"value": world * B * T * args.steps / e2e_s, "unit": "frames/s",
                 "h2d_bytes_per_step": int(wave_host.numel() * 4), "d2h_bytes_per_step": int(out_host.numel() * 4),
@@ -250,7 +268,8 @@ def main():
                      "frac": achieved / tf_peak if tf_peak else None, "traffic": None,
                      "kernel": "GSN recurrence (all layers of all sequence models of one step)",
                      "algorithmic_flops_per_step": rec_flops, "kernel_ms_per_step": rec_ms,
-                     "share_of_step": rec_ms / (dev_ms / args.steps), "peak_source": peak_src},
+                     "share_of_step": rec_ms / serial_ms, "serial_step_ms": serial_ms,
+                     "peak_source": peak_src},
     }
     if world == 1 and not args.no_cpu_baseline:
         times, cores = time_cpu_port(synth, cfg, B, T, 3, 1)

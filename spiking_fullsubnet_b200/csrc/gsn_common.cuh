@@ -36,8 +36,13 @@ int fail(int code, const char* fmt, ...);
 static inline cudaStream_t as_stream(gsn_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 __device__ __forceinline__ float sigmoid_f32(float x) {
-  // same formula as the reference's torch.sigmoid: 1 / (1 + exp(-x)), full-precision expf and division
-  return 1.0f / (1.0f + expf(-x));
+  // the reference's torch.sigmoid formula 1 / (1 + exp(-x)) with full-precision expf; the division is
+  // MUFU.RCP + one Newton step (<= 1 ulp, branch-free so several evaluations interleave).  The clamp keeps
+  // 1 + exp(-x) finite; sigmoid(-87) ~ 1.6e-38 is already below fp32's normal range.
+  const float d = 1.0f + expf(-fmaxf(x, -87.0f));
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+  return fmaf(r, fmaf(-d, r, 1.0f), r);
 }
 
 // c_t and h_t of one neuron from the gate pre-activations (ESN:146-151)

@@ -14,9 +14,12 @@
 //     REGISTERS for the whole sequence, writes the spike trace (coalesced over neurons), and the warp
 //     ballots the new spikes into 1 bit each;
 //   * exchange: the bit words go to the staging buffer of EVERY CTA of the cluster through distributed
-//     shared memory (st.shared::cluster) + a remote mbarrier arrive; each CTA then expands the bits of
-//     its NT rows x H neurons back into the bf16 B operand for frame t+1.
-// One 128-thread warpgroup does everything; thread 0 issues the MMAs (single-thread tcgen05.mma).
+//     shared memory with st.async (bytes counted on the receiver's mbarrier: no fence, no arrive); each
+//     CTA then expands the bits of its NT rows x H neurons back into the bf16 B operand for frame t+1.
+// 4 x G warps: warp w works on TMEM lane quarter w%4 (its 32 neurons) and on rows [ (w/4)*NT/G, ... ) of
+// the tile; one elected lane of warp 0 issues the MMAs (single-thread tcgen05.mma).
+#include <stdlib.h>
+
 #include "gsn_common.cuh"
 #include "gsn_tc.cuh"
 
@@ -35,6 +38,7 @@ struct RecTcParams {
   float* hT;
   float* cT;
   int T, R, H, Kmma;    // Kmma = round_up(H, 16)
+  unsigned long long* prof;  // [8] cycle counters of CTA 0 / thread 0 (workspace), see tools/tc_profile.py
 };
 
 constexpr int kTcPlanes = 3;
@@ -64,14 +68,21 @@ __device__ __forceinline__ void split3(float w, uint32_t& hi, uint32_t& mid, uin
   lo = __float_as_uint(r2) >> 16;
 }
 
-template <int NT>
-__global__ void __launch_bounds__(128, 1) k_recurrence_tc(const RecTcParams p) {
+template <int NT, int G>
+__global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams p) {
+  constexpr int NTHREADS = 128 * G;
+  constexpr int CPT = NT / G;                 // accumulator columns (= rows of the tile) per thread
+  constexpr int CH = CPT < 8 ? CPT : 8;       // columns processed together (instruction-level parallelism)
+  constexpr int MAXT = (NT * 40 + NTHREADS - 1) / NTHREADS;  // B-operand rebuild tasks per thread (Kmma <= 320)
+  static_assert(CPT == 4 || CPT == 8 || CPT == 16, "NT / G must be 4, 8 or 16");
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3;    // TMEM lane quarter this warp may access
+  const int g = warp >> 2;   // column group: rows [g*CPT, g*CPT + CPT) of the tile
   const uint32_t C = tc::cluster_nctarank(), slice = tc::cluster_ctarank();
   const int row0 = (blockIdx.x / C) * NT;
   const int H = p.H, R = p.R, T = p.T, Kmma = p.Kmma;
-  const int j = slice * 128 + tid;  // this thread's neuron
+  const int j = slice * 128 + q * 32 + lane;  // this thread's neuron (= TMEM lane q*32 + lane)
   const bool jv = j < H;
   const int KWp = tc_kw_padded(C);
 
@@ -86,18 +97,32 @@ __global__ void __launch_bounds__(128, 1) k_recurrence_tc(const RecTcParams p) {
 
   if (tid == 0) {
     tc::mbar_init(bar_mma, 1);
-    tc::mbar_init(&bar_bits[0], 4 * C);
-    tc::mbar_init(&bar_bits[1], 4 * C);
+    tc::mbar_init(&bar_bits[0], 1);  // one local arrive (expect_tx) + the bytes of every slice's bit words
+    tc::mbar_init(&bar_bits[1], 1);
     tc::fence_mbar_init();
   }
   if (warp == 0) tc::tmem_alloc<kTmemCols>(tmem_slot);
 
-  // B operand of frame 0: the initial spikes h0 (zeros when null).  byte(n,k) = (n/8)*SBO + (k/8)*128 + (n%8)*16
+  // B-operand rebuild tasks of this thread: (row n, 8 consecutive k) -> one 16-byte store.
+  //   byte(n, k) = (n/8)*SBO + (k/8)*128 + (n%8)*16 ;  8 consecutive threads fill one 128-byte core matrix
   const uint32_t SBO = 16u * Kmma;
   const int k8n = Kmma / 8;
-  for (int i = tid; i < NT * k8n; i += 128) {
+  uint32_t task_dst[MAXT], task_src[MAXT];
+#pragma unroll
+  for (int it = 0; it < MAXT; ++it) {
+    const int i = tid + NTHREADS * it;
     const int nlo = i & 7, k8 = (i >> 3) % k8n, nhi = (i >> 3) / k8n;
-    const int n = nhi * 8 + nlo, row = row0 + n;
+    const int n = nhi * 8 + nlo;
+    task_dst[it] = i < NT * k8n ? (uint32_t)(nhi * SBO + k8 * 128 + nlo * 16) : 0xFFFFFFFFu;
+    task_src[it] = (uint32_t)(n * KWp + (k8 >> 2)) | ((uint32_t)(8 * (k8 & 3)) << 24);
+  }
+  // frame 0: the initial spikes h0 (zeros when null)
+#pragma unroll
+  for (int it = 0; it < MAXT; ++it) {
+    if (task_dst[it] == 0xFFFFFFFFu) continue;
+    const int i = tid + NTHREADS * it;
+    const int nlo = i & 7, k8 = (i >> 3) % k8n, nhi = (i >> 3) / k8n;
+    const int row = row0 + nhi * 8 + nlo;
     uint32_t v[4] = {0, 0, 0, 0};
     if (p.h0 && row < R) {
 #pragma unroll
@@ -106,34 +131,35 @@ __global__ void __launch_bounds__(128, 1) k_recurrence_tc(const RecTcParams p) {
         if (k < H && p.h0[(size_t)row * H + k] != 0.f) v[e >> 1] |= kOneBf16 << (16 * (e & 1));
       }
     }
-    *reinterpret_cast<uint4*>(sB + (size_t)nhi * SBO + k8 * 128 + nlo * 16) = make_uint4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<uint4*>(sB + task_dst[it]) = make_uint4(v[0], v[1], v[2], v[3]);
   }
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  const uint32_t lane_base = (uint32_t)(q * 32) << 16;
   const uint32_t tmem_d = tmem;                       // accumulator: columns [0, NT)
   const uint32_t tmem_a = tmem + NT;                  // plane pl: columns [NT + pl*Kmma/2, ...)
   const uint32_t plane_cols = Kmma / 2;
 
-  // recurrent weights of this thread's neuron -> three exact bf16 planes in TMEM (lane = neuron)
+  // recurrent weights of this thread's neuron -> three exact bf16 planes in TMEM (lane = neuron);
+  // the G warps that share a lane quarter split the K range between them
   {
     const float* wrow = p.w_hh + (size_t)(jv ? j : 0) * H;
-    for (int c0 = 0; c0 < (int)plane_cols; c0 += 8) {
+    for (int c0 = 8 * g; c0 < (int)plane_cols; c0 += 8 * G) {
       uint32_t vh[8], vm[8], vl[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
+      for (int u = 0; u < 8; ++u) {
         uint32_t h2[2], m2[2], l2[2];
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const int k = 2 * (c0 + q) + e;
+          const int k = 2 * (c0 + u) + e;
           const float w = (jv && k < H) ? __ldg(wrow + k) : 0.f;
           split3(w, h2[e], m2[e], l2[e]);
         }
-        vh[q] = h2[0] | (h2[1] << 16);
-        vm[q] = m2[0] | (m2[1] << 16);
-        vl[q] = l2[0] | (l2[1] << 16);
+        vh[u] = h2[0] | (h2[1] << 16);
+        vm[u] = m2[0] | (m2[1] << 16);
+        vl[u] = l2[0] | (l2[1] << 16);
       }
       tc::tmem_st8(tmem_a + lane_base + 0 * plane_cols + c0, vl);  // plane 0 = lo (issued first)
       tc::tmem_st8(tmem_a + lane_base + 1 * plane_cols + c0, vm);
@@ -146,123 +172,169 @@ __global__ void __launch_bounds__(128, 1) k_recurrence_tc(const RecTcParams p) {
   const float bf = p.bias[jj], bc = p.bias[H + jj];
   const float bs = p.bn_scale ? p.bn_scale[jj] : 1.0f;
   const float bt = p.bn_shift ? p.bn_shift[jj] : 0.0f;
-  float c[NT];
+  float c[CPT];
+  uint32_t boff[CPT];      // byte offset of (row, neuron) inside one frame of a [T, R, H] fp32 tensor
+  uint32_t valid = 0;      // bit i: row i of my group exists and my neuron exists
 #pragma unroll
-  for (int n = 0; n < NT; ++n) {
-    const int row = row0 + n;
-    c[n] = (p.c0 && jv && row < R) ? p.c0[(size_t)row * H + j] : 0.f;
+  for (int i = 0; i < CPT; ++i) {
+    const int row = row0 + g * CPT + i;
+    const bool ok = jv && row < R;
+    valid |= ok ? 1u << i : 0u;
+    boff[i] = ok ? ((uint32_t)row * (uint32_t)H + (uint32_t)j) * 4u : 0u;
+    c[i] = (p.c0 && ok) ? *reinterpret_cast<const float*>(reinterpret_cast<const char*>(p.c0) + boff[i]) : 0.f;
   }
-  // all barriers of the cluster are initialised before anybody arrives remotely
+  const size_t frame_bytes = (size_t)R * H * sizeof(float);
+
+  // spike-bit exchange: lane l < CPT*C of every warp sends word (l % CPT) of its warp to CTA (l / CPT);
+  // the remote staging cell and the remote barrier are fixed per frame parity
+  uint32_t snd_cell0 = 0, snd_cell1 = 0, snd_bar0 = 0, snd_bar1 = 0;
+  const bool sender = lane < CPT * (int)C;
+  if (sender) {
+    const int i = lane % CPT;
+    const uint32_t r = lane / CPT;
+    snd_cell0 = tc::map_to_rank(bits + ((size_t)0 * NT + g * CPT + i) * KWp + slice * 4 + q, r);
+    snd_cell1 = tc::map_to_rank(bits + ((size_t)1 * NT + g * CPT + i) * KWp + slice * 4 + q, r);
+    snd_bar0 = tc::map_to_rank(&bar_bits[0], r);
+    snd_bar1 = tc::map_to_rank(&bar_bits[1], r);
+  }
+  // all barriers of the cluster are initialised before anybody stores remotely
+  tc::tc_fence_before();
   tc::cluster_sync_all();
+  tc::tc_fence_after();
 
   const uint32_t idesc = tc::make_idesc_f16(128, NT, true);
   const uint64_t desc_b0 = tc::make_smem_desc(tc::smem_u32(sB), 128, SBO);
   const int ksteps = Kmma / 16;
+  const uint32_t bits_bytes = (uint32_t)NT * 4u * C * 4u;  // every slice sends 4 words per row
   bool alive = true;
+  float hval[CPT];
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) hval[i] = 0.f;
 
+  // trace of frame t (spikes, membrane) -> global, coalesced over neurons
+  auto store_frame = [&](int t) {
+    char* hf = reinterpret_cast<char*>(p.h_out) + (size_t)t * frame_bytes;
+    char* cf = p.c_out ? reinterpret_cast<char*>(p.c_out) + (size_t)t * frame_bytes : nullptr;
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+      if ((valid >> i) & 1u) {
+        *reinterpret_cast<float*>(hf + boff[i]) = hval[i];
+        if (cf) *reinterpret_cast<float*>(cf + boff[i]) = c[i];
+      }
+    }
+  };
+
+  long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (int t = 0; t < T; ++t) {
+    const int par = t & 1;
+    const long long q0 = clock64();
     // ---- recurrent product of frame t: D = W_hh[slice] . h_{t-1}^T --------------------------------
-    tc::fence_proxy_async_smem();  // B operand was written through the generic proxy
+    tc::fence_proxy_async_smem();  // the B operand was written through the generic proxy
     tc::tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    const long long q1 = clock64();
+    if (warp == 0) {
       tc::tc_fence_after();
-      uint32_t acc = 0;
+      if (tc::elect_one()) {
+        tc::mbar_arrive_expect_tx(&bar_bits[par], bits_bytes);  // arm this frame's spike-bit exchange
+        uint32_t acc = 0;
 #pragma unroll 1
-      for (int pl = 0; pl < kTcPlanes; ++pl) {
-        const uint32_t a0 = tmem_a + pl * plane_cols;
-#pragma unroll 4
-        for (int ks = 0; ks < ksteps; ++ks) {
-          tc::mma_ts(tmem_d, a0 + ks * 8, desc_b0 + (uint64_t)(ks * 16), idesc, acc);
-          acc = 1;
+        for (int pl = 0; pl < kTcPlanes; ++pl) {
+          const uint32_t a0 = tmem_a + pl * plane_cols;
+#pragma unroll 2
+          for (int ks = 0; ks < ksteps; ++ks) {
+            tc::mma_ts(tmem_d, a0 + ks * 8, desc_b0 + (uint64_t)(ks * 16), idesc, acc);
+            acc = 1;
+          }
         }
+        tc::mma_commit(bar_mma);
       }
-      tc::mma_commit(bar_mma);
+      __syncwarp();
     }
-    // input projection of frame t for my neuron, all rows (coalesced over neurons); overlaps the MMAs
-    float xp[NT];
+    const long long q2 = clock64();
+    // ---- work hidden under the MMAs: trace of frame t-1 out, input projection of frame t in ----------
+    if (t > 0) store_frame(t - 1);
+    float xf_[CPT], xg_[CPT];
+    {
+      const char* xf = reinterpret_cast<const char*>(p.xproj) + (size_t)t * frame_bytes;
+      float xp[CPT];
 #pragma unroll
-    for (int n = 0; n < NT; ++n) {
-      const int row = row0 + n;
-      xp[n] = (jv && row < R) ? __ldg(p.xproj + ((size_t)t * R + row) * H + j) : 0.f;
+      for (int i = 0; i < CPT; ++i)
+        xp[i] = (valid >> i) & 1u ? __ldg(reinterpret_cast<const float*>(xf + boff[i])) : 0.f;
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) {  // reference order: (x W_ih^T + bias) + h W_hh^T   (ESN:140-145)
+        xf_[i] = __fadd_rn(xp[i], bf);
+        xg_[i] = __fadd_rn(xp[i], bc);
+      }
     }
     if (!tc::mbar_wait(bar_mma, t & 1)) { alive = false; break; }
     tc::tc_fence_after();
+    const long long q3 = clock64();
 
-    // ---- leak / BatchNorm / threshold; spikes -> bit words ----------------------------------------
-    const int par = t & 1;
-    uint32_t myword[(NT + 31) / 32];
+    // ---- leak / BatchNorm / threshold, CH columns at a time; spikes -> one bit each -----------------
+    uint32_t myw = 0;
 #pragma unroll
-    for (int q = 0; q < (NT + 31) / 32; ++q) myword[q] = 0;
-#pragma unroll
-    for (int n0 = 0; n0 < NT; n0 += 16) {
-      uint32_t zr[16];
-      tc::tmem_ld16(tmem_d + lane_base + n0, zr);
+    for (int i0 = 0; i0 < CPT; i0 += CH) {
+      uint32_t zr[CH];
+      tc::tmem_ld<CH>(tmem_d + lane_base + g * CPT + i0, zr);
       tc::tmem_wait_ld();
+      float sg[CH], gh[CH];
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const int n = n0 + q, row = row0 + n;
-        const float z = __uint_as_float(zr[q]);
-        // reference order: (x W_ih^T + bias) + h W_hh^T   (ESN:140-145)
-        const float f_hat = __fadd_rn(__fadd_rn(xp[n], bf), z);
-        const float g_hat = __fadd_rn(__fadd_rn(xp[n], bc), z);
-        const float cn = gsu_membrane(f_hat, g_hat, c[n], bs, bt);
-        c[n] = cn;
-        const bool ok = jv && row < R;
-        const bool spike = ok && cn >= 0.f;
-        if (ok) {
-          const size_t o = ((size_t)t * R + row) * H + j;
-          p.h_out[o] = spike ? 1.0f : 0.0f;
-          if (p.c_out) p.c_out[o] = cn;
-        }
+      for (int u = 0; u < CH; ++u) {
+        const float z = __uint_as_float(zr[u]);
+        sg[u] = sigmoid_f32(__fadd_rn(xf_[i0 + u], z));
+        gh[u] = __fadd_rn(xg_[i0 + u], z);
+      }
+#pragma unroll
+      for (int u = 0; u < CH; ++u) {
+        float cn = __fadd_rn(__fmul_rn(sg[u], c[i0 + u]), __fmul_rn(__fsub_rn(1.0f, sg[u]), gh[u]));
+        cn = __fadd_rn(__fmul_rn(cn, bs), bt);
+        c[i0 + u] = cn;
+        const bool spike = ((valid >> (i0 + u)) & 1u) && cn >= 0.f;
+        hval[i0 + u] = spike ? 1.0f : 0.0f;
         const uint32_t w = __ballot_sync(0xffffffffu, spike);
-        if (lane == (n & 31)) myword[n >> 5] = w;
+        myw = (lane % CPT) == (i0 + u) ? w : myw;
       }
     }
-    // ---- exchange the bits with every CTA of the cluster (DSMEM), then rebuild the B operand -------
-    {
-      uint32_t* dst = bits + (size_t)par * NT * KWp;
-#pragma unroll
-      for (int q = 0; q < (NT + 31) / 32; ++q) {
-        const int n = q * 32 + lane;
-        if (n < NT) {
-          uint32_t* cell = dst + n * KWp + slice * 4 + warp;
-          for (uint32_t r = 0; r < C; ++r) tc::st_cluster_u32(tc::map_to_rank(cell, r), myword[q]);
-        }
-      }
-      __syncwarp();
-      if (lane == 0)
-        for (uint32_t r = 0; r < C; ++r) tc::mbar_arrive_cluster(&bar_bits[par], r);
-    }
+    const long long q4 = clock64();
+    // ---- exchange: ONE asynchronous DSMEM store per sending lane into the staging buffer of a CTA of the
+    //      cluster; the bytes are counted on the receiver's mbarrier (no fence, no arrive on this side) ----
+    if (sender) tc::st_async_u32(par ? snd_cell1 : snd_cell0, myw, par ? snd_bar1 : snd_bar0);
+    const long long q5 = clock64();
     if (!tc::mbar_wait(&bar_bits[par], (t >> 1) & 1)) { alive = false; break; }
+    const long long q6 = clock64();
+    // ---- rebuild the bf16 B operand (spikes of frame t, all H neurons of my rows) from the bits -------
     {
       const uint32_t* src = bits + (size_t)par * NT * KWp;
-      for (int i = tid; i < NT * k8n; i += 128) {
-        const int nlo = i & 7, k8 = (i >> 3) % k8n, nhi = (i >> 3) / k8n;
-        const int n = nhi * 8 + nlo;
-        const uint32_t b8 = (src[n * KWp + (k8 >> 2)] >> (8 * (k8 & 3))) & 0xFFu;
+#pragma unroll
+      for (int it = 0; it < MAXT; ++it) {
+        if (task_dst[it] == 0xFFFFFFFFu) continue;
+        const uint32_t b8 = (src[task_src[it] & 0xFFFFFFu] >> (task_src[it] >> 24)) & 0xFFu;
         uint32_t v[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e)
           v[e] = ((b8 >> (2 * e)) & 1u ? kOneBf16 : 0u) | ((b8 >> (2 * e + 1)) & 1u ? (kOneBf16 << 16) : 0u);
-        *reinterpret_cast<uint4*>(sB + (size_t)nhi * SBO + k8 * 128 + nlo * 16) = make_uint4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<uint4*>(sB + task_dst[it]) = make_uint4(v[0], v[1], v[2], v[3]);
       }
     }
+    const long long q7 = clock64();
+    pc[0] += q1 - q0; pc[1] += q2 - q1; pc[2] += q3 - q2; pc[3] += q4 - q3;
+    pc[4] += q5 - q4; pc[5] += q6 - q5; pc[6] += q7 - q6; pc[7] += q7 - q0;
   }
   if (!alive) __trap();  // a broken pipeline fails loudly instead of hanging the device
+  if (p.prof && blockIdx.x == 0 && tid == 0)
+    for (int i = 0; i < 8; ++i) p.prof[i] = (unsigned long long)pc[i];
 
-  if (jv) {
+  store_frame(T - 1);
 #pragma unroll
-    for (int n = 0; n < NT; ++n) {
-      const int row = row0 + n;
-      if (row < R) {
-        if (p.cT) p.cT[(size_t)row * H + j] = c[n];
-        if (p.hT) p.hT[(size_t)row * H + j] = p.h_out[((size_t)(T - 1) * R + row) * H + j];
-      }
+  for (int i = 0; i < CPT; ++i) {
+    if ((valid >> i) & 1u) {
+      if (p.cT) *reinterpret_cast<float*>(reinterpret_cast<char*>(p.cT) + boff[i]) = c[i];
+      if (p.hT) *reinterpret_cast<float*>(reinterpret_cast<char*>(p.hT) + boff[i]) = hval[i];
     }
   }
   tc::tc_fence_before();
-  tc::cluster_sync_all();  // nobody leaves while a peer may still write into its staging buffer
+  tc::cluster_sync_all();  // nobody leaves while a peer may still store into its staging buffer
   if (warp == 0) tc::tmem_dealloc<kTmemCols>(tmem);
 }
 
@@ -274,6 +346,7 @@ static int tc_pick_nt(int R, int H, int sm_count) {
   int best = 0;
   for (int nt : {16, 32, 64}) {
     if (cols_a + nt > (int)kTmemCols) break;
+    if ((nt / 4) * C > 32) break;  // one sending lane per (row of the group, destination CTA)
     best = nt;
     if ((long long)((R + nt - 1) / nt) * C <= sm_count) break;  // whole problem co-resident
   }
@@ -289,13 +362,13 @@ bool recurrence_tc_supported(int R, int H, int shared) {
 
 size_t recurrence_tc_workspace(int, int, int) { return 256; }
 
-template <int NT>
+template <int NT, int G>
 static int launch_nt(const RecTcParams& p, int C, cudaStream_t st) {
   const size_t smem = tc_smem_bytes<NT>(p.Kmma, C);
-  GSN_CUDA(cudaFuncSetAttribute(k_recurrence_tc<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  GSN_CUDA(cudaFuncSetAttribute(k_recurrence_tc<NT, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(((p.R + NT - 1) / NT) * C));
-  cfg.blockDim = dim3(128);
+  cfg.blockDim = dim3(128 * G);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -305,24 +378,26 @@ static int launch_nt(const RecTcParams& p, int C, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  GSN_CUDA(cudaLaunchKernelEx(&cfg, k_recurrence_tc<NT>, p));
+  GSN_CUDA(cudaLaunchKernelEx(&cfg, k_recurrence_tc<NT, G>, p));
   return GSN_OK;
 }
 
 int launch_recurrence_tc(const float* xproj, const float* w_hh, const float* bias, const float* bn_scale,
                          const float* bn_shift, const float* h0, const float* c0, float* h_out, float* c_out,
-                         float* hT, float* cT, int T, int R, int H, int shared, void*, cudaStream_t st) {
+                         float* hT, float* cT, int T, int R, int H, int shared, void* workspace, cudaStream_t st) {
   GSN_REQUIRE(shared, "gsn_layer_recurrence(TCGEN05): unshared gate weights are not supported");
   int dev = 0, sms = 148;
   GSN_CUDA(cudaGetDevice(&dev));
   GSN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  RecTcParams p{xproj, w_hh, bias, bn_scale, bn_shift, h0, c0, h_out, c_out, hT, cT, T, R, H, (H + 15) / 16 * 16};
+  RecTcParams p{xproj, w_hh, bias, bn_scale, bn_shift, h0, c0, h_out, c_out, hT, cT, T, R, H, (H + 15) / 16 * 16,
+                reinterpret_cast<unsigned long long*>(workspace)};
   const int C = (H + 127) / 128;
   const int nt = tc_pick_nt(R, H, sms);
+  static const int g_env = getenv("GSN_TC_GROUPS") ? atoi(getenv("GSN_TC_GROUPS")) : 0;  // dev knob
   switch (nt) {
-    case 16: return launch_nt<16>(p, C, st);
-    case 32: return launch_nt<32>(p, C, st);
-    case 64: return launch_nt<64>(p, C, st);
+    case 16: return g_env == 2 ? launch_nt<16, 2>(p, C, st) : launch_nt<16, 4>(p, C, st);
+    case 32: return g_env == 2 ? launch_nt<32, 2>(p, C, st) : launch_nt<32, 4>(p, C, st);
+    case 64: return launch_nt<64, 4>(p, C, st);
     default: return fail(GSN_ENOSUP, "gsn_layer_recurrence(TCGEN05): H=%d does not fit tensor memory", H);
   }
 }

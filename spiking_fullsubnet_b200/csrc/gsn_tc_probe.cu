@@ -94,7 +94,61 @@ __global__ void __launch_bounds__(128)
   if (warp == 0) tc::tmem_dealloc<512>(tmem);
 }
 
+// timing probe: `reps` x (K/16) back-to-back MMAs of shape 128 x N x 16, operands uninitialised.
+__global__ void __launch_bounds__(128) k_tc_mma_timing(long long* out, int N, int K, int reps, int a_in_tmem) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (128 + N) * K / 2; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (tid == 0) {
+    tc::mbar_init(&bar, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc<512>(&tmem_base_slot);
+  tc::tc_fence_before();
+  tc::fence_proxy_async_smem();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+  const uint32_t lbo = 128, sbo = 16u * K;
+  long long t0 = 0, t1 = 0, t2 = 0;
+  if (warp == 0) {
+    uint32_t leader;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(leader));
+    if (leader) {
+      const uint32_t idesc = tc::make_idesc_f16(128, N, true);
+      const uint64_t da0 = tc::make_smem_desc(tc::smem_u32(smem), lbo, sbo);
+      const uint64_t db0 = tc::make_smem_desc(tc::smem_u32(smem + 128 * K * 2), lbo, sbo);
+      t0 = clock64();
+      for (int r = 0; r < reps; ++r)
+        for (int ks = 0; ks < K / 16; ++ks) {
+          if (a_in_tmem) tc::mma_ts(tmem, tmem + 256 + ks * 8, db0 + (uint64_t)(ks * 16), idesc, 1);
+          else tc::mma_ss(tmem, da0 + (uint64_t)(ks * 16), db0 + (uint64_t)(ks * 16), idesc, 1);
+        }
+      tc::mma_commit(&bar);
+      t1 = clock64();
+    }
+    __syncwarp();
+  }
+  tc::mbar_wait(&bar, 0);
+  t2 = clock64();
+  if (tid == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<512>(tmem);
+}
+
 }  // namespace gsn
+
+extern "C" GSN_API int gsn_tc_mma_timing(long long* out, int N, int K, int reps, int a_in_tmem, gsn_stream_t stream) {
+  const size_t smem = (size_t)(128 + N) * K * 2;
+  GSN_REQUIRE(smem <= 200 * 1024, "gsn_tc_mma_timing: operands do not fit shared memory");
+  GSN_CUDA(cudaFuncSetAttribute(gsn::k_tc_mma_timing, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gsn::k_tc_mma_timing<<<1, 128, smem, gsn::as_stream(stream)>>>(out, N, K, reps, a_in_tmem);
+  GSN_LAUNCH_CHECK("k_tc_mma_timing");
+  return GSN_OK;
+}
 
 extern "C" int gsn_tc_selftest(const float* a, const float* b, float* d, int* status, int N, int K,
                                int a_in_tmem, int swap_lbo_sbo, int use_fp16, gsn_stream_t stream) {

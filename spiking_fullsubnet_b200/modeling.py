@@ -62,11 +62,14 @@ class GSUCell(nn.Module):
         bn = self.batchnorm
         key = (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version,
                bn.weight.data_ptr(), bn.running_var.data_ptr())
-        if self._bn_cache is None or self._bn_cache[0] != key:
+        capturing = bn.weight.is_cuda and torch.cuda.is_current_stream_capturing()
+        if capturing or self._bn_cache is None or self._bn_cache[0] != key:
             with torch.no_grad():
                 invstd = 1.0 / torch.sqrt(bn.running_var + bn.eps)
                 alpha = (invstd * bn.weight).contiguous()
                 beta = (bn.bias - bn.running_mean * alpha).contiguous()
+            if capturing:  # the fold becomes part of the CUDA graph, so replays see updated statistics
+                return alpha, beta
             self._bn_cache = (key, alpha, beta)
         return self._bn_cache[1], self._bn_cache[2]
 
@@ -215,6 +218,16 @@ def coef_layout(proj, B, N, df, S):
     return v.permute(1, 5, 6, 2, 4, 0, 3).reshape(B, df, S, N * fc, T, 2)
 
 
+_BAND_STREAMS = {}
+
+
+def _band_streams(device, n):
+    key = (device.index, n)
+    if key not in _BAND_STREAMS:
+        _BAND_STREAMS[key] = [torch.cuda.Stream(device=device) for _ in range(n)]
+    return _BAND_STREAMS[key]
+
+
 class SubbandModel(nn.Module):
     def __init__(self, freq_cutoffs, center_freq_sizes, neighbor_freq_sizes, df_orders, num_spks, **kwargs):
         super().__init__()
@@ -228,26 +241,51 @@ class SubbandModel(nn.Module):
         self.neighbor_freq_sizes = neighbor_freq_sizes
         self.df_orders = df_orders
         self.num_spks = num_spks
+        self.concurrent_bands = True
 
     def run_time_major(self, cm, fb):
         """cm [T,B,F] compressed magnitude, fb [T,B,f_fb] full-band output (tiled by index) ->
         list of proj outputs [T, B*N_i, P_i] and the per-band all_layer_outputs (MSF:216-263)."""
         T, B, F = cm.shape
-        projs, all_outs = [], []
-        for i, m in enumerate(self.sb_models):
-            lo, hi = self.freq_cutoffs[i], self.freq_cutoffs[i + 1]
-            ctr, nbr = self.center_freq_sizes[i], self.neighbor_freq_sizes[i]
+        for i in range(len(self.sb_models)):
+            lo, hi, ctr = self.freq_cutoffs[i], self.freq_cutoffs[i + 1], self.center_freq_sizes[i]
             if (hi - lo) % ctr != 0:
                 raise ValueError(f"Number of frequency bins must be divisible by the center frequency."
                                  f"GOT: ctr_freq={ctr}, upper_cutoff_freq={hi}, lower_cutoff_freq={lo}")
+
+        def run_band(i):
+            m = self.sb_models[i]
+            lo, hi = self.freq_cutoffs[i], self.freq_cutoffs[i + 1]
+            ctr, nbr = self.center_freq_sizes[i], self.neighbor_freq_sizes[i]
             lnw = m.pre_layer_norm.weight.detach() if m.use_pre_layer_norm else None
             lnb = m.pre_layer_norm.bias.detach() if m.use_pre_layer_norm else None
             eps = m.pre_layer_norm.eps if m.use_pre_layer_norm else 1e-5
             x = ops.subband_features(cm, fb, (hi - lo) // ctr, lo, ctr, nbr, lnw, lnb, eps)
             proj, _, all_out = m.run_time_major(x)
-            projs.append(proj)
-            all_outs.append(all_out)
-        return projs, all_outs
+            return proj, all_out
+
+        n = len(self.sb_models)
+        if not self.concurrent_bands or n == 1:
+            res = [run_band(i) for i in range(n)]
+        else:
+            # the bands are independent recurrences on different weights: fork one stream per band so
+            # their (latency-bound, few-CTA) kernels share the 148 SMs, then join on the caller's stream
+            main = torch.cuda.current_stream(cm.device)
+            streams = _band_streams(cm.device, n)
+            fork = torch.cuda.Event()
+            fork.record(main)
+            res = []
+            for i in range(n):
+                streams[i].wait_event(fork)
+                with torch.cuda.stream(streams[i]):
+                    res.append(run_band(i))
+                    done = torch.cuda.Event()
+                    done.record(streams[i])
+                main.wait_event(done)
+                if not torch.cuda.is_current_stream_capturing():
+                    for t in [res[-1][0]] + res[-1][1]:
+                        t.record_stream(main)
+        return [r[0] for r in res], [r[1] for r in res]
 
     def forward(self, noisy_input, fb_output):
         """noisy_input [B,1,F,T], fb_output [B,1,F,T] (already tiled) -> (coef list, all_layer_outputs)."""
@@ -295,6 +333,16 @@ class SpikingFullSubNet(nn.Module):
         self.subband_model = None
         self.fb_input_size, self.n_fft, self.hop_length, self.win_length = fb_input_size, n_fft, hop_length, win_length
         self.fdrc, self.df_orders, self.num_spks = fdrc, df_orders, num_spks
+        self.use_cuda_graph = False
+        self._graphs = {}
+
+    def enable_cuda_graph(self, flag=True):
+        """Replay the hot path (`network`) from a CUDA graph captured per input shape: ~35 kernel launches
+        on 4 streams become one graph launch.  The returned tensors are the graph's static output buffers
+        and are OVERWRITTEN by the next call with the same input shape (clone them to keep them)."""
+        self.use_cuda_graph = bool(flag)
+        self._graphs = {}
+        return self
 
     def set_backend(self, backend):
         """'auto' | 'simt' | 'tcgen05' for every recurrence of the model."""
@@ -308,6 +356,26 @@ class SpikingFullSubNet(nn.Module):
         """mag [B, n_fft//2+1, T] -> (projs: list of [T, B*N_i, P_i], fb_all, sb_all)."""
         if not mag.is_cuda:
             raise RuntimeError("spiking_fullsubnet_b200 has no CPU path: move the model and input to CUDA")
+        if not self.use_cuda_graph or torch.cuda.is_current_stream_capturing():
+            return self._network(mag)
+        key = (tuple(mag.shape), mag.device.index, self.training)
+        entry = self._graphs.get(key)
+        if entry is None:
+            static_in = torch.empty_like(mag, memory_format=torch.contiguous_format)
+            static_in.copy_(mag)
+            with torch.no_grad():
+                self._network(static_in)  # warm-up outside the capture (lazy CUDA initialisation)
+                torch.cuda.synchronize(mag.device)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    static_out = self._network(static_in)
+            entry = self._graphs[key] = (graph, static_in, static_out)
+        graph, static_in, static_out = entry
+        static_in.copy_(mag)
+        graph.replay()
+        return static_out
+
+    def _network(self, mag):
         F = mag.shape[1]
         cm = ops.compress_mag(mag.contiguous(), F - 1, self.fdrc)  # drops the last bin, MSF:436
         fbm = self.fb_model

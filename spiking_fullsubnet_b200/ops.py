@@ -10,6 +10,7 @@ from . import _lib
 _ACT = {None: 0, False: 0, "tanh": 1, "sigmoid": 2, "relu": 3}
 _bound_device = [None]
 LAUNCHES = [0]   # number of libgsn_b200 kernels enqueued so far (bench.py reports it)
+LAST_WS = [None]  # workspace of the last recurrence call (tcgen05 backend: 8 cycle counters of CTA 0)
 PROFILE = None   # bench.py sets a list: (algorithmic flops, start event, stop event) per recurrence call
 
 
@@ -104,6 +105,7 @@ def layer_recurrence(xproj, w_hh, bias, bn_scale=None, bn_shift=None, shared=Tru
                                         _ptr(h0), _ptr(c0), _ptr(h), _ptr(c), _ptr(hT), _ptr(cT), T, R, H,
                                         int(shared), be, ws.data_ptr() + off, st))
     LAUNCHES[0] += 2  # weight preparation + the recurrence kernel
+    LAST_WS[0] = (ws, off // 4)
     if PROFILE is not None:
         e1.record()
         PROFILE.append((2.0 * T * R * gH * H, e0, e1))

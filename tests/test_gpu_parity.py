@@ -203,3 +203,24 @@ def test_properties_at_full_size_S():
     flips = sum(float((a != b).float().sum()) for a, b in zip(fb_all[1:-1], fb_s[1:-1]))
     total = sum(a.numel() for a in fb_all[1:-1])
     assert flips / total < 1e-4, f"back ends disagree on {flips / total:.2e} of full-band spikes"
+
+
+def test_cuda_graph_replay_matches_eager():
+    """The captured CUDA graph of the hot path reproduces the eager launch sequence bit for bit, also after
+    the input changes and after BatchNorm statistics change (the fold is part of the graph)."""
+    cfg = synth.tiny_cfg()
+    m = _model(cfg, synth.make_params(cfg, 9))
+    mags = [_t(synth.make_mag(2, 33, 30, s)) for s in (1, 2)]
+    with torch.no_grad():
+        eager = [[p.clone() for p in m.network(x)[0]] for x in mags]
+        m.enable_cuda_graph(True)
+        for x, ref in zip(mags + mags, eager + eager):
+            out = m.network(x)[0]
+            assert all(torch.equal(a, b) for a, b in zip(out, ref))
+        bn = m.fb_model.sequence_model.layers[0].cell.batchnorm
+        bn.running_mean.add_(0.05)
+        got = [p.clone() for p in m.network(mags[0])[0]]
+        m.enable_cuda_graph(False)
+        want = m.network(mags[0])[0]
+    assert all(torch.equal(a, b) for a, b in zip(got, want))
+    assert not all(torch.equal(a, b) for a, b in zip(got, eager[0]))
