@@ -35,6 +35,7 @@ def parse():
     ap.add_argument("--seconds", type=float, default=4.0)
     ap.add_argument("--backend", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chunks", type=int, default=8, help="frame chunks of the wavefront schedule (graph mode)")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of "
                     "replaying the captured CUDA graph")
     return ap.parse_args()
@@ -175,7 +176,7 @@ def main():
     ops.LAUNCHES[0] = 0
     step()  # eager pass: counts the kernels one step launches
     launches_per_step = ops.LAUNCHES[0]
-    model.enable_cuda_graph(not args.no_graph)
+    model.enable_cuda_graph(not args.no_graph, frame_chunks=args.chunks)
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
@@ -257,7 +258,8 @@ def main():
         "data": "synthetic",
         "config": dict(wl, l2="flushed between timed iterations (256 MiB write)",
                        recurrence_backends=backends,
-                       launch="CUDA graph replay of the step (captured once per shape)" if not args.no_graph
+                       launch=f"CUDA graph replay of the step, frame-chunked wavefront ({args.chunks} chunks, one "
+                              f"stream per model x layer)" if not args.no_graph
                        else "eager enqueue from Python"),
         "clocks": sampler.summary(),
         "e2e": {"value": world * B * T * args.steps / e2e_s, "unit": "frames/s",

@@ -108,6 +108,13 @@ GSN_API int gsn_deepfilter_band(const float* proj, const float* spec_re, const f
                         float* out_im, int T, int B, int N, int ctr, int df, int S, int lo, int F,
                         int F_out, gsn_stream_t stream);
 
+/* ---- optional launch trace (development / profiling aid) ------------------------------------------------
+ * device_buffer (>= 64 + 32*n bytes of device memory) receives one 32-byte record per traced kernel launch:
+ * {u64 start_ns, u64 end_ns (%globaltimer of CTA 0), i32 kind (1 linear, 2 recurrence, 3 features), a, b, c}.
+ * Header: u32 count, u32 capacity.  NULL disables.  The pointer is baked into launches when they are enqueued
+ * (so enable it before capturing a CUDA graph).                                                          */
+GSN_API int gsn_trace_set(void* device_buffer, size_t bytes);
+
 /* ---- self test of the tcgen05 operand encodings ------------------------------------------------
  * d[128, N] = a[128, K] @ b[N, K]^T on one CTA with the operand layouts of the recurrence kernel
  * (K-major no-swizzle shared memory; a_in_tmem != 0 keeps A resident in tensor memory).  a and b must

@@ -31,6 +31,7 @@ SIGNATURES = {
     "gsn_layer_recurrence": (_i, [_p] * 11 + [_i] * 5 + [_p, _p]),
     "gsn_layer_recurrence_pick_backend": (_i, [_i, _i, _i]),
     "gsn_deepfilter_band": (_i, [_p] * 5 + [_i] * 9 + [_p]),
+    "gsn_trace_set": (_i, [_p, _sz]),
     "gsn_tc_selftest": (_i, [_p] * 4 + [_i] * 5 + [_p]),
 }
 

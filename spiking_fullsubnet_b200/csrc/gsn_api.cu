@@ -10,6 +10,9 @@ char* err_buf() {
   return buf;
 }
 
+static TraceBuf* g_trace = nullptr;
+TraceBuf* trace_buffer() { return g_trace; }
+
 int fail(int code, const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -35,6 +38,16 @@ bool recurrence_tc_supported(int R, int H, int shared);
 extern "C" int gsn_abi_version(void) { return GSN_ABI_VERSION; }
 
 extern "C" const char* gsn_last_error(void) { return gsn::err_buf(); }
+
+extern "C" int gsn_trace_set(void* device_buffer, size_t bytes) {
+  if (device_buffer == nullptr) { gsn::g_trace = nullptr; return GSN_OK; }
+  GSN_REQUIRE(bytes >= 64 + sizeof(gsn::TraceRec), "gsn_trace_set: buffer too small");
+  unsigned int hdr[16] = {0};
+  hdr[1] = (unsigned int)((bytes - 64) / sizeof(gsn::TraceRec));
+  GSN_CUDA(cudaMemcpy(device_buffer, hdr, sizeof(hdr), cudaMemcpyHostToDevice));
+  gsn::g_trace = reinterpret_cast<gsn::TraceBuf*>(device_buffer);
+  return GSN_OK;
+}
 
 extern "C" int gsn_bind_device(int device) {
   GSN_CUDA(cudaSetDevice(device));

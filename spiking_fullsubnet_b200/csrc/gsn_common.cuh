@@ -35,6 +35,37 @@ int fail(int code, const char* fmt, ...);
 
 static inline cudaStream_t as_stream(gsn_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// ---- optional device-side launch trace (gsn_trace_set): CTA 0 of a kernel stamps %globaltimer at entry/exit
+struct TraceRec {
+  unsigned long long t0, t1;
+  int kind, a, b, c;
+};
+struct TraceBuf {  // lives in device memory; header then records
+  unsigned int count, capacity;
+  unsigned int pad[14];
+  TraceRec rec[1];
+};
+TraceBuf* trace_buffer();  // host side: current buffer or nullptr (gsn_api.cu)
+
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ int trace_begin(TraceBuf* tb, int kind, int a, int b, int c) {
+  if (tb == nullptr || blockIdx.x != 0 || blockIdx.y != 0 || blockIdx.z != 0 || threadIdx.x != 0 || threadIdx.y != 0)
+    return -1;
+  const unsigned int slot = atomicAdd(&tb->count, 1u);
+  if (slot >= tb->capacity) return -1;
+  tb->rec[slot].kind = kind; tb->rec[slot].a = a; tb->rec[slot].b = b; tb->rec[slot].c = c;
+  tb->rec[slot].t1 = 0;
+  tb->rec[slot].t0 = global_ns();
+  return (int)slot;
+}
+__device__ __forceinline__ void trace_end(TraceBuf* tb, int slot) {
+  if (slot >= 0) tb->rec[slot].t1 = global_ns();
+}
+
 __device__ __forceinline__ float sigmoid_f32(float x) {
   // the reference's torch.sigmoid formula 1 / (1 + exp(-x)) with full-precision expf; the division is
   // MUFU.RCP + one Newton step (<= 1 ulp, branch-free so several evaluations interleave).  The clamp keeps

@@ -38,7 +38,9 @@ constexpr int kMaxPerLane = 32;
 __global__ void __launch_bounds__(256) k_subband_features(
     const float* __restrict__ cm, int f_cm, const float* __restrict__ fb, int f_fb,
     float* __restrict__ x, int T, int B, int N, int lo, int ctr, int nbr,
-    const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps) {
+    const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps, TraceBuf* tb) {
+  const int tslot = trace_begin(tb, 3, T, B * N, ctr + 2 * nbr + (fb ? ctr : 0));
+  trace_end(tb, tslot);  // entry stamp only (warps exit independently)
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int R = B * N;
@@ -174,7 +176,7 @@ extern "C" int gsn_subband_features(const float* cm, int f_cm, const float* fb, 
   const long long blocks = (warps + 7) / 8;
   GSN_REQUIRE(blocks < 2147483647LL, "gsn_subband_features: too many rows");
   gsn::k_subband_features<<<(unsigned)blocks, 256, 0, gsn::as_stream(stream)>>>(
-      cm, f_cm, fb, f_fb, x, T, B, N, lo, ctr, nbr, ln_weight, ln_bias, ln_eps);
+      cm, f_cm, fb, f_fb, x, T, B, N, lo, ctr, nbr, ln_weight, ln_bias, ln_eps, gsn::trace_buffer());
   GSN_LAUNCH_CHECK("k_subband_features");
   return GSN_OK;
 }

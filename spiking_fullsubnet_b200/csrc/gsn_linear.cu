@@ -17,10 +17,14 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   }
 }
 
-__global__ void __launch_bounds__(256)
+// Software pipelined: the global loads of k-slab i+1 are in flight (registers) while slab i is multiplied
+// out of shared memory.  <= 96 registers so that a CTA fits beside a resident 512-thread recurrence CTA
+// (wavefront schedule: the projections of chunk k+1 run while the recurrences of chunk k occupy the SMs).
+__global__ void __launch_bounds__(256, 2)
     k_linear_f32(const float* __restrict__ a, const float* __restrict__ w,
                  const float* __restrict__ bias, float* __restrict__ out,
-                 float* __restrict__ out_act, int act, long long M, int K, int N) {
+                 float* __restrict__ out_act, int act, long long M, int K, int N, TraceBuf* tb) {
+  const int tslot = trace_begin(tb, 1, (int)M, K, N);
   __shared__ __align__(16) float As[LBK][LBM + 4];
   __shared__ __align__(16) float Ws[LBK][LBN + 4];
   const long long m0 = (long long)blockIdx.x * LBM;
@@ -36,19 +40,34 @@ __global__ void __launch_bounds__(256)
 
   // loader mapping: 16 consecutive threads cover the 16 k of one row (64 contiguous bytes)
   const int lk = tid & 15, lr = tid >> 4;  // lr 0..15
-  for (int k0 = 0; k0 < K; k0 += LBK) {
+  const float* ap[LBM / 16];
+  const float* wp[LBN / 16];
+#pragma unroll
+  for (int i = 0; i < LBM / 16; ++i) {
+    const long long m = m0 + lr + 16 * i;
+    ap[i] = m < M ? a + m * K : nullptr;
+  }
+#pragma unroll
+  for (int i = 0; i < LBN / 16; ++i) {
+    const int n = n0 + lr + 16 * i;
+    wp[i] = n < N ? w + (size_t)n * K : nullptr;
+  }
+  float ra[LBM / 16], rw[LBN / 16];
+  auto fetch = [&](int k0) {
     const int k = k0 + lk;
 #pragma unroll
-    for (int i = 0; i < LBM / 16; ++i) {
-      const long long m = m0 + lr + 16 * i;
-      As[lk][lr + 16 * i] = (m < M && k < K) ? a[m * K + k] : 0.f;
-    }
+    for (int i = 0; i < LBM / 16; ++i) ra[i] = (ap[i] && k < K) ? __ldg(ap[i] + k) : 0.f;
 #pragma unroll
-    for (int i = 0; i < LBN / 16; ++i) {
-      const int n = n0 + lr + 16 * i;
-      Ws[lk][lr + 16 * i] = (n < N && k < K) ? w[(size_t)n * K + k] : 0.f;
-    }
+    for (int i = 0; i < LBN / 16; ++i) rw[i] = (wp[i] && k < K) ? __ldg(wp[i] + k) : 0.f;
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < K; k0 += LBK) {
+#pragma unroll
+    for (int i = 0; i < LBM / 16; ++i) As[lk][lr + 16 * i] = ra[i];
+#pragma unroll
+    for (int i = 0; i < LBN / 16; ++i) Ws[lk][lr + 16 * i] = rw[i];
     __syncthreads();
+    if (k0 + LBK < K) fetch(k0 + LBK);
 #pragma unroll
     for (int kk = 0; kk < LBK; ++kk) {
       const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][tm * 8]);
@@ -76,6 +95,7 @@ __global__ void __launch_bounds__(256)
       if (out_act) out_act[m * N + n] = apply_act(v, act);
     }
   }
+  trace_end(tb, tslot);
 }
 
 }  // namespace gsn
@@ -90,7 +110,8 @@ extern "C" int gsn_linear_f32(const float* a, const float* w, const float* bias,
   const int gy = (N + gsn::LBN - 1) / gsn::LBN;
   GSN_REQUIRE(gx < 2147483647LL && gy <= 65535, "gsn_linear_f32: grid too large");
   dim3 grid((unsigned)gx, gy);
-  gsn::k_linear_f32<<<grid, 256, 0, gsn::as_stream(stream)>>>(a, w, bias, out, out_act, act, M, K, N);
+  gsn::k_linear_f32<<<grid, 256, 0, gsn::as_stream(stream)>>>(a, w, bias, out, out_act, act, M, K, N,
+                                                             gsn::trace_buffer());
   GSN_LAUNCH_CHECK("k_linear_f32");
   return GSN_OK;
 }

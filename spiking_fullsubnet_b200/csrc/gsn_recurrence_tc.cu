@@ -39,6 +39,7 @@ struct RecTcParams {
   float* cT;
   int T, R, H, Kmma;    // Kmma = round_up(H, 16)
   unsigned long long* prof;  // [8] cycle counters of CTA 0 / thread 0 (workspace), see tools/tc_profile.py
+  TraceBuf* trace;
 };
 
 constexpr int kTcPlanes = 3;
@@ -68,7 +69,7 @@ __device__ __forceinline__ void split3(float w, uint32_t& hi, uint32_t& mid, uin
   lo = __float_as_uint(r2) >> 16;
 }
 
-template <int NT, int G>
+template <int NT, int G, bool PROF>
 __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams p) {
   constexpr int NTHREADS = 128 * G;
   constexpr int CPT = NT / G;                 // accumulator columns (= rows of the tile) per thread
@@ -76,6 +77,7 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
   constexpr int MAXT = (NT * 40 + NTHREADS - 1) / NTHREADS;  // B-operand rebuild tasks per thread (Kmma <= 320)
   static_assert(CPT == 4 || CPT == 8 || CPT == 16, "NT / G must be 4, 8 or 16");
   extern __shared__ __align__(1024) uint8_t smem[];
+  const int tslot = trace_begin(p.trace, 2, p.T, p.R, p.H);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3;    // TMEM lane quarter this warp may access
   const int g = warp >> 2;   // column group: rows [g*CPT, g*CPT + CPT) of the tile
@@ -227,12 +229,12 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
   long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (int t = 0; t < T; ++t) {
     const int par = t & 1;
-    const long long q0 = clock64();
+    const long long q0 = PROF ? clock64() : 0;
     // ---- recurrent product of frame t: D = W_hh[slice] . h_{t-1}^T --------------------------------
     tc::fence_proxy_async_smem();  // the B operand was written through the generic proxy
     tc::tc_fence_before();
     __syncthreads();
-    const long long q1 = clock64();
+    const long long q1 = PROF ? clock64() : 0;
     if (warp == 0) {
       tc::tc_fence_after();
       if (tc::elect_one()) {
@@ -251,7 +253,7 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
       }
       __syncwarp();
     }
-    const long long q2 = clock64();
+    const long long q2 = PROF ? clock64() : 0;
     // ---- work hidden under the MMAs: trace of frame t-1 out, input projection of frame t in ----------
     if (t > 0) store_frame(t - 1);
     float xf_[CPT], xg_[CPT];
@@ -269,7 +271,7 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
     }
     if (!tc::mbar_wait(bar_mma, t & 1)) { alive = false; break; }
     tc::tc_fence_after();
-    const long long q3 = clock64();
+    const long long q3 = PROF ? clock64() : 0;
 
     // ---- leak / BatchNorm / threshold, CH columns at a time; spikes -> one bit each -----------------
     uint32_t myw = 0;
@@ -296,13 +298,13 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
         myw = (lane % CPT) == (i0 + u) ? w : myw;
       }
     }
-    const long long q4 = clock64();
+    const long long q4 = PROF ? clock64() : 0;
     // ---- exchange: ONE asynchronous DSMEM store per sending lane into the staging buffer of a CTA of the
     //      cluster; the bytes are counted on the receiver's mbarrier (no fence, no arrive on this side) ----
     if (sender) tc::st_async_u32(par ? snd_cell1 : snd_cell0, myw, par ? snd_bar1 : snd_bar0);
-    const long long q5 = clock64();
+    const long long q5 = PROF ? clock64() : 0;
     if (!tc::mbar_wait(&bar_bits[par], (t >> 1) & 1)) { alive = false; break; }
-    const long long q6 = clock64();
+    const long long q6 = PROF ? clock64() : 0;
     // ---- rebuild the bf16 B operand (spikes of frame t, all H neurons of my rows) from the bits -------
     {
       const uint32_t* src = bits + (size_t)par * NT * KWp;
@@ -317,12 +319,14 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
         *reinterpret_cast<uint4*>(sB + task_dst[it]) = make_uint4(v[0], v[1], v[2], v[3]);
       }
     }
-    const long long q7 = clock64();
-    pc[0] += q1 - q0; pc[1] += q2 - q1; pc[2] += q3 - q2; pc[3] += q4 - q3;
-    pc[4] += q5 - q4; pc[5] += q6 - q5; pc[6] += q7 - q6; pc[7] += q7 - q0;
+    const long long q7 = PROF ? clock64() : 0;
+    if (PROF) {
+      pc[0] += q1 - q0; pc[1] += q2 - q1; pc[2] += q3 - q2; pc[3] += q4 - q3;
+      pc[4] += q5 - q4; pc[5] += q6 - q5; pc[6] += q7 - q6; pc[7] += q7 - q0;
+    }
   }
   if (!alive) __trap();  // a broken pipeline fails loudly instead of hanging the device
-  if (p.prof && blockIdx.x == 0 && tid == 0)
+  if (PROF && p.prof && blockIdx.x == 0 && tid == 0)
     for (int i = 0; i < 8; ++i) p.prof[i] = (unsigned long long)pc[i];
 
   store_frame(T - 1);
@@ -336,6 +340,7 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
   tc::tc_fence_before();
   tc::cluster_sync_all();  // nobody leaves while a peer may still store into its staging buffer
   if (warp == 0) tc::tmem_dealloc<kTmemCols>(tmem);
+  trace_end(p.trace, tslot);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -362,10 +367,11 @@ bool recurrence_tc_supported(int R, int H, int shared) {
 
 size_t recurrence_tc_workspace(int, int, int) { return 256; }
 
-template <int NT, int G>
+template <int NT, int G, bool PROF>
 static int launch_nt(const RecTcParams& p, int C, cudaStream_t st) {
   const size_t smem = tc_smem_bytes<NT>(p.Kmma, C);
-  GSN_CUDA(cudaFuncSetAttribute(k_recurrence_tc<NT, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  GSN_CUDA(cudaFuncSetAttribute(k_recurrence_tc<NT, G, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(((p.R + NT - 1) / NT) * C));
   cfg.blockDim = dim3(128 * G);
@@ -378,7 +384,7 @@ static int launch_nt(const RecTcParams& p, int C, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  GSN_CUDA(cudaLaunchKernelEx(&cfg, k_recurrence_tc<NT, G>, p));
+  GSN_CUDA(cudaLaunchKernelEx(&cfg, k_recurrence_tc<NT, G, PROF>, p));
   return GSN_OK;
 }
 
@@ -390,14 +396,14 @@ int launch_recurrence_tc(const float* xproj, const float* w_hh, const float* bia
   GSN_CUDA(cudaGetDevice(&dev));
   GSN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   RecTcParams p{xproj, w_hh, bias, bn_scale, bn_shift, h0, c0, h_out, c_out, hT, cT, T, R, H, (H + 15) / 16 * 16,
-                reinterpret_cast<unsigned long long*>(workspace)};
+                reinterpret_cast<unsigned long long*>(workspace), trace_buffer()};
   const int C = (H + 127) / 128;
   const int nt = tc_pick_nt(R, H, sms);
-  static const int g_env = getenv("GSN_TC_GROUPS") ? atoi(getenv("GSN_TC_GROUPS")) : 0;  // dev knob
+  static const bool prof = getenv("GSN_TC_PROF") != nullptr;  // dev knob: per-phase cycle counters
   switch (nt) {
-    case 16: return g_env == 2 ? launch_nt<16, 2>(p, C, st) : launch_nt<16, 4>(p, C, st);
-    case 32: return g_env == 2 ? launch_nt<32, 2>(p, C, st) : launch_nt<32, 4>(p, C, st);
-    case 64: return launch_nt<64, 4>(p, C, st);
+    case 16: return prof ? launch_nt<16, 4, true>(p, C, st) : launch_nt<16, 4, false>(p, C, st);
+    case 32: return prof ? launch_nt<32, 4, true>(p, C, st) : launch_nt<32, 4, false>(p, C, st);
+    case 64: return prof ? launch_nt<64, 4, true>(p, C, st) : launch_nt<64, 4, false>(p, C, st);
     default: return fail(GSN_ENOSUP, "gsn_layer_recurrence(TCGEN05): H=%d does not fit tensor memory", H);
   }
 }

@@ -196,6 +196,69 @@ class SequenceModel(nn.Module):
         return act.permute(1, 2, 0), all_out
 
 
+class _SeqPlan:
+    """Pre-allocated buffers of one sequence model for the frame-chunked wavefront schedule: the full
+    [T,R,.] tensors every chunk writes its slice of, the carried (h,c) per layer and chunk boundary, the
+    folded BatchNorm affines and one recurrence workspace per layer.  Everything is allocated up front on
+    the caller's stream and stays alive until the streams have joined."""
+
+    def __init__(self, model, T, R, nchunks, device, backend):
+        self.m = model
+        stack = model.sequence_model
+        self.L = len(stack.layers)
+        f32 = dict(device=device, dtype=torch.float32)
+        self.x = torch.empty((T, R, model.input_size), **f32)
+        self.xproj, self.h, self.hs, self.cs, self.bn, self.ws = [], [], [], [], [], []
+        for layer in stack.layers:
+            cell = layer.cell
+            if cell.use_bn and cell.batchnorm.training:
+                raise NotImplementedError("training-mode BatchNorm inside the GSN recurrence is not "
+                                          "implemented yet; call model.eval()")
+            H = cell.hidden_size
+            g = 1 if cell.shared_weights else 2
+            self.xproj.append(torch.empty((T, R, g * H), **f32))
+            self.h.append(torch.empty((T, R, H), **f32))
+            self.hs.append(torch.zeros((nchunks + 1, R, H), **f32))
+            self.cs.append(torch.zeros((nchunks + 1, R, H), **f32))
+            self.bn.append(cell.folded_bn())
+            self.ws.append(ops.recurrence_workspace(R, H, cell.shared_weights, backend, device))
+        self.backend = backend
+        if isinstance(model.proj, nn.Linear):
+            self.proj = torch.empty((T, R, model.proj_size), **f32)
+            self.act = torch.empty_like(self.proj) if model._act else self.proj
+        else:
+            self.proj = self.act = None
+
+    def run_pre(self, l, k, t0, t1):
+        """Input-to-hidden product of frames [t0,t1) of layer l (no dependence on the layer's own state)."""
+        cell = self.m.sequence_model.layers[l].cell
+        inp = self.x[t0:t1] if l == 0 else self.h[l - 1][t0:t1]
+        ops.linear(inp, cell.weight_ih.detach(), out=self.xproj[l][t0:t1])
+
+    def run_rec(self, l, k, t0, t1):
+        """Recurrence of frames [t0,t1) of layer l from the state carried out of chunk k-1."""
+        cell = self.m.sequence_model.layers[l].cell
+        a, b = self.bn[l]
+        ops.layer_recurrence(self.xproj[l][t0:t1], cell.weight_hh.detach(), cell.bias_ih.detach(), a, b,
+                             shared=cell.shared_weights, h0=self.hs[l][k], c0=self.cs[l][k],
+                             out_h=self.h[l][t0:t1], out_hT=self.hs[l][k + 1], out_cT=self.cs[l][k + 1],
+                             backend=self.backend, workspace=self.ws[l])
+
+    def run_post(self, k, t0, t1):
+        """Output projection (+ activation) of frames [t0,t1)."""
+        m = self.m
+        if self.proj is not None:
+            ops.linear(self.h[-1][t0:t1], m.proj.weight.detach(), m.proj.bias.detach(), act=m._act,
+                       out=self.proj[t0:t1], out_act=self.act[t0:t1] if m._act else None)
+
+    def outputs(self):
+        """(proj_out, activated, all_layer_outputs) exactly as SequenceModel.run_time_major returns them."""
+        last = self.h[-1]
+        if self.proj is None:
+            return last, self.m.output_activate_function(last), [self.x] + self.h + [last]
+        return self.proj, self.act, [self.x] + self.h + [self.proj]
+
+
 class SubBandSequenceModel(SequenceModel):
     def __init__(self, df_order, num_spks, *args, **kwargs):
         super().__init__(*args, **kwargs)
@@ -221,10 +284,10 @@ def coef_layout(proj, B, N, df, S):
 _BAND_STREAMS = {}
 
 
-def _band_streams(device, n):
-    key = (device.index, n)
+def _band_streams(device, n, priority=0):
+    key = (device.index, n, priority)
     if key not in _BAND_STREAMS:
-        _BAND_STREAMS[key] = [torch.cuda.Stream(device=device) for _ in range(n)]
+        _BAND_STREAMS[key] = [torch.cuda.Stream(device=device, priority=priority) for _ in range(n)]
     return _BAND_STREAMS[key]
 
 
@@ -334,13 +397,19 @@ class SpikingFullSubNet(nn.Module):
         self.fb_input_size, self.n_fft, self.hop_length, self.win_length = fb_input_size, n_fft, hop_length, win_length
         self.fdrc, self.df_orders, self.num_spks = fdrc, df_orders, num_spks
         self.use_cuda_graph = False
+        self.frame_chunks = 1
         self._graphs = {}
 
-    def enable_cuda_graph(self, flag=True):
-        """Replay the hot path (`network`) from a CUDA graph captured per input shape: ~35 kernel launches
-        on 4 streams become one graph launch.  The returned tensors are the graph's static output buffers
-        and are OVERWRITTEN by the next call with the same input shape (clone them to keep them)."""
+    def enable_cuda_graph(self, flag=True, frame_chunks=8):
+        """Replay the hot path (`network`) from a CUDA graph captured per input shape.  With
+        `frame_chunks` > 1 the captured schedule is a frame-chunked WAVEFRONT: every (sequence model, layer)
+        gets its own stream and processes the T frames in `frame_chunks` pieces, carrying (h, c) between
+        pieces, so layer 2 / the sub-band models start on chunk k as soon as layer 1 / the full-band model
+        finish it (the recurrences are causal).  Results are bit-identical to the unchunked schedule.
+        The returned tensors are the graph's static output buffers and are OVERWRITTEN by the next call
+        with the same input shape (clone them to keep them)."""
         self.use_cuda_graph = bool(flag)
+        self.frame_chunks = max(1, int(frame_chunks))
         self._graphs = {}
         return self
 
@@ -368,7 +437,8 @@ class SpikingFullSubNet(nn.Module):
                 torch.cuda.synchronize(mag.device)
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
-                    static_out = self._network(static_in)
+                    static_out = (self._network_wavefront(static_in, self.frame_chunks)
+                                  if self.frame_chunks > 1 else self._network(static_in))
             entry = self._graphs[key] = (graph, static_in, static_out)
         graph, static_in, static_out = entry
         static_in.copy_(mag)
@@ -391,6 +461,94 @@ class SpikingFullSubNet(nn.Module):
             raise ValueError(f"full-band output ({fb_act.shape[2]} bins x {rep}) does not cover {F - 1} bins")
         projs, sb_all = self.sb_model.run_time_major(cm, fb_act)
         return projs, fb_all, sb_all
+
+    def _network_wavefront(self, mag, nchunks):
+        """Same results as `_network`, scheduled as a frame-chunked wavefront over one stream per
+        (sequence model, layer); meant to be captured into a CUDA graph (see enable_cuda_graph)."""
+        dev = mag.device
+        B, F, T = mag.shape
+        nchunks = max(1, min(nchunks, T))
+        bounds = [(T * i // nchunks, T * (i + 1) // nchunks) for i in range(nchunks)]
+        main = torch.cuda.current_stream(dev)
+        fbm, sbm = self.fb_model, self.sb_model
+        rep = (self.n_fft // 2 + 1) // self.fb_input_size
+        if rep * fbm.proj_size < F - 1 and isinstance(fbm.proj, nn.Linear):
+            raise ValueError(f"full-band output ({fbm.proj_size} bins x {rep}) does not cover {F - 1} bins")
+        cm = ops.compress_mag(mag.contiguous(), F - 1, self.fdrc)
+        backend = fbm.sequence_model.backend
+        fbp = _SeqPlan(fbm, T, B, nchunks, dev, backend)
+        geo, sbps = [], []
+        for i, m in enumerate(sbm.sb_models):
+            lo, hi, ctr = sbm.freq_cutoffs[i], sbm.freq_cutoffs[i + 1], sbm.center_freq_sizes[i]
+            if (hi - lo) % ctr != 0:
+                raise ValueError(f"Number of frequency bins must be divisible by the center frequency."
+                                 f"GOT: ctr_freq={ctr}, upper_cutoff_freq={hi}, lower_cutoff_freq={lo}")
+            geo.append(((hi - lo) // ctr, lo, ctr, sbm.neighbor_freq_sizes[i]))
+            sbps.append(_SeqPlan(m, T, B * geo[-1][0], nchunks, dev, m.sequence_model.backend))
+
+        def ln(m):
+            if not m.use_pre_layer_norm:
+                return None, None, 1e-5
+            return m.pre_layer_norm.weight.detach(), m.pre_layer_norm.bias.detach(), m.pre_layer_norm.eps
+
+        # streams per sequence model: pre[l] (input projections), rec[l] (recurrences), post (proj)
+        # (the latency-critical recurrences get high-priority streams so their CTAs are placed first)
+        plans = [fbp] + sbps
+        lo_streams = _band_streams(dev, sum(p.L + 1 for p in plans), priority=0)
+        hi_streams = _band_streams(dev, sum(p.L for p in plans), priority=-1)
+        streams = lo_streams + hi_streams
+        groups, o_lo, o_hi = [], 0, 0
+        for p in plans:
+            groups.append((lo_streams[o_lo:o_lo + p.L], hi_streams[o_hi:o_hi + p.L], lo_streams[o_lo + p.L]))
+            o_lo += p.L + 1
+            o_hi += p.L
+        fork = torch.cuda.Event()
+        fork.record(main)
+        for st in streams:
+            st.wait_event(fork)
+
+        def staged(stream, waits, fn):
+            for w in waits:
+                if w is not None:
+                    stream.wait_event(w)
+            with torch.cuda.stream(stream):
+                fn()
+                ev = torch.cuda.Event()
+                ev.record(stream)
+            return ev
+
+        def run_model(p, group, k, t0, t1, feed, feed_ev):
+            """chunk k of one sequence model; `feed` fills p.x[t0:t1] (runs on the layer-0 pre stream)."""
+            pre, rec, post = group
+            ev = None
+            for l in range(p.L):
+                def do_pre(l=l):
+                    if l == 0:
+                        feed()
+                    p.run_pre(l, k, t0, t1)
+                e_pre = staged(pre[l], [feed_ev if l == 0 else ev], do_pre)
+                ev = staged(rec[l], [e_pre], lambda l=l: p.run_rec(l, k, t0, t1))
+            return staged(post, [ev], lambda: p.run_post(k, t0, t1))
+
+        w_fb, b_fb, e_fb = ln(fbm)
+        for k, (t0, t1) in enumerate(bounds):
+            ev_fb = run_model(fbp, groups[0], k, t0, t1,
+                              lambda: ops.subband_features(cm[t0:t1], None, 1, 0, self.fb_input_size, 0, w_fb,
+                                                           b_fb, e_fb, out=fbp.x[t0:t1]), None)
+            for bi, (p, (N, lo, ctr, nbr)) in enumerate(zip(sbps, geo)):
+                w_sb, b_sb, e_sb = ln(p.m)
+                run_model(p, groups[1 + bi], k, t0, t1,
+                          lambda p=p, N=N, lo=lo, ctr=ctr, nbr=nbr, w_sb=w_sb, b_sb=b_sb, e_sb=e_sb:
+                          ops.subband_features(cm[t0:t1], fbp.act[t0:t1], N, lo, ctr, nbr, w_sb, b_sb, e_sb,
+                                               out=p.x[t0:t1]), ev_fb)
+        for st in streams:
+            done = torch.cuda.Event()
+            done.record(st)
+            main.wait_event(done)
+        _, _, fb_all = fbp.outputs()
+        outs = [p.outputs() for p in sbps]
+        self._keepalive = (cm, fbp, sbps)  # buffers referenced by the captured graph
+        return [o[0] for o in outs], fb_all, [o[2] for o in outs]
 
     def coefficients(self, mag):
         """Deep-filter coefficient tensors [B, df_i, S, F_i, T, 2] in the reference layout."""

@@ -51,39 +51,56 @@ def compress_mag(mag, f_keep, fdrc):
     return cm
 
 
-def subband_features(cm, fb, N, lo, ctr, nbr, ln_weight=None, ln_bias=None, eps=1e-5):
+def _out(out, shape, like):
+    if out is None:
+        return torch.empty(shape, device=like.device, dtype=torch.float32)
+    if tuple(out.shape) != tuple(shape):
+        raise ValueError(f"out has shape {tuple(out.shape)}, expected {tuple(shape)}")
+    return out
+
+
+def subband_features(cm, fb, N, lo, ctr, nbr, ln_weight=None, ln_bias=None, eps=1e-5, out=None):
     """Gather (+reflect, + tiled full-band output) + LayerNorm -> x [T, B*N, K] (MSF:241-312, 111-112)."""
-    lib, st = _prep(cm, fb, ln_weight, ln_bias)
+    lib, st = _prep(cm, fb, ln_weight, ln_bias, out)
     T, B, f_cm = cm.shape
     K = ctr + 2 * nbr + (ctr if fb is not None else 0)
     f_fb = fb.shape[2] if fb is not None else 0
-    x = torch.empty((T, B * N, K), device=cm.device, dtype=torch.float32)
+    x = _out(out, (T, B * N, K), cm)
     _lib.check(lib.gsn_subband_features(_ptr(cm), f_cm, _ptr(fb), f_fb, _ptr(x), T, B, N, lo, ctr, nbr,
                                         _ptr(ln_weight), _ptr(ln_bias), float(eps), st))
     LAUNCHES[0] += 1
     return x
 
 
-def linear(a, w, bias=None, act=None):
+def linear(a, w, bias=None, act=None, out=None, out_act=None):
     """out[..., N] = a[..., K] @ w[N,K]^T + bias (fp32 FMA).  Returns out, or (out, act(out)) if act."""
-    lib, st = _prep(a, w, bias)
+    lib, st = _prep(a, w, bias, out, out_act)
     K = a.shape[-1]
     N = w.shape[0]
     if w.shape[1] != K:
         raise ValueError(f"linear: a[..., {K}] vs w{tuple(w.shape)}")
     M = a.numel() // K
-    out = torch.empty(a.shape[:-1] + (N,), device=a.device, dtype=torch.float32)
+    out = _out(out, a.shape[:-1] + (N,), a)
     code = _ACT[act]
-    out_act = torch.empty_like(out) if code else None
+    out_act = _out(out_act, out.shape, a) if code else None
     _lib.check(lib.gsn_linear_f32(_ptr(a), _ptr(w), _ptr(bias), _ptr(out), _ptr(out_act), code, M, K, N, st))
     LAUNCHES[0] += 1
     return (out, out_act) if code else out
 
 
+def recurrence_workspace(R, H, shared, backend, device):
+    """A 256-byte aligned workspace tensor view for layer_recurrence (reusable across calls of one layer)."""
+    nbytes = _lib.load().gsn_layer_recurrence_workspace_bytes(R, H, int(shared), _lib.BACKENDS[backend])
+    ws = torch.empty((max(nbytes, 256) + 255) // 4 + 1, device=device, dtype=torch.float32)
+    off = ((-ws.data_ptr()) % 256) // 4
+    return ws[off:]
+
+
 def layer_recurrence(xproj, w_hh, bias, bn_scale=None, bn_shift=None, shared=True, want_c=False,
-                     h0=None, c0=None, want_state=False, backend="auto"):
+                     h0=None, c0=None, want_state=False, backend="auto", out_h=None, out_c=None, out_hT=None,
+                     out_cT=None, workspace=None):
     """One GSULayer over all frames (ESN:75-81 / 132-153).  xproj [T,R,gH] -> h [T,R,H] (and c, (hT,cT))."""
-    lib, st = _prep(xproj, w_hh, bias, bn_scale, bn_shift, h0, c0)
+    lib, st = _prep(xproj, w_hh, bias, bn_scale, bn_shift, h0, c0, out_h, out_c, out_hT, out_cT)
     T, R, gH = xproj.shape
     H = w_hh.shape[1]
     if gH != (H if shared else 2 * H) or w_hh.shape[0] != gH or bias.numel() != 2 * H:
@@ -91,13 +108,14 @@ def layer_recurrence(xproj, w_hh, bias, bn_scale=None, bn_shift=None, shared=Tru
                          f"w_hh{tuple(w_hh.shape)} bias{tuple(bias.shape)} shared={shared}")
     be = _lib.BACKENDS[backend]
     dev = xproj.device
-    h = torch.empty((T, R, H), device=dev, dtype=torch.float32)
-    c = torch.empty((T, R, H), device=dev, dtype=torch.float32) if want_c else None
-    hT = torch.empty((R, H), device=dev, dtype=torch.float32) if want_state else None
-    cT = torch.empty((R, H), device=dev, dtype=torch.float32) if want_state else None
-    nbytes = lib.gsn_layer_recurrence_workspace_bytes(R, H, int(shared), be)
-    ws = torch.empty((max(nbytes, 256) + 255) // 4 + 1, device=dev, dtype=torch.float32)
-    off = (-ws.data_ptr()) % 256
+    h = _out(out_h, (T, R, H), xproj)
+    c = _out(out_c, (T, R, H), xproj) if (want_c or out_c is not None) else None
+    hT = _out(out_hT, (R, H), xproj) if (want_state or out_hT is not None) else None
+    cT = _out(out_cT, (R, H), xproj) if (want_state or out_cT is not None) else None
+    ws = workspace if workspace is not None else recurrence_workspace(R, H, shared, backend, dev)
+    off = 0
+    if ws.data_ptr() % 256:
+        raise ValueError("workspace must be 256-byte aligned (use ops.recurrence_workspace)")
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -105,7 +123,7 @@ def layer_recurrence(xproj, w_hh, bias, bn_scale=None, bn_shift=None, shared=Tru
                                         _ptr(h0), _ptr(c0), _ptr(h), _ptr(c), _ptr(hT), _ptr(cT), T, R, H,
                                         int(shared), be, ws.data_ptr() + off, st))
     LAUNCHES[0] += 2  # weight preparation + the recurrence kernel
-    LAST_WS[0] = (ws, off // 4)
+    LAST_WS[0] = (ws, 0)
     if PROFILE is not None:
         e1.record()
         PROFILE.append((2.0 * T * R * gH * H, e0, e1))

@@ -206,14 +206,19 @@ def test_properties_at_full_size_S():
 
 
 def test_cuda_graph_replay_matches_eager():
-    """The captured CUDA graph of the hot path reproduces the eager launch sequence bit for bit, also after
-    the input changes and after BatchNorm statistics change (the fold is part of the graph)."""
+    """The captured CUDA graph of the hot path (plain and frame-chunked wavefront schedule) reproduces the
+    eager launch sequence bit for bit, also after the input changes and after BatchNorm statistics change
+    (the fold is part of the graph)."""
     cfg = synth.tiny_cfg()
     m = _model(cfg, synth.make_params(cfg, 9))
     mags = [_t(synth.make_mag(2, 33, 30, s)) for s in (1, 2)]
     with torch.no_grad():
         eager = [[p.clone() for p in m.network(x)[0]] for x in mags]
-        m.enable_cuda_graph(True)
+        m.enable_cuda_graph(True, frame_chunks=1)
+        for x, ref in zip(mags, eager):
+            out = m.network(x)[0]
+            assert all(torch.equal(a, b) for a, b in zip(out, ref))
+        m.enable_cuda_graph(True, frame_chunks=4)  # frame-chunked wavefront schedule
         for x, ref in zip(mags + mags, eager + eager):
             out = m.network(x)[0]
             assert all(torch.equal(a, b) for a, b in zip(out, ref))

@@ -7,6 +7,8 @@ import time
 import numpy as np
 import torch
 
+os.environ.setdefault("GSN_TC_PROF", "1")
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from spiking_fullsubnet_b200 import ops  # noqa: E402
 
