@@ -145,7 +145,7 @@ _ACT = {
 
 
 def sequence_model_forward(inp, params, prefix, num_layers, shared, activation=None,
-                           dtype=np.float32, return_c=False):
+                           dtype=np.float32, return_c=False, proj="proj"):
     """inp [R,K,T] -> (out [R,P,T], all_layer_outputs [x_norm, h1..hL, proj_out] each [T,R,.]).
 
     Follows MSF:81-125: 'b f t -> t b f', optional pre_layer_norm, stack, proj (Linear or Identity),
@@ -158,9 +158,9 @@ def sequence_model_forward(inp, params, prefix, num_layers, shared, activation=N
     res = gsn_stack_forward(x, params, prefix + "sequence_model.", num_layers, shared, dtype,
                             return_c=return_c)
     out, all_out = res[0], res[1]
-    if prefix + "proj.weight" in params:  # MSF:118
-        out = out @ np.asarray(params[prefix + "proj.weight"], dtype=dtype).T \
-            + np.asarray(params[prefix + "proj.bias"], dtype=dtype)
+    if prefix + proj + ".weight" in params:  # MSF:118 (surface B: fc_output_layer, model_low_freq.py:126)
+        out = out @ np.asarray(params[prefix + proj + ".weight"], dtype=dtype).T \
+            + np.asarray(params[prefix + proj + ".bias"], dtype=dtype)
     all_out = all_out + [out]  # MSF:119
     if activation in _ACT:  # MSF:54-61,122
         out = _ACT[activation](out)
@@ -248,6 +248,44 @@ def spiking_fullsubnet_network(mag, params, cfg, dtype=np.float32):
         out, all_out = sequence_model_forward(x, params, f"sb_model.sb_models.{i}.",
                                               cfg["sb_num_layers"], shared, None, dtype)
         coefs.append(subband_coef_layout(out, mag.shape[0], ctr, df, num_spks))
+        sb_all.append(all_out)
+    return coefs, fb_all, sb_all
+
+
+# --------------------------------------------------------------------------------------------
+# a10: surface B, recipes/intel_ndns/spiking_fullsubnet_freeze_phase/model_low_freq.py (MLF)
+# --------------------------------------------------------------------------------------------
+EPSILON = np.finfo(float).eps  # audiozen/constant.py:11
+
+
+def offline_laplace_norm(x):
+    """MLF:146-172: divide by the utterance-level mean over every non-batch dim."""
+    mu = x.mean(axis=tuple(range(1, x.ndim)), keepdims=True, dtype=x.dtype)
+    return (x / (mu + x.dtype.type(EPSILON))).astype(x.dtype)
+
+
+def separator_network(mag, params, cfg, dtype=np.float32):
+    """MLF:574-586: mag [B, n_fft//2+1, T] -> (coef list [B,df,F_i,T,2], fb_all, sb_all), offline laplace norm."""
+    assert cfg["norm_type"] == "offline_laplace_norm"
+    shared = cfg.get("shared_weights", False)
+    B = mag.shape[0]
+    cm = compress_mag(mag, cfg["fdrc"], dtype)[:, :-1, :]
+    nf = cm.shape[1]
+    fb_in = offline_laplace_norm(np.ascontiguousarray(cm[:, : cfg["fb_freqs"], :]))
+    act = {"Tanh": "tanh", "ReLU": "relu"}.get(cfg.get("fb_output_activate_function") or None)
+    fb_out, fb_all = sequence_model_forward(fb_in, params, "fb_model.", 2, shared, act, dtype,
+                                            proj="fc_output_layer")
+    fb_tiled = np.tile(fb_out, (1, cfg["num_freqs"] // cfg["fb_freqs"], 1))
+    cuts = [0] + list(cfg["freq_cutoffs"]) + [nf]
+    coefs, sb_all = [], []
+    for i, (ctr, nbr, df) in enumerate(zip(cfg["sb_num_center_freqs"], cfg["sb_num_neighbor_freqs"],
+                                           cfg["sb_df_orders"])):
+        x = subband_inputs(cm, fb_tiled, cuts[i], cuts[i + 1], ctr, nbr)  # [B*N, K, T]
+        x = offline_laplace_norm(x.reshape(B, -1)).reshape(x.shape)  # MLF:475 over (N, 1, K, T) jointly
+        sact = {"Tanh": "tanh", "ReLU": "relu"}.get(cfg.get("sb_output_activate_function") or None)
+        out, all_out = sequence_model_forward(x, params, f"sb_model.sb_models.{i}.", 2, shared, sact, dtype,
+                                              proj="fc_output_layer")
+        coefs.append(subband_coef_layout(out, B, ctr, df, 1)[:, :, 0])  # MLF:257-263 (no speaker dim)
         sb_all.append(all_out)
     return coefs, fb_all, sb_all
 

@@ -122,3 +122,38 @@ def make_mag(batch, num_bins, num_frames, seed):
     rs = np.random.RandomState(seed)
     env = 0.2 + rs.uniform(0, 1, (batch, num_bins, 1)) * np.linspace(1.0, 0.3, num_bins)[None, :, None]
     return (np.abs(rs.standard_normal((batch, num_bins, num_frames))) * env).astype(np.float32)
+
+
+# model_zoo/intel_ndns/spike_fsb/baseline_s/baseline_s.toml [model_g.args] (surface B, zoo "S")
+CFG_ZOO_S = dict(sr=16000, fdrc=0.5, n_fft=512, fb_freqs=64, hop_length=128, win_length=512, num_freqs=256,
+                 sequence_model="GSU", fb_hidden_size=240, fb_output_activate_function=False,
+                 freq_cutoffs=[32, 128], sb_df_orders=[3, 1, 1], sb_num_center_freqs=[4, 32, 64],
+                 sb_num_neighbor_freqs=[15, 15, 15], fb_num_center_freqs=[4, 32, 64],
+                 fb_num_neighbor_freqs=[0, 0, 0], sb_hidden_size=160, sb_output_activate_function=False,
+                 norm_type="offline_laplace_norm", shared_weights=True, bn=True)
+
+
+def tiny_cfg_b(**over):
+    """Structurally complete surface-B (`Separator`) config, small enough for golden traces."""
+    cfg = dict(sr=16000, fdrc=0.5, n_fft=64, fb_freqs=8, hop_length=16, win_length=64, num_freqs=32,
+               sequence_model="GSU", fb_hidden_size=48, fb_output_activate_function=False, freq_cutoffs=[8, 24],
+               sb_df_orders=[3, 2, 1], sb_num_center_freqs=[2, 4, 8], sb_num_neighbor_freqs=[3, 3, 3],
+               fb_num_center_freqs=[2, 4, 8], fb_num_neighbor_freqs=[0, 0, 0], sb_hidden_size=40,
+               sb_output_activate_function=False, norm_type="offline_laplace_norm", shared_weights=True, bn=True)
+    cfg.update(over)
+    return cfg
+
+
+def make_params_b(cfg, seed):
+    """state_dict (numpy) for surface B `Separator(**cfg)`: surface-A layout without LayerNorm and with
+    `fc_output_layer` in place of `proj`."""
+    rs = np.random.RandomState(seed)
+    shared, bn = cfg.get("shared_weights", False), cfg.get("bn", False)
+    p = _seq_model_params(rs, "fb_model.", cfg["fb_freqs"], cfg["fb_hidden_size"], 2, cfg["fb_freqs"], shared, bn,
+                          False)
+    for i, (ctr, nbr, fc, fn, df) in enumerate(zip(cfg["sb_num_center_freqs"], cfg["sb_num_neighbor_freqs"],
+                                                   cfg["fb_num_center_freqs"], cfg["fb_num_neighbor_freqs"],
+                                                   cfg["sb_df_orders"])):
+        p.update(_seq_model_params(rs, f"sb_model.sb_models.{i}.", (ctr + 2 * nbr) + (fc + 2 * fn),
+                                   cfg["sb_hidden_size"], 2, 2 * ctr * df, shared, bn, False))
+    return {k.replace(".proj.", ".fc_output_layer."): v for k, v in p.items()}

@@ -26,8 +26,8 @@
 namespace gsn {
 
 struct RecTcParams {
-  const float* xproj;   // [T, R, H]
-  const float* w_hh;    // [H, H]
+  const float* xproj;   // [T, R, gH]
+  const float* w_hh;    // [gH, H]
   const float* bias;    // [2H]
   const float* bn_scale;
   const float* bn_shift;
@@ -46,15 +46,17 @@ constexpr int kTcPlanes = 3;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kOneBf16 = 0x3F80u;
 
-__host__ __device__ inline int tc_kw_padded(int C) { return 4 * C + 1; }  // odd stride: conflict-free reads
+// bit words per row in the staging buffer (+1: odd stride, conflict-free reads); wps = words per CTA slice
+__host__ __device__ inline int tc_kw_padded(int C, int wps) { return wps * C + 1; }
 
 template <int NT>
-__host__ __device__ inline size_t tc_smem_bytes(int Kmma, int C) {
+__host__ __device__ inline size_t tc_smem_bytes(int Kmma, int C, bool shared) {
   size_t b = (size_t)NT * Kmma * 2;                       // B operand
   b = (b + 127) / 128 * 128;
-  b += (size_t)2 * NT * tc_kw_padded(C) * 4;              // bit staging, double buffered
+  b += (size_t)2 * NT * tc_kw_padded(C, shared ? 4 : 2) * 4;  // bit staging, double buffered
   b = (b + 15) / 16 * 16;
   b += 64;                                                // barriers + tmem slot
+  if (!shared) b += (size_t)NT * 64 * 4;                  // cell-gate accumulators handed across lanes
   return b;
 }
 
@@ -69,11 +71,16 @@ __device__ __forceinline__ void split3(float w, uint32_t& hi, uint32_t& mid, uin
   lo = __float_as_uint(r2) >> 16;
 }
 
-template <int NT, int G, bool PROF>
+template <int NT, int G, bool PROF, bool SHARED>
 __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams p) {
   constexpr int NTHREADS = 128 * G;
   constexpr int CPT = NT / G;                 // accumulator columns (= rows of the tile) per thread
-  constexpr int CH = CPT < 8 ? CPT : 8;       // columns processed together (instruction-level parallelism)
+  constexpr int CH = SHARED ? (CPT < 8 ? CPT : 8) : CPT;  // columns processed together (ILP)
+  // SHARED gates: a CTA owns 128 neurons (TMEM lane = neuron).  Unshared gates (w_hh [2H,H]): a CTA owns 64
+  // neurons; lanes 0-63 accumulate their forget-gate rows, lanes 64-127 the cell-gate rows of the SAME neurons,
+  // which are handed to lanes 0-63 through shared memory once per frame.
+  constexpr int NS = SHARED ? 128 : 64;
+  constexpr int WPS = NS / 32;
   constexpr int MAXT = (NT * 40 + NTHREADS - 1) / NTHREADS;  // B-operand rebuild tasks per thread (Kmma <= 320)
   static_assert(CPT == 4 || CPT == 8 || CPT == 16, "NT / G must be 4, 8 or 16");
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -84,9 +91,13 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
   const uint32_t C = tc::cluster_nctarank(), slice = tc::cluster_ctarank();
   const int row0 = (blockIdx.x / C) * NT;
   const int H = p.H, R = p.R, T = p.T, Kmma = p.Kmma;
-  const int j = slice * 128 + q * 32 + lane;  // this thread's neuron (= TMEM lane q*32 + lane)
+  const int tl = q * 32 + lane;                    // this thread's TMEM lane
+  const bool isg = !SHARED && tl >= 64;            // lane holds a cell-gate row (unshared only)
+  const int j = slice * NS + (SHARED ? tl : (tl & 63));  // this thread's neuron
   const bool jv = j < H;
-  const int KWp = tc_kw_padded(C);
+  const bool comp = jv && !isg;                    // this thread integrates the membrane of neuron j
+  const int gH = SHARED ? H : 2 * H;
+  const int KWp = tc_kw_padded(C, WPS);
 
   uint8_t* sB = smem;
   size_t off = ((size_t)NT * Kmma * 2 + 127) / 128 * 128;
@@ -96,6 +107,7 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
   uint64_t* bar_mma = reinterpret_cast<uint64_t*>(smem + off);
   uint64_t* bar_bits = bar_mma + 1;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 3);
+  float* zg = reinterpret_cast<float*>(smem + off + 64);  // [NT][64], unshared only
 
   if (tid == 0) {
     tc::mbar_init(bar_mma, 1);
@@ -147,7 +159,7 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
   // recurrent weights of this thread's neuron -> three exact bf16 planes in TMEM (lane = neuron);
   // the G warps that share a lane quarter split the K range between them
   {
-    const float* wrow = p.w_hh + (size_t)(jv ? j : 0) * H;
+    const float* wrow = p.w_hh + (size_t)(jv ? (isg ? H + j : j) : 0) * H;
     for (int c0 = 8 * g; c0 < (int)plane_cols; c0 += 8 * G) {
       uint32_t vh[8], vm[8], vl[8];
 #pragma unroll
@@ -180,22 +192,29 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
 #pragma unroll
   for (int i = 0; i < CPT; ++i) {
     const int row = row0 + g * CPT + i;
-    const bool ok = jv && row < R;
+    const bool ok = comp && row < R;
     valid |= ok ? 1u << i : 0u;
     boff[i] = ok ? ((uint32_t)row * (uint32_t)H + (uint32_t)j) * 4u : 0u;
     c[i] = (p.c0 && ok) ? *reinterpret_cast<const float*>(reinterpret_cast<const char*>(p.c0) + boff[i]) : 0.f;
   }
   const size_t frame_bytes = (size_t)R * H * sizeof(float);
+  const size_t xframe_bytes = (size_t)R * gH * sizeof(float);
+  uint32_t xoff[CPT];      // byte offset of my forget-gate input projection inside one [R, gH] frame
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) {
+    const int row = row0 + g * CPT + i;
+    xoff[i] = ((valid >> i) & 1u) ? ((uint32_t)row * (uint32_t)gH + (uint32_t)j) * 4u : 0u;
+  }
 
   // spike-bit exchange: lane l < CPT*C of every warp sends word (l % CPT) of its warp to CTA (l / CPT);
   // the remote staging cell and the remote barrier are fixed per frame parity
   uint32_t snd_cell0 = 0, snd_cell1 = 0, snd_bar0 = 0, snd_bar1 = 0;
-  const bool sender = lane < CPT * (int)C;
+  const bool sender = q < WPS && lane < CPT * (int)C;
   if (sender) {
     const int i = lane % CPT;
     const uint32_t r = lane / CPT;
-    snd_cell0 = tc::map_to_rank(bits + ((size_t)0 * NT + g * CPT + i) * KWp + slice * 4 + q, r);
-    snd_cell1 = tc::map_to_rank(bits + ((size_t)1 * NT + g * CPT + i) * KWp + slice * 4 + q, r);
+    snd_cell0 = tc::map_to_rank(bits + ((size_t)0 * NT + g * CPT + i) * KWp + slice * WPS + q, r);
+    snd_cell1 = tc::map_to_rank(bits + ((size_t)1 * NT + g * CPT + i) * KWp + slice * WPS + q, r);
     snd_bar0 = tc::map_to_rank(&bar_bits[0], r);
     snd_bar1 = tc::map_to_rank(&bar_bits[1], r);
   }
@@ -207,7 +226,7 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
   const uint32_t idesc = tc::make_idesc_f16(128, NT, true);
   const uint64_t desc_b0 = tc::make_smem_desc(tc::smem_u32(sB), 128, SBO);
   const int ksteps = Kmma / 16;
-  const uint32_t bits_bytes = (uint32_t)NT * 4u * C * 4u;  // every slice sends 4 words per row
+  const uint32_t bits_bytes = (uint32_t)NT * WPS * C * 4u;  // every slice sends WPS words per row
   bool alive = true;
   float hval[CPT];
 #pragma unroll
@@ -258,15 +277,18 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
     if (t > 0) store_frame(t - 1);
     float xf_[CPT], xg_[CPT];
     {
-      const char* xf = reinterpret_cast<const char*>(p.xproj) + (size_t)t * frame_bytes;
-      float xp[CPT];
+      const char* xf = reinterpret_cast<const char*>(p.xproj) + (size_t)t * xframe_bytes;
+      float xp[CPT], xq[CPT];
 #pragma unroll
-      for (int i = 0; i < CPT; ++i)
-        xp[i] = (valid >> i) & 1u ? __ldg(reinterpret_cast<const float*>(xf + boff[i])) : 0.f;
+      for (int i = 0; i < CPT; ++i) {
+        const bool ok = (valid >> i) & 1u;
+        xp[i] = ok ? __ldg(reinterpret_cast<const float*>(xf + xoff[i])) : 0.f;
+        xq[i] = SHARED ? xp[i] : (ok ? __ldg(reinterpret_cast<const float*>(xf + xoff[i]) + H) : 0.f);
+      }
 #pragma unroll
       for (int i = 0; i < CPT; ++i) {  // reference order: (x W_ih^T + bias) + h W_hh^T   (ESN:140-145)
         xf_[i] = __fadd_rn(xp[i], bf);
-        xg_[i] = __fadd_rn(xp[i], bc);
+        xg_[i] = __fadd_rn(xq[i], bc);
       }
     }
     if (!tc::mbar_wait(bar_mma, t & 1)) { alive = false; break; }
@@ -281,11 +303,18 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
       tc::tmem_ld<CH>(tmem_d + lane_base + g * CPT + i0, zr);
       tc::tmem_wait_ld();
       float sg[CH], gh[CH];
+      if (!SHARED) {  // cell-gate accumulators move from lanes 64-127 to the neuron's lane (0-63)
+        if (isg) {
+#pragma unroll
+          for (int u = 0; u < CH; ++u) zg[(g * CPT + i0 + u) * 64 + (tl & 63)] = __uint_as_float(zr[u]);
+        }
+        __syncthreads();
+      }
 #pragma unroll
       for (int u = 0; u < CH; ++u) {
         const float z = __uint_as_float(zr[u]);
         sg[u] = sigmoid_f32(__fadd_rn(xf_[i0 + u], z));
-        gh[u] = __fadd_rn(xg_[i0 + u], z);
+        gh[u] = __fadd_rn(xg_[i0 + u], SHARED ? z : (isg ? 0.f : zg[(g * CPT + i0 + u) * 64 + (tl & 63)]));
       }
 #pragma unroll
       for (int u = 0; u < CH; ++u) {
@@ -344,8 +373,8 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
 }
 
 // ------------------------------------------------------------------------------------------------
-static int tc_pick_nt(int R, int H, int sm_count) {
-  const int C = (H + 127) / 128;
+static int tc_pick_nt(int R, int H, int shared, int sm_count) {
+  const int C = shared ? (H + 127) / 128 : (H + 63) / 64;
   const int Kmma = (H + 15) / 16 * 16;
   const int cols_a = kTcPlanes * Kmma / 2;
   int best = 0;
@@ -359,18 +388,18 @@ static int tc_pick_nt(int R, int H, int sm_count) {
 }
 
 bool recurrence_tc_supported(int R, int H, int shared) {
-  if (!shared || R <= 0 || H < 16) return false;
-  const int C = (H + 127) / 128;
-  if (C > 8) return false;
-  return tc_pick_nt(R, H, 148) > 0;
+  if (R <= 0 || H < 16) return false;
+  const int C = shared ? (H + 127) / 128 : (H + 63) / 64;
+  if (C > 8) return false;  // portable cluster size
+  return tc_pick_nt(R, H, shared, 148) > 0;
 }
 
 size_t recurrence_tc_workspace(int, int, int) { return 256; }
 
-template <int NT, int G, bool PROF>
+template <int NT, int G, bool PROF, bool SHARED>
 static int launch_nt(const RecTcParams& p, int C, cudaStream_t st) {
-  const size_t smem = tc_smem_bytes<NT>(p.Kmma, C);
-  GSN_CUDA(cudaFuncSetAttribute(k_recurrence_tc<NT, G, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  const size_t smem = tc_smem_bytes<NT>(p.Kmma, C, SHARED);
+  GSN_CUDA(cudaFuncSetAttribute(k_recurrence_tc<NT, G, PROF, SHARED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(((p.R + NT - 1) / NT) * C));
@@ -384,26 +413,33 @@ static int launch_nt(const RecTcParams& p, int C, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  GSN_CUDA(cudaLaunchKernelEx(&cfg, k_recurrence_tc<NT, G, PROF>, p));
+  GSN_CUDA(cudaLaunchKernelEx(&cfg, k_recurrence_tc<NT, G, PROF, SHARED>, p));
   return GSN_OK;
 }
 
 int launch_recurrence_tc(const float* xproj, const float* w_hh, const float* bias, const float* bn_scale,
                          const float* bn_shift, const float* h0, const float* c0, float* h_out, float* c_out,
                          float* hT, float* cT, int T, int R, int H, int shared, void* workspace, cudaStream_t st) {
-  GSN_REQUIRE(shared, "gsn_layer_recurrence(TCGEN05): unshared gate weights are not supported");
   int dev = 0, sms = 148;
   GSN_CUDA(cudaGetDevice(&dev));
   GSN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   RecTcParams p{xproj, w_hh, bias, bn_scale, bn_shift, h0, c0, h_out, c_out, hT, cT, T, R, H, (H + 15) / 16 * 16,
                 reinterpret_cast<unsigned long long*>(workspace), trace_buffer()};
-  const int C = (H + 127) / 128;
-  const int nt = tc_pick_nt(R, H, sms);
+  const int C = shared ? (H + 127) / 128 : (H + 63) / 64;
+  const int nt = tc_pick_nt(R, H, shared, sms);
   static const bool prof = getenv("GSN_TC_PROF") != nullptr;  // dev knob: per-phase cycle counters
+  if (!shared) {
+    switch (nt) {
+      case 16: return launch_nt<16, 4, false, false>(p, C, st);
+      case 32: return launch_nt<32, 4, false, false>(p, C, st);
+      case 64: return launch_nt<64, 4, false, false>(p, C, st);
+      default: return fail(GSN_ENOSUP, "gsn_layer_recurrence(TCGEN05): H=%d does not fit tensor memory", H);
+    }
+  }
   switch (nt) {
-    case 16: return prof ? launch_nt<16, 4, true>(p, C, st) : launch_nt<16, 4, false>(p, C, st);
-    case 32: return prof ? launch_nt<32, 4, true>(p, C, st) : launch_nt<32, 4, false>(p, C, st);
-    case 64: return prof ? launch_nt<64, 4, true>(p, C, st) : launch_nt<64, 4, false>(p, C, st);
+    case 16: return prof ? launch_nt<16, 4, true, true>(p, C, st) : launch_nt<16, 4, false, true>(p, C, st);
+    case 32: return prof ? launch_nt<32, 4, true, true>(p, C, st) : launch_nt<32, 4, false, true>(p, C, st);
+    case 64: return prof ? launch_nt<64, 4, true, true>(p, C, st) : launch_nt<64, 4, false, true>(p, C, st);
     default: return fail(GSN_ENOSUP, "gsn_layer_recurrence(TCGEN05): H=%d does not fit tensor memory", H);
   }
 }

@@ -28,7 +28,7 @@ from . import ops
 MemoryState = namedtuple("MemoryState", ["hx", "cx"])
 
 __all__ = ["MemoryState", "efficient_spiking_neuron", "GSUCell", "GSULayer", "StackedGSU",
-           "SequenceModel", "SubBandSequenceModel", "SubbandModel", "SpikingFullSubNet", "CirmGSN"]
+           "SequenceModel", "SubBandSequenceModel", "SubbandModel", "SpikingFullSubNet", "CirmGSN", "Separator"]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -633,3 +633,197 @@ class CirmGSN(nn.Module):
             return y.reshape(B, self.num_spks, L), all_out
         enh = enh[:, 0]
         return _istft(enh, self.n_fft, self.hop_length, self.win_length, L), enh.abs()
+
+
+# ------------------------------------------------------------------------------------------------
+# surface B: the frozen competition model (recipes/intel_ndns/spiking_fullsubnet_freeze_phase/model_low_freq.py)
+# ------------------------------------------------------------------------------------------------
+EPSILON = 2.220446049250313e-16  # np.finfo(float).eps, audiozen/constant.py:11
+
+
+class _FreezeSequenceModel(nn.Module):
+    """`SequenceModel` of surface B (model_low_freq.py:42-139): no pre-LayerNorm, `fc_output_layer` instead of
+    `proj`, activation selected by capitalised name.  Only sequence_model="GSU" is on the GSN path."""
+
+    def __init__(self, input_size, output_size, hidden_size, num_layers, bidirectional, sequence_model="GSU",
+                 output_activate_function="Tanh", num_groups=4, mogrify_steps=5, dropout=0.0,
+                 shared_weights=False, bn=False):
+        super().__init__()
+        if sequence_model != "GSU":
+            raise NotImplementedError(f"Not implemented {sequence_model}")
+        self.sequence_model = efficient_spiking_neuron(input_size, hidden_size, num_layers,
+                                                       shared_weights=shared_weights, bn=bn)
+        if int(output_size):
+            self.fc_output_layer = nn.Linear(hidden_size * (2 if bidirectional else 1), output_size)
+        if output_activate_function:
+            mods = {"Tanh": nn.Tanh, "ReLU": nn.ReLU, "ReLU6": nn.ReLU6, "LeakyReLU": nn.LeakyReLU,
+                    "PReLU": nn.PReLU}
+            if output_activate_function not in mods:
+                raise NotImplementedError(f"Not implemented activation function {output_activate_function}")
+            self.activate_function = mods[output_activate_function]()
+        self.output_activate_function_name = output_activate_function
+        self.output_size, self.input_size, self.hidden_size, self.num_layers = output_size, input_size, hidden_size, num_layers
+        self.sequence_model_name = sequence_model
+
+    def run_time_major(self, x):
+        """x [T,R,K] (already normalised) -> (fc_out [T,R,P], activated, all_layer_outputs)."""
+        out, _, trace = self.sequence_model(x, None)
+        if int(self.output_size):
+            out = ops.linear(out, self.fc_output_layer.weight.detach(), self.fc_output_layer.bias.detach())
+            trace = trace + [out]
+        act = self.activate_function(out) if self.output_activate_function_name else out
+        return out, act, trace
+
+    def forward(self, x):
+        """x [B,F,T] -> ([B,P,T], all_layer_outputs) (model_low_freq.py:98-139)."""
+        assert x.dim() == 3, f"Shape is {x.shape}."
+        if not x.is_cuda:
+            raise RuntimeError("spiking_fullsubnet_b200 has no CPU path: move the model and input to CUDA")
+        _, act, trace = self.run_time_major(x.permute(2, 0, 1).contiguous())
+        return act.permute(1, 2, 0).contiguous(), trace
+
+
+class _FreezeSubBandWrapper(_FreezeSequenceModel):
+    def __init__(self, df_order, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.df_order = df_order
+
+
+def _utterance_norm(x, B, norm_type):
+    """model_low_freq.py:146-217 on a time-major tensor x [T, B*N, K]: statistics per utterance over all of
+    its (sub-band, feature, frame) entries -- the reference reduces dims 1.. of [B, N, 1, K, T] (:162, :475)."""
+    T = x.shape[0]
+    v = x.view(T, B, -1)
+    if norm_type == "offline_laplace_norm":
+        mu = v.mean(dim=(0, 2), keepdim=True)
+        return (v / (mu + EPSILON)).view_as(x)
+    if norm_type == "offline_gaussian_norm":
+        mu = v.mean(dim=(0, 2), keepdim=True)
+        std = v.permute(1, 0, 2).reshape(B, -1).std(dim=1).view(1, B, 1)
+        return ((v - mu) / (std + EPSILON)).view_as(x)
+    if norm_type == "cumulative_laplace_norm":
+        raise NotImplementedError(
+            "cumulative_laplace_norm: the reference itself fails on the 5-D sub-band input "
+            "(model_low_freq.py:181, SURVEY 7.3-7); the zoo checkpoints use offline_laplace_norm")
+    raise NotImplementedError("You must set up a type of Norm. e.g. offline_laplace_norm, "
+                              "cumulative_laplace_norm, forgetting_norm, etc.")
+
+
+class _FreezeSubbandModel(nn.Module):
+    def __init__(self, freq_cutoffs, sb_num_center_freqs, sb_num_neighbor_freqs, fb_num_center_freqs,
+                 fb_num_neighbor_freqs, sb_df_orders, sequence_model, hidden_size, activate_function=False,
+                 norm_type="offline_laplace_norm", shared_weights=False, bn=False):
+        super().__init__()
+        if any(n != 0 for n in fb_num_neighbor_freqs) or list(fb_num_center_freqs) != list(sb_num_center_freqs):
+            raise NotImplementedError("full-band neighbour bins / centre sizes different from the sub-band ones "
+                                      "are not used by any shipped config and are not implemented")
+        self.sb_models = nn.ModuleList([
+            _FreezeSubBandWrapper(df_order=d, input_size=(c + n * 2) + (fc + fn * 2), output_size=c * 2 * d,
+                                  hidden_size=hidden_size, num_layers=2, sequence_model=sequence_model,
+                                  bidirectional=False, output_activate_function=activate_function,
+                                  shared_weights=shared_weights, bn=bn)
+            for c, n, fc, fn, d in zip(sb_num_center_freqs, sb_num_neighbor_freqs, fb_num_center_freqs,
+                                       fb_num_neighbor_freqs, sb_df_orders)])
+        self.freq_cutoffs = freq_cutoffs
+        self.sb_num_center_freqs, self.sb_num_neighbor_freqs = sb_num_center_freqs, sb_num_neighbor_freqs
+        self.fb_num_center_freqs, self.fb_num_neighbor_freqs = fb_num_center_freqs, fb_num_neighbor_freqs
+        self.norm_type = norm_type
+
+    def band_edges(self, num_freqs):
+        """[(lo, hi)] per sub-band model from the interior cut-offs (model_low_freq.py:439-447)."""
+        cuts = [0] + list(self.freq_cutoffs) + [num_freqs]
+        return [(cuts[i], cuts[i + 1]) for i in range(len(self.sb_models))]
+
+    def run_time_major(self, cm, fb):
+        T, B, F = cm.shape
+        projs, traces = [], []
+        for i, (m, (lo, hi)) in enumerate(zip(self.sb_models, self.band_edges(F))):
+            ctr, nbr = self.sb_num_center_freqs[i], self.sb_num_neighbor_freqs[i]
+            if (hi - lo) % ctr != 0:
+                raise ValueError(f"The number of center frequencies should be divisible by the subband freqency "
+                                 f"interval. Got num_center_freqs={ctr}, upper_cutoff_freq={hi}, and "
+                                 f"lower_cutoff_freq={lo}.")
+            x = ops.subband_features(cm, fb, (hi - lo) // ctr, lo, ctr, nbr)
+            x = _utterance_norm(x, B, self.norm_type).contiguous()
+            proj, act, trace = m.run_time_major(x)
+            projs.append(act)
+            traces.append(trace)
+        return projs, traces
+
+
+class Separator(nn.Module):
+    """Surface B `model_low_freq.Separator` (:485-618): same network as SpikingFullSubNet with utterance-level
+    laplace normalisation instead of LayerNorm; the class the model-zoo checkpoints were trained with.
+    forward(wave [B,L] or [B,1,L]) -> (enhanced_y, enhanced_mag, fb_all_layer_outputs, sb_all_layer_outputs)."""
+
+    def __init__(self, sr, n_fft, hop_length, win_length, fdrc, num_freqs, fb_freqs, freq_cutoffs,
+                 sb_num_center_freqs, sb_num_neighbor_freqs, fb_num_center_freqs, fb_num_neighbor_freqs,
+                 fb_hidden_size, sb_hidden_size, sb_df_orders, sequence_model, fb_output_activate_function,
+                 sb_output_activate_function, norm_type, shared_weights=False, bn=False):
+        super().__init__()
+        self.n_fft, self.hop_length, self.win_length, self.fdrc = n_fft, hop_length, win_length, fdrc
+        self.freq_cutoffs, self.sb_df_orders = freq_cutoffs, sb_df_orders
+        self.num_repeats, self.fb_freqs = num_freqs // fb_freqs, fb_freqs
+        self.norm_type = norm_type
+        _utterance_norm(torch.zeros(1, 1, 1), 1, norm_type)  # unknown / unsupported norm types fail here
+        self.fb_model = _FreezeSequenceModel(input_size=fb_freqs, output_size=fb_freqs, hidden_size=fb_hidden_size,
+                                             num_layers=2, bidirectional=False, sequence_model=sequence_model,
+                                             output_activate_function=fb_output_activate_function,
+                                             shared_weights=shared_weights, bn=bn)
+        self.sb_model = _FreezeSubbandModel(freq_cutoffs=freq_cutoffs, sb_num_center_freqs=sb_num_center_freqs,
+                                            sb_num_neighbor_freqs=sb_num_neighbor_freqs,
+                                            fb_num_center_freqs=fb_num_center_freqs,
+                                            fb_num_neighbor_freqs=fb_num_neighbor_freqs, sb_df_orders=sb_df_orders,
+                                            hidden_size=sb_hidden_size, sequence_model=sequence_model,
+                                            activate_function=sb_output_activate_function,
+                                            shared_weights=shared_weights, bn=bn, norm_type=norm_type)
+
+    def set_backend(self, backend):
+        for m in self.modules():
+            if isinstance(m, StackedGSU):
+                m.backend = backend
+        return self
+
+    def network(self, mag):
+        """mag [B, n_fft//2+1, T] -> (sub-band fc outputs: list of [T, B*N_i, P_i], fb_all, sb_all)
+        (model_low_freq.py:574-586)."""
+        if not mag.is_cuda:
+            raise RuntimeError("spiking_fullsubnet_b200 has no CPU path: move the model and input to CUDA")
+        B, F, T = mag.shape
+        cm = ops.compress_mag(mag.contiguous(), F - 1, self.fdrc)
+        x = ops.subband_features(cm, None, 1, 0, self.fb_freqs, 0)
+        x = _utterance_norm(x, B, self.norm_type).contiguous()
+        _, fb_act, fb_all = self.fb_model.run_time_major(x)
+        if self.num_repeats * fb_act.shape[2] < F - 1:
+            raise ValueError("full-band output does not cover the spectrum")
+        projs, sb_all = self.sb_model.run_time_major(cm, fb_act.contiguous())
+        return projs, fb_all, sb_all
+
+    def coefficients(self, mag):
+        """[B, df, F_i, T, 2] per band: '(b n) (c fc df) t -> b df (n fc) t c' (model_low_freq.py:257-263)."""
+        projs, fb_all, sb_all = self.network(mag)
+        B = mag.shape[0]
+        return [coef_layout(p, B, p.shape[1] // B, d, 1)[:, :, 0] for p, d in zip(projs, self.sb_df_orders)], \
+            fb_all, sb_all
+
+    def forward(self, noisy_y):
+        ndim = noisy_y.dim()
+        assert ndim in (2, 3), "Input must be 2D (B, T) or 3D tensor (B, 1, T)"
+        if ndim == 3:
+            assert noisy_y.size(1) == 1, "Input must be 2D (B, T) or 3D tensor (B, 1, T)"
+            noisy_y = noisy_y.squeeze(1)
+        B, L = noisy_y.shape
+        cmp = _stft(noisy_y, self.n_fft, self.hop_length, self.win_length)
+        projs, fb_all, sb_all = self.network(cmp.abs().contiguous())
+        sre, sim = cmp.real.contiguous(), cmp.imag.contiguous()
+        ore, oim = sre.unsqueeze(1).clone(), sim.unsqueeze(1).clone()
+        lo = 0
+        for i, (p, (a, b)) in enumerate(zip(projs, self.sb_model.band_edges(cmp.shape[1] - 1))):
+            ctr = self.sb_model.sb_num_center_freqs[i]
+            n = (b - a) // ctr
+            ops.deepfilter_band(p.contiguous(), sre, sim, ore, oim, n, ctr, self.sb_df_orders[i], 1, lo)
+            lo += n * ctr
+        enh = torch.complex(ore[:, 0], oim[:, 0])
+        y = torch.istft(enh, self.n_fft, self.hop_length, self.win_length,
+                        window=torch.hann_window(self.win_length, device=noisy_y.device), length=L)
+        return y, enh.abs(), fb_all, sb_all

@@ -20,10 +20,13 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 REF = os.environ.get("GSN_REFERENCE_ROOT", "/root/reference")
 sys.path.insert(0, ROOT)
 
-for n in ["librosa", "soundfile", "matplotlib", "matplotlib.pyplot"]:
+for n in ["librosa", "soundfile", "matplotlib", "matplotlib.pyplot", "onnxruntime", "pesq", "pystoi", "accelerate"]:
     sys.modules.setdefault(n, types.ModuleType(n))
 sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+sys.modules["pesq"].pesq = sys.modules["pystoi"].stoi = None
+sys.modules["accelerate"].__version__ = "stub"
 sys.path.insert(0, REF)
+sys.path.insert(0, REF + "/recipes/intel_ndns/spiking_fullsubnet_freeze_phase")  # surface B imports by bare name
 
 from audiozen.models.spiking_fullsubnet import modeling_spiking_fullsubnet as MSF  # noqa: E402
 from audiozen.models.spiking_fullsubnet.efficient_spiking_neuron import GSUCell  # noqa: E402
@@ -106,6 +109,38 @@ def run_surface_a(name, cfg, seed, batch, num_samples, with_c):
     print(name, {k: (v.shape if hasattr(v, "shape") else v) for k, v in d.items() if k != "cfg"})
 
 
+def run_surface_b(name, cfg, params, seed, batch, num_samples, store_weights=False):
+    """Surface B `Separator` (recipes/.../model_low_freq.py:485-618)."""
+    import model_low_freq as MLF  # noqa: E402  (reference module, imported from the recipe directory)
+    torch.manual_seed(0)
+    model = MLF.Separator(**cfg)
+    load_params(model, params)
+    wave = synth.make_wave(batch, num_samples, seed + 1)
+    x = torch.from_numpy(wave)
+    with torch.no_grad():
+        mag = model.stft(x)[0]
+        enh_y, enh_mag, fb_all, sb_all = model(x)
+        # coefficient tensors: re-run the network part (MLF:574-586)
+        cm = (mag.unsqueeze(1) ** cfg["fdrc"])[..., :-1, :]
+        fb_in = model.norm(cm[..., : cfg["fb_freqs"], :]).squeeze(1)
+        fb_out, _ = model.fb_model(fb_in)
+        coefs, _ = model.sb_model(cm, fb_out.unsqueeze(1).repeat(1, 1, cfg["num_freqs"] // cfg["fb_freqs"], 1))
+    d = {"cfg": json.dumps(cfg), "seed": seed, "wave": wave, "mag": mag.numpy(), "enh_y": enh_y.numpy(),
+         "enh_mag": enh_mag.numpy(), "fb_x": fb_all[0].numpy(), "fb_proj": fb_all[-1].numpy()}
+    for i, c in enumerate(coefs):
+        d[f"coef{i}"] = c.numpy()
+    for l in range(2):
+        d[f"fb_h{l}"] = pack(fb_all[1 + l])
+    for i, al in enumerate(sb_all):
+        d[f"sb{i}_x"] = al[0].numpy()
+        for l in range(2):
+            d[f"sb{i}_h{l}"] = pack(al[1 + l])
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
+    if store_weights:
+        np.savez_compressed(os.path.join(HERE, name + "_weights.npz"), **{k: np.asarray(v) for k, v in params.items()})
+    print(name, {k: (v.shape if hasattr(v, "shape") else v) for k, v in d.items() if k != "cfg"})
+
+
 def run_cirm(name, cfg, seed, batch, num_samples):
     torch.manual_seed(0)
     model = CGN.Model(**cfg)
@@ -142,5 +177,12 @@ if __name__ == "__main__":
                                                    sb_num_layers=1, fb_num_layers=3), 103, 2, 16 * 20, True)
     run_cirm("tiny_cirm", dict(synth.CFG_CIRM, n_fft=64, hop_length=16, win_length=64, input_size=33,
                                hidden_size=40, num_layers=3, proj_size=33, df_order=2), 104, 2, 16 * 30)
+    # surface B: tiny structural fixture + the TRAINED model-zoo S checkpoint on a 1 s clip (protocol P3)
+    cfgb = synth.tiny_cfg_b()
+    run_surface_b("tiny_surface_b", cfgb, synth.make_params_b(cfgb, 105), 105, 2, 16 * 33)
+    zoo = torch.load(REF + "/model_zoo/intel_ndns/spike_fsb/baseline_s/checkpoints/best/pytorch_model.bin",
+                     map_location="cpu")
+    run_surface_b("zoo_s_1s", synth.CFG_ZOO_S, {k: v.numpy() for k, v in zoo.items()}, 106, 2, 16000,
+                  store_weights=True)
     # config 1 of BASELINE.json: single 1 s clip, baseline_m, CPU forward (protocol P2)
     run_surface_a("cfg1_baseline_m_1s", synth.CFG_M, 20220815, 1, 16000, False)

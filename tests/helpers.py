@@ -35,3 +35,8 @@ def spike_flip_stats(a, b):
     if diff.any():
         first = int(np.argmax(diff.reshape(diff.shape[0], -1).any(axis=1)))
     return frac, first
+
+
+def load_golden_weights(name):
+    z = np.load(os.path.join(GOLDEN, name + "_weights.npz"), allow_pickle=False)
+    return {k: z[k] for k in z.files}

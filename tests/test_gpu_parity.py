@@ -229,3 +229,41 @@ def test_cuda_graph_replay_matches_eager():
         want = m.network(mags[0])[0]
     assert all(torch.equal(a, b) for a, b in zip(got, want))
     assert not all(torch.equal(a, b) for a, b in zip(got, eager[0]))
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("name", ["tiny_surface_b", "zoo_s_1s"])
+def test_surface_b_vs_golden(name, backend):
+    """Surface B `Separator`: tiny fixture and the TRAINED model-zoo S checkpoint (loads strict=True).
+    Trained weights are chaotic (protocol P3): spike flips are bounded by the reference's own
+    noise floor (3.5e-4) and the waveform must stay within 1e-3 relative when nothing flipped."""
+    from spiking_fullsubnet_b200 import Separator
+    from tests.helpers import load_golden_weights
+    g = load_golden(name)
+    cfg = g["cfg"]
+    params = load_golden_weights(name) if name.startswith("zoo") else synth.make_params_b(cfg, g["seed"])
+    m = Separator(**cfg)
+    m.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in params.items()}, strict=True)
+    m = m.eval().to(DEV).set_backend(backend)
+    with torch.no_grad():
+        coefs, fb_all, sb_all = m.coefficients(_t(g["mag"]))
+        enh_y, enh_mag, _, _ = m(_t(g["wave"]))
+    assert _rel(fb_all[0].cpu().numpy(), g["fb_x"]) < 1e-4
+    flips = total = 0
+    for l in range(2):
+        ref = unpack(g[f"fb_h{l}"], cfg["fb_hidden_size"])
+        flips += (fb_all[1 + l].cpu().numpy() != ref).sum()
+        total += ref.size
+    for i in range(3):
+        for l in range(2):
+            ref = unpack(g[f"sb{i}_h{l}"], cfg["sb_hidden_size"])
+            flips += (sb_all[i][1 + l].cpu().numpy() != ref).sum()
+            total += ref.size
+    print(f"{name}/{backend}: {flips} of {total} spikes differ from the reference")
+    assert flips / total <= 3.5e-4
+    if flips == 0:
+        for i in range(3):
+            assert coefs[i].shape == g[f"coef{i}"].shape
+            assert _rel(coefs[i].cpu().numpy(), g[f"coef{i}"]) < 1e-3
+        assert _rel(enh_y.cpu().numpy(), g["enh_y"]) < 1e-3
+        assert _rel(enh_mag.cpu().numpy(), g["enh_mag"]) < 1e-3

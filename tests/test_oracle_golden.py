@@ -116,3 +116,31 @@ def test_deepfilter_and_backward_consistency():
     t, f = 5, 2
     want = sum(spec[1, f, t - 2 + d] * (coef[1, d, 0, f, t, 0] + 1j * coef[1, d, 0, f, t, 1]) for d in range(3))
     assert abs(y[1, 0, f, t] - want) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["tiny_surface_b", "zoo_s_1s"])
+def test_surface_b_network(name):
+    """Surface B (`Separator`, offline laplace norm); `zoo_s_1s` uses the TRAINED model-zoo S checkpoint.
+    With trained weights the path is chaotic: numpy-vs-MKL summation order may flip a
+    spike, so the bound is the reference's own noise floor (3.5e-4 flips)."""
+    from tests.helpers import load_golden_weights
+    g = load_golden(name)
+    cfg = g["cfg"]
+    params = load_golden_weights(name) if name.startswith("zoo") else synth.make_params_b(cfg, g["seed"])
+    coefs, fb_all, sb_all = O.separator_network(g["mag"], params, cfg)
+    assert _rel(fb_all[0], g["fb_x"]) < 1e-5
+    flips = total = 0
+    for l in range(2):
+        ref = unpack(g[f"fb_h{l}"], cfg["fb_hidden_size"])
+        flips += (fb_all[1 + l] != ref).sum()
+        total += ref.size
+    for i in range(3):
+        for l in range(2):
+            ref = unpack(g[f"sb{i}_h{l}"], cfg["sb_hidden_size"])
+            flips += (sb_all[i][1 + l] != ref).sum()
+            total += ref.size
+    assert flips / total <= 3.5e-4, f"{flips} of {total} spikes differ"
+    if flips == 0:
+        for i in range(3):
+            assert coefs[i].shape == g[f"coef{i}"].shape
+            assert _rel(coefs[i], g[f"coef{i}"]) < 1e-4
