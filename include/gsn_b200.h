@@ -78,6 +78,13 @@ GSN_API int gsn_subband_features(const float* cm, int f_cm, const float* fb, int
 GSN_API int gsn_linear_f32(const float* a, const float* w, const float* bias, float* out, float* out_act,
                    int act, int64_t M, int K, int N, gsn_stream_t stream);
 
+/* Same product for SPIKE inputs (layers >= 1: the previous layer's h; proj: the last layer's h) on tcgen05:
+ * `a` must hold values exactly representable in bf16 ({0,1} spikes); the fp32 weights are split into three
+ * exact bf16 planes kept in tensor memory, so the result is an fp32 sum of exact products.  K <= 320, K % 4 == 0,
+ * a 16-byte aligned.  sm_budget as for gsn_layer_recurrence (0 = whole device).                            */
+GSN_API int gsn_linear_spikes(const float* a, const float* w, const float* bias, float* out, float* out_act,
+                              int act, int64_t M, int K, int N, int sm_budget, gsn_stream_t stream);
+
 /* ---- the recurrence: GSULayer.forward ESN:75-81 over GSUCell.forward ESN:132-153 ----------------
  * For t = 0..T-1, rows r, neurons j:
  *   z      = xproj[t, r, :] + h_{t-1}[r, :] @ w_hh^T            (xproj = x @ w_ih^T, no bias)
@@ -89,12 +96,15 @@ GSN_API int gsn_linear_f32(const float* a, const float* w, const float* bias, fl
  * xproj [T, R, gH], w_hh [gH, H] (g = 1 shared, 2 unshared), bias [2H].
  * h0 / c0 [R, H] may be NULL (zeros, MSF:100-106).  h_out [T, R, H] fp32 {0,1} (the trace entry of
  * all_layer_outputs, ESN:60); c_out [T, R, H] optional (NULL) membrane trace; hT / cT [R, H] optional.
- * workspace: gsn_layer_recurrence_workspace_bytes(R, H, shared, backend) bytes, 256-byte aligned.   */
+ * workspace: gsn_layer_recurrence_workspace_bytes(R, H, shared, backend) bytes, 256-byte aligned.
+ * sm_budget: number of SMs this launch should plan for (0 = the whole device).  Callers that run several
+ * recurrences concurrently (sub-band models, wavefront schedule) pass each one's share, so that the row tile
+ * NT is chosen large enough for all of them to be co-resident.                                          */
 GSN_API size_t gsn_layer_recurrence_workspace_bytes(int R, int H, int shared, int backend);
 GSN_API int gsn_layer_recurrence(const float* xproj, const float* w_hh, const float* bias,
                          const float* bn_scale, const float* bn_shift, const float* h0,
                          const float* c0, float* h_out, float* c_out, float* hT, float* cT, int T,
-                         int R, int H, int shared, int backend, void* workspace,
+                         int R, int H, int shared, int backend, int sm_budget, void* workspace,
                          gsn_stream_t stream);
 /* which backend GSN_BACKEND_AUTO resolves to for this shape (GSN_BACKEND_SIMT / _TCGEN05). */
 GSN_API int gsn_layer_recurrence_pick_backend(int R, int H, int shared);

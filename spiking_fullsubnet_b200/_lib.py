@@ -27,8 +27,9 @@ SIGNATURES = {
     "gsn_compress_mag": (_i, [_p, _p, _i, _i, _i, _i, _f, _p]),
     "gsn_subband_features": (_i, [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p, _p, _f, _p]),
     "gsn_linear_f32": (_i, [_p, _p, _p, _p, _p, _i, _i64, _i, _i, _p]),
+    "gsn_linear_spikes": (_i, [_p, _p, _p, _p, _p, _i, _i64, _i, _i, _i, _p]),
     "gsn_layer_recurrence_workspace_bytes": (_sz, [_i, _i, _i, _i]),
-    "gsn_layer_recurrence": (_i, [_p] * 11 + [_i] * 5 + [_p, _p]),
+    "gsn_layer_recurrence": (_i, [_p] * 11 + [_i] * 6 + [_p, _p]),
     "gsn_layer_recurrence_pick_backend": (_i, [_i, _i, _i]),
     "gsn_deepfilter_band": (_i, [_p] * 5 + [_i] * 9 + [_p]),
     "gsn_trace_set": (_i, [_p, _sz]),

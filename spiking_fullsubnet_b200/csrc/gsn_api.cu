@@ -28,7 +28,7 @@ int launch_recurrence_simt(const float*, const float*, const float*, const float
 size_t recurrence_simt_workspace(int H, int shared);
 // gsn_recurrence_tc.cu
 int launch_recurrence_tc(const float*, const float*, const float*, const float*, const float*,
-                         const float*, const float*, float*, float*, float*, float*, int, int, int, int,
+                         const float*, const float*, float*, float*, float*, float*, int, int, int, int, int,
                          void*, cudaStream_t);
 size_t recurrence_tc_workspace(int R, int H, int shared);
 bool recurrence_tc_supported(int R, int H, int shared);
@@ -82,8 +82,8 @@ extern "C" size_t gsn_layer_recurrence_workspace_bytes(int R, int H, int shared,
 extern "C" int gsn_layer_recurrence(const float* xproj, const float* w_hh, const float* bias,
                                     const float* bn_scale, const float* bn_shift, const float* h0,
                                     const float* c0, float* h_out, float* c_out, float* hT, float* cT,
-                                    int T, int R, int H, int shared, int backend, void* workspace,
-                                    gsn_stream_t stream) {
+                                    int T, int R, int H, int shared, int backend, int sm_budget,
+                                    void* workspace, gsn_stream_t stream) {
   GSN_REQUIRE(xproj && w_hh && bias && h_out && workspace, "gsn_layer_recurrence: null pointer");
   GSN_REQUIRE(T > 0 && R > 0 && H > 0, "gsn_layer_recurrence: bad shape T=%d R=%d H=%d", T, R, H);
   GSN_REQUIRE((bn_scale == nullptr) == (bn_shift == nullptr), "gsn_layer_recurrence: bn params");
@@ -99,7 +99,7 @@ extern "C" int gsn_layer_recurrence(const float* xproj, const float* w_hh, const
       return gsn::fail(GSN_ENOSUP, "gsn_layer_recurrence(TCGEN05): shape R=%d H=%d shared=%d not supported",
                        R, H, shared);
     return gsn::launch_recurrence_tc(xproj, w_hh, bias, bn_scale, bn_shift, h0, c0, h_out, c_out, hT,
-                                     cT, T, R, H, shared, workspace, st);
+                                     cT, T, R, H, shared, sm_budget, workspace, st);
   }
   return gsn::fail(GSN_EINVAL, "gsn_layer_recurrence: unknown backend %d", backend);
 }

@@ -1,0 +1,250 @@
+// tcgen05 linear for SPIKE inputs:  out[M,N] = a[M,K] @ w[N,K]^T + bias,  a in {0,1} (any bf16-exact values).
+// Used for the input-to-hidden product of layers >= 1 (ESN:141 with the previous layer's spikes as input) and
+// for proj (MSF:118): both have an exactly-bf16 left operand, so with the fp32 weights split into three exact
+// bf16 planes (w = hi + mid + lo) every product is exact and the result is an fp32 sum of exact terms -- the
+// same argument as for the recurrence (gsn_recurrence_tc.cu).
+//
+// Same "weights stationary in TMEM, swap-AB" layout as the recurrence: CTA (slice, p) owns the 128 output
+// features [128 slice, +128) -- their weight rows live in tensor memory as the A operand for the whole kernel --
+// and walks over row tiles p, p+P, p+2P, ... (persistent).  Per tile: NT rows of `a` are converted to a bf16
+// K-major B operand in shared memory (double buffered), D[128 features x NT rows] accumulates 3*K/16 MMAs in
+// one of two TMEM accumulators, and the epilogue (bias, optional activation, coalesced stores over features)
+// of tile i runs while the tensor pipe works on tile i+1 and the loads of tile i+2 are in flight.
+#include "gsn_common.cuh"
+#include "gsn_tc.cuh"
+
+namespace gsn {
+
+constexpr uint32_t kLinTmemCols = 512;
+
+__device__ __forceinline__ float lin_act(float v, int act) {
+  switch (act) {
+    case 1: return tanhf(v);
+    case 2: return 1.0f / (1.0f + expf(-v));
+    case 3: return fmaxf(v, 0.f);
+    default: return v;
+  }
+}
+
+__device__ __forceinline__ void lin_split3(float w, uint32_t& hi, uint32_t& mid, uint32_t& lo) {
+  const uint32_t wb = __float_as_uint(w);
+  hi = wb >> 16;
+  const float r1 = w - __uint_as_float(wb & 0xFFFF0000u);
+  const uint32_t r1b = __float_as_uint(r1);
+  mid = r1b >> 16;
+  const float r2 = r1 - __uint_as_float(r1b & 0xFFFF0000u);
+  lo = __float_as_uint(r2) >> 16;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(256, 1)
+    k_linear_tc(const float* __restrict__ a, const float* __restrict__ w, const float* __restrict__ bias,
+                float* __restrict__ out, float* __restrict__ out_act, int act, long long M, int K, int N,
+                int Kmma, TraceBuf* tb) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tslot = trace_begin(tb, 4, (int)M, K, N);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, g = warp >> 2;  // lane quarter / row half
+  const int slice = blockIdx.x;
+  const int P = gridDim.y;
+  const long long ntiles_all = (M + NT - 1) / NT;
+  const int j = slice * 128 + q * 32 + lane;  // output feature of this thread (TMEM lane)
+  const bool jv = j < N;
+
+  const uint32_t SBO = 16u * Kmma;
+  const size_t b_bytes = ((size_t)NT * Kmma * 2 + 127) / 128 * 128;
+  uint8_t* const sB0 = smem;
+  uint8_t* const sB1 = smem + b_bytes;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * b_bytes);  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+
+  if (tid == 0) {
+    tc::mbar_init(&bar[0], 1);
+    tc::mbar_init(&bar[1], 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc<kLinTmemCols>(tmem_slot);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+  const uint32_t tmem_d0 = tmem, tmem_d1 = tmem + NT;
+  const uint32_t tmem_a = tmem + 2 * NT;
+  const uint32_t plane_cols = Kmma / 2;
+
+  // weights of my feature -> three exact bf16 planes in TMEM (the two row-half warps split the K range)
+  {
+    const float* wrow = w + (size_t)(jv ? j : 0) * K;
+    for (int c0 = 8 * g; c0 < (int)plane_cols; c0 += 16) {
+      uint32_t vh[8], vm[8], vl[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        uint32_t h2[2], m2[2], l2[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int k = 2 * (c0 + u) + e;
+          lin_split3((jv && k < K) ? __ldg(wrow + k) : 0.f, h2[e], m2[e], l2[e]);
+        }
+        vh[u] = h2[0] | (h2[1] << 16);
+        vm[u] = m2[0] | (m2[1] << 16);
+        vl[u] = l2[0] | (l2[1] << 16);
+      }
+      tc::tmem_st8(tmem_a + lane_base + 0 * plane_cols + c0, vl);
+      tc::tmem_st8(tmem_a + lane_base + 1 * plane_cols + c0, vm);
+      tc::tmem_st8(tmem_a + lane_base + 2 * plane_cols + c0, vh);
+    }
+    tc::tmem_wait_st();
+  }
+  const float bj = (bias && jv) ? bias[j] : 0.f;
+
+  // B operand of one row tile: (row n, 8 consecutive k) -> 16 bytes; 8 consecutive threads fill one core matrix.
+  // UNR tasks per thread are loaded before any is converted, so 2*UNR 16-byte loads are in flight per thread.
+  const int k8n = Kmma / 8;
+  const int ntask = NT * k8n;
+  constexpr int UNR = 4;
+  auto convert = [&](long long tile, uint8_t* dst) {
+    const long long r0 = tile * NT;
+    for (int base = tid; base < ntask; base += 256 * UNR) {
+      float4 x0[UNR], x1[UNR];
+      uint32_t doff[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int i = base + 256 * u;
+        const int nlo = i & 7, k8 = (i >> 3) % k8n, nhi = (i >> 3) / k8n;
+        const long long row = r0 + nhi * 8 + nlo;
+        doff[u] = i < ntask ? (uint32_t)(nhi * SBO + k8 * 128 + nlo * 16) : 0xFFFFFFFFu;
+        x0[u] = x1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < ntask && row < M) {
+          const float* src = a + row * K + k8 * 8;
+          if (k8 * 8 + 8 <= K) {
+            x0[u] = __ldg(reinterpret_cast<const float4*>(src));
+            x1[u] = __ldg(reinterpret_cast<const float4*>(src) + 1);
+          } else {
+            float t8[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) t8[e] = (k8 * 8 + e < K) ? __ldg(src + e) : 0.f;
+            x0[u] = make_float4(t8[0], t8[1], t8[2], t8[3]);
+            x1[u] = make_float4(t8[4], t8[5], t8[6], t8[7]);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        if (doff[u] == 0xFFFFFFFFu) continue;
+        const float xs[8] = {x0[u].x, x0[u].y, x0[u].z, x0[u].w, x1[u].x, x1[u].y, x1[u].z, x1[u].w};
+        uint32_t v[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          v[e >> 1] |= (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(xs[e])) << (16 * (e & 1));
+        *reinterpret_cast<uint4*>(dst + doff[u]) = make_uint4(v[0], v[1], v[2], v[3]);
+      }
+    }
+  };
+
+  const uint32_t idesc = tc::make_idesc_f16(128, NT, true);
+  const int ksteps = Kmma / 16;
+  auto issue = [&](int buf) {  // warp 0 only
+    tc::tc_fence_after();
+    if (tc::elect_one()) {
+      const uint64_t desc_b0 = tc::make_smem_desc(tc::smem_u32(buf ? sB1 : sB0), 128, SBO);
+      const uint32_t td = buf ? tmem_d1 : tmem_d0;
+      uint32_t acc = 0;
+#pragma unroll 1
+      for (int pl = 0; pl < 3; ++pl) {
+        const uint32_t a0 = tmem_a + pl * plane_cols;
+#pragma unroll 2
+        for (int ks = 0; ks < ksteps; ++ks) {
+          tc::mma_ts(td, a0 + ks * 8, desc_b0 + (uint64_t)(ks * 16), idesc, acc);
+          acc = 1;
+        }
+      }
+      tc::mma_commit(buf ? &bar[1] : &bar[0]);
+    }
+    __syncwarp();
+  };
+
+  // tiles of this CTA: p, p+P, ...
+  const long long first = blockIdx.y;
+  const long long my_tiles = first < ntiles_all ? (ntiles_all - first + P - 1) / P : 0;
+  bool alive = true;
+  if (my_tiles > 0) {
+    convert(first, sB0);
+    tc::fence_proxy_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) issue(0);
+  }
+  for (long long i = 0; i < my_tiles; ++i) {
+    const int cur = (int)(i & 1), nxt = cur ^ 1;
+    const long long tile = first + i * P;
+    if (i + 1 < my_tiles) convert(tile + P, nxt ? sB1 : sB0);  // overlaps MMA(i)
+    tc::fence_proxy_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    if (!tc::mbar_wait(cur ? &bar[1] : &bar[0], (uint32_t)((i >> 1) & 1))) { alive = false; break; }
+    tc::tc_fence_after();
+    if (i + 1 < my_tiles && warp == 0) issue(nxt);  // tensor pipe works on tile i+1 during this epilogue
+    // epilogue of tile i: thread = feature j, rows [g*NT/2, +NT/2) of the tile; coalesced over features
+    const long long r0 = tile * NT + g * (NT / 2);
+#pragma unroll
+    for (int c0 = 0; c0 < NT / 2; c0 += 8) {
+      uint32_t zr[8];
+      tc::tmem_ld8((cur ? tmem_d1 : tmem_d0) + lane_base + g * (NT / 2) + c0, zr);
+      tc::tmem_wait_ld();
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const long long row = r0 + c0 + u;
+        if (jv && row < M) {
+          const float v = __uint_as_float(zr[u]) + bj;
+          out[row * N + j] = v;
+          if (out_act) out_act[row * N + j] = lin_act(v, act);
+        }
+      }
+    }
+  }
+  if (!alive) __trap();
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<kLinTmemCols>(tmem);
+  trace_end(tb, tslot);
+}
+
+template <int NT>
+static int launch_linear_tc(const float* a, const float* w, const float* bias, float* out, float* out_act,
+                            int act, long long M, int K, int N, int sm_budget, cudaStream_t st) {
+  const int Kmma = (K + 15) / 16 * 16;
+  size_t smem = 2 * (((size_t)NT * Kmma * 2 + 127) / 128 * 128) + 64;
+  if (smem < tc::kTmemExclusiveSmem) smem = tc::kTmemExclusiveSmem;
+  GSN_CUDA(cudaFuncSetAttribute(k_linear_tc<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, sms = 148;
+  GSN_CUDA(cudaGetDevice(&dev));
+  GSN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (sm_budget > 0 && sm_budget < sms) sms = sm_budget;
+  const int slices = (N + 127) / 128;
+  const long long ntiles = (M + NT - 1) / NT;
+  long long P = sms / slices;
+  if (P < 1) P = 1;
+  if (P > ntiles) P = ntiles;
+  dim3 grid((unsigned)slices, (unsigned)P);
+  k_linear_tc<NT><<<grid, 256, smem, st>>>(a, w, bias, out, out_act, act, M, K, N, Kmma, trace_buffer());
+  GSN_LAUNCH_CHECK("k_linear_tc");
+  return GSN_OK;
+}
+
+}  // namespace gsn
+
+extern "C" int gsn_linear_spikes(const float* a, const float* w, const float* bias, float* out, float* out_act,
+                                 int act, int64_t M, int K, int N, int sm_budget, gsn_stream_t stream) {
+  GSN_REQUIRE(a && w && out, "gsn_linear_spikes: null pointer");
+  GSN_REQUIRE(M > 0 && K > 0 && N > 0, "gsn_linear_spikes: bad shape M=%lld K=%d N=%d", (long long)M, K, N);
+  GSN_REQUIRE(act >= 0 && act <= 3, "gsn_linear_spikes: unknown activation %d", act);
+  GSN_REQUIRE(K % 4 == 0, "gsn_linear_spikes: K=%d must be a multiple of 4 (16-byte row alignment)", K);
+  GSN_REQUIRE((reinterpret_cast<uintptr_t>(a) & 15) == 0, "gsn_linear_spikes: a must be 16-byte aligned");
+  const int Kmma = (K + 15) / 16 * 16;
+  if (3 * Kmma / 2 + 2 * 64 <= 512)
+    return gsn::launch_linear_tc<64>(a, w, bias, out, out_act, act, M, K, N, sm_budget, gsn::as_stream(stream));
+  if (3 * Kmma / 2 + 2 * 16 <= 512)
+    return gsn::launch_linear_tc<16>(a, w, bias, out, out_act, act, M, K, N, sm_budget, gsn::as_stream(stream));
+  return gsn::fail(GSN_ENOSUP, "gsn_linear_spikes: K=%d does not fit tensor memory (K <= 320)", K);
+}

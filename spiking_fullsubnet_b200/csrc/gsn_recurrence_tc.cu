@@ -398,7 +398,8 @@ size_t recurrence_tc_workspace(int, int, int) { return 256; }
 
 template <int NT, int G, bool PROF, bool SHARED>
 static int launch_nt(const RecTcParams& p, int C, cudaStream_t st) {
-  const size_t smem = tc_smem_bytes<NT>(p.Kmma, C, SHARED);
+  size_t smem = tc_smem_bytes<NT>(p.Kmma, C, SHARED);
+  if (smem < tc::kTmemExclusiveSmem) smem = tc::kTmemExclusiveSmem;
   GSN_CUDA(cudaFuncSetAttribute(k_recurrence_tc<NT, G, PROF, SHARED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)smem));
   cudaLaunchConfig_t cfg = {};
@@ -419,13 +420,15 @@ static int launch_nt(const RecTcParams& p, int C, cudaStream_t st) {
 
 int launch_recurrence_tc(const float* xproj, const float* w_hh, const float* bias, const float* bn_scale,
                          const float* bn_shift, const float* h0, const float* c0, float* h_out, float* c_out,
-                         float* hT, float* cT, int T, int R, int H, int shared, void* workspace, cudaStream_t st) {
+                         float* hT, float* cT, int T, int R, int H, int shared, int sm_budget, void* workspace,
+                         cudaStream_t st) {
   int dev = 0, sms = 148;
   GSN_CUDA(cudaGetDevice(&dev));
   GSN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   RecTcParams p{xproj, w_hh, bias, bn_scale, bn_shift, h0, c0, h_out, c_out, hT, cT, T, R, H, (H + 15) / 16 * 16,
                 reinterpret_cast<unsigned long long*>(workspace), trace_buffer()};
   const int C = shared ? (H + 127) / 128 : (H + 63) / 64;
+  if (sm_budget > 0 && sm_budget < sms) sms = sm_budget;
   const int nt = tc_pick_nt(R, H, shared, sms);
   static const bool prof = getenv("GSN_TC_PROF") != nullptr;  // dev knob: per-phase cycle counters
   if (!shared) {

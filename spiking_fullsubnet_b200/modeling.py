@@ -91,21 +91,35 @@ class GSULayer(nn.Module):
         return h, MemoryState(hT, cT)
 
 
-def _run_layer(cell, x, state, want_c, backend):
+def _cluster_ctas(rows, H, shared):
+    """CTAs per 16-row tile x tiles: the SM demand of one recurrence at the finest row tiling."""
+    return ((rows + 15) // 16) * ((H + 127) // 128 if shared else (H + 63) // 64)
+
+
+def _sm_budgets(demands, total=148, floor=4):
+    """Split the SMs between concurrently running recurrences in proportion to their demand (0 = no cap when
+    everything fits at the finest tiling)."""
+    if sum(demands) <= total:
+        return [0] * len(demands)
+    return [max(floor, int(total * d / sum(demands))) for d in demands]
+
+
+def _run_layer(cell, x, state, want_c, backend, sm_budget=0, spikes_in=False):
     if cell.use_bn and cell.batchnorm.training:
         raise NotImplementedError("training-mode BatchNorm inside the GSN recurrence is not implemented "
                                   "yet; call model.eval()")
     if not x.is_cuda:
         raise RuntimeError("spiking_fullsubnet_b200 has no CPU path: move the model and input to CUDA")
     x = x.contiguous()
-    xproj = ops.linear(x, cell.weight_ih.detach())  # bias joins in the recurrence, in reference order
+    # (bias joins in the recurrence, in the reference's order; layers >= 1 see the previous layer's spikes)
+    xproj = ops.linear(x, cell.weight_ih.detach(), spikes=spikes_in, sm_budget=sm_budget)
     a, b = cell.folded_bn()
     h0 = c0 = None
     if state is not None:
         h0, c0 = state[0].contiguous(), state[1].contiguous()
     return ops.layer_recurrence(xproj, cell.weight_hh.detach(), cell.bias_ih.detach(), a, b,
                                 shared=cell.shared_weights, want_c=want_c, h0=h0, c0=c0,
-                                want_state=True, backend=backend)
+                                want_state=True, backend=backend, sm_budget=sm_budget)
 
 
 class StackedGSU(nn.Module):
@@ -114,6 +128,7 @@ class StackedGSU(nn.Module):
         self.layers = nn.ModuleList([layer(*first_layer_args)] +
                                     [layer(*other_layer_args) for _ in range(num_layers - 1)])
         self.backend = "auto"
+        self.sm_budget = 0  # SMs to plan for (0 = whole device); set by callers that run stacks concurrently
 
     def forward(self, input, states=None, want_c=False):
         """(ESN:50-62) input [T,R,K], states list of (h,c) or None (zeros) ->
@@ -123,7 +138,8 @@ class StackedGSU(nn.Module):
         self.last_c = []
         for i, layer in enumerate(self.layers):
             st = None if states is None else states[i]
-            h, c, (hT, cT) = _run_layer(layer.cell, out, st, want_c, self.backend)
+            h, c, (hT, cT) = _run_layer(layer.cell, out, st, want_c, self.backend, self.sm_budget,
+                                        spikes_in=i > 0)
             out_states.append(MemoryState(hT, cT))
             trace.append(h)
             self.last_c.append(c)
@@ -174,7 +190,8 @@ class SequenceModel(nn.Module):
         """x [T,R,K] already normalised -> (proj_out [T,R,P], activated [T,R,P], all_layer_outputs)."""
         out, _, trace = self.sequence_model(x, None)
         if isinstance(self.proj, nn.Linear):
-            res = ops.linear(out, self.proj.weight.detach(), self.proj.bias.detach(), act=self._act)
+            res = ops.linear(out, self.proj.weight.detach(), self.proj.bias.detach(), act=self._act,
+                             spikes=True, sm_budget=self.sequence_model.sm_budget)
             proj, act = res if self._act else (res, res)
         else:
             proj = out
@@ -204,6 +221,8 @@ class _SeqPlan:
 
     def __init__(self, model, T, R, nchunks, device, backend):
         self.m = model
+        self.sm_budget = 0       # SMs the recurrences of this model plan for (0 = whole device)
+        self.lin_budget = 0      # SMs the tcgen05 linears of this model plan for
         stack = model.sequence_model
         self.L = len(stack.layers)
         f32 = dict(device=device, dtype=torch.float32)
@@ -233,7 +252,8 @@ class _SeqPlan:
         """Input-to-hidden product of frames [t0,t1) of layer l (no dependence on the layer's own state)."""
         cell = self.m.sequence_model.layers[l].cell
         inp = self.x[t0:t1] if l == 0 else self.h[l - 1][t0:t1]
-        ops.linear(inp, cell.weight_ih.detach(), out=self.xproj[l][t0:t1])
+        ops.linear(inp, cell.weight_ih.detach(), out=self.xproj[l][t0:t1], spikes=l > 0,
+                   sm_budget=self.lin_budget)
 
     def run_rec(self, l, k, t0, t1):
         """Recurrence of frames [t0,t1) of layer l from the state carried out of chunk k-1."""
@@ -242,14 +262,15 @@ class _SeqPlan:
         ops.layer_recurrence(self.xproj[l][t0:t1], cell.weight_hh.detach(), cell.bias_ih.detach(), a, b,
                              shared=cell.shared_weights, h0=self.hs[l][k], c0=self.cs[l][k],
                              out_h=self.h[l][t0:t1], out_hT=self.hs[l][k + 1], out_cT=self.cs[l][k + 1],
-                             backend=self.backend, workspace=self.ws[l])
+                             backend=self.backend, workspace=self.ws[l], sm_budget=self.sm_budget)
 
     def run_post(self, k, t0, t1):
         """Output projection (+ activation) of frames [t0,t1)."""
         m = self.m
         if self.proj is not None:
             ops.linear(self.h[-1][t0:t1], m.proj.weight.detach(), m.proj.bias.detach(), act=m._act,
-                       out=self.proj[t0:t1], out_act=self.act[t0:t1] if m._act else None)
+                       out=self.proj[t0:t1], out_act=self.act[t0:t1] if m._act else None, spikes=True,
+                       sm_budget=self.lin_budget)
 
     def outputs(self):
         """(proj_out, activated, all_layer_outputs) exactly as SequenceModel.run_time_major returns them."""
@@ -328,6 +349,12 @@ class SubbandModel(nn.Module):
             return proj, all_out
 
         n = len(self.sb_models)
+        demands = [_cluster_ctas(B * ((self.freq_cutoffs[i + 1] - self.freq_cutoffs[i]) // self.center_freq_sizes[i]),
+                                 m.hidden_size, m.sequence_model.layers[0].cell.shared_weights)
+                   for i, m in enumerate(self.sb_models)]
+        budgets = _sm_budgets(demands) if self.concurrent_bands and n > 1 else [0] * n
+        for m, b in zip(self.sb_models, budgets):
+            m.sequence_model.sm_budget = b
         if not self.concurrent_bands or n == 1:
             res = [run_band(i) for i in range(n)]
         else:
@@ -438,7 +465,8 @@ class SpikingFullSubNet(nn.Module):
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
                     static_out = (self._network_wavefront(static_in, self.frame_chunks)
-                                  if self.frame_chunks > 1 else self._network(static_in))
+                                  if self.frame_chunks > 1 and self._fits_wavefront(static_in.shape[0])
+                                  else self._network(static_in))
             entry = self._graphs[key] = (graph, static_in, static_out)
         graph, static_in, static_out = entry
         static_in.copy_(mag)
@@ -461,6 +489,18 @@ class SpikingFullSubNet(nn.Module):
             raise ValueError(f"full-band output ({fb_act.shape[2]} bins x {rep}) does not cover {F - 1} bins")
         projs, sb_all = self.sb_model.run_time_major(cm, fb_act)
         return projs, fb_all, sb_all
+
+    def _fits_wavefront(self, B):
+        """The wavefront schedule keeps every (model, layer) recurrence resident at once; it only pays off
+        when all of them fit on the 148 SMs at the finest row tiling."""
+        sb = self.sb_model
+        total = 0
+        for m, rows in [(self.fb_model, B)] + [
+                (m, B * ((sb.freq_cutoffs[i + 1] - sb.freq_cutoffs[i]) // sb.center_freq_sizes[i]))
+                for i, m in enumerate(sb.sb_models)]:
+            cell = m.sequence_model.layers[0].cell
+            total += _cluster_ctas(rows, cell.hidden_size, cell.shared_weights) * m.num_layers
+        return total <= 148
 
     def _network_wavefront(self, mag, nchunks):
         """Same results as `_network`, scheduled as a frame-chunked wavefront over one stream per
@@ -485,6 +525,21 @@ class SpikingFullSubNet(nn.Module):
                                  f"GOT: ctr_freq={ctr}, upper_cutoff_freq={hi}, lower_cutoff_freq={lo}")
             geo.append(((hi - lo) // ctr, lo, ctr, sbm.neighbor_freq_sizes[i]))
             sbps.append(_SeqPlan(m, T, B * geo[-1][0], nchunks, dev, m.sequence_model.backend))
+
+        # every (model, layer) recurrence runs concurrently in the wavefront: split the SMs between them
+        plans_all = [fbp] + sbps
+        demands = []
+        for p_ in plans_all:
+            cell0 = p_.m.sequence_model.layers[0].cell
+            demands += [_cluster_ctas(p_.x.shape[1], cell0.hidden_size, cell0.shared_weights)] * p_.L
+        bud = _sm_budgets(demands)
+        # SMs left over by the resident recurrence CTAs are what the (persistent) tcgen05 linears can get
+        free = max(8, 148 - sum(min(d, b) if b else d for d, b in zip(demands, bud)))
+        o_ = 0
+        for p_ in plans_all:
+            p_.sm_budget = bud[o_]
+            p_.lin_budget = max(8, free)
+            o_ += p_.L
 
         def ln(m):
             if not m.use_pre_layer_norm:
@@ -669,7 +724,8 @@ class _FreezeSequenceModel(nn.Module):
         """x [T,R,K] (already normalised) -> (fc_out [T,R,P], activated, all_layer_outputs)."""
         out, _, trace = self.sequence_model(x, None)
         if int(self.output_size):
-            out = ops.linear(out, self.fc_output_layer.weight.detach(), self.fc_output_layer.bias.detach())
+            out = ops.linear(out, self.fc_output_layer.weight.detach(), self.fc_output_layer.bias.detach(),
+                             spikes=True)
             trace = trace + [out]
         act = self.activate_function(out) if self.output_activate_function_name else out
         return out, act, trace

@@ -72,8 +72,13 @@ def subband_features(cm, fb, N, lo, ctr, nbr, ln_weight=None, ln_bias=None, eps=
     return x
 
 
-def linear(a, w, bias=None, act=None, out=None, out_act=None):
-    """out[..., N] = a[..., K] @ w[N,K]^T + bias (fp32 FMA).  Returns out, or (out, act(out)) if act."""
+TC_LINEAR = [True]  # spike-input linears on tcgen05 (set False to force the fp32 CUDA-core kernel)
+
+
+def linear(a, w, bias=None, act=None, out=None, out_act=None, spikes=False, sm_budget=0):
+    """out[..., N] = a[..., K] @ w[N,K]^T + bias.  Returns out, or (out, act(out)) if act.
+    spikes=True promises that `a` holds {0,1} (a spike trace): the product then runs on tcgen05 with the
+    weights as exact bf16x3 planes (gsn_linear_spikes); otherwise fp32 FMA on CUDA cores (gsn_linear_f32)."""
     lib, st = _prep(a, w, bias, out, out_act)
     K = a.shape[-1]
     N = w.shape[0]
@@ -83,7 +88,11 @@ def linear(a, w, bias=None, act=None, out=None, out_act=None):
     out = _out(out, a.shape[:-1] + (N,), a)
     code = _ACT[act]
     out_act = _out(out_act, out.shape, a) if code else None
-    _lib.check(lib.gsn_linear_f32(_ptr(a), _ptr(w), _ptr(bias), _ptr(out), _ptr(out_act), code, M, K, N, st))
+    if spikes and TC_LINEAR[0] and K % 4 == 0 and K <= 320 and a.data_ptr() % 16 == 0:
+        _lib.check(lib.gsn_linear_spikes(_ptr(a), _ptr(w), _ptr(bias), _ptr(out), _ptr(out_act), code, M, K, N,
+                                         int(sm_budget), st))
+    else:
+        _lib.check(lib.gsn_linear_f32(_ptr(a), _ptr(w), _ptr(bias), _ptr(out), _ptr(out_act), code, M, K, N, st))
     LAUNCHES[0] += 1
     return (out, out_act) if code else out
 
@@ -98,7 +107,7 @@ def recurrence_workspace(R, H, shared, backend, device):
 
 def layer_recurrence(xproj, w_hh, bias, bn_scale=None, bn_shift=None, shared=True, want_c=False,
                      h0=None, c0=None, want_state=False, backend="auto", out_h=None, out_c=None, out_hT=None,
-                     out_cT=None, workspace=None):
+                     out_cT=None, workspace=None, sm_budget=0):
     """One GSULayer over all frames (ESN:75-81 / 132-153).  xproj [T,R,gH] -> h [T,R,H] (and c, (hT,cT))."""
     lib, st = _prep(xproj, w_hh, bias, bn_scale, bn_shift, h0, c0, out_h, out_c, out_hT, out_cT)
     T, R, gH = xproj.shape
@@ -121,7 +130,7 @@ def layer_recurrence(xproj, w_hh, bias, bn_scale=None, bn_shift=None, shared=Tru
         e0.record()
     _lib.check(lib.gsn_layer_recurrence(_ptr(xproj), _ptr(w_hh), _ptr(bias), _ptr(bn_scale), _ptr(bn_shift),
                                         _ptr(h0), _ptr(c0), _ptr(h), _ptr(c), _ptr(hT), _ptr(cT), T, R, H,
-                                        int(shared), be, ws.data_ptr() + off, st))
+                                        int(shared), be, int(sm_budget), ws.data_ptr() + off, st))
     LAUNCHES[0] += 2  # weight preparation + the recurrence kernel
     LAST_WS[0] = (ws, 0)
     if PROFILE is not None:

@@ -85,3 +85,15 @@ def test_coef_layout_matches_oracle_index_map():
     want = O.subband_coef_layout(np.transpose(proj, (1, 2, 0)), B, ctr, df, S)
     got = coef_layout(torch.from_numpy(proj), B, N, df, S).numpy()
     assert np.array_equal(got, want)
+
+
+def test_shipped_shapes_run_on_tcgen05():
+    """No silent fp32-SIMT fallback for any shipped model size (S/M/L/XL, cirm_gsn) at bench batch sizes."""
+    from oracle import gsn_oracle as O
+    from spiking_fullsubnet_b200 import ops
+    for name, cfg in synth.CONFIGS.items():
+        for B in (1, 32, 64):
+            for _, rows, _, H, _ in O.model_rows_and_shapes(cfg, B):
+                assert ops.pick_backend(rows, H, cfg["shared_weights"]) == "tcgen05", (name, B, rows, H)
+    assert ops.pick_backend(32, 268, True) == "tcgen05"  # cirm_gsn default
+    assert ops.pick_backend(480, 512, True) == "simt"    # H > 320 does not fit tensor memory with 3 planes

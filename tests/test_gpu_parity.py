@@ -267,3 +267,22 @@ def test_surface_b_vs_golden(name, backend):
             assert _rel(coefs[i].cpu().numpy(), g[f"coef{i}"]) < 1e-3
         assert _rel(enh_y.cpu().numpy(), g["enh_y"]) < 1e-3
         assert _rel(enh_mag.cpu().numpy(), g["enh_mag"]) < 1e-3
+
+
+@pytest.mark.parametrize("M,K,N", [(1, 16, 8), (130, 160, 160), (1000, 240, 64), (777, 256, 256), (300, 320, 320),
+                                   (515, 268, 1542), (64, 224, 448), (5000, 160, 24)])
+def test_linear_spikes_is_exact(M, K, N):
+    """gsn_linear_spikes (tcgen05, weights as exact bf16x3 planes): with {0,1} inputs the result is the fp32 sum of
+    exact products -- compared with a float64 product it agrees to fp32 accumulation accuracy, and with the fp32
+    CUDA-core kernel to a few ulp."""
+    rs = np.random.RandomState(M + K)
+    a = (rs.uniform(size=(M, K)) < 0.45).astype(np.float32)
+    w = rs.uniform(-0.1, 0.1, (N, K)).astype(np.float32)
+    b = rs.uniform(-0.1, 0.1, N).astype(np.float32)
+    ref = a.astype(np.float64) @ w.astype(np.float64).T + b
+    out_tc, act_tc = ops.linear(_t(a), _t(w), _t(b), act="tanh", spikes=True)
+    out_f32 = ops.linear(_t(a), _t(w), _t(b))
+    scale = np.abs(ref).max()
+    assert np.abs(out_tc.cpu().numpy() - ref).max() <= 2e-6 * scale
+    assert np.abs(out_tc.cpu().numpy() - out_f32.cpu().numpy()).max() <= 2e-6 * scale
+    assert np.abs(act_tc.cpu().numpy() - np.tanh(ref)).max() <= 1e-5
