@@ -35,7 +35,7 @@ def parse():
     ap.add_argument("--seconds", type=float, default=4.0)
     ap.add_argument("--backend", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--chunks", type=int, default=8, help="frame chunks of the wavefront schedule (graph mode)")
+    ap.add_argument("--chunks", type=int, default=16, help="frame chunks of the wavefront schedule (graph mode)")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of "
                     "replaying the captured CUDA graph")
     return ap.parse_args()
@@ -177,6 +177,10 @@ def main():
     step()  # eager pass: counts the kernels one step launches
     launches_per_step = ops.LAUNCHES[0]
     model.enable_cuda_graph(not args.no_graph, frame_chunks=args.chunks)
+    if not args.no_graph:
+        ops.LAUNCHES[0] = 0
+        step()  # eager warm-up (launches_per_step kernels) + capture of the replayed schedule
+        launches_per_step = ops.LAUNCHES[0] - launches_per_step  # kernels inside the captured graph
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
