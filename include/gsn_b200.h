@@ -109,6 +109,31 @@ GSN_API int gsn_layer_recurrence(const float* xproj, const float* w_hh, const fl
 /* which backend GSN_BACKEND_AUTO resolves to for this shape (GSN_BACKEND_SIMT / _TCGEN05). */
 GSN_API int gsn_layer_recurrence_pick_backend(int R, int H, int shared);
 
+/* ---- training path of the recurrence (fp32 CUDA cores, cooperative launch) -------------------------------
+ * Forward: GSUCell.forward ESN:132-153 over all frames with nn.BatchNorm1d in TRAINING mode when training != 0
+ * (batch statistics over the R rows per frame, biased variance; running_mean / running_var updated in place
+ * every frame with `momentum` and the unbiased variance, ESN:149-150), eval-mode statistics otherwise;
+ * bn_weight == NULL means no BatchNorm.  Besides h_out / c_out [T,R,H] it saves what BPTT needs:
+ * f_out = sigmoid(forget gate), g_out = cell-gate pre-activation, xhat_out = normalised pre-BN membrane
+ * [T,R,H] and invstd_out [T,H] (the last two only with batch statistics).  Zero initial state (MSF:100-106).
+ * Backward: BPTT with the Triangle surrogate max(0, 1-|c|) (ESN:95-101) and the batch-statistics BatchNorm
+ * backward.  dh_out [T,R,H] = dL/dh_t; dz [T,R,gH] = dL/d(gate pre-activations) = dL/dxproj,
+ * from which dW_hh = dz^T h_{t-1}, dW_ih = dz^T x, dx = dz W_ih are plain GEMMs; dbias_part [ceil(R/8), 2H]
+ * per-CTA partial sums of dL/dbias; dgamma / dbeta [H] BatchNorm affine gradients (batch statistics only).
+ * workspace: gsn_layer_train_workspace_bytes(R, H, shared) bytes, 256-byte aligned.  H <= 512.            */
+GSN_API size_t gsn_layer_train_workspace_bytes(int R, int H, int shared);
+GSN_API int gsn_layer_train_forward(const float* xproj, const float* w_hh, const float* bias,
+                                    const float* bn_weight, const float* bn_bias, float* running_mean,
+                                    float* running_var, float* h_out, float* c_out, float* f_out, float* g_out,
+                                    float* xhat_out, float* invstd_out, int T, int R, int H, int shared,
+                                    int training, float momentum, float eps, void* workspace,
+                                    gsn_stream_t stream);
+GSN_API int gsn_layer_train_backward(const float* dh_out, const float* w_hh, const float* c, const float* f,
+                                     const float* g, const float* xhat, const float* invstd,
+                                     const float* bn_weight, const float* running_var, float* dz,
+                                     float* dbias_part, float* dgamma, float* dbeta, int T, int R, int H,
+                                     int shared, int training, float eps, void* workspace, gsn_stream_t stream);
+
 /* ---- back end: deep filter (MSF:315-346) -- "next" row f1 ----------------------
  * Applies the coefficients straight from the sub-band proj output, skipping the 6-D rearrangement:
  *   proj [T, B*N, P] with p = ((c2*ctr + fc)*df + d)*S + s   (MSF:160-167)

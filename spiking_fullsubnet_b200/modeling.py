@@ -12,8 +12,9 @@ Reference modules mirrored (paths relative to the reference root):
   CGN = audiozen/models/cirm_gsn/modeling_cirm_gsn.py (Model :162)
 
 The modules hold parameters only; there is no per-frame Python loop and no CPU / eager fallback:
-CPU tensors raise.  Training-mode BatchNorm statistics and the backward pass are not implemented yet
-(forward raises in train mode when bn=True), see DESIGN.md.
+CPU tensors raise.  Inference (no grad, eval mode) takes the fused path below; when gradients are required
+or BatchNorm is in training mode, `forward` takes the autograd path of `training.py` (CUDA forward/BPTT
+kernels for the recurrence, differentiable torch ops around it).
 """
 from __future__ import annotations
 
@@ -104,10 +105,17 @@ def _sm_budgets(demands, total=148, floor=4):
     return [max(floor, int(total * d / sum(demands))) for d in demands]
 
 
+def _needs_autograd(module):
+    """True when the call must go through the autograd path: gradients are being recorded for some parameter,
+    or a BatchNorm of the module is in training mode (batch statistics, running-stat updates)."""
+    if torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters()):
+        return True
+    return any(isinstance(m, nn.BatchNorm1d) and m.training for m in module.modules())
+
+
 def _run_layer(cell, x, state, want_c, backend, sm_budget=0, spikes_in=False):
     if cell.use_bn and cell.batchnorm.training:
-        raise NotImplementedError("training-mode BatchNorm inside the GSN recurrence is not implemented "
-                                  "yet; call model.eval()")
+        raise RuntimeError("internal error: training-mode BatchNorm reached the inference kernels")
     if not x.is_cuda:
         raise RuntimeError("spiking_fullsubnet_b200 has no CPU path: move the model and input to CUDA")
     x = x.contiguous()
@@ -133,6 +141,12 @@ class StackedGSU(nn.Module):
     def forward(self, input, states=None, want_c=False):
         """(ESN:50-62) input [T,R,K], states list of (h,c) or None (zeros) ->
         (output [T,R,H], output_states, all_layer_output = [input, h1..hL])."""
+        if _needs_autograd(self):
+            # training path: zero initial state (what every caller of the reference passes, MSF:100-106)
+            from . import training
+            out, trace = training.run_stack(self, input.contiguous())
+            self.last_c = [None] * len(self.layers)
+            return out, [MemoryState(t[-1], None) for t in trace[1:]], trace
         out = input
         out_states, trace = [], [input]
         self.last_c = []
@@ -231,8 +245,7 @@ class _SeqPlan:
         for layer in stack.layers:
             cell = layer.cell
             if cell.use_bn and cell.batchnorm.training:
-                raise NotImplementedError("training-mode BatchNorm inside the GSN recurrence is not "
-                                          "implemented yet; call model.eval()")
+                raise RuntimeError("the inference schedule needs model.eval(); training goes through forward()")
             H = cell.hidden_size
             g = 1 if cell.shared_weights else 2
             self.xproj.append(torch.empty((T, R, g * H), **f32))
@@ -614,6 +627,11 @@ class SpikingFullSubNet(nn.Module):
 
     def forward(self, input):
         assert input.ndim == 2, f"Input tensor must be 2D, but got {input.ndim}D."
+        if not input.is_cuda:
+            raise RuntimeError("spiking_fullsubnet_b200 has no CPU path: move the model and input to CUDA")
+        if _needs_autograd(self):
+            from . import training
+            return training.spiking_fullsubnet_forward(self, input)
         B, L = input.shape
         cmp = _stft(input, self.n_fft, self.hop_length, self.win_length)  # [B,F,T] complex
         mag = cmp.abs().contiguous()

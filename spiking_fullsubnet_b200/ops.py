@@ -152,3 +152,53 @@ def deepfilter_band(proj, spec_re, spec_im, out_re, out_im, N, ctr, df, S, lo):
     _lib.check(lib.gsn_deepfilter_band(_ptr(proj), _ptr(spec_re), _ptr(spec_im), _ptr(out_re), _ptr(out_im),
                                        T, B, N, ctr, df, S, lo, F, F_out, st))
     LAUNCHES[0] += 1
+
+
+def _train_ws(R, H, shared, device):
+    nbytes = _lib.load().gsn_layer_train_workspace_bytes(R, H, int(shared))
+    ws = torch.empty((nbytes + 255) // 4 + 64, device=device, dtype=torch.float32)
+    return ws[((-ws.data_ptr()) % 256) // 4:]
+
+
+def layer_train_forward(xproj, w_hh, bias, bn_weight, bn_bias, running_mean, running_var, training, momentum, eps,
+                        shared):
+    """Training-path forward of one GSULayer (ESN:75-81 / 132-153, BatchNorm with batch statistics when
+    `training`).  Returns (h, c, f, g, xhat, invstd); running statistics are updated in place."""
+    lib, st = _prep(xproj, w_hh, bias, bn_weight, bn_bias, running_mean, running_var)
+    T, R, gH = xproj.shape
+    H = w_hh.shape[1]
+    dev = xproj.device
+    new = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)  # noqa: E731
+    h, c, f, g = new(T, R, H), new(T, R, H), new(T, R, H), new(T, R, H)
+    batch_stats = bn_weight is not None and training
+    xhat = new(T, R, H) if batch_stats else None
+    invstd = new(T, H) if batch_stats else None
+    ws = _train_ws(R, H, shared, dev)
+    _lib.check(lib.gsn_layer_train_forward(_ptr(xproj), _ptr(w_hh), _ptr(bias), _ptr(bn_weight), _ptr(bn_bias),
+                                           _ptr(running_mean), _ptr(running_var), _ptr(h), _ptr(c), _ptr(f), _ptr(g),
+                                           _ptr(xhat), _ptr(invstd), T, R, H, int(shared), int(bool(training)),
+                                           float(momentum), float(eps), ws.data_ptr(), st))
+    LAUNCHES[0] += 2
+    return h, c, f, g, xhat, invstd
+
+
+def layer_train_backward(dh, w_hh, c, f, g, xhat, invstd, bn_weight, running_var, training, eps, shared):
+    """BPTT of one GSULayer (surrogate gradient, BatchNorm backward).  Returns (dz [T,R,gH], dbias [2H],
+    dgamma [H] | None, dbeta [H] | None)."""
+    lib, st = _prep(dh, w_hh, c, f, g, xhat, invstd, bn_weight, running_var)
+    T, R, H = dh.shape
+    gH = w_hh.shape[0]
+    dev = dh.device
+    dz = torch.empty((T, R, gH), device=dev, dtype=torch.float32)
+    nblocks = (R + 7) // 8
+    dbias_part = torch.empty((nblocks, 2 * H), device=dev, dtype=torch.float32)
+    batch_stats = bn_weight is not None and training
+    dgamma = torch.empty(H, device=dev, dtype=torch.float32) if batch_stats else None
+    dbeta = torch.empty(H, device=dev, dtype=torch.float32) if batch_stats else None
+    ws = _train_ws(R, H, shared, dev)
+    _lib.check(lib.gsn_layer_train_backward(_ptr(dh), _ptr(w_hh), _ptr(c), _ptr(f), _ptr(g), _ptr(xhat), _ptr(invstd),
+                                            _ptr(bn_weight), _ptr(running_var), _ptr(dz), _ptr(dbias_part),
+                                            _ptr(dgamma), _ptr(dbeta), T, R, H, int(shared), int(bool(training)),
+                                            float(eps), ws.data_ptr(), st))
+    LAUNCHES[0] += 1
+    return dz, dbias_part.sum(dim=0), dgamma, dbeta

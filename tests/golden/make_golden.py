@@ -141,6 +141,35 @@ def run_surface_b(name, cfg, params, seed, batch, num_samples, store_weights=Fal
     print(name, {k: (v.shape if hasattr(v, "shape") else v) for k, v in d.items() if k != "cfg"})
 
 
+def run_train(name, cfg, seed, batch, num_samples):
+    """One TRAINING step of surface A on the reference: train-mode BatchNorm (batch statistics per frame,
+    running-stat updates) and autograd BPTT through the Triangle surrogate (ESN:84-101)."""
+    torch.manual_seed(0)
+    model = MSF.SpikingFullSubNet(**cfg)
+    params = synth.make_params(cfg, seed)
+    load_params(model, params)
+    model.train()
+    wave = synth.make_wave(batch, num_samples, seed + 1)
+    target = synth.make_wave(batch, num_samples, seed + 2)
+    x = torch.from_numpy(wave)
+    enh_y, enh_mag, fb_all, sb_all = model(x)
+    loss = (enh_y * torch.from_numpy(target)).sum() + enh_mag.pow(2).mean()
+    loss.backward()
+    d = {"cfg": json.dumps(cfg), "seed": seed, "wave": wave, "target": target, "loss": loss.detach().numpy(),
+         "enh_y": enh_y.detach().numpy()}
+    for l in range(cfg["fb_num_layers"]):
+        d[f"fb_h{l}"] = pack(fb_all[1 + l])
+    for i, al in enumerate(sb_all):
+        for l in range(cfg["sb_num_layers"]):
+            d[f"sb{i}_h{l}"] = pack(al[1 + l])
+    for k, p in model.named_parameters():
+        d["grad__" + k] = p.grad.numpy()
+    for k, b in model.named_buffers():
+        d["buf__" + k] = b.detach().numpy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
+    print(name, "loss", float(loss), {k: v.shape for k, v in d.items() if k.startswith("grad__")}.__len__(), "grads")
+
+
 def run_cirm(name, cfg, seed, batch, num_samples):
     torch.manual_seed(0)
     model = CGN.Model(**cfg)
@@ -177,6 +206,9 @@ if __name__ == "__main__":
                                                    sb_num_layers=1, fb_num_layers=3), 103, 2, 16 * 20, True)
     run_cirm("tiny_cirm", dict(synth.CFG_CIRM, n_fft=64, hop_length=16, win_length=64, input_size=33,
                                hidden_size=40, num_layers=3, proj_size=33, df_order=2), 104, 2, 16 * 30)
+    # training step (config 4 in miniature): gradients of every parameter + updated BatchNorm buffers
+    run_train("tiny_train_shared_bn", synth.tiny_cfg(), 107, 3, 16 * 19)
+    run_train("tiny_train_unshared_nobn", synth.tiny_cfg(shared_weights=False, bn=False), 108, 2, 16 * 15)
     # surface B: tiny structural fixture + the TRAINED model-zoo S checkpoint on a 1 s clip (protocol P3)
     cfgb = synth.tiny_cfg_b()
     run_surface_b("tiny_surface_b", cfgb, synth.make_params_b(cfgb, 105), 105, 2, 16 * 33)

@@ -286,3 +286,70 @@ def test_linear_spikes_is_exact(M, K, N):
     assert np.abs(out_tc.cpu().numpy() - ref).max() <= 2e-6 * scale
     assert np.abs(out_tc.cpu().numpy() - out_f32.cpu().numpy()).max() <= 2e-6 * scale
     assert np.abs(act_tc.cpu().numpy() - np.tanh(ref)).max() <= 1e-5
+
+
+@pytest.mark.parametrize("name", ["tiny_train_shared_bn", "tiny_train_unshared_nobn"])
+def test_training_step_vs_golden(name):
+    """Protocol P4: one training step (train-mode BatchNorm, BPTT with the Triangle surrogate) against the
+    reference's autograd on CPU: same spikes, loss, updated BatchNorm buffers and gradients of EVERY parameter
+    (max|delta| <= 2e-3 * max|ref| per tensor: fp32 BPTT through ~20 frames in a different summation order)."""
+    g = load_golden(name)
+    cfg = g["cfg"]
+    m = SpikingFullSubNet(**cfg)
+    m.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in golden_params(g).items()}, strict=True)
+    m = m.to(DEV).train()
+    enh_y, enh_mag, fb_all, sb_all = m(_t(g["wave"]))
+    loss = (enh_y * _t(g["target"])).sum() + enh_mag.pow(2).mean()
+    loss.backward()
+    for l in range(cfg["fb_num_layers"]):
+        assert np.array_equal(fb_all[1 + l].detach().cpu().numpy(), unpack(g[f"fb_h{l}"], cfg["fb_hidden_size"]))
+    for i in range(3):
+        for l in range(cfg["sb_num_layers"]):
+            assert np.array_equal(sb_all[i][1 + l].detach().cpu().numpy(),
+                                  unpack(g[f"sb{i}_h{l}"], cfg["sb_hidden_size"]))
+    assert abs(float(loss) - float(g["loss"])) <= 1e-3 * abs(float(g["loss"]))
+    assert _rel(enh_y.detach().cpu().numpy(), g["enh_y"]) < 1e-3
+    for k, b in m.named_buffers():
+        ref = g["buf__" + k]
+        got = b.detach().cpu().numpy()
+        if ref.dtype.kind == "i":
+            assert int(got) == int(ref), k
+        else:
+            assert np.abs(got - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max()), k
+    worst = 0.0
+    for k, p in m.named_parameters():
+        ref = g["grad__" + k]
+        assert p.grad is not None, k
+        err = np.abs(p.grad.cpu().numpy() - ref).max() / (np.abs(ref).max() + 1e-12)
+        worst = max(worst, err)
+        assert err <= 2e-3, f"{k}: gradient rel err {err:.2e}"
+    print(f"{name}: worst gradient rel err {worst:.2e}")
+
+
+def test_layer_backward_vs_oracle_eval_bn():
+    """gsn_layer_train_backward with EVAL-mode BatchNorm against the oracle's BPTT restatement (fp64)."""
+    from spiking_fullsubnet_b200.training import GSNLayerFn
+    from spiking_fullsubnet_b200.modeling import GSUCell
+    rs = np.random.RandomState(5)
+    T, R, K, H = 12, 11, 7, 40
+    for shared in (True, False):
+        p = synth._seq_model_params(rs, "m.", K, H, 1, 0, shared, True, False)
+        q = "m.sequence_model.layers.0.cell."
+        cell = GSUCell(K, H, shared, True)
+        cell.load_state_dict({k[len(q):]: torch.from_numpy(np.array(v)) for k, v in p.items()})
+        cell = cell.to(DEV).eval()
+        x = rs.standard_normal((T, R, K)).astype(np.float32)
+        d_out = rs.standard_normal((T, R, H)).astype(np.float32)
+        xt = _t(x).requires_grad_(True)
+        xproj = torch.nn.functional.linear(xt, cell.weight_ih)
+        h = GSNLayerFn.apply(xproj, cell.weight_hh, cell.bias_ih, cell.batchnorm.weight, cell.batchnorm.bias, cell)
+        (h * _t(d_out)).sum().backward()
+        _, trace, cs = O.gsn_stack_forward(x, p, "m.sequence_model.", 1, shared, return_c=True)
+        assert np.array_equal(h.detach().cpu().numpy(), trace[1])
+        bn = {k: p[q + "batchnorm." + k] for k in ("weight", "bias", "running_mean", "running_var")}
+        ref = O.gsn_layer_backward(x, trace[1], cs[0], d_out, p[q + "weight_ih"], p[q + "weight_hh"], p[q + "bias_ih"],
+                                   bn, shared)
+        for got, want, nm in [(xt.grad, ref["dx"], "dx"), (cell.weight_ih.grad, ref["dw_ih"], "dw_ih"),
+                              (cell.weight_hh.grad, ref["dw_hh"], "dw_hh"), (cell.bias_ih.grad, ref["dbias"], "dbias")]:
+            err = np.abs(got.cpu().numpy() - want).max() / (np.abs(want).max() + 1e-12)
+            assert err < 1e-4, (shared, nm, err)
