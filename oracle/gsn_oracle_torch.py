@@ -16,7 +16,21 @@ import torch.nn.functional as F
 from . import gsn_oracle as O
 
 
-def _stack(x, params, prefix, L, shared):
+class _Triangle(torch.autograd.Function):
+    """Heaviside forward, triangular surrogate max(0, 1-|c|) backward (restates ESN:84-101, gamma = 1)."""
+
+    @staticmethod
+    def forward(ctx, c):
+        ctx.save_for_backward(c)
+        return c.ge(0.0).float()
+
+    @staticmethod
+    def backward(ctx, grad):
+        (c,) = ctx.saved_tensors
+        return grad * (1.0 - c.abs()).clamp(min=0)
+
+
+def _stack(x, params, prefix, L, shared, train_state=None):
     T, R, _ = x.shape
     trace = [x]
     cur = x
@@ -40,20 +54,21 @@ def _stack(x, params, prefix, L, shared):
             c = f * c + (1 - f) * g
             if bn:
                 c = F.batch_norm(c, params[p + "batchnorm.running_mean"], params[p + "batchnorm.running_var"],
-                                 params[p + "batchnorm.weight"], params[p + "batchnorm.bias"], False, 0.1, 1e-5)
-            h = c.ge(0.0).float()
+                                 params[p + "batchnorm.weight"], params[p + "batchnorm.bias"],
+                                 train_state is not None, 0.1, 1e-5)
+            h = _Triangle.apply(c) if train_state is not None else c.ge(0.0).float()
             outs.append(h)
         cur = torch.stack(outs)
         trace.append(cur)
     return cur, trace
 
 
-def _sequence_model(inp, params, prefix, L, shared, act):
+def _sequence_model(inp, params, prefix, L, shared, act, train_state=None):
     x = inp.permute(2, 0, 1)
     if prefix + "pre_layer_norm.weight" in params:
         x = F.layer_norm(x, (x.shape[-1],), params[prefix + "pre_layer_norm.weight"],
                          params[prefix + "pre_layer_norm.bias"])
-    out, trace = _stack(x.contiguous(), params, prefix + "sequence_model.", L, shared)
+    out, trace = _stack(x.contiguous(), params, prefix + "sequence_model.", L, shared, train_state)
     if prefix + "proj.weight" in params:
         out = F.linear(out, params[prefix + "proj.weight"], params[prefix + "proj.bias"])
     trace = trace + [out]
@@ -71,15 +86,30 @@ def to_torch(params):
     return {k: torch.from_numpy(np.array(v)) for k, v in params.items()}
 
 
+def spiking_fullsubnet_train_step(mag, params, cfg):
+    """Forward in training mode (batch-statistics BatchNorm) + backward of a stand-in loss (mean square of the
+    coefficients) through the surrogate gradient: the CPU cost of the path inside one training step."""
+    leaf = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+            for k, v in params.items()}
+    coefs, _, _ = _network(mag, leaf, cfg, train_state=True)
+    loss = sum(c.pow(2).mean() for c in coefs)
+    loss.backward()
+    return float(loss.detach())
+
+
 @torch.no_grad()
 def spiking_fullsubnet_network(mag, params, cfg):
     """mag torch [B,F,T] -> (coef list, fb_all, sb_all); MSF:434-447 on torch CPU."""
+    return _network(mag, params, cfg, None)
+
+
+def _network(mag, params, cfg, train_state):
     shared = cfg.get("shared_weights", False)
     S = cfg.get("num_spks", 1)
     cm = (mag ** cfg["fdrc"])[:, :-1, :]
     act = cfg.get("fb_output_activate_function")
     fb_out, fb_all = _sequence_model(cm[:, : cfg["fb_input_size"], :], params, "fb_model.",
-                                     cfg["fb_num_layers"], shared, act if isinstance(act, str) else None)
+                                     cfg["fb_num_layers"], shared, act if isinstance(act, str) else None, train_state)
     rep = (cfg["n_fft"] // 2 + 1) // cfg["fb_input_size"]
     fb_tiled = fb_out.repeat(1, rep, 1)
     B, Fq, T = cm.shape
@@ -92,7 +122,7 @@ def spiking_fullsubnet_network(mag, params, cfg):
         x = torch.cat([cm[:, qi, :], fb_tiled[:, qf, :]], dim=2)
         N = qi.shape[0]
         out, trace = _sequence_model(x.reshape(B * N, x.shape[2], T), params, f"sb_model.sb_models.{i}.",
-                                     cfg["sb_num_layers"], shared, None)
+                                     cfg["sb_num_layers"], shared, None, train_state)
         o = out.reshape(B, N, 2, ctr, df, S, T).permute(0, 4, 5, 1, 3, 6, 2).reshape(B, df, S, N * ctr, T, 2)
         coefs.append(o)
         sb_all.append(trace)
