@@ -36,7 +36,9 @@ extern "C" {
 /* recurrence back ends */
 #define GSN_BACKEND_AUTO 0
 #define GSN_BACKEND_SIMT 1     /* fp32 CUDA-core kernel: any H <= 512, the on-device fp32 arbiter */
-#define GSN_BACKEND_TCGEN05 2  /* tcgen05/TMEM kernel, recurrent weights split in exact bf16 planes */
+#define GSN_BACKEND_TCGEN05 2  /* tcgen05/TMEM kernel, recurrent weights split in exact bf16 planes (H <= 320) */
+#define GSN_BACKEND_TCGEN05_I8 3  /* tcgen05 kind::i8: weights as 32-bit (H <= 448) / 24-bit row-scaled fixed point
+                                     in byte planes, exact int32 accumulation (H <= 512) */
 
 typedef void* gsn_stream_t;
 
@@ -106,7 +108,7 @@ GSN_API int gsn_layer_recurrence(const float* xproj, const float* w_hh, const fl
                          const float* c0, float* h_out, float* c_out, float* hT, float* cT, int T,
                          int R, int H, int shared, int backend, int sm_budget, void* workspace,
                          gsn_stream_t stream);
-/* which backend GSN_BACKEND_AUTO resolves to for this shape (GSN_BACKEND_SIMT / _TCGEN05). */
+/* which backend GSN_BACKEND_AUTO resolves to for this shape (GSN_BACKEND_SIMT / _TCGEN05 / _TCGEN05_I8). */
 GSN_API int gsn_layer_recurrence_pick_backend(int R, int H, int shared);
 
 /* ---- training path of the recurrence (fp32 CUDA cores, cooperative launch) -------------------------------

@@ -13,8 +13,8 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libgsn_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "gsn_b200.h")
 
 GSN_OK, GSN_EINVAL, GSN_ECUDA, GSN_ENOSUP = 0, 1, 2, 3
-BACKEND_AUTO, BACKEND_SIMT, BACKEND_TCGEN05 = 0, 1, 2
-BACKENDS = {"auto": BACKEND_AUTO, "simt": BACKEND_SIMT, "tcgen05": BACKEND_TCGEN05}
+BACKEND_AUTO, BACKEND_SIMT, BACKEND_TCGEN05, BACKEND_TCGEN05_I8 = 0, 1, 2, 3
+BACKENDS = {"auto": BACKEND_AUTO, "simt": BACKEND_SIMT, "tcgen05": BACKEND_TCGEN05, "tcgen05_i8": BACKEND_TCGEN05_I8}
 
 _p, _i, _f, _i64, _sz = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_size_t
 

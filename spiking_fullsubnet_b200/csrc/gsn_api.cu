@@ -32,6 +32,11 @@ int launch_recurrence_tc(const float*, const float*, const float*, const float*,
                          void*, cudaStream_t);
 size_t recurrence_tc_workspace(int R, int H, int shared);
 bool recurrence_tc_supported(int R, int H, int shared);
+// gsn_recurrence_tc_i8.cu
+int launch_recurrence_i8(const float*, const float*, const float*, const float*, const float*,
+                         const float*, const float*, float*, float*, float*, float*, int, int, int, int, int,
+                         void*, cudaStream_t);
+bool recurrence_i8_supported(int R, int H, int shared);
 
 }  // namespace gsn
 
@@ -67,7 +72,9 @@ extern "C" int gsn_device_info(int* sm_count, int* cc_major, int* cc_minor, int*
 }
 
 extern "C" int gsn_layer_recurrence_pick_backend(int R, int H, int shared) {
-  return gsn::recurrence_tc_supported(R, H, shared) ? GSN_BACKEND_TCGEN05 : GSN_BACKEND_SIMT;
+  if (gsn::recurrence_tc_supported(R, H, shared)) return GSN_BACKEND_TCGEN05;
+  if (gsn::recurrence_i8_supported(R, H, shared)) return GSN_BACKEND_TCGEN05_I8;
+  return GSN_BACKEND_SIMT;
 }
 
 extern "C" size_t gsn_layer_recurrence_workspace_bytes(int R, int H, int shared, int backend) {
@@ -75,7 +82,7 @@ extern "C" size_t gsn_layer_recurrence_workspace_bytes(int R, int H, int shared,
   size_t a = gsn::recurrence_simt_workspace(H, shared);
   size_t b = gsn::recurrence_tc_supported(R, H, shared) ? gsn::recurrence_tc_workspace(R, H, shared) : 0;
   if (backend == GSN_BACKEND_SIMT) return a;
-  if (backend == GSN_BACKEND_TCGEN05) return b;
+  if (backend == GSN_BACKEND_TCGEN05 || backend == GSN_BACKEND_TCGEN05_I8) return 256;
   return a > b ? a : b;
 }
 
@@ -100,6 +107,13 @@ extern "C" int gsn_layer_recurrence(const float* xproj, const float* w_hh, const
                        R, H, shared);
     return gsn::launch_recurrence_tc(xproj, w_hh, bias, bn_scale, bn_shift, h0, c0, h_out, c_out, hT,
                                      cT, T, R, H, shared, sm_budget, workspace, st);
+  }
+  if (backend == GSN_BACKEND_TCGEN05_I8) {
+    if (!gsn::recurrence_i8_supported(R, H, shared))
+      return gsn::fail(GSN_ENOSUP, "gsn_layer_recurrence(TCGEN05_I8): shape R=%d H=%d shared=%d not supported",
+                       R, H, shared);
+    return gsn::launch_recurrence_i8(xproj, w_hh, bias, bn_scale, bn_shift, h0, c0, h_out, c_out, hT, cT, T, R, H,
+                                     shared, sm_budget, workspace, st);
   }
   return gsn::fail(GSN_EINVAL, "gsn_layer_recurrence: unknown backend %d", backend);
 }

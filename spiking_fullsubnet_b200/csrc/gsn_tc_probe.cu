@@ -139,7 +139,89 @@ __global__ void __launch_bounds__(128) k_tc_mma_timing(long long* out, int N, in
   if (warp == 0) tc::tmem_dealloc<512>(tmem);
 }
 
+// int8 probe: d[128,N] (int32) = a[128,K] (int8, resident in TMEM: 4 consecutive k per 32-bit column) x
+// b[N,K] (uint8, K-major no-swizzle shared memory: 8 rows x 16 bytes core matrices), K = 32 per instruction.
+__global__ void __launch_bounds__(128)
+    k_tc_probe_i8(const int* __restrict__ a, const int* __restrict__ b, int* __restrict__ d, long long* timing,
+                  int N, int K, int a_signed, int reps) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t lbo = 128, sbo = 8u * K;
+  uint8_t* sB = smem;
+  for (int i = tid; i < N * K; i += 128) {
+    const int r = i / K, k = i % K;
+    sB[(r / 8) * sbo + (k / 16) * lbo + (r % 8) * 16 + (k % 16)] = (uint8_t)b[i];
+  }
+  if (tid == 0) {
+    tc::mbar_init(&bar, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc<512>(&tmem_base_slot);
+  tc::tc_fence_before();
+  tc::fence_proxy_async_smem();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+  const uint32_t tmem_d = tmem, tmem_a = tmem + 256;
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  for (int c0 = 0; c0 < K / 4; c0 += 8) {
+    uint32_t v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[j] = 0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[j] |= ((uint32_t)(a[tid * K + 4 * (c0 + j) + e] & 0xFF)) << (8 * e);
+    }
+    tc::tmem_st8(tmem_a + lane_base + c0, v);
+  }
+  tc::tmem_wait_st();
+  tc::tc_fence_before();
+  __syncthreads();
+  long long t0 = 0, t1 = 0;
+  if (warp == 0) {
+    tc::tc_fence_after();
+    if (tc::elect_one()) {
+      const uint32_t idesc = tc::make_idesc_i8(128, N, a_signed != 0, false);
+      const uint64_t db0 = tc::make_smem_desc(tc::smem_u32(sB), lbo, sbo);
+      t0 = clock64();
+      for (int r = 0; r < reps; ++r)
+        for (int ks = 0; ks < K / 32; ++ks)
+          tc::mma_i8_ts(tmem_d, tmem_a + ks * 8, db0 + (uint64_t)(ks * 16), idesc, (r | ks) > 0);
+      tc::mma_commit(&bar);
+      t1 = clock64();
+    }
+    __syncwarp();
+  }
+  const bool ok = tc::mbar_wait(&bar, 0);
+  const long long t2 = clock64();
+  tc::tc_fence_after();
+  if (ok) {
+    for (int c0 = 0; c0 < N; c0 += 16) {
+      uint32_t v[16];
+      tc::tmem_ld16(tmem_d + lane_base + c0, v);
+      tc::tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) d[tid * N + c0 + j] = (int)v[j];
+    }
+  }
+  if (tid == 0) { timing[0] = ok ? t1 - t0 : -1; timing[1] = t2 - t0; }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<512>(tmem);
+}
+
 }  // namespace gsn
+
+extern "C" GSN_API int gsn_tc_probe_i8(const int* a, const int* b, int* d, long long* timing, int N, int K,
+                                       int a_signed, int reps, gsn_stream_t stream) {
+  const size_t smem = (size_t)N * K;
+  GSN_CUDA(cudaFuncSetAttribute(gsn::k_tc_probe_i8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gsn::k_tc_probe_i8<<<1, 128, smem, gsn::as_stream(stream)>>>(a, b, d, timing, N, K, a_signed, reps);
+  GSN_LAUNCH_CHECK("k_tc_probe_i8");
+  return GSN_OK;
+}
 
 extern "C" GSN_API int gsn_tc_mma_timing(long long* out, int N, int K, int reps, int a_in_tmem, gsn_stream_t stream) {
   const size_t smem = (size_t)(128 + N) * K * 2;

@@ -140,7 +140,7 @@ def layer_recurrence(xproj, w_hh, bias, bn_scale=None, bn_shift=None, shared=Tru
 
 
 def pick_backend(R, H, shared):
-    return {1: "simt", 2: "tcgen05"}[_lib.load().gsn_layer_recurrence_pick_backend(R, H, int(shared))]
+    return {1: "simt", 2: "tcgen05", 3: "tcgen05_i8"}[_lib.load().gsn_layer_recurrence_pick_backend(R, H, int(shared))]
 
 
 def deepfilter_band(proj, spec_re, spec_im, out_re, out_im, N, ctr, df, S, lo):

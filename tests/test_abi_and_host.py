@@ -96,4 +96,4 @@ def test_shipped_shapes_run_on_tcgen05():
             for _, rows, _, H, _ in O.model_rows_and_shapes(cfg, B):
                 assert ops.pick_backend(rows, H, cfg["shared_weights"]) == "tcgen05", (name, B, rows, H)
     assert ops.pick_backend(32, 268, True) == "tcgen05"  # cirm_gsn default
-    assert ops.pick_backend(480, 512, True) == "simt"    # H > 320 does not fit tensor memory with 3 planes
+    assert ops.pick_backend(480, 512, True) == "tcgen05_i8"  # H > 320: bf16x3 planes do not fit TMEM, int8 do

@@ -15,7 +15,7 @@ from tests.helpers import SURFACE_A, golden_params, load_golden, spike_flip_stat
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-BACKENDS = ["simt", "auto"]
+BACKENDS = ["simt", "auto", "tcgen05_i8"]
 
 
 def _rel(a, b):

@@ -16,6 +16,9 @@ NAMES = ["sync_top", "mma_issue", "xp_issue+mma_wait", "ld+math+ballot", "dsmem_
          "total"]
 
 
+BACKEND = os.environ.get("GSN_PROFILE_BACKEND", "tcgen05")
+
+
 def run(R, H, T):
     dev = "cuda"
     rs = np.random.RandomState(0)
@@ -24,11 +27,11 @@ def run(R, H, T):
     w = torch.from_numpy(rs.uniform(-s, s, (H, H)).astype(np.float32)).to(dev)
     b = torch.from_numpy(rs.uniform(-s, s, 2 * H).astype(np.float32)).to(dev)
     for _ in range(2):
-        ops.layer_recurrence(xproj, w, b, backend="tcgen05")
+        ops.layer_recurrence(xproj, w, b, backend=BACKEND)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    ops.layer_recurrence(xproj, w, b, backend="tcgen05")
+    ops.layer_recurrence(xproj, w, b, backend=BACKEND)
     e1.record()
     torch.cuda.synchronize()
     ws, off = ops.LAST_WS[0]
