@@ -394,3 +394,18 @@ def algorithmic_flops_per_frame(cfg):
         L = cfg["fb_num_layers"] if name == "fb" else cfg["sb_num_layers"]
         total += rows * (g * 2 * H * K + (L - 1) * g * 2 * H * H + L * g * 2 * H * H + 2 * H * P)
     return total
+
+
+# --------------------------------------------------------------------------------------------
+# f4: SynOps / NeuronOps accounting (audiozen/metric.py:303-340)
+# --------------------------------------------------------------------------------------------
+def compute_synops(fb_all, sb_all, shared_weights=True):
+    s = 0.0
+    for trace in [fb_all] + list(sb_all):
+        for i in range(1, len(trace) - 1):
+            s += float((trace[i] > 0).mean()) * trace[i].shape[-1] * (trace[i + 1].shape[-1] + trace[i].shape[-1])
+    return s if shared_weights else 2 * s
+
+
+def compute_neuronops(fb_all, sb_all):
+    return float(sum(t.shape[-1] for t in fb_all) + sum(t.shape[-1] for tr in sb_all for t in tr))

@@ -97,3 +97,18 @@ def test_shipped_shapes_run_on_tcgen05():
                 assert ops.pick_backend(rows, H, cfg["shared_weights"]) == "tcgen05", (name, B, rows, H)
     assert ops.pick_backend(32, 268, True) == "tcgen05"  # cirm_gsn default
     assert ops.pick_backend(480, 512, True) == "tcgen05_i8"  # H > 320: bf16x3 planes do not fit TMEM, int8 do
+
+
+def test_synops_accounting_matches_reference_formula():
+    """metrics.compute_synops / compute_neuronops (audiozen/metric.py:303-340) on the golden traces."""
+    from oracle import gsn_oracle as O
+    from spiking_fullsubnet_b200 import metrics
+    from tests.helpers import golden_params
+    g = load_golden("tiny_shared_bn")
+    _, fb_all, sb_all = O.spiking_fullsubnet_network(g["mag"], golden_params(g), g["cfg"])
+    want_s, want_n = O.compute_synops(fb_all, sb_all), O.compute_neuronops(fb_all, sb_all)
+    tf = [torch.from_numpy(t) for t in fb_all]
+    ts = [[torch.from_numpy(t) for t in tr] for tr in sb_all]
+    assert abs(metrics.compute_synops(tf, ts) - want_s) <= 1e-4 * want_s
+    assert metrics.compute_neuronops(tf, ts) == want_n
+    assert abs(metrics.compute_synops(tf, ts, shared_weights=False) - 2 * want_s) <= 2e-4 * want_s
