@@ -413,6 +413,37 @@ def _istft(spec, n_fft, hop, win, length):
     return torch.istft(spec, n_fft, hop, win, window=window, length=length)
 
 
+_ISTFT_ENV = {}
+
+
+def _istft_nosync(spec, n_fft, hop, win, length):
+    """torch.istft(center=True, hann window, normalized=False) without its host-synchronising window-envelope
+    check, so it can be enqueued asynchronously / captured in a CUDA graph: inverse real FFT of every frame,
+    synthesis window, overlap-add (F.fold), division by the overlap-added squared window (cached per shape),
+    removal of the n_fft//2 centre padding.  spec complex [B,F,T] -> [B,length]."""
+    assert win == n_fft, "win_length != n_fft is not used by any recipe"
+    B, F, T = spec.shape
+    window = torch.hann_window(n_fft, device=spec.device)
+    frames = torch.fft.irfft(spec.transpose(1, 2), n=n_fft, dim=-1) * window          # [B,T,n_fft]
+    full = n_fft + hop * (T - 1)
+    y = torch.nn.functional.fold(frames.transpose(1, 2), output_size=(1, full), kernel_size=(1, n_fft),
+                                 stride=(1, hop)).reshape(B, full)
+    key = (n_fft, hop, T, length, spec.device.index)
+    capturing = spec.is_cuda and torch.cuda.is_current_stream_capturing()
+    env = _ISTFT_ENV.get(key)
+    if env is None or capturing:
+        wsq = (window * window).reshape(1, n_fft, 1).expand(1, n_fft, T)
+        env = torch.nn.functional.fold(wsq, output_size=(1, full), kernel_size=(1, n_fft),
+                                       stride=(1, hop)).reshape(1, full)
+        if not capturing:
+            _ISTFT_ENV[key] = env
+    start = n_fft // 2
+    out = y[:, start:start + length] / env[:, start:start + length]
+    if out.shape[1] < length:
+        out = torch.nn.functional.pad(out, (0, length - out.shape[1]))
+    return out
+
+
 class SpikingFullSubNet(nn.Module):
     """Surface A (MSF:349-474).  forward(wave [B,L]) ->
     (enh_y [B,L], enh_mag [B,F,T], fb_all_layer_outputs, sb_all_layer_outputs), or for num_spks > 1
@@ -465,9 +496,11 @@ class SpikingFullSubNet(nn.Module):
         """mag [B, n_fft//2+1, T] -> (projs: list of [T, B*N_i, P_i], fb_all, sb_all)."""
         if not mag.is_cuda:
             raise RuntimeError("spiking_fullsubnet_b200 has no CPU path: move the model and input to CUDA")
-        if not self.use_cuda_graph or torch.cuda.is_current_stream_capturing():
+        if torch.cuda.is_current_stream_capturing():
+            return self._network_sched(mag) if self.use_cuda_graph else self._network(mag)
+        if not self.use_cuda_graph:
             return self._network(mag)
-        key = (tuple(mag.shape), mag.device.index, self.training)
+        key = ("network", tuple(mag.shape), mag.device.index)
         entry = self._graphs.get(key)
         if entry is None:
             static_in = torch.empty_like(mag, memory_format=torch.contiguous_format)
@@ -477,9 +510,7 @@ class SpikingFullSubNet(nn.Module):
                 torch.cuda.synchronize(mag.device)
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
-                    static_out = (self._network_wavefront(static_in, self.frame_chunks)
-                                  if self.frame_chunks > 1 and self._fits_wavefront(static_in.shape[0])
-                                  else self._network(static_in))
+                    static_out = self._network_sched(static_in)
             entry = self._graphs[key] = (graph, static_in, static_out)
         graph, static_in, static_out = entry
         static_in.copy_(mag)
@@ -502,6 +533,12 @@ class SpikingFullSubNet(nn.Module):
             raise ValueError(f"full-band output ({fb_act.shape[2]} bins x {rep}) does not cover {F - 1} bins")
         projs, sb_all = self.sb_model.run_time_major(cm, fb_act)
         return projs, fb_all, sb_all
+
+    def _network_sched(self, mag):
+        """The schedule a captured graph replays: frame-chunked wavefront when it applies, else band streams."""
+        if self.frame_chunks > 1 and self._fits_wavefront(mag.shape[0]):
+            return self._network_wavefront(mag, self.frame_chunks)
+        return self._network(mag)
 
     def _fits_wavefront(self, B):
         """The wavefront schedule keeps every (model, layer) recurrence resident at once; it only pays off
@@ -632,6 +669,39 @@ class SpikingFullSubNet(nn.Module):
         if _needs_autograd(self):
             from . import training
             return training.spiking_fullsubnet_forward(self, input)
+        if not self.use_cuda_graph or torch.cuda.is_current_stream_capturing():
+            return self._forward_infer(input)
+        # the whole forward() (STFT -> network -> deep filter -> iSTFT) replayed from one CUDA graph per shape
+        key = ("forward", tuple(input.shape), input.device.index)
+        entry = self._graphs.get(key)
+        if entry is None:
+            static_in = input.clone()
+            with torch.no_grad():
+                self._forward_infer(static_in)  # warm-up outside the capture (cuFFT plans, lazy CUDA init)
+                torch.cuda.synchronize(input.device)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    static_out = self._forward_infer(static_in)
+            entry = self._graphs[key] = (graph, static_in, static_out)
+        graph, static_in, static_out = entry
+        static_in.copy_(input)
+        graph.replay()
+        return static_out
+
+    def _forward_infer(self, input):
+        enh, fb_all, sb_all = self._forward_spec(input)
+        return self._finish(enh, fb_all, sb_all, input.shape[1])
+
+    def _finish(self, enh, fb_all, sb_all, L):
+        """enh complex [B,S,F,T] -> the reference's return tuple (iSTFT, MSF:463-474)."""
+        B, S, F, T = enh.shape
+        if S > 1:
+            y = _istft_nosync(enh.reshape(B * S, F, T), self.n_fft, self.hop_length, self.win_length, L)
+            return y.reshape(B, S, L), fb_all, sb_all
+        enh = enh[:, 0]
+        return _istft_nosync(enh, self.n_fft, self.hop_length, self.win_length, L), enh.abs(), fb_all, sb_all
+
+    def _forward_spec(self, input):
         B, L = input.shape
         cmp = _stft(input, self.n_fft, self.hop_length, self.win_length)  # [B,F,T] complex
         mag = cmp.abs().contiguous()
@@ -648,12 +718,7 @@ class SpikingFullSubNet(nn.Module):
             n = (cuts[i + 1] - cuts[i]) // ctrs[i]
             ops.deepfilter_band(p, sre, sim, ore, oim, n, ctrs[i], self.df_orders[i], S, lo)
             lo += n * ctrs[i]
-        enh = torch.complex(ore, oim)
-        if S > 1:
-            y = _istft(enh.reshape(B * S, F, T), self.n_fft, self.hop_length, self.win_length, L)
-            return y.reshape(B, S, L), fb_all, sb_all
-        enh = enh[:, 0]
-        return _istft(enh, self.n_fft, self.hop_length, self.win_length, L), enh.abs(), fb_all, sb_all
+        return torch.complex(ore, oim), fb_all, sb_all
 
 
 class CirmGSN(nn.Module):

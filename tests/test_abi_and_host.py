@@ -112,3 +112,14 @@ def test_synops_accounting_matches_reference_formula():
     assert abs(metrics.compute_synops(tf, ts) - want_s) <= 1e-4 * want_s
     assert metrics.compute_neuronops(tf, ts) == want_n
     assert abs(metrics.compute_synops(tf, ts, shared_weights=False) - 2 * want_s) <= 2e-4 * want_s
+
+
+def test_sync_free_istft_matches_torch_istft():
+    """The inference path's iSTFT (no host-synchronising envelope check, graph-capturable) against torch.istft."""
+    from spiking_fullsubnet_b200.modeling import _istft, _istft_nosync, _stft
+    torch.manual_seed(0)
+    for n, h, L in [(512, 128, 16000), (64, 16, 624), (256, 64, 8000), (512, 128, 16123)]:
+        x = torch.randn(2, L)
+        spec = _stft(x, n, h, n) * (1 + 0.1 * torch.randn(2, n // 2 + 1, 1 + L // h))
+        a, b = _istft(spec, n, h, n, L), _istft_nosync(spec, n, h, n, L)
+        assert a.shape == b.shape and float((a - b).abs().max() / a.abs().max()) < 2e-6

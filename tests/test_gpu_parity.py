@@ -353,3 +353,17 @@ def test_layer_backward_vs_oracle_eval_bn():
                               (cell.weight_hh.grad, ref["dw_hh"], "dw_hh"), (cell.bias_ih.grad, ref["dbias"], "dbias")]:
             err = np.abs(got.cpu().numpy() - want).max() / (np.abs(want).max() + 1e-12)
             assert err < 1e-4, (shared, nm, err)
+
+
+def test_cuda_graph_full_forward_matches_eager():
+    """forward() with STFT -> wavefront network -> deep filter replayed from a CUDA graph equals the eager call."""
+    g = load_golden("tiny_shared_bn")
+    m = _model(g["cfg"], golden_params(g))
+    waves = [_t(g["wave"]), _t(g["wave"][:, ::-1].copy())]
+    with torch.no_grad():
+        eager = [[t.clone() for t in m(w)[:2]] for w in waves]
+        m.enable_cuda_graph(True, frame_chunks=4)
+        for w, ref in zip(waves + waves, eager + eager):
+            out = m(w)
+            assert torch.equal(out[0], ref[0]) and torch.equal(out[1], ref[1])
+    assert _rel(eager[0][0].cpu().numpy(), g["enh_y"]) < 1e-3
