@@ -92,9 +92,9 @@ class GSULayer(nn.Module):
         return h, MemoryState(hT, cT)
 
 
-def _cluster_ctas(rows, H, shared):
-    """CTAs per 16-row tile x tiles: the SM demand of one recurrence at the finest row tiling."""
-    return ((rows + 15) // 16) * ((H + 127) // 128 if shared else (H + 63) // 64)
+def _cluster_ctas(rows, H, shared, nt=16):
+    """CTAs of one recurrence at row tiling `nt` (16 = finest, 64 = coarsest): its SM demand."""
+    return ((rows + nt - 1) // nt) * ((H + 127) // 128 if shared else (H + 63) // 64)
 
 
 def _sm_budgets(demands, total=148, floor=4):
@@ -444,7 +444,52 @@ def _istft_nosync(spec, n_fft, hop, win, length):
     return out
 
 
-class SpikingFullSubNet(nn.Module):
+class _GraphedNetwork:
+    """CUDA-graph replay of `network()` for the drop-in models: `_network(mag)` is the eager launch sequence,
+    `_network_sched(mag)` what gets captured (subclasses may substitute a different schedule)."""
+
+    use_cuda_graph = False
+    frame_chunks = 1
+
+    def enable_cuda_graph(self, flag=True, frame_chunks=8):
+        """Replay the hot path from a CUDA graph captured per input shape (the returned tensors are the graph's
+        static output buffers, OVERWRITTEN by the next call with the same shape).  `frame_chunks` > 1 selects the
+        frame-chunked wavefront schedule where the model supports it (SpikingFullSubNet)."""
+        self.use_cuda_graph = bool(flag)
+        self.frame_chunks = max(1, int(frame_chunks))
+        self._graphs = {}
+        return self
+
+    def _network_sched(self, mag):
+        return self._network(mag)
+
+    def network(self, mag):
+        if not mag.is_cuda:
+            raise RuntimeError("spiking_fullsubnet_b200 has no CPU path: move the model and input to CUDA")
+        if torch.cuda.is_current_stream_capturing():
+            return self._network_sched(mag) if self.use_cuda_graph else self._network(mag)
+        if not self.use_cuda_graph:
+            return self._network(mag)
+        graphs = self.__dict__.setdefault("_graphs", {})
+        key = ("network", tuple(mag.shape), mag.device.index)
+        entry = graphs.get(key)
+        if entry is None:
+            static_in = torch.empty_like(mag, memory_format=torch.contiguous_format)
+            static_in.copy_(mag)
+            with torch.no_grad():
+                self._network(static_in)  # warm-up outside the capture (lazy CUDA initialisation)
+                torch.cuda.synchronize(mag.device)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    static_out = self._network_sched(static_in)
+            entry = graphs[key] = (graph, static_in, static_out)
+        graph, static_in, static_out = entry
+        static_in.copy_(mag)
+        graph.replay()
+        return static_out
+
+
+class SpikingFullSubNet(_GraphedNetwork, nn.Module):
     """Surface A (MSF:349-474).  forward(wave [B,L]) ->
     (enh_y [B,L], enh_mag [B,F,T], fb_all_layer_outputs, sb_all_layer_outputs), or for num_spks > 1
     (enh_y [B,S,L], fb_all_layer_outputs, sb_all_layer_outputs)."""
@@ -471,19 +516,6 @@ class SpikingFullSubNet(nn.Module):
         self.frame_chunks = 1
         self._graphs = {}
 
-    def enable_cuda_graph(self, flag=True, frame_chunks=8):
-        """Replay the hot path (`network`) from a CUDA graph captured per input shape.  With
-        `frame_chunks` > 1 the captured schedule is a frame-chunked WAVEFRONT: every (sequence model, layer)
-        gets its own stream and processes the T frames in `frame_chunks` pieces, carrying (h, c) between
-        pieces, so layer 2 / the sub-band models start on chunk k as soon as layer 1 / the full-band model
-        finish it (the recurrences are causal).  Results are bit-identical to the unchunked schedule.
-        The returned tensors are the graph's static output buffers and are OVERWRITTEN by the next call
-        with the same input shape (clone them to keep them)."""
-        self.use_cuda_graph = bool(flag)
-        self.frame_chunks = max(1, int(frame_chunks))
-        self._graphs = {}
-        return self
-
     def set_backend(self, backend):
         """'auto' | 'simt' | 'tcgen05' for every recurrence of the model."""
         for m in self.modules():
@@ -491,32 +523,8 @@ class SpikingFullSubNet(nn.Module):
                 m.backend = backend
         return self
 
-    # the hot path: magnitude in -> sub-band proj outputs (the coefficients) out  (MSF:434-447)
-    def network(self, mag):
-        """mag [B, n_fft//2+1, T] -> (projs: list of [T, B*N_i, P_i], fb_all, sb_all)."""
-        if not mag.is_cuda:
-            raise RuntimeError("spiking_fullsubnet_b200 has no CPU path: move the model and input to CUDA")
-        if torch.cuda.is_current_stream_capturing():
-            return self._network_sched(mag) if self.use_cuda_graph else self._network(mag)
-        if not self.use_cuda_graph:
-            return self._network(mag)
-        key = ("network", tuple(mag.shape), mag.device.index)
-        entry = self._graphs.get(key)
-        if entry is None:
-            static_in = torch.empty_like(mag, memory_format=torch.contiguous_format)
-            static_in.copy_(mag)
-            with torch.no_grad():
-                self._network(static_in)  # warm-up outside the capture (lazy CUDA initialisation)
-                torch.cuda.synchronize(mag.device)
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
-                    static_out = self._network_sched(static_in)
-            entry = self._graphs[key] = (graph, static_in, static_out)
-        graph, static_in, static_out = entry
-        static_in.copy_(mag)
-        graph.replay()
-        return static_out
-
+    # the hot path: magnitude in -> sub-band proj outputs (the coefficients) out  (MSF:434-447).
+    # network(mag [B, n_fft//2+1, T]) -> (projs: list of [T, B*N_i, P_i], fb_all, sb_all); see _GraphedNetwork.
     def _network(self, mag):
         F = mag.shape[1]
         cm = ops.compress_mag(mag.contiguous(), F - 1, self.fdrc)  # drops the last bin, MSF:436
@@ -542,7 +550,8 @@ class SpikingFullSubNet(nn.Module):
 
     def _fits_wavefront(self, B):
         """The wavefront schedule keeps every (model, layer) recurrence resident at once; it only pays off
-        when all of them fit on the 148 SMs at the finest row tiling."""
+        when all of them fit on the 148 SMs at the finest row tiling (measured: with coarser tiles, L and XL at
+        batch 32 are slower in the wavefront than with band streams)."""
         sb = self.sb_model
         total = 0
         for m, rows in [(self.fb_model, B)] + [
@@ -721,7 +730,7 @@ class SpikingFullSubNet(nn.Module):
         return torch.complex(ore, oim), fb_all, sb_all
 
 
-class CirmGSN(nn.Module):
+class CirmGSN(_GraphedNetwork, nn.Module):
     """cirm_gsn `Model` (CGN:162-244): one full-band GSN over all bins emitting deep-filter coefficients."""
 
     def __init__(self, n_fft, hop_length, win_length, fdrc, input_size, hidden_size, num_layers, proj_size,
@@ -736,7 +745,7 @@ class CirmGSN(nn.Module):
         self.fb_input_size, self.n_fft, self.hop_length, self.win_length = input_size, n_fft, hop_length, win_length
         self.fdrc, self.df_order, self.num_spks = fdrc, df_order, num_spks
 
-    def network(self, mag):
+    def _network(self, mag):
         """mag [B,F,T] -> (activated proj [T,B,P], all_layer_outputs)."""
         fbm = self.fb_model
         cm = ops.compress_mag(mag.contiguous(), mag.shape[1], self.fdrc)
@@ -757,6 +766,11 @@ class CirmGSN(nn.Module):
 
     def forward(self, input):
         assert input.ndim == 2, f"Input tensor must be 2D, but got {input.ndim}D."
+        if not input.is_cuda:
+            raise RuntimeError("spiking_fullsubnet_b200 has no CPU path: move the model and input to CUDA")
+        if _needs_autograd(self):
+            from . import training
+            return training.cirm_gsn_forward(self, input)
         B, L = input.shape
         cmp = _stft(input, self.n_fft, self.hop_length, self.win_length)
         coef, all_out = self.coefficients(cmp.abs().contiguous())  # [B,d,S,F,T,2]
@@ -890,7 +904,7 @@ class _FreezeSubbandModel(nn.Module):
         return projs, traces
 
 
-class Separator(nn.Module):
+class Separator(_GraphedNetwork, nn.Module):
     """Surface B `model_low_freq.Separator` (:485-618): same network as SpikingFullSubNet with utterance-level
     laplace normalisation instead of LayerNorm; the class the model-zoo checkpoints were trained with.
     forward(wave [B,L] or [B,1,L]) -> (enhanced_y, enhanced_mag, fb_all_layer_outputs, sb_all_layer_outputs)."""
@@ -923,11 +937,9 @@ class Separator(nn.Module):
                 m.backend = backend
         return self
 
-    def network(self, mag):
+    def _network(self, mag):
         """mag [B, n_fft//2+1, T] -> (sub-band fc outputs: list of [T, B*N_i, P_i], fb_all, sb_all)
         (model_low_freq.py:574-586)."""
-        if not mag.is_cuda:
-            raise RuntimeError("spiking_fullsubnet_b200 has no CPU path: move the model and input to CUDA")
         B, F, T = mag.shape
         cm = ops.compress_mag(mag.contiguous(), F - 1, self.fdrc)
         x = ops.subband_features(cm, None, 1, 0, self.fb_freqs, 0)
@@ -951,6 +963,11 @@ class Separator(nn.Module):
         if ndim == 3:
             assert noisy_y.size(1) == 1, "Input must be 2D (B, T) or 3D tensor (B, 1, T)"
             noisy_y = noisy_y.squeeze(1)
+        if not noisy_y.is_cuda:
+            raise RuntimeError("spiking_fullsubnet_b200 has no CPU path: move the model and input to CUDA")
+        if _needs_autograd(self):
+            from . import training
+            return training.separator_forward(self, noisy_y)
         B, L = noisy_y.shape
         cmp = _stft(noisy_y, self.n_fft, self.hop_length, self.win_length)
         projs, fb_all, sb_all = self.network(cmp.abs().contiguous())

@@ -87,8 +87,14 @@ def run_stack(stack, x):
 
 
 def run_sequence_model(m, x):
-    """x [T,R,K] already normalised -> (activated output [T,R,P], all_layer_outputs) (MSF:115-122)."""
+    """x [T,R,K] already normalised -> (activated output [T,R,P], all_layer_outputs) (MSF:115-122; surface B:
+    model_low_freq.py:98-139 with `fc_output_layer` / `activate_function`)."""
     out, trace = run_stack(m.sequence_model, x)
+    if hasattr(m, "fc_output_layer") or hasattr(m, "output_size"):  # surface B naming
+        if int(m.output_size):
+            out = m.fc_output_layer(out)
+            trace = trace + [out]
+        return (m.activate_function(out) if m.output_activate_function_name else out), trace
     out = m.proj(out)
     trace = trace + [out]
     return m.output_activate_function(out), trace
@@ -146,3 +152,69 @@ def spiking_fullsubnet_forward(model, wave):
         return y.reshape(B, S, L), fb_all, sb_all
     enh = enh[:, 0]
     return _istft(enh, model.n_fft, model.hop_length, model.win_length, L), enh.abs(), fb_all, sb_all
+
+
+def _utterance_norm(x, B, norm_type):
+    """Differentiable twin of modeling._utterance_norm (model_low_freq.py:146-217) on x [T, B*N, K]."""
+    from .modeling import EPSILON
+    T = x.shape[0]
+    v = x.reshape(T, B, -1)
+    mu = v.mean(dim=(0, 2), keepdim=True)
+    if norm_type == "offline_laplace_norm":
+        return (v / (mu + EPSILON)).reshape(x.shape)
+    std = v.permute(1, 0, 2).reshape(B, -1).std(dim=1).view(1, B, 1)
+    return ((v - mu) / (std + EPSILON)).reshape(x.shape)
+
+
+def separator_forward(model, wave):
+    """Surface B `Separator.forward` (model_low_freq.py:561-618) on the autograd path."""
+    from .modeling import _stft, coef_layout
+    B, L = wave.shape
+    cmp = _stft(wave, model.n_fft, model.hop_length, model.win_length)
+    mag = cmp.abs()
+    Fq = mag.shape[1] - 1
+    cm = (mag ** model.fdrc)[:, :-1, :].permute(2, 0, 1)  # [T,B,256]
+    T = cm.shape[0]
+    x = _utterance_norm(cm[..., : model.fb_freqs], B, model.norm_type)
+    fb_act, fb_all = run_sequence_model(model.fb_model, x.contiguous())
+    sbm = model.sb_model
+    coefs, sb_all = [], []
+    for i, (m, (lo, hi)) in enumerate(zip(sbm.sb_models, sbm.band_edges(Fq))):
+        ctr, nbr = sbm.sb_num_center_freqs[i], sbm.sb_num_neighbor_freqs[i]
+        qi = unfold_index(lo, hi, ctr, nbr, Fq, cm.device)
+        qf = unfold_index(lo, hi, ctr, 0, Fq, cm.device) % fb_act.shape[2]
+        N = qi.shape[0]
+        xb = torch.cat([cm[:, :, qi], fb_act[:, :, qf]], dim=-1).reshape(T, B * N, -1)
+        xb = _utterance_norm(xb, B, model.norm_type)
+        act, trace = run_sequence_model(m, xb.contiguous())
+        coefs.append(coef_layout(act, B, N, model.sb_df_orders[i], 1))
+        sb_all.append(trace)
+    enh, lo = [], 0
+    for coef, order in zip(coefs, model.sb_df_orders):
+        nf = coef.shape[3]
+        enh.append(deepfilter(cmp[:, lo:lo + nf], coef, order))
+        lo += nf
+    enh = torch.cat(enh + [cmp[:, None, lo:]], dim=2)[:, 0]
+    y = torch.istft(enh, model.n_fft, model.hop_length, model.win_length,
+                    window=torch.hann_window(model.win_length, device=wave.device), length=L)
+    return y, enh.abs(), fb_all, sb_all
+
+
+def cirm_gsn_forward(model, wave):
+    """cirm_gsn `Model.forward` (CGN:206-244) on the autograd path."""
+    from .modeling import _istft, _stft
+    B, L = wave.shape
+    cmp = _stft(wave, model.n_fft, model.hop_length, model.win_length)
+    cm = (cmp.abs() ** model.fdrc).permute(2, 0, 1)  # all bins (CGN:226)
+    fbm = model.fb_model
+    x = fbm.pre_layer_norm(cm) if fbm.use_pre_layer_norm else cm
+    act, all_out = run_sequence_model(fbm, x.contiguous())
+    T, _, P = act.shape
+    d, S = model.df_order, model.num_spks
+    coef = act.reshape(T, B, 2, d, S, P // (2 * d * S)).permute(1, 3, 4, 5, 0, 2)  # b d s f t c
+    enh = deepfilter(cmp, coef, d)  # [B,S,F,T]
+    if S > 1:
+        y = _istft(enh.reshape(B * S, *enh.shape[2:]), model.n_fft, model.hop_length, model.win_length, L)
+        return y.reshape(B, S, L), [all_out]
+    enh = enh[:, 0]
+    return _istft(enh, model.n_fft, model.hop_length, model.win_length, L), enh.abs()
