@@ -9,6 +9,8 @@
 // partial sums, cross a grid barrier (cooperative launch guarantees co-residency) and every CTA reduces the
 // partials in the same fixed order (deterministic, identical on all CTAs).
 // Layout as k_recurrence_simt: one CTA owns RT = 8 rows, thread j owns neuron j of those rows.
+#include <stdlib.h>
+
 #include "gsn_common.cuh"
 
 namespace gsn {
@@ -37,6 +39,98 @@ __device__ __forceinline__ bool grid_barrier(unsigned int* counter, unsigned int
   return ok;
 }
 
+// acc[r] += sum_k s[k][r] * W[k][col]  (and acc2 with column col2) for the RT rows of this CTA, thread = column.
+// W [Kdim][ld] fp32 in global memory is either RESIDENT in shared memory (`wsm` holds all of it) or streamed
+// through `wsm` in 16-row slabs with cp.async double buffering (coalesced 16-byte copies, L2 -> smem), instead
+// of one 4-byte read-only load per thread per k.
+constexpr int TR_KB = 16;
+constexpr int TR_NST = 4;
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void stage_rows(float* dst, const float* W, int k0, int nrows, int ld) {
+  const int chunks = nrows * (ld / 4);  // 16-byte chunks, rows are contiguous in both places
+  for (int i = threadIdx.x; i < chunks; i += blockDim.x) cp_async16(dst + 4 * i, W + (size_t)k0 * ld + 4 * i);
+}
+
+template <int RT, bool TWO>
+__device__ __forceinline__ void rows_times_w(const float* __restrict__ W, int Kdim, int ld, int col, int col2,
+                                             bool active, const float* s, float* wsm, bool resident,
+                                             float (&acc)[RT], float (&acc2)[RT]) {
+  auto fma_rows = [&](const float* wrow, int k) {
+    const float w1 = wrow[col];
+    const float w2 = TWO ? wrow[col2] : 0.f;
+    const float4 s0 = *reinterpret_cast<const float4*>(s + k * RT);
+    const float4 s1 = *reinterpret_cast<const float4*>(s + k * RT + 4);
+    const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+      acc[r] = fmaf(sv[r], w1, acc[r]);
+      if (TWO) acc2[r] = fmaf(sv[r], w2, acc2[r]);
+    }
+  };
+  if (resident) {
+    if (active) {
+#pragma unroll 8
+      for (int k = 0; k < Kdim; ++k) fma_rows(wsm + (size_t)k * ld, k);
+    }
+    return;
+  }
+  // TR_NST-deep ring of TR_KB-row slabs: TR_NST-1 slabs (L2 round trips) are in flight while one is multiplied
+  const int nslab = (Kdim + TR_KB - 1) / TR_KB;
+#pragma unroll
+  for (int st = 0; st < TR_NST - 1; ++st) {
+    if (st < nslab) stage_rows(wsm + (size_t)st * TR_KB * ld, W, st * TR_KB, min(TR_KB, Kdim - st * TR_KB), ld);
+    cp_async_commit();
+  }
+  for (int sidx = 0; sidx < nslab; ++sidx) {
+    const int k0 = sidx * TR_KB;
+    const int pre = sidx + TR_NST - 1;
+    if (pre < nslab)
+      stage_rows(wsm + (size_t)(pre % TR_NST) * TR_KB * ld, W, pre * TR_KB, min(TR_KB, Kdim - pre * TR_KB), ld);
+    cp_async_commit();
+    cp_async_wait<TR_NST - 1>();
+    __syncthreads();  // slab sidx has landed for every thread
+    if (active) {
+      const float* cur = wsm + (size_t)(sidx % TR_NST) * TR_KB * ld;
+      const int kn = min(TR_KB, Kdim - k0);
+#pragma unroll 8
+      for (int kk = 0; kk < kn; ++kk) fma_rows(cur + (size_t)kk * ld, k0 + kk);
+    }
+    __syncthreads();  // everybody is done with this buffer before it is refilled
+  }
+  cp_async_wait<0>();
+}
+
+// deterministic cross-CTA sum of the per-CTA partials of one frame: loads are issued 8 at a time, the adds keep
+// the fixed order b = 0, 1, 2, ...
+__device__ __forceinline__ void reduce_partials(const float* part, unsigned int nblocks, int H, int j, bool active,
+                                                float& a1, float& a2) {
+  a1 = 0.f;
+  a2 = 0.f;
+  if (!active) return;
+  for (unsigned int b0 = 0; b0 < nblocks; b0 += 8) {
+    float v1[8], v2[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const bool ok = b0 + u < nblocks;
+      v1[u] = ok ? __ldcg(part + ((size_t)(b0 + u) * 2 + 0) * H + j) : 0.f;
+      v2[u] = ok ? __ldcg(part + ((size_t)(b0 + u) * 2 + 1) * H + j) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      a1 += v1[u];
+      a2 += v2[u];
+    }
+  }
+}
+
 struct TrainFwdParams {
   const float* xproj;   // [T,R,gH]
   const float* wt;      // [H,gH]  transposed recurrent weights (workspace)
@@ -55,11 +149,13 @@ struct TrainFwdParams {
   unsigned int* counter;
   int T, R, H, training;
   float momentum, eps;
+  int resident;         // the transposed weights fit shared memory next to the spikes
+  long long* prof;      // [6] cycle counters of CTA 0 (development aid, GSN_TRAIN_PROF) or null
 };
 
 template <bool SHARED>
 __global__ void __launch_bounds__(512) k_rec_train_fwd(const TrainFwdParams p) {
-  extern __shared__ __align__(16) float sh[];  // [2][H][RT] spikes
+  extern __shared__ __align__(16) float sh[];  // [2][H][RT] spikes, then the weight slabs / resident weights
   constexpr int RT = TR_RT;
   const int H = p.H, R = p.R, T = p.T;
   const int gH = SHARED ? H : 2 * H;
@@ -68,6 +164,13 @@ __global__ void __launch_bounds__(512) k_rec_train_fwd(const TrainFwdParams p) {
   const bool active = j < H;
   const int jj = active ? j : 0;
   const unsigned int nblocks = gridDim.x;
+  float* wsm = sh + (size_t)2 * H * RT;
+  const bool resident = p.resident != 0;
+  if (resident) {  // the whole transposed weight matrix fits shared memory: load it once
+    stage_rows(wsm, p.wt, 0, H, gH);
+    cp_async_commit();
+    cp_async_wait<0>();
+  }
   const float bf = p.bias[jj], bc = p.bias[H + jj];
   const bool bn = p.bn_w != nullptr;
   const float gam = bn ? p.bn_w[jj] : 1.f, bet = bn ? p.bn_b[jj] : 0.f;
@@ -88,7 +191,9 @@ __global__ void __launch_bounds__(512) k_rec_train_fwd(const TrainFwdParams p) {
   float shift = 0.f;  // shift for the one-pass variance: the previous frame's mean
   __syncthreads();
 
+  long long pc[6] = {0, 0, 0, 0, 0, 0};
   for (int t = 0; t < T; ++t) {
+    const long long q0 = p.prof ? clock64() : 0;
     const float* cur = sh + (size_t)(t & 1) * H * RT;
     float* nxt = sh + (size_t)((t & 1) ^ 1) * H * RT;
     float xf[RT], xg[RT];
@@ -103,21 +208,8 @@ __global__ void __launch_bounds__(512) k_rec_train_fwd(const TrainFwdParams p) {
     float af[RT], ag[RT];
 #pragma unroll
     for (int r = 0; r < RT; ++r) { af[r] = 0.f; ag[r] = 0.f; }
-    if (active) {
-#pragma unroll 4
-      for (int k = 0; k < H; ++k) {
-        const float wf = __ldg(p.wt + (size_t)k * gH + j);
-        const float wg = SHARED ? 0.f : __ldg(p.wt + (size_t)k * gH + H + j);
-        const float4 s0 = *reinterpret_cast<const float4*>(cur + k * RT);
-        const float4 s1 = *reinterpret_cast<const float4*>(cur + k * RT + 4);
-        const float s[RT] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-#pragma unroll
-        for (int r = 0; r < RT; ++r) {
-          af[r] = fmaf(s[r], wf, af[r]);
-          if (!SHARED) ag[r] = fmaf(s[r], wg, ag[r]);
-        }
-      }
-    }
+    rows_times_w<RT, !SHARED>(p.wt, H, gH, jj, H + jj, active, cur, wsm, resident, af, ag);
+    const long long q1 = p.prof ? clock64() : 0;
     float fv[RT], gv[RT], ct[RT];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -133,20 +225,18 @@ __global__ void __launch_bounds__(512) k_rec_train_fwd(const TrainFwdParams p) {
       }
     }
     float mean = 0.f, invstd = 1.f;
+    long long q2 = 0, q3 = 0;
     if (batch_stats) {
       float* part = p.partial + (size_t)(t & 1) * nblocks * 2 * H;
       if (active) {
         part[((size_t)blockIdx.x * 2 + 0) * H + j] = s1;
         part[((size_t)blockIdx.x * 2 + 1) * H + j] = s2;
       }
+      q2 = p.prof ? clock64() : 0;
       if (!grid_barrier(p.counter, nblocks, epoch)) __trap();
-      float a1 = 0.f, a2 = 0.f;
-      if (active) {
-        for (unsigned int b = 0; b < nblocks; ++b) {
-          a1 += __ldcg(part + ((size_t)b * 2 + 0) * H + j);
-          a2 += __ldcg(part + ((size_t)b * 2 + 1) * H + j);
-        }
-      }
+      q3 = p.prof ? clock64() : 0;
+      float a1, a2;
+      reduce_partials(part, nblocks, H, j, active, a1, a2);
       const float m1 = a1 / (float)R;                 // E[x - shift]
       const float var = fmaxf(a2 / (float)R - m1 * m1, 0.f);  // biased variance
       mean = shift + m1;
@@ -159,6 +249,7 @@ __global__ void __launch_bounds__(512) k_rec_train_fwd(const TrainFwdParams p) {
       shift = mean;
       if (blockIdx.x == 0 && active) p.invstd_out[(size_t)t * H + j] = invstd;
     }
+    const long long q4 = p.prof ? clock64() : 0;
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
       const int row = row0 + r;
@@ -180,7 +271,13 @@ __global__ void __launch_bounds__(512) k_rec_train_fwd(const TrainFwdParams p) {
       }
     }
     __syncthreads();
+    if (p.prof) {
+      const long long q5 = clock64();
+      pc[0] += q1 - q0; pc[1] += q2 - q1; pc[2] += q3 - q2; pc[3] += q4 - q3; pc[4] += q5 - q4; pc[5] += q5 - q0;
+    }
   }
+  if (p.prof && blockIdx.x == 0 && j == 0)
+    for (int i = 0; i < 6; ++i) p.prof[i] = pc[i];
   if (batch_stats && blockIdx.x == 0 && active) {
     p.run_mean[j] = rmean;
     p.run_var[j] = rvar;
@@ -205,11 +302,12 @@ struct TrainBwdParams {
   unsigned int* counter;
   int T, R, H, training;
   float eps;
+  int resident;
 };
 
 template <bool SHARED>
 __global__ void __launch_bounds__(512) k_rec_train_bwd(const TrainBwdParams p) {
-  extern __shared__ __align__(16) float sh[];  // [2][gH][RT] dz of the later frame
+  extern __shared__ __align__(16) float sh[];  // [2][gH][RT] dz of the later frame, then weight slabs / weights
   constexpr int RT = TR_RT;
   const int H = p.H, R = p.R, T = p.T;
   const int gH = SHARED ? H : 2 * H;
@@ -218,6 +316,13 @@ __global__ void __launch_bounds__(512) k_rec_train_bwd(const TrainBwdParams p) {
   const bool active = j < H;
   const int jj = active ? j : 0;
   const unsigned int nblocks = gridDim.x;
+  float* wsm = sh + (size_t)2 * gH * RT;
+  const bool resident = p.resident != 0;
+  if (resident) {
+    stage_rows(wsm, p.w_hh, 0, gH, H);
+    cp_async_commit();
+    cp_async_wait<0>();
+  }
   const bool bn = p.bn_w != nullptr;
   const bool batch_stats = bn && p.training;
   const float gam = bn ? p.bn_w[jj] : 1.f;
@@ -234,20 +339,10 @@ __global__ void __launch_bounds__(512) k_rec_train_bwd(const TrainBwdParams p) {
     const float* later = sh + (size_t)(t & 1) * gH * RT;        // dz_{t+1} (zeros for t = T-1)
     float* mine = sh + (size_t)((t & 1) ^ 1) * gH * RT;         // dz_t for frame t-1
     // dh_t = dL/dh_t (from above) + dz_{t+1} @ W_hh   (thread j = column j of W_hh, coalesced)
-    float dh[RT];
+    float dh[RT], dh_unused[RT];
 #pragma unroll
     for (int r = 0; r < RT; ++r) dh[r] = 0.f;
-    if (active) {
-#pragma unroll 4
-      for (int m = 0; m < gH; ++m) {
-        const float w = __ldg(p.w_hh + (size_t)m * H + j);
-        const float4 s0 = *reinterpret_cast<const float4*>(later + m * RT);
-        const float4 s1 = *reinterpret_cast<const float4*>(later + m * RT + 4);
-        const float s[RT] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-#pragma unroll
-        for (int r = 0; r < RT; ++r) dh[r] = fmaf(s[r], w, dh[r]);
-      }
-    }
+    rows_times_w<RT, false>(p.w_hh, gH, H, jj, 0, active, later, wsm, resident, dh, dh_unused);
     float dc[RT], xh[RT], fv[RT], gv[RT], cp[RT];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -273,13 +368,8 @@ __global__ void __launch_bounds__(512) k_rec_train_bwd(const TrainBwdParams p) {
         part[((size_t)blockIdx.x * 2 + 1) * H + j] = s2;
       }
       if (!grid_barrier(p.counter, nblocks, epoch)) __trap();
-      float a1 = 0.f, a2 = 0.f;
-      if (active) {
-        for (unsigned int b = 0; b < nblocks; ++b) {
-          a1 += __ldcg(part + ((size_t)b * 2 + 0) * H + j);
-          a2 += __ldcg(part + ((size_t)b * 2 + 1) * H + j);
-        }
-      }
+      float a1, a2;
+      reduce_partials(part, nblocks, H, j, active, a1, a2);
       acc_db += a1;
       acc_dg += a2;
       m1 = a1 / (float)R;
@@ -387,10 +477,15 @@ extern "C" int gsn_layer_train_forward(const float* xproj, const float* w_hh, co
   dim3 tb(32, 8), tg((H + 31) / 32, (gH + 31) / 32);
   gsn::k_transpose_f32<<<tg, tb, 0, st>>>(w_hh, wt, gH, H);  // [gH,H] -> [H,gH]
   GSN_LAUNCH_CHECK("k_transpose_f32");
+  GSN_REQUIRE(H % 4 == 0, "gsn_layer_train_forward: H=%d must be a multiple of 4", H);
+  const size_t spikes = (size_t)2 * H * gsn::TR_RT * sizeof(float);
+  const size_t all_w = (size_t)H * gH * sizeof(float);
+  const int resident = spikes + all_w <= 200 * 1024;
+  const size_t smem = spikes + (resident ? all_w : (size_t)gsn::TR_NST * gsn::TR_KB * gH * sizeof(float));
   gsn::TrainFwdParams p{xproj, wt, bias, bn_weight, bn_bias, running_mean, running_var, h_out, c_out, f_out, g_out,
-                        xhat_out, invstd_out, partial, counter, T, R, H, training, momentum, eps};
+                        xhat_out, invstd_out, partial, counter, T, R, H, training, momentum, eps, resident,
+                        getenv("GSN_TRAIN_PROF") ? reinterpret_cast<long long*>(counter) + 2 : nullptr};
   const int threads = ((H + 31) / 32) * 32;
-  const size_t smem = (size_t)2 * H * gsn::TR_RT * sizeof(float);
   return shared ? gsn::coop_launch(gsn::k_rec_train_fwd<true>, p, nblocks, threads, smem, st, "gsn_layer_train_forward")
                 : gsn::coop_launch(gsn::k_rec_train_fwd<false>, p, nblocks, threads, smem, st, "gsn_layer_train_forward");
 }
@@ -413,10 +508,14 @@ extern "C" int gsn_layer_train_backward(const float* dh_out, const float* w_hh, 
   float* partial = wt + (size_t)H * gH + (size_t)4 * nblocks * H;  // second scratch region
   unsigned int* counter = reinterpret_cast<unsigned int*>(wt + (size_t)H * gH + (size_t)8 * nblocks * H);
   GSN_CUDA(cudaMemsetAsync(counter, 0, 64, st));
+  GSN_REQUIRE(H % 4 == 0, "gsn_layer_train_backward: H=%d must be a multiple of 4", H);
+  const size_t dzs = (size_t)2 * gH * gsn::TR_RT * sizeof(float);
+  const size_t all_w = (size_t)H * gH * sizeof(float);
+  const int resident = dzs + all_w <= 200 * 1024;
+  const size_t smem = dzs + (resident ? all_w : (size_t)gsn::TR_NST * gsn::TR_KB * H * sizeof(float));
   gsn::TrainBwdParams p{dh_out, w_hh, c, f, g, xhat, invstd, bn_weight, running_var, dz, dbias_part, dgamma, dbeta,
-                        partial, counter, T, R, H, training, eps};
+                        partial, counter, T, R, H, training, eps, resident};
   const int threads = ((H + 31) / 32) * 32;
-  const size_t smem = (size_t)2 * gH * gsn::TR_RT * sizeof(float);
   return shared ? gsn::coop_launch(gsn::k_rec_train_bwd<true>, p, nblocks, threads, smem, st, "gsn_layer_train_backward")
                 : gsn::coop_launch(gsn::k_rec_train_bwd<false>, p, nblocks, threads, smem, st, "gsn_layer_train_backward");
 }

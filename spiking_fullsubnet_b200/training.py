@@ -111,6 +111,37 @@ def deepfilter(spec, coef, order):
     return out
 
 
+def _fork_join(device, thunks):
+    """Run independent pieces of the forward on forked streams and join them on the caller's stream."""
+    from .modeling import _band_streams
+    if len(thunks) == 1:
+        return [thunks[0]()]
+    main = torch.cuda.current_stream(device)
+    streams = _band_streams(device, len(thunks))
+    fork = torch.cuda.Event()
+    fork.record(main)
+    results = []
+    for st, fn in zip(streams, thunks):
+        st.wait_event(fork)
+        with torch.cuda.stream(st):
+            res = fn()
+            done = torch.cuda.Event()
+            done.record(st)
+        main.wait_event(done)
+        for t in _tensors(res):
+            t.record_stream(main)
+        results.append(res)
+    return results
+
+
+def _tensors(obj):
+    if torch.is_tensor(obj):
+        yield obj
+    elif isinstance(obj, (list, tuple)):
+        for o in obj:
+            yield from _tensors(o)
+
+
 def spiking_fullsubnet_forward(model, wave):
     """SpikingFullSubNet.forward (MSF:415-474) on the autograd path."""
     from .modeling import _istft, _stft, coef_layout
@@ -128,7 +159,8 @@ def spiking_fullsubnet_forward(model, wave):
     T = cm.shape[0]
     S = model.num_spks
     coefs, sb_all = [], []
-    for i, m in enumerate(sbm.sb_models):
+
+    def band(i, m):
         lo, hi = sbm.freq_cutoffs[i], sbm.freq_cutoffs[i + 1]
         ctr, nbr = sbm.center_freq_sizes[i], sbm.neighbor_freq_sizes[i]
         qi = unfold_index(lo, hi, ctr, nbr, Fq, cm.device)          # [N, ctr+2nbr]
@@ -138,8 +170,13 @@ def spiking_fullsubnet_forward(model, wave):
         if m.use_pre_layer_norm:
             xb = m.pre_layer_norm(xb)
         act, trace = run_sequence_model(m, xb.contiguous())
-        coefs.append(coef_layout(act, B, N, sbm.df_orders[i], S))
-        sb_all.append(trace)
+        return coef_layout(act, B, N, sbm.df_orders[i], S), trace
+
+    # the sub-band models are independent: one stream each, forward AND backward (autograd replays every
+    # backward node on the stream of its forward), so their latency-bound recurrence kernels overlap
+    for c, tr in _fork_join(cm.device, [lambda i=i, m=m: band(i, m) for i, m in enumerate(sbm.sb_models)]):
+        coefs.append(c)
+        sb_all.append(tr)
     enh, lo = [], 0
     for coef, order in zip(coefs, model.df_orders):
         nf = coef.shape[3]
@@ -179,7 +216,8 @@ def separator_forward(model, wave):
     fb_act, fb_all = run_sequence_model(model.fb_model, x.contiguous())
     sbm = model.sb_model
     coefs, sb_all = [], []
-    for i, (m, (lo, hi)) in enumerate(zip(sbm.sb_models, sbm.band_edges(Fq))):
+
+    def band(i, m, lo, hi):
         ctr, nbr = sbm.sb_num_center_freqs[i], sbm.sb_num_neighbor_freqs[i]
         qi = unfold_index(lo, hi, ctr, nbr, Fq, cm.device)
         qf = unfold_index(lo, hi, ctr, 0, Fq, cm.device) % fb_act.shape[2]
@@ -187,8 +225,12 @@ def separator_forward(model, wave):
         xb = torch.cat([cm[:, :, qi], fb_act[:, :, qf]], dim=-1).reshape(T, B * N, -1)
         xb = _utterance_norm(xb, B, model.norm_type)
         act, trace = run_sequence_model(m, xb.contiguous())
-        coefs.append(coef_layout(act, B, N, model.sb_df_orders[i], 1))
-        sb_all.append(trace)
+        return coef_layout(act, B, N, model.sb_df_orders[i], 1), trace
+
+    for c, tr in _fork_join(cm.device, [lambda i=i, m=m, lo=lo, hi=hi: band(i, m, lo, hi)
+                                        for i, (m, (lo, hi)) in enumerate(zip(sbm.sb_models, sbm.band_edges(Fq)))]):
+        coefs.append(c)
+        sb_all.append(tr)
     enh, lo = [], 0
     for coef, order in zip(coefs, model.sb_df_orders):
         nf = coef.shape[3]
