@@ -130,6 +130,17 @@ GSN_API int gsn_layer_train_forward(const float* xproj, const float* w_hh, const
                                     float* xhat_out, float* invstd_out, int T, int R, int H, int shared,
                                     int training, float momentum, float eps, void* workspace,
                                     gsn_stream_t stream);
+/* The same training forward on tcgen05 (gsn_recurrence_tc.cu with TRAIN = true: weights stationary in TMEM, the
+ * per-frame BatchNorm statistics reduced over row groups, row tiles and a grid barrier; cooperative cluster
+ * launch).  Shared gate weights, H <= 320, H % 4 == 0; gsn_layer_train_tc_supported() tells.  Same outputs.  */
+GSN_API int gsn_layer_train_tc_supported(int R, int H, int shared);
+GSN_API size_t gsn_layer_train_tc_workspace_bytes(int R, int H);
+GSN_API int gsn_layer_train_forward_tc(const float* xproj, const float* w_hh, const float* bias,
+                                       const float* bn_weight, const float* bn_bias, float* running_mean,
+                                       float* running_var, float* h_out, float* c_out, float* f_out, float* g_out,
+                                       float* xhat_out, float* invstd_out, int T, int R, int H, int training,
+                                       float momentum, float eps, int sm_budget, void* workspace,
+                                       gsn_stream_t stream);
 GSN_API int gsn_layer_train_backward(const float* dh_out, const float* w_hh, const float* c, const float* f,
                                      const float* g, const float* xhat, const float* invstd,
                                      const float* bn_weight, const float* running_var, float* dz,

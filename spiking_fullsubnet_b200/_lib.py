@@ -32,6 +32,9 @@ SIGNATURES = {
     "gsn_layer_recurrence": (_i, [_p] * 11 + [_i] * 6 + [_p, _p]),
     "gsn_layer_train_workspace_bytes": (_sz, [_i, _i, _i]),
     "gsn_layer_train_forward": (_i, [_p] * 13 + [_i] * 5 + [_f, _f, _p, _p]),
+    "gsn_layer_train_tc_supported": (_i, [_i, _i, _i]),
+    "gsn_layer_train_tc_workspace_bytes": (_sz, [_i, _i]),
+    "gsn_layer_train_forward_tc": (_i, [_p] * 13 + [_i] * 4 + [_f, _f, _i, _p, _p]),
     "gsn_layer_train_backward": (_i, [_p] * 13 + [_i] * 5 + [_f, _p, _p]),
     "gsn_layer_recurrence_pick_backend": (_i, [_i, _i, _i]),
     "gsn_deepfilter_band": (_i, [_p] * 5 + [_i] * 9 + [_p]),

@@ -86,4 +86,26 @@ __device__ __forceinline__ float gsu_membrane(float f_hat, float g_hat, float c_
   return c;
 }
 
+// sense-free monotonic grid barrier; `counter` is zeroed by the host before the launch
+__device__ __forceinline__ bool grid_barrier(unsigned int* counter, unsigned int nblocks, unsigned int& epoch) {
+  __syncthreads();
+  bool ok = true;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int target = (epoch + 1u) * nblocks;
+    atomicAdd(counter, 1u);
+    unsigned int polls = 0;
+    while (true) {
+      unsigned int v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      if (v >= target) break;
+      if (++polls > (1u << 26)) { ok = false; break; }
+    }
+    __threadfence();
+  }
+  ok = __syncthreads_and(ok);
+  ++epoch;
+  return ok;
+}
+
 }  // namespace gsn

@@ -40,6 +40,19 @@ struct RecTcParams {
   int T, R, H, Kmma;    // Kmma = round_up(H, 16)
   unsigned long long* prof;  // [8] cycle counters of CTA 0 / thread 0 (workspace), see tools/tc_profile.py
   TraceBuf* trace;
+  // training path only (TRAIN kernels; bn_scale / bn_shift are unused there)
+  const float* bn_w;         // [H] BatchNorm affine or null (no BatchNorm)
+  const float* bn_b;
+  float* run_mean;           // [H] running statistics: read (eval) / updated every frame (batch statistics)
+  float* run_var;
+  float* f_out;              // [T,R,H] saved for BPTT: sigmoid(forget gate)
+  float* g_out;              // [T,R,H] cell-gate pre-activation
+  float* xhat_out;           // [T,R,H] normalised pre-BN membrane (batch statistics only)
+  float* invstd_out;         // [T,H]
+  float* partial;            // [2][tiles][2][C*128] per-tile sums of the BatchNorm statistics
+  unsigned int* counter;     // grid barrier
+  float momentum, eps;
+  int batch_stats;
 };
 
 constexpr int kTcPlanes = 3;
@@ -57,6 +70,7 @@ __host__ __device__ inline size_t tc_smem_bytes(int Kmma, int C, bool shared) {
   b = (b + 15) / 16 * 16;
   b += 64;                                                // barriers + tmem slot
   if (!shared) b += (size_t)NT * 64 * 4;                  // cell-gate accumulators handed across lanes
+  b += 4 * 128 * 2 * 4;                                   // training: cross-group reduction scratch
   return b;
 }
 
@@ -71,11 +85,12 @@ __device__ __forceinline__ void split3(float w, uint32_t& hi, uint32_t& mid, uin
   lo = __float_as_uint(r2) >> 16;
 }
 
-template <int NT, int G, bool PROF, bool SHARED>
+template <int NT, int G, bool PROF, bool SHARED, bool TRAIN>
 __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams p) {
+  static_assert(!TRAIN || SHARED, "the tcgen05 training forward handles shared gate weights only");
   constexpr int NTHREADS = 128 * G;
   constexpr int CPT = NT / G;                 // accumulator columns (= rows of the tile) per thread
-  constexpr int CH = SHARED ? (CPT < 8 ? CPT : 8) : CPT;  // columns processed together (ILP)
+  constexpr int CH = (SHARED && !TRAIN) ? (CPT < 8 ? CPT : 8) : CPT;  // columns processed together (ILP)
   // SHARED gates: a CTA owns 128 neurons (TMEM lane = neuron).  Unshared gates (w_hh [2H,H]): a CTA owns 64
   // neurons; lanes 0-63 accumulate their forget-gate rows, lanes 64-127 the cell-gate rows of the SAME neurons,
   // which are handed to lanes 0-63 through shared memory once per frame.
@@ -108,6 +123,7 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
   uint64_t* bar_bits = bar_mma + 1;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 3);
   float* zg = reinterpret_cast<float*>(smem + off + 64);  // [NT][64], unshared only
+  float* red = reinterpret_cast<float*>(smem + off + 64);  // [G][128][2], TRAIN only (SHARED: zg unused)
 
   if (tid == 0) {
     tc::mbar_init(bar_mma, 1);
@@ -184,8 +200,25 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
 
   const int jj = jv ? j : 0;
   const float bf = p.bias[jj], bc = p.bias[H + jj];
-  const float bs = p.bn_scale ? p.bn_scale[jj] : 1.0f;
-  const float bt = p.bn_shift ? p.bn_shift[jj] : 0.0f;
+  float bs = p.bn_scale ? p.bn_scale[jj] : 1.0f;   // BatchNorm as y = x * bs + bt
+  float bt = p.bn_shift ? p.bn_shift[jj] : 0.0f;
+  // training path: affine / statistics handled here instead of the pre-folded bn_scale / bn_shift
+  const bool has_bn = TRAIN && p.bn_w != nullptr;
+  const bool batch_stats = has_bn && p.batch_stats;
+  const float gam = has_bn ? p.bn_w[jj] : 1.f, bet = has_bn ? p.bn_b[jj] : 0.f;
+  float rmean = has_bn ? p.run_mean[jj] : 0.f, rvar = has_bn ? p.run_var[jj] : 1.f;
+  if (TRAIN) {
+    bs = 1.f;
+    bt = 0.f;
+    if (has_bn && !batch_stats) {  // eval-mode fold, as torch's CPU kernel does it
+      bs = gam * (1.0f / sqrtf(rvar + p.eps));
+      bt = bet - rmean * bs;
+    }
+  }
+  const unsigned int ntiles = gridDim.x / C, tile = blockIdx.x / C;
+  const int Hp = (int)C * 128;
+  unsigned int epoch = 0;
+  float shift = 0.f;  // one-pass variance is taken around the previous frame's mean
   float c[CPT];
   uint32_t boff[CPT];      // byte offset of (row, neuron) inside one frame of a [T, R, H] fp32 tensor
   uint32_t valid = 0;      // bit i: row i of my group exists and my neuron exists
@@ -228,7 +261,7 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
   const int ksteps = Kmma / 16;
   const uint32_t bits_bytes = (uint32_t)NT * WPS * C * 4u;  // every slice sends WPS words per row
   bool alive = true;
-  float hval[CPT];
+  float hval[CPT], fsave[TRAIN ? CPT : 1], gsave[TRAIN ? CPT : 1], xsave[TRAIN ? CPT : 1];
 #pragma unroll
   for (int i = 0; i < CPT; ++i) hval[i] = 0.f;
 
@@ -241,6 +274,12 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
       if ((valid >> i) & 1u) {
         *reinterpret_cast<float*>(hf + boff[i]) = hval[i];
         if (cf) *reinterpret_cast<float*>(cf + boff[i]) = c[i];
+        if (TRAIN && p.f_out) {
+          *reinterpret_cast<float*>(reinterpret_cast<char*>(p.f_out) + (size_t)t * frame_bytes + boff[i]) = fsave[i];
+          *reinterpret_cast<float*>(reinterpret_cast<char*>(p.g_out) + (size_t)t * frame_bytes + boff[i]) = gsave[i];
+          if (batch_stats)
+            *reinterpret_cast<float*>(reinterpret_cast<char*>(p.xhat_out) + (size_t)t * frame_bytes + boff[i]) = xsave[i];
+        }
       }
     }
   };
@@ -316,10 +355,72 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
         sg[u] = sigmoid_f32(__fadd_rn(xf_[i0 + u], z));
         gh[u] = __fadd_rn(xg_[i0 + u], SHARED ? z : (isg ? 0.f : zg[(g * CPT + i0 + u) * 64 + (tl & 63)]));
       }
+      float ctil[CH];
+#pragma unroll
+      for (int u = 0; u < CH; ++u)
+        ctil[u] = __fadd_rn(__fmul_rn(sg[u], c[i0 + u]), __fmul_rn(__fsub_rn(1.0f, sg[u]), gh[u]));
+      float mean = 0.f, invstd = 1.f;
+      if (TRAIN && batch_stats) {
+        // per-frame BatchNorm statistics over ALL rows of the sequence model: my rows -> the 4 row groups of the
+        // CTA (shared memory) -> all row tiles (global partials + grid barrier), summed in a fixed order
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+          if ((valid >> (i0 + u)) & 1u) {
+            const float d = ctil[u] - shift;
+            s1 += d;
+            s2 += d * d;
+          }
+        }
+        red[(g * 128 + tl) * 2 + 0] = s1;
+        red[(g * 128 + tl) * 2 + 1] = s2;
+        __syncthreads();
+        float* part = p.partial + (size_t)par * ntiles * 2 * Hp;
+        if (g == 0) {
+          float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+          for (int gg = 0; gg < G; ++gg) {
+            t1 += red[(gg * 128 + tl) * 2 + 0];
+            t2 += red[(gg * 128 + tl) * 2 + 1];
+          }
+          part[((size_t)tile * 2 + 0) * Hp + slice * 128 + tl] = t1;
+          part[((size_t)tile * 2 + 1) * Hp + slice * 128 + tl] = t2;
+        }
+        if (!grid_barrier(p.counter, gridDim.x, epoch)) __trap();
+        float a1 = 0.f, a2 = 0.f;
+        for (unsigned int b0 = 0; b0 < ntiles; b0 += 8) {
+          float v1[8], v2[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const bool ok = b0 + u < ntiles;
+            v1[u] = ok ? __ldcg(part + ((size_t)(b0 + u) * 2 + 0) * Hp + slice * 128 + tl) : 0.f;
+            v2[u] = ok ? __ldcg(part + ((size_t)(b0 + u) * 2 + 1) * Hp + slice * 128 + tl) : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            a1 += v1[u];
+            a2 += v2[u];
+          }
+        }
+        const float m1 = a1 / (float)R;
+        const float var = fmaxf(a2 / (float)R - m1 * m1, 0.f);  // biased variance
+        mean = shift + m1;
+        invstd = 1.0f / sqrtf(var + p.eps);
+        bs = gam * invstd;
+        bt = bet - mean * bs;
+        rmean = (1.f - p.momentum) * rmean + p.momentum * mean;
+        rvar = (1.f - p.momentum) * rvar + p.momentum * (var * (float)R / (float)(R - 1));
+        shift = mean;
+        if (tile == 0 && g == 0 && jv) p.invstd_out[(size_t)t * H + j] = invstd;
+      }
 #pragma unroll
       for (int u = 0; u < CH; ++u) {
-        float cn = __fadd_rn(__fmul_rn(sg[u], c[i0 + u]), __fmul_rn(__fsub_rn(1.0f, sg[u]), gh[u]));
-        cn = __fadd_rn(__fmul_rn(cn, bs), bt);
+        if (TRAIN) {
+          fsave[i0 + u] = sg[u];
+          gsave[i0 + u] = gh[u];
+          xsave[i0 + u] = (ctil[u] - mean) * invstd;
+        }
+        float cn = __fadd_rn(__fmul_rn(ctil[u], bs), bt);
         c[i0 + u] = cn;
         const bool spike = ((valid >> (i0 + u)) & 1u) && cn >= 0.f;
         hval[i0 + u] = spike ? 1.0f : 0.0f;
@@ -359,6 +460,10 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
     for (int i = 0; i < 8; ++i) p.prof[i] = (unsigned long long)pc[i];
 
   store_frame(T - 1);
+  if (TRAIN && batch_stats && tile == 0 && g == 0 && jv) {
+    p.run_mean[j] = rmean;
+    p.run_var[j] = rvar;
+  }
 #pragma unroll
   for (int i = 0; i < CPT; ++i) {
     if ((valid >> i) & 1u) {
@@ -396,25 +501,27 @@ bool recurrence_tc_supported(int R, int H, int shared) {
 
 size_t recurrence_tc_workspace(int, int, int) { return 256; }
 
-template <int NT, int G, bool PROF, bool SHARED>
+template <int NT, int G, bool PROF, bool SHARED, bool TRAIN = false>
 static int launch_nt(const RecTcParams& p, int C, cudaStream_t st) {
   size_t smem = tc_smem_bytes<NT>(p.Kmma, C, SHARED);
   if (smem < tc::kTmemExclusiveSmem) smem = tc::kTmemExclusiveSmem;
-  GSN_CUDA(cudaFuncSetAttribute(k_recurrence_tc<NT, G, PROF, SHARED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)smem));
+  GSN_CUDA(cudaFuncSetAttribute(k_recurrence_tc<NT, G, PROF, SHARED, TRAIN>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(((p.R + NT - 1) / NT) * C));
   cfg.blockDim = dim3(128 * G);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = C;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeCooperative;  // training: the per-frame grid barrier needs co-residency
+  attr[1].val.cooperative = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  GSN_CUDA(cudaLaunchKernelEx(&cfg, k_recurrence_tc<NT, G, PROF, SHARED>, p));
+  cfg.numAttrs = TRAIN ? 2 : 1;
+  GSN_CUDA(cudaLaunchKernelEx(&cfg, k_recurrence_tc<NT, G, PROF, SHARED, TRAIN>, p));
   return GSN_OK;
 }
 
@@ -425,8 +532,10 @@ int launch_recurrence_tc(const float* xproj, const float* w_hh, const float* bia
   int dev = 0, sms = 148;
   GSN_CUDA(cudaGetDevice(&dev));
   GSN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  RecTcParams p{xproj, w_hh, bias, bn_scale, bn_shift, h0, c0, h_out, c_out, hT, cT, T, R, H, (H + 15) / 16 * 16,
-                reinterpret_cast<unsigned long long*>(workspace), trace_buffer()};
+  RecTcParams p{};
+  p.xproj = xproj; p.w_hh = w_hh; p.bias = bias; p.bn_scale = bn_scale; p.bn_shift = bn_shift; p.h0 = h0; p.c0 = c0;
+  p.h_out = h_out; p.c_out = c_out; p.hT = hT; p.cT = cT; p.T = T; p.R = R; p.H = H; p.Kmma = (H + 15) / 16 * 16;
+  p.prof = reinterpret_cast<unsigned long long*>(workspace); p.trace = trace_buffer();
   const int C = shared ? (H + 127) / 128 : (H + 63) / 64;
   if (sm_budget > 0 && sm_budget < sms) sms = sm_budget;
   const int nt = tc_pick_nt(R, H, shared, sms);
@@ -444,6 +553,50 @@ int launch_recurrence_tc(const float* xproj, const float* w_hh, const float* bia
     case 32: return prof ? launch_nt<32, 4, true, true>(p, C, st) : launch_nt<32, 4, false, true>(p, C, st);
     case 64: return prof ? launch_nt<64, 4, true, true>(p, C, st) : launch_nt<64, 4, false, true>(p, C, st);
     default: return fail(GSN_ENOSUP, "gsn_layer_recurrence(TCGEN05): H=%d does not fit tensor memory", H);
+  }
+}
+
+// ---- training forward on tcgen05 (shared gate weights): same kernel with TRAIN = true, cooperative launch ----
+bool recurrence_tc_train_supported(int R, int H, int shared) {
+  return shared && H % 4 == 0 && recurrence_tc_supported(R, H, shared);
+}
+
+size_t recurrence_tc_train_workspace(int R, int H) {
+  const size_t C = (H + 127) / 128, tiles = (R + 15) / 16;
+  return (2 * tiles * 2 * C * 128) * sizeof(float) + 256;
+}
+
+int launch_recurrence_tc_train(const float* xproj, const float* w_hh, const float* bias, const float* bn_w,
+                               const float* bn_b, float* run_mean, float* run_var, float* h_out, float* c_out,
+                               float* f_out, float* g_out, float* xhat_out, float* invstd_out, int T, int R, int H,
+                               int training, float momentum, float eps, int sm_budget, void* workspace,
+                               cudaStream_t st) {
+  int dev = 0, sms = 148;
+  GSN_CUDA(cudaGetDevice(&dev));
+  GSN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int C = (H + 127) / 128;
+  const int all_sms = sms;
+  if (sm_budget > 0 && sm_budget < sms) sms = sm_budget;
+  int nt = tc_pick_nt(R, H, 1, sms);
+  // one CTA per SM (TMEM-exclusive shared memory request): the cooperative grid must fit the device
+  while (nt > 0 && nt < 64 && (long long)((R + nt - 1) / nt) * C > all_sms) nt *= 2;
+  if (nt == 0 || (long long)((R + nt - 1) / nt) * C > all_sms)
+    return fail(GSN_ENOSUP, "gsn_layer_train_forward_tc: R=%d H=%d does not fit one cooperative grid", R, H);
+  RecTcParams p{};
+  p.xproj = xproj; p.w_hh = w_hh; p.bias = bias; p.h_out = h_out; p.c_out = c_out; p.T = T; p.R = R; p.H = H;
+  p.Kmma = (H + 15) / 16 * 16; p.trace = trace_buffer();
+  p.bn_w = bn_w; p.bn_b = bn_b; p.run_mean = run_mean; p.run_var = run_var; p.f_out = f_out; p.g_out = g_out;
+  p.xhat_out = xhat_out; p.invstd_out = invstd_out; p.momentum = momentum; p.eps = eps;
+  p.batch_stats = (bn_w != nullptr && training) ? 1 : 0;
+  const size_t tiles = (R + nt - 1) / nt;
+  p.partial = reinterpret_cast<float*>(workspace);
+  p.counter = reinterpret_cast<unsigned int*>(p.partial + 2 * tiles * 2 * C * 128);
+  GSN_CUDA(cudaMemsetAsync(p.counter, 0, 64, st));
+  switch (nt) {
+    case 16: return launch_nt<16, 4, false, true, true>(p, C, st);
+    case 32: return launch_nt<32, 4, false, true, true>(p, C, st);
+    case 64: return launch_nt<64, 4, false, true, true>(p, C, st);
+    default: return fail(GSN_ENOSUP, "gsn_layer_train_forward_tc: unsupported tile");
   }
 }
 

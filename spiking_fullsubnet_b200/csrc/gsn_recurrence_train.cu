@@ -17,28 +17,6 @@ namespace gsn {
 
 constexpr int TR_RT = 8;
 
-// sense-free monotonic grid barrier; `counter` is zeroed by the host before the launch
-__device__ __forceinline__ bool grid_barrier(unsigned int* counter, unsigned int nblocks, unsigned int& epoch) {
-  __syncthreads();
-  bool ok = true;
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned int target = (epoch + 1u) * nblocks;
-    atomicAdd(counter, 1u);
-    unsigned int polls = 0;
-    while (true) {
-      unsigned int v;
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-      if (v >= target) break;
-      if (++polls > (1u << 26)) { ok = false; break; }
-    }
-    __threadfence();
-  }
-  ok = __syncthreads_and(ok);
-  ++epoch;
-  return ok;
-}
-
 // acc[r] += sum_k s[k][r] * W[k][col]  (and acc2 with column col2) for the RT rows of this CTA, thread = column.
 // W [Kdim][ld] fp32 in global memory is either RESIDENT in shared memory (`wsm` holds all of it) or streamed
 // through `wsm` in 16-row slabs with cp.async double buffering (coalesced 16-byte copies, L2 -> smem), instead
@@ -444,6 +422,44 @@ static int coop_launch(K kernel, const P& params, int blocks, int threads, size_
 }
 
 }  // namespace gsn
+
+namespace gsn {
+bool recurrence_tc_train_supported(int R, int H, int shared);
+size_t recurrence_tc_train_workspace(int R, int H);
+int launch_recurrence_tc_train(const float*, const float*, const float*, const float*, const float*, float*, float*,
+                               float*, float*, float*, float*, float*, float*, int, int, int, int, float, float, int,
+                               void*, cudaStream_t);
+}  // namespace gsn
+
+extern "C" int gsn_layer_train_tc_supported(int R, int H, int shared) {
+  return gsn::recurrence_tc_train_supported(R, H, shared) ? 1 : 0;
+}
+
+extern "C" size_t gsn_layer_train_tc_workspace_bytes(int R, int H) {
+  return R > 0 && H > 0 ? gsn::recurrence_tc_train_workspace(R, H) : 0;
+}
+
+extern "C" int gsn_layer_train_forward_tc(const float* xproj, const float* w_hh, const float* bias,
+                                          const float* bn_weight, const float* bn_bias, float* running_mean,
+                                          float* running_var, float* h_out, float* c_out, float* f_out, float* g_out,
+                                          float* xhat_out, float* invstd_out, int T, int R, int H, int training,
+                                          float momentum, float eps, int sm_budget, void* workspace,
+                                          gsn_stream_t stream) {
+  GSN_REQUIRE(xproj && w_hh && bias && h_out && c_out && f_out && g_out && workspace,
+              "gsn_layer_train_forward_tc: null pointer");
+  GSN_REQUIRE(T > 0 && R > 0 && H > 0, "gsn_layer_train_forward_tc: bad shape T=%d R=%d H=%d", T, R, H);
+  GSN_REQUIRE((bn_weight == nullptr) == (bn_bias == nullptr), "gsn_layer_train_forward_tc: bn params");
+  GSN_REQUIRE(!bn_weight || (running_mean && running_var), "gsn_layer_train_forward_tc: running statistics missing");
+  GSN_REQUIRE(!(bn_weight && training) || R > 1, "Expected more than 1 value per channel when training (rows=%d)", R);
+  GSN_REQUIRE(!(bn_weight && training) || (xhat_out && invstd_out),
+              "gsn_layer_train_forward_tc: training needs the saved-tensor outputs");
+  GSN_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "gsn_layer_train_forward_tc: workspace alignment");
+  if (!gsn::recurrence_tc_train_supported(R, H, 1))
+    return gsn::fail(GSN_ENOSUP, "gsn_layer_train_forward_tc: shape R=%d H=%d not supported", R, H);
+  return gsn::launch_recurrence_tc_train(xproj, w_hh, bias, bn_weight, bn_bias, running_mean, running_var, h_out,
+                                         c_out, f_out, g_out, xhat_out, invstd_out, T, R, H, training, momentum, eps,
+                                         sm_budget, workspace, gsn::as_stream(stream));
+}
 
 // workspace layout (floats): [wt: H*gH] [partial: 2*nblocks*2*H] [counter: 64 bytes]
 extern "C" size_t gsn_layer_train_workspace_bytes(int R, int H, int shared) {

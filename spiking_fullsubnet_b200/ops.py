@@ -72,6 +72,7 @@ def subband_features(cm, fb, N, lo, ctr, nbr, ln_weight=None, ln_bias=None, eps=
     return x
 
 
+TC_TRAIN = [True]   # training forward on tcgen05 where supported (False: fp32 CUDA-core kernel)
 TC_LINEAR = [True]  # spike-input linears on tcgen05 (set False to force the fp32 CUDA-core kernel)
 
 
@@ -173,6 +174,18 @@ def layer_train_forward(xproj, w_hh, bias, bn_weight, bn_bias, running_mean, run
     batch_stats = bn_weight is not None and training
     xhat = new(T, R, H) if batch_stats else None
     invstd = new(T, H) if batch_stats else None
+    if TC_TRAIN[0] and lib.gsn_layer_train_tc_supported(R, H, int(shared)):
+        nbytes = lib.gsn_layer_train_tc_workspace_bytes(R, H)
+        ws = torch.empty((nbytes + 255) // 4 + 64, device=dev, dtype=torch.float32)
+        ws = ws[((-ws.data_ptr()) % 256) // 4:]
+        rc = lib.gsn_layer_train_forward_tc(_ptr(xproj), _ptr(w_hh), _ptr(bias), _ptr(bn_weight), _ptr(bn_bias),
+                                            _ptr(running_mean), _ptr(running_var), _ptr(h), _ptr(c), _ptr(f), _ptr(g),
+                                            _ptr(xhat), _ptr(invstd), T, R, H, int(bool(training)), float(momentum),
+                                            float(eps), 0, ws.data_ptr(), st)
+        if rc != _lib.GSN_ENOSUP:
+            _lib.check(rc)
+            LAUNCHES[0] += 1
+            return h, c, f, g, xhat, invstd
     ws = _train_ws(R, H, shared, dev)
     _lib.check(lib.gsn_layer_train_forward(_ptr(xproj), _ptr(w_hh), _ptr(bias), _ptr(bn_weight), _ptr(bn_bias),
                                            _ptr(running_mean), _ptr(running_var), _ptr(h), _ptr(c), _ptr(f), _ptr(g),

@@ -399,3 +399,35 @@ def test_separator_and_cirm_graph_and_autograd_paths():
             if "batchnorm" in k:
                 continue  # eval-mode BatchNorm affine is frozen on this path
             assert p.grad is not None and torch.isfinite(p.grad).all() and float(p.grad.abs().max()) > 0, k
+
+
+@pytest.mark.parametrize("R,H,bn,training", [(300, 160, True, True), (37, 240, True, True), (64, 320, True, False),
+                                             (130, 224, False, False)])
+def test_train_forward_tcgen05_vs_simt(R, H, bn, training):
+    """The tcgen05 training forward (batch-statistics BatchNorm through a grid barrier) against the fp32 CUDA-core
+    training kernel: identical spikes, saved tensors and running statistics within fp32 summation noise."""
+    rs = np.random.RandomState(R + H)
+    T = 40
+    s = 1 / np.sqrt(H)
+    xproj = _t(rs.uniform(-1, 1, (T, R, H)).astype(np.float32))
+    w = _t(rs.uniform(-s, s, (H, H)).astype(np.float32))
+    b = _t(rs.uniform(-s, s, 2 * H).astype(np.float32))
+    outs = []
+    for tc_on in (True, False):
+        ops.TC_TRAIN[0] = tc_on
+        g_ = _t(rs.uniform(0.6, 1.0, H).astype(np.float32)) if bn else None
+        rs2 = np.random.RandomState(1)
+        gam = _t(rs2.uniform(0.6, 1.0, H).astype(np.float32)) if bn else None
+        bet = _t(rs2.normal(0, 0.1, H).astype(np.float32)) if bn else None
+        rm = _t(rs2.normal(0, 0.1, H).astype(np.float32)) if bn else None
+        rv = _t(rs2.uniform(1.0, 2.0, H).astype(np.float32)) if bn else None
+        res = ops.layer_train_forward(xproj, w, b, gam, bet, rm, rv, training, 0.1, 1e-5, True)
+        outs.append((res, rm, rv))
+    ops.TC_TRAIN[0] = True
+    (a, rma, rva), (bb, rmb, rvb) = outs
+    assert torch.equal(a[0], bb[0]), "spikes differ between the tcgen05 and the CUDA-core training forward"
+    for x, y in zip(a[1:], bb[1:]):
+        if x is not None:
+            assert float((x - y).abs().max()) <= 2e-5 * max(1.0, float(y.abs().max()))
+    if bn:
+        assert float((rma - rmb).abs().max()) < 1e-5 and float((rva - rvb).abs().max()) < 1e-5
