@@ -44,9 +44,12 @@ __device__ __forceinline__ void rows_times_w(const float* __restrict__ W, int Kd
   auto fma_rows = [&](const float* wrow, int k) {
     const float w1 = wrow[col];
     const float w2 = TWO ? wrow[col2] : 0.f;
-    const float4 s0 = *reinterpret_cast<const float4*>(s + k * RT);
-    const float4 s1 = *reinterpret_cast<const float4*>(s + k * RT + 4);
-    const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    float sv[RT];
+#pragma unroll
+    for (int q4 = 0; q4 < RT / 4; ++q4) {
+      const float4 s4 = *reinterpret_cast<const float4*>(s + k * RT + 4 * q4);
+      sv[4 * q4] = s4.x; sv[4 * q4 + 1] = s4.y; sv[4 * q4 + 2] = s4.z; sv[4 * q4 + 3] = s4.w;
+    }
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
       acc[r] = fmaf(sv[r], w1, acc[r]);
@@ -283,10 +286,11 @@ struct TrainBwdParams {
   int resident;
 };
 
-template <bool SHARED>
-__global__ void __launch_bounds__(512) k_rec_train_bwd(const TrainBwdParams p) {
+// RT = 8 rows per CTA (any H <= 512) or RT = 16 (H <= 256: half the CTAs -> half the weight streaming and a
+// quarter of the all-to-all partial traffic, which is what bounds large row counts)
+template <bool SHARED, int RT>
+__global__ void __launch_bounds__(RT == 8 ? 512 : 256) k_rec_train_bwd(const TrainBwdParams p) {
   extern __shared__ __align__(16) float sh[];  // [2][gH][RT] dz of the later frame, then weight slabs / weights
-  constexpr int RT = TR_RT;
   const int H = p.H, R = p.R, T = p.T;
   const int gH = SHARED ? H : 2 * H;
   const int j = threadIdx.x;
@@ -519,19 +523,27 @@ extern "C" int gsn_layer_train_backward(const float* dh_out, const float* w_hh, 
   GSN_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "gsn_layer_train_backward: workspace alignment");
   cudaStream_t st = gsn::as_stream(stream);
   const int gH = shared ? H : 2 * H;
-  const int nblocks = (R + gsn::TR_RT - 1) / gsn::TR_RT;
+  const int nb8 = (R + gsn::TR_RT - 1) / gsn::TR_RT;   // workspace / dbias_part are sized for 8-row CTAs
+  // 16-row CTAs only where the all-to-all partial traffic clearly dominates (measured: no gain at R = 768)
+  const int rt = (H <= 256 && nb8 > 128) ? 16 : 8;
+  const int nblocks = (R + rt - 1) / rt;
   float* wt = reinterpret_cast<float*>(workspace);
-  float* partial = wt + (size_t)H * gH + (size_t)4 * nblocks * H;  // second scratch region
-  unsigned int* counter = reinterpret_cast<unsigned int*>(wt + (size_t)H * gH + (size_t)8 * nblocks * H);
+  float* partial = wt + (size_t)H * gH + (size_t)4 * nb8 * H;  // second scratch region
+  unsigned int* counter = reinterpret_cast<unsigned int*>(wt + (size_t)H * gH + (size_t)8 * nb8 * H);
   GSN_CUDA(cudaMemsetAsync(counter, 0, 64, st));
+  GSN_CUDA(cudaMemsetAsync(dbias_part, 0, (size_t)nb8 * 2 * H * sizeof(float), st));  // rows >= nblocks stay zero
   GSN_REQUIRE(H % 4 == 0, "gsn_layer_train_backward: H=%d must be a multiple of 4", H);
-  const size_t dzs = (size_t)2 * gH * gsn::TR_RT * sizeof(float);
+  const size_t dzs = (size_t)2 * gH * rt * sizeof(float);
   const size_t all_w = (size_t)H * gH * sizeof(float);
   const int resident = dzs + all_w <= 200 * 1024;
   const size_t smem = dzs + (resident ? all_w : (size_t)gsn::TR_NST * gsn::TR_KB * H * sizeof(float));
   gsn::TrainBwdParams p{dh_out, w_hh, c, f, g, xhat, invstd, bn_weight, running_var, dz, dbias_part, dgamma, dbeta,
                         partial, counter, T, R, H, training, eps, resident};
   const int threads = ((H + 31) / 32) * 32;
-  return shared ? gsn::coop_launch(gsn::k_rec_train_bwd<true>, p, nblocks, threads, smem, st, "gsn_layer_train_backward")
-                : gsn::coop_launch(gsn::k_rec_train_bwd<false>, p, nblocks, threads, smem, st, "gsn_layer_train_backward");
+  const char* nm = "gsn_layer_train_backward";
+  if (rt == 16)
+    return shared ? gsn::coop_launch(gsn::k_rec_train_bwd<true, 16>, p, nblocks, threads, smem, st, nm)
+                  : gsn::coop_launch(gsn::k_rec_train_bwd<false, 16>, p, nblocks, threads, smem, st, nm);
+  return shared ? gsn::coop_launch(gsn::k_rec_train_bwd<true, 8>, p, nblocks, threads, smem, st, nm)
+                : gsn::coop_launch(gsn::k_rec_train_bwd<false, 8>, p, nblocks, threads, smem, st, nm);
 }

@@ -431,3 +431,54 @@ def test_train_forward_tcgen05_vs_simt(R, H, bn, training):
             assert float((x - y).abs().max()) <= 2e-5 * max(1.0, float(y.abs().max()))
     if bn:
         assert float((rma - rmb).abs().max()) < 1e-5 and float((rva - rvb).abs().max()) < 1e-5
+
+
+def test_layer_training_large_rows_vs_torch_autograd():
+    """Rows > 256 exercise the 16-row backward CTAs and multi-tile batch statistics: one GSU layer, train-mode
+    BatchNorm, against a float64 torch-autograd restatement (Triangle surrogate) on the same device."""
+    from spiking_fullsubnet_b200.modeling import GSUCell
+    from spiking_fullsubnet_b200.training import GSNLayerFn
+
+    class Tri(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, c):
+            ctx.save_for_backward(c)
+            return (c >= 0).to(c.dtype)
+
+        @staticmethod
+        def backward(ctx, g):
+            (c,) = ctx.saved_tensors
+            return g * (1 - c.abs()).clamp(min=0)
+
+    torch.manual_seed(0)
+    T, R, K, H = 7, 1100, 12, 64
+    cell = GSUCell(K, H, True, True).to(DEV).train()
+    with torch.no_grad():
+        cell.batchnorm.weight.uniform_(0.6, 1.0)
+        cell.batchnorm.bias.normal_(0, 0.1)
+    x = torch.randn(T, R, K, device=DEV)
+    d_out = torch.randn(T, R, H, device=DEV)
+    # reference in float64
+    p64 = {k: v.detach().double().requires_grad_(True) for k, v in cell.named_parameters()}
+    h = torch.zeros(R, H, device=DEV, dtype=torch.float64)
+    c = torch.zeros_like(h)
+    hs = []
+    for t in range(T):
+        z = x[t].double() @ p64["weight_ih"].t() + h @ p64["weight_hh"].t()
+        f = torch.sigmoid(z + p64["bias_ih"][:H])
+        g = z + p64["bias_ih"][H:]
+        c = f * c + (1 - f) * g
+        c = torch.nn.functional.batch_norm(c, None, None, p64["batchnorm.weight"], p64["batchnorm.bias"], True, 0.1, 1e-5)
+        h = Tri.apply(c)
+        hs.append(h)
+    href = torch.stack(hs)
+    (href * d_out.double()).sum().backward()
+    # product path
+    xproj = torch.nn.functional.linear(x, cell.weight_ih)
+    hp = GSNLayerFn.apply(xproj, cell.weight_hh, cell.bias_ih, cell.batchnorm.weight, cell.batchnorm.bias, cell)
+    (hp * d_out).sum().backward()
+    assert torch.equal(hp.detach().double(), href.detach()), "spikes differ from the float64 reference"
+    for k, p in cell.named_parameters():
+        ref = p64[k].grad
+        err = float((p.grad.double() - ref).abs().max() / (ref.abs().max() + 1e-12))
+        assert err < 1e-3, (k, err)
