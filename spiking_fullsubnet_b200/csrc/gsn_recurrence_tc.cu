@@ -38,6 +38,7 @@ struct RecTcParams {
   float* hT;
   float* cT;
   int T, R, H, Kmma;    // Kmma = round_up(H, 16)
+  int wpitch;           // > 0: stage the CTA's weight rows in shared memory (row pitch in floats), else direct loads
   unsigned long long* prof;  // [8] cycle counters of CTA 0 / thread 0 (workspace), see tools/tc_profile.py
   TraceBuf* trace;
   // training path only (TRAIN kernels; bn_scale / bn_shift are unused there)
@@ -71,8 +72,12 @@ __host__ __device__ inline size_t tc_smem_bytes(int Kmma, int C, bool shared) {
   b += 64;                                                // barriers + tmem slot
   if (!shared) b += (size_t)NT * 64 * 4;                  // cell-gate accumulators handed across lanes
   b += 4 * 128 * 2 * 4;                                   // training: cross-group reduction scratch
-  return b;
+  return (b + 127) / 128 * 128;
 }
+
+// Row pitch (floats) of the weight staging area: rows are 16-byte aligned (bulk copies) and pitch/4 is odd, so the
+// 8 lanes of one shared-memory phase read their 16 bytes from 8 different bank groups.
+__host__ __device__ inline int tc_wpitch(int H) { return ((H / 4) & 1) ? H : H + 4; }
 
 // exact 3-way split of an fp32 value into bf16 planes by truncation: w == hi + mid + lo
 __device__ __forceinline__ void split3(float w, uint32_t& hi, uint32_t& mid, uint32_t& lo) {
@@ -98,8 +103,10 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
   constexpr int WPS = NS / 32;
   constexpr int MAXT = (NT * 40 + NTHREADS - 1) / NTHREADS;  // B-operand rebuild tasks per thread (Kmma <= 320)
   static_assert(CPT == 4 || CPT == 8 || CPT == 16, "NT / G must be 4, 8 or 16");
+  constexpr bool PF = CPT <= 8 || (SHARED && !TRAIN);  // prefetch xproj one frame ahead where registers allow
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tslot = trace_begin(p.trace, 2, p.T, p.R, p.H);
+  const long long e0 = PROF ? clock64() : 0;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3;    // TMEM lane quarter this warp may access
   const int g = warp >> 2;   // column group: rows [g*CPT, g*CPT + CPT) of the tile
@@ -121,17 +128,32 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
   off = (off + 15) / 16 * 16;
   uint64_t* bar_mma = reinterpret_cast<uint64_t*>(smem + off);
   uint64_t* bar_bits = bar_mma + 1;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 3);
+  uint64_t* bar_w = bar_mma + 3;     // weight staging (bulk copies)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 4);
   float* zg = reinterpret_cast<float*>(smem + off + 64);  // [NT][64], unshared only
   float* red = reinterpret_cast<float*>(smem + off + 64);  // [G][128][2], TRAIN only (SHARED: zg unused)
+  const float* wst = reinterpret_cast<const float*>(smem + tc_smem_bytes<NT>(Kmma, C, SHARED));  // [128][wpitch]
 
+  // this thread's recurrent weight row (TMEM lane tl): staged with ONE 1-D bulk copy per row (coalesced, TMA unit)
+  const float* wrow = p.w_hh + (size_t)(jv ? (isg ? H + j : j) : 0) * H;
   if (tid == 0) {
     tc::mbar_init(bar_mma, 1);
     tc::mbar_init(&bar_bits[0], 1);  // one local arrive (expect_tx) + the bytes of every slice's bit words
     tc::mbar_init(&bar_bits[1], 1);
+    tc::mbar_init(bar_w, 1);
     tc::fence_mbar_init();
+    if (p.wpitch > 0) {
+      const int first = (int)slice * NS;
+      const int nrows = (H - first < NS ? H - first : NS) * (SHARED ? 1 : 2);
+      tc::mbar_arrive_expect_tx(bar_w, (uint32_t)nrows * (uint32_t)H * 4u);
+    }
   }
   if (warp == 0) tc::tmem_alloc<kTmemCols>(tmem_slot);
+  if (p.wpitch > 0) {
+    __syncthreads();  // the barrier is initialised and armed before any copy can complete on it
+    if (g == 0 && jv)
+      tc::bulk_g2s(const_cast<float*>(wst) + (size_t)tl * p.wpitch, wrow, (uint32_t)H * 4u, bar_w);
+  }
 
   // B-operand rebuild tasks of this thread: (row n, 8 consecutive k) -> one 16-byte store.
   //   byte(n, k) = (n/8)*SBO + (k/8)*128 + (n%8)*16 ;  8 consecutive threads fill one 128-byte core matrix
@@ -166,6 +188,7 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
+  const long long e1 = PROF ? clock64() : 0;
   const uint32_t tmem = *tmem_slot;
   const uint32_t lane_base = (uint32_t)(q * 32) << 16;
   const uint32_t tmem_d = tmem;                       // accumulator: columns [0, NT)
@@ -175,18 +198,31 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
   // recurrent weights of this thread's neuron -> three exact bf16 planes in TMEM (lane = neuron);
   // the G warps that share a lane quarter split the K range between them
   {
-    const float* wrow = p.w_hh + (size_t)(jv ? (isg ? H + j : j) : 0) * H;
+    const bool staged = p.wpitch > 0;
+    if (staged && !tc::mbar_wait(bar_w, 0)) __trap();
+    const float* srow = wst + (size_t)tl * p.wpitch;
     for (int c0 = 8 * g; c0 < (int)plane_cols; c0 += 8 * G) {
+      float wv[16];
+      if (staged) {
+#pragma unroll
+        for (int v4 = 0; v4 < 4; ++v4) {
+          const int k = 2 * c0 + 4 * v4;
+          const float4 x = (jv && k < H) ? *reinterpret_cast<const float4*>(srow + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+          wv[4 * v4 + 0] = x.x; wv[4 * v4 + 1] = x.y; wv[4 * v4 + 2] = x.z; wv[4 * v4 + 3] = x.w;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int k = 2 * c0 + e;
+          wv[e] = (jv && k < H) ? __ldg(wrow + k) : 0.f;
+        }
+      }
       uint32_t vh[8], vm[8], vl[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         uint32_t h2[2], m2[2], l2[2];
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int k = 2 * (c0 + u) + e;
-          const float w = (jv && k < H) ? __ldg(wrow + k) : 0.f;
-          split3(w, h2[e], m2[e], l2[e]);
-        }
+        for (int e = 0; e < 2; ++e) split3(wv[2 * u + e], h2[e], m2[e], l2[e]);
         vh[u] = h2[0] | (h2[1] << 16);
         vm[u] = m2[0] | (m2[1] << 16);
         vl[u] = l2[0] | (l2[1] << 16);
@@ -197,6 +233,7 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
     }
     tc::tmem_wait_st();
   }
+  const long long e2 = PROF ? clock64() : 0;
 
   const int jj = jv ? j : 0;
   const float bf = p.bias[jj], bc = p.bias[H + jj];
@@ -284,7 +321,21 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
     }
   };
 
+  // input projection of one frame -> registers, always fetched ONE FRAME AHEAD of its use
+  float xn[CPT], xqn[SHARED ? 1 : CPT];
+  auto load_xproj = [&](int t) {
+    const char* xf = reinterpret_cast<const char*>(p.xproj) + (size_t)t * xframe_bytes;
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+      const bool ok = (valid >> i) & 1u;
+      xn[i] = ok ? __ldg(reinterpret_cast<const float*>(xf + xoff[i])) : 0.f;
+      if (!SHARED) xqn[i] = ok ? __ldg(reinterpret_cast<const float*>(xf + xoff[i]) + H) : 0.f;
+    }
+  };
+  if (PF) load_xproj(0);
+
   long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long e3 = PROF ? clock64() : 0;
   for (int t = 0; t < T; ++t) {
     const int par = t & 1;
     const long long q0 = PROF ? clock64() : 0;
@@ -315,21 +366,13 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
     // ---- work hidden under the MMAs: trace of frame t-1 out, input projection of frame t in ----------
     if (t > 0) store_frame(t - 1);
     float xf_[CPT], xg_[CPT];
-    {
-      const char* xf = reinterpret_cast<const char*>(p.xproj) + (size_t)t * xframe_bytes;
-      float xp[CPT], xq[CPT];
+    if (!PF) load_xproj(t);
 #pragma unroll
-      for (int i = 0; i < CPT; ++i) {
-        const bool ok = (valid >> i) & 1u;
-        xp[i] = ok ? __ldg(reinterpret_cast<const float*>(xf + xoff[i])) : 0.f;
-        xq[i] = SHARED ? xp[i] : (ok ? __ldg(reinterpret_cast<const float*>(xf + xoff[i]) + H) : 0.f);
-      }
-#pragma unroll
-      for (int i = 0; i < CPT; ++i) {  // reference order: (x W_ih^T + bias) + h W_hh^T   (ESN:140-145)
-        xf_[i] = __fadd_rn(xp[i], bf);
-        xg_[i] = __fadd_rn(xq[i], bc);
-      }
+    for (int i = 0; i < CPT; ++i) {  // reference order: (x W_ih^T + bias) + h W_hh^T   (ESN:140-145)
+      xf_[i] = __fadd_rn(xn[i], bf);
+      xg_[i] = __fadd_rn(SHARED ? xn[i] : xqn[i], bc);
     }
+    if (PF && t + 1 < T) load_xproj(t + 1);  // consumed one frame later: a full frame of latency tolerance
     if (!tc::mbar_wait(bar_mma, t & 1)) { alive = false; break; }
     tc::tc_fence_after();
     const long long q3 = PROF ? clock64() : 0;
@@ -456,6 +499,7 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
     }
   }
   if (!alive) __trap();  // a broken pipeline fails loudly instead of hanging the device
+  const long long e4 = PROF ? clock64() : 0;
   if (PROF && p.prof && blockIdx.x == 0 && tid == 0)
     for (int i = 0; i < 8; ++i) p.prof[i] = (unsigned long long)pc[i];
 
@@ -474,6 +518,10 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
   tc::tc_fence_before();
   tc::cluster_sync_all();  // nobody leaves while a peer may still store into its staging buffer
   if (warp == 0) tc::tmem_dealloc<kTmemCols>(tmem);
+  if (PROF && p.prof && blockIdx.x == 0 && tid == 0) {  // launch-constant phases: alloc + h0, weights, state, loop, exit
+    const long long e5 = clock64();
+    p.prof[8] = e1 - e0; p.prof[9] = e2 - e1; p.prof[10] = e3 - e2; p.prof[11] = e4 - e3; p.prof[12] = e5 - e4;
+  }
   trace_end(p.trace, tslot);
 }
 
@@ -502,8 +550,18 @@ bool recurrence_tc_supported(int R, int H, int shared) {
 size_t recurrence_tc_workspace(int, int, int) { return 256; }
 
 template <int NT, int G, bool PROF, bool SHARED, bool TRAIN = false>
-static int launch_nt(const RecTcParams& p, int C, cudaStream_t st) {
+static int launch_nt(const RecTcParams& p_in, int C, cudaStream_t st) {
+  RecTcParams p = p_in;
   size_t smem = tc_smem_bytes<NT>(p.Kmma, C, SHARED);
+  // weight rows staged through shared memory with bulk copies when they are 16-byte aligned and the area fits
+  p.wpitch = 0;
+  if (p.H % 4 == 0 && (reinterpret_cast<uintptr_t>(p.w_hh) & 15) == 0) {
+    const size_t stage = (size_t)128 * tc_wpitch(p.H) * sizeof(float);
+    if (smem + stage <= tc::kMaxDynamicSmem) {
+      p.wpitch = tc_wpitch(p.H);
+      smem += stage;
+    }
+  }
   if (smem < tc::kTmemExclusiveSmem) smem = tc::kTmemExclusiveSmem;
   GSN_CUDA(cudaFuncSetAttribute(k_recurrence_tc<NT, G, PROF, SHARED, TRAIN>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

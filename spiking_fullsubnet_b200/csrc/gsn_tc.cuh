@@ -105,6 +105,7 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 // CTA holds them.  Requesting more than half of the SM's shared memory makes two such CTAs mutually exclusive on
 // an SM, so the hardware block scheduler queues the second one instead of parking it inside the allocator.
 constexpr size_t kTmemExclusiveSmem = 116 * 1024;
+constexpr size_t kMaxDynamicSmem = 227 * 1024;  // opt-in dynamic shared memory per CTA on sm_100
 template <uint32_t COLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {  // one full warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
