@@ -87,6 +87,12 @@ GSN_API int gsn_linear_f32(const float* a, const float* w, const float* bias, fl
 GSN_API int gsn_linear_spikes(const float* a, const float* w, const float* bias, float* out, float* out_act,
                               int act, int64_t M, int K, int N, int sm_budget, gsn_stream_t stream);
 
+/* gsn_linear_spikes with the spike trace bit-packed: a_bits [M, ceil(K/32)] uint32 as written by
+ * gsn_layer_recurrence_bits / gsn_pack_spikes.  K <= 320; no alignment requirement.                       */
+GSN_API int gsn_linear_spike_bits(const uint32_t* a_bits, const float* w, const float* bias, float* out,
+                                  float* out_act, int act, int64_t M, int K, int N, int sm_budget,
+                                  gsn_stream_t stream);
+
 /* ---- the recurrence: GSULayer.forward ESN:75-81 over GSUCell.forward ESN:132-153 ----------------
  * For t = 0..T-1, rows r, neurons j:
  *   z      = xproj[t, r, :] + h_{t-1}[r, :] @ w_hh^T            (xproj = x @ w_ih^T, no bias)
@@ -108,6 +114,17 @@ GSN_API int gsn_layer_recurrence(const float* xproj, const float* w_hh, const fl
                          const float* c0, float* h_out, float* c_out, float* hT, float* cT, int T,
                          int R, int H, int shared, int backend, int sm_budget, void* workspace,
                          gsn_stream_t stream);
+/* Same call with one more output: h_bits [T, R, W] uint32, W = ceil(H/32), the SAME spike trace bit-packed
+ * (neuron n of row r at frame t = bit n%32 of h_bits[t, r, n/32]; bits of neurons >= H are 0).  The tcgen05 kernel
+ * writes the ballot words it exchanges between CTAs anyway; other back ends pack h_out afterwards
+ * (gsn_pack_spikes).  It is what gsn_linear_spike_bits reads: 1 bit instead of 4 bytes per spike.  May be NULL. */
+GSN_API int gsn_layer_recurrence_bits(const float* xproj, const float* w_hh, const float* bias,
+                         const float* bn_scale, const float* bn_shift, const float* h0,
+                         const float* c0, float* h_out, float* c_out, float* hT, float* cT, uint32_t* h_bits,
+                         int T, int R, int H, int shared, int backend, int sm_budget, void* workspace,
+                         gsn_stream_t stream);
+/* bits[r, w] (W = ceil(H/32) words per row) from an fp32 {0,1} trace h [rows, H]. */
+GSN_API int gsn_pack_spikes(const float* h, uint32_t* bits, int64_t rows, int H, gsn_stream_t stream);
 /* which backend GSN_BACKEND_AUTO resolves to for this shape (GSN_BACKEND_SIMT / _TCGEN05 / _TCGEN05_I8). */
 GSN_API int gsn_layer_recurrence_pick_backend(int R, int H, int shared);
 

@@ -29,7 +29,7 @@ size_t recurrence_simt_workspace(int H, int shared);
 // gsn_recurrence_tc.cu
 int launch_recurrence_tc(const float*, const float*, const float*, const float*, const float*,
                          const float*, const float*, float*, float*, float*, float*, int, int, int, int, int,
-                         void*, cudaStream_t);
+                         void*, uint32_t*, cudaStream_t);
 size_t recurrence_tc_workspace(int R, int H, int shared);
 bool recurrence_tc_supported(int R, int H, int shared);
 // gsn_recurrence_tc_i8.cu
@@ -86,11 +86,11 @@ extern "C" size_t gsn_layer_recurrence_workspace_bytes(int R, int H, int shared,
   return a > b ? a : b;
 }
 
-extern "C" int gsn_layer_recurrence(const float* xproj, const float* w_hh, const float* bias,
-                                    const float* bn_scale, const float* bn_shift, const float* h0,
-                                    const float* c0, float* h_out, float* c_out, float* hT, float* cT,
-                                    int T, int R, int H, int shared, int backend, int sm_budget,
-                                    void* workspace, gsn_stream_t stream) {
+extern "C" int gsn_layer_recurrence_bits(const float* xproj, const float* w_hh, const float* bias,
+                                         const float* bn_scale, const float* bn_shift, const float* h0,
+                                         const float* c0, float* h_out, float* c_out, float* hT, float* cT,
+                                         uint32_t* h_bits, int T, int R, int H, int shared, int backend,
+                                         int sm_budget, void* workspace, gsn_stream_t stream) {
   GSN_REQUIRE(xproj && w_hh && bias && h_out && workspace, "gsn_layer_recurrence: null pointer");
   GSN_REQUIRE(T > 0 && R > 0 && H > 0, "gsn_layer_recurrence: bad shape T=%d R=%d H=%d", T, R, H);
   GSN_REQUIRE((bn_scale == nullptr) == (bn_shift == nullptr), "gsn_layer_recurrence: bn params");
@@ -98,22 +98,34 @@ extern "C" int gsn_layer_recurrence(const float* xproj, const float* w_hh, const
               "gsn_layer_recurrence: workspace must be 256-byte aligned");
   if (backend == GSN_BACKEND_AUTO) backend = gsn_layer_recurrence_pick_backend(R, H, shared);
   cudaStream_t st = gsn::as_stream(stream);
-  if (backend == GSN_BACKEND_SIMT)
-    return gsn::launch_recurrence_simt(xproj, w_hh, bias, bn_scale, bn_shift, h0, c0, h_out, c_out, hT,
-                                       cT, T, R, H, shared, workspace, st);
-  if (backend == GSN_BACKEND_TCGEN05) {
+  int rc;
+  if (backend == GSN_BACKEND_SIMT) {
+    rc = gsn::launch_recurrence_simt(xproj, w_hh, bias, bn_scale, bn_shift, h0, c0, h_out, c_out, hT,
+                                     cT, T, R, H, shared, workspace, st);
+  } else if (backend == GSN_BACKEND_TCGEN05) {
     if (!gsn::recurrence_tc_supported(R, H, shared))
       return gsn::fail(GSN_ENOSUP, "gsn_layer_recurrence(TCGEN05): shape R=%d H=%d shared=%d not supported",
                        R, H, shared);
     return gsn::launch_recurrence_tc(xproj, w_hh, bias, bn_scale, bn_shift, h0, c0, h_out, c_out, hT,
-                                     cT, T, R, H, shared, sm_budget, workspace, st);
-  }
-  if (backend == GSN_BACKEND_TCGEN05_I8) {
+                                     cT, T, R, H, shared, sm_budget, workspace, h_bits, st);  // packs in-kernel
+  } else if (backend == GSN_BACKEND_TCGEN05_I8) {
     if (!gsn::recurrence_i8_supported(R, H, shared))
       return gsn::fail(GSN_ENOSUP, "gsn_layer_recurrence(TCGEN05_I8): shape R=%d H=%d shared=%d not supported",
                        R, H, shared);
-    return gsn::launch_recurrence_i8(xproj, w_hh, bias, bn_scale, bn_shift, h0, c0, h_out, c_out, hT, cT, T, R, H,
-                                     shared, sm_budget, workspace, st);
+    rc = gsn::launch_recurrence_i8(xproj, w_hh, bias, bn_scale, bn_shift, h0, c0, h_out, c_out, hT, cT, T, R, H,
+                                   shared, sm_budget, workspace, st);
+  } else {
+    return gsn::fail(GSN_EINVAL, "gsn_layer_recurrence: unknown backend %d", backend);
   }
-  return gsn::fail(GSN_EINVAL, "gsn_layer_recurrence: unknown backend %d", backend);
+  if (rc == GSN_OK && h_bits) rc = gsn_pack_spikes(h_out, h_bits, (int64_t)T * R, H, stream);
+  return rc;
+}
+
+extern "C" int gsn_layer_recurrence(const float* xproj, const float* w_hh, const float* bias,
+                                    const float* bn_scale, const float* bn_shift, const float* h0,
+                                    const float* c0, float* h_out, float* c_out, float* hT, float* cT,
+                                    int T, int R, int H, int shared, int backend, int sm_budget,
+                                    void* workspace, gsn_stream_t stream) {
+  return gsn_layer_recurrence_bits(xproj, w_hh, bias, bn_scale, bn_shift, h0, c0, h_out, c_out, hT, cT, nullptr,
+                                   T, R, H, shared, backend, sm_budget, workspace, stream);
 }

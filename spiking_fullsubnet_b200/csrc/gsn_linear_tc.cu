@@ -36,11 +36,17 @@ __device__ __forceinline__ void lin_split3(float w, uint32_t& hi, uint32_t& mid,
   lo = __float_as_uint(r2) >> 16;
 }
 
-template <int NT>
+// Row pitch (floats) of the weight staging area: 16-byte aligned rows, pitch/4 odd (conflict-free 16-byte reads
+// by 8 consecutive lanes = 8 consecutive rows).
+static inline __host__ __device__ int lin_wpitch(int K) { return ((K / 4) & 1) ? K : K + 4; }
+
+// BITS: `a_bits` holds the spike trace bit-packed ([M, W] uint32, W = ceil(K/32), neuron k = bit k%32 of word
+// k/32, as the recurrence kernels emit it): 1 bit instead of 4 bytes read per spike.
+template <int NT, bool BITS>
 __global__ void __launch_bounds__(256, 1)
-    k_linear_tc(const float* __restrict__ a, const float* __restrict__ w, const float* __restrict__ bias,
-                float* __restrict__ out, float* __restrict__ out_act, int act, long long M, int K, int N,
-                int Kmma, TraceBuf* tb) {
+    k_linear_tc(const float* __restrict__ a, const uint32_t* __restrict__ a_bits, const float* __restrict__ w,
+                const float* __restrict__ bias, float* __restrict__ out, float* __restrict__ out_act, int act,
+                long long M, int K, int N, int Kmma, int wpitch, TraceBuf* tb) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tslot = trace_begin(tb, 4, (int)M, K, N);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -55,18 +61,32 @@ __global__ void __launch_bounds__(256, 1)
   const size_t b_bytes = ((size_t)NT * Kmma * 2 + 127) / 128 * 128;
   uint8_t* const sB0 = smem;
   uint8_t* const sB1 = smem + b_bytes;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * b_bytes);  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+  // the weight staging area of the prologue shares the bytes of the two B buffers (and may extend past them)
+  const size_t stage_bytes = wpitch > 0 ? (size_t)128 * wpitch * 4 : 0;
+  const size_t bar_off = ((2 * b_bytes > stage_bytes ? 2 * b_bytes : stage_bytes) + 127) / 128 * 128;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + bar_off);  // [2] MMA completion, [1] weight staging
+  uint64_t* bar_w = bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 3);
+  float* wst = reinterpret_cast<float*>(smem);
+  const float* wrow = w + (size_t)(jv ? j : 0) * K;
 
   if (tid == 0) {
     tc::mbar_init(&bar[0], 1);
     tc::mbar_init(&bar[1], 1);
+    tc::mbar_init(bar_w, 1);
     tc::fence_mbar_init();
+    if (wpitch > 0) {
+      const int nrows = N - slice * 128 < 128 ? N - slice * 128 : 128;
+      tc::mbar_arrive_expect_tx(bar_w, (uint32_t)nrows * (uint32_t)K * 4u);
+    }
   }
   if (warp == 0) tc::tmem_alloc<kLinTmemCols>(tmem_slot);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
+  // one 1-D bulk copy (TMA unit) per weight row of this CTA's 128 output features: coalesced, asynchronous
+  if (wpitch > 0 && g == 0 && jv)
+    tc::bulk_g2s(wst + (size_t)(q * 32 + lane) * wpitch, wrow, (uint32_t)K * 4u, bar_w);
   const uint32_t tmem = *tmem_slot;
   const uint32_t lane_base = (uint32_t)(q * 32) << 16;
   const uint32_t tmem_d0 = tmem, tmem_d1 = tmem + NT;
@@ -75,17 +95,31 @@ __global__ void __launch_bounds__(256, 1)
 
   // weights of my feature -> three exact bf16 planes in TMEM (the two row-half warps split the K range)
   {
-    const float* wrow = w + (size_t)(jv ? j : 0) * K;
+    const bool staged = wpitch > 0;
+    if (staged && !tc::mbar_wait(bar_w, 0)) __trap();
+    const float* srow = wst + (size_t)(q * 32 + lane) * wpitch;
     for (int c0 = 8 * g; c0 < (int)plane_cols; c0 += 16) {
+      float wv[16];
+      if (staged) {
+#pragma unroll
+        for (int v4 = 0; v4 < 4; ++v4) {
+          const int k = 2 * c0 + 4 * v4;
+          const float4 x = (jv && k < K) ? *reinterpret_cast<const float4*>(srow + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+          wv[4 * v4 + 0] = x.x; wv[4 * v4 + 1] = x.y; wv[4 * v4 + 2] = x.z; wv[4 * v4 + 3] = x.w;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int k = 2 * c0 + e;
+          wv[e] = (jv && k < K) ? __ldg(wrow + k) : 0.f;
+        }
+      }
       uint32_t vh[8], vm[8], vl[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         uint32_t h2[2], m2[2], l2[2];
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int k = 2 * (c0 + u) + e;
-          lin_split3((jv && k < K) ? __ldg(wrow + k) : 0.f, h2[e], m2[e], l2[e]);
-        }
+        for (int e = 0; e < 2; ++e) lin_split3(wv[2 * u + e], h2[e], m2[e], l2[e]);
         vh[u] = h2[0] | (h2[1] << 16);
         vm[u] = m2[0] | (m2[1] << 16);
         vl[u] = l2[0] | (l2[1] << 16);
@@ -95,6 +129,7 @@ __global__ void __launch_bounds__(256, 1)
       tc::tmem_st8(tmem_a + lane_base + 2 * plane_cols + c0, vh);
     }
     tc::tmem_wait_st();
+    if (staged) __syncthreads();  // the staging bytes become the B buffers
   }
   const float bj = (bias && jv) ? bias[j] : 0.f;
 
@@ -103,8 +138,22 @@ __global__ void __launch_bounds__(256, 1)
   const int k8n = Kmma / 8;
   const int ntask = NT * k8n;
   constexpr int UNR = 4;
+  const int Wb = (K + 31) / 32;  // words per row of the bit-packed trace
   auto convert = [&](long long tile, uint8_t* dst) {
     const long long r0 = tile * NT;
+    if (BITS) {
+      for (int i = tid; i < ntask; i += 256) {
+        const int nlo = i & 7, k8 = (i >> 3) % k8n, nhi = (i >> 3) / k8n;
+        const long long row = r0 + nhi * 8 + nlo;
+        const uint32_t b8 = row < M ? (__ldg(a_bits + row * Wb + (k8 >> 2)) >> (8 * (k8 & 3))) & 0xFFu : 0u;
+        uint32_t v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          v[e] = ((b8 >> (2 * e)) & 1u ? 0x3F80u : 0u) | ((b8 >> (2 * e + 1)) & 1u ? 0x3F800000u : 0u);
+        *reinterpret_cast<uint4*>(dst + (uint32_t)(nhi * SBO + k8 * 128 + nlo * 16)) = make_uint4(v[0], v[1], v[2], v[3]);
+      }
+      return;
+    }
     for (int base = tid; base < ntask; base += 256 * UNR) {
       float4 x0[UNR], x1[UNR];
       uint32_t doff[UNR];
@@ -210,13 +259,22 @@ __global__ void __launch_bounds__(256, 1)
   trace_end(tb, tslot);
 }
 
-template <int NT>
-static int launch_linear_tc(const float* a, const float* w, const float* bias, float* out, float* out_act,
-                            int act, long long M, int K, int N, int sm_budget, cudaStream_t st) {
+template <int NT, bool BITS>
+static int launch_linear_tc(const float* a, const uint32_t* a_bits, const float* w, const float* bias, float* out,
+                            float* out_act, int act, long long M, int K, int N, int sm_budget, cudaStream_t st) {
   const int Kmma = (K + 15) / 16 * 16;
-  size_t smem = 2 * (((size_t)NT * Kmma * 2 + 127) / 128 * 128) + 64;
+  const size_t b2 = 2 * (((size_t)NT * Kmma * 2 + 127) / 128 * 128);
+  // weight rows staged through shared memory with bulk copies when they are 16-byte aligned
+  int wpitch = 0;
+  size_t stage = 0;
+  if (K % 4 == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0) {
+    wpitch = lin_wpitch(K);
+    stage = (size_t)128 * wpitch * sizeof(float);
+    if (stage + 192 > tc::kMaxDynamicSmem) { wpitch = 0; stage = 0; }
+  }
+  size_t smem = ((b2 > stage ? b2 : stage) + 127) / 128 * 128 + 64;
   if (smem < tc::kTmemExclusiveSmem) smem = tc::kTmemExclusiveSmem;
-  GSN_CUDA(cudaFuncSetAttribute(k_linear_tc<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  GSN_CUDA(cudaFuncSetAttribute(k_linear_tc<NT, BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 148;
   GSN_CUDA(cudaGetDevice(&dev));
   GSN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -227,9 +285,33 @@ static int launch_linear_tc(const float* a, const float* w, const float* bias, f
   if (P < 1) P = 1;
   if (P > ntiles) P = ntiles;
   dim3 grid((unsigned)slices, (unsigned)P);
-  k_linear_tc<NT><<<grid, 256, smem, st>>>(a, w, bias, out, out_act, act, M, K, N, Kmma, trace_buffer());
+  k_linear_tc<NT, BITS><<<grid, 256, smem, st>>>(a, a_bits, w, bias, out, out_act, act, M, K, N, Kmma, wpitch,
+                                                 trace_buffer());
   GSN_LAUNCH_CHECK("k_linear_tc");
   return GSN_OK;
+}
+
+template <bool BITS>
+static int dispatch_linear_tc(const float* a, const uint32_t* a_bits, const float* w, const float* bias, float* out,
+                              float* out_act, int act, long long M, int K, int N, int sm_budget, cudaStream_t st) {
+  const int Kmma = (K + 15) / 16 * 16;
+  if (3 * Kmma / 2 + 2 * 64 <= 512)
+    return launch_linear_tc<64, BITS>(a, a_bits, w, bias, out, out_act, act, M, K, N, sm_budget, st);
+  if (3 * Kmma / 2 + 2 * 16 <= 512)
+    return launch_linear_tc<16, BITS>(a, a_bits, w, bias, out, out_act, act, M, K, N, sm_budget, st);
+  return fail(GSN_ENOSUP, "gsn_linear_spikes: K=%d does not fit tensor memory (K <= 320)", K);
+}
+
+// fp32 {0,1} trace -> bit-packed trace (one warp per 32 neurons of a row)
+__global__ void __launch_bounds__(256) k_pack_spikes(const float* __restrict__ h, uint32_t* __restrict__ bits,
+                                                     long long rows, int H, int W) {
+  const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gw >= rows * W) return;
+  const long long r = gw / W;
+  const int wd = (int)(gw % W), k = wd * 32 + lane;
+  const uint32_t word = __ballot_sync(0xffffffffu, k < H && h[r * H + k] != 0.f);
+  if (lane == 0) bits[gw] = word;
 }
 
 }  // namespace gsn
@@ -241,10 +323,27 @@ extern "C" int gsn_linear_spikes(const float* a, const float* w, const float* bi
   GSN_REQUIRE(act >= 0 && act <= 3, "gsn_linear_spikes: unknown activation %d", act);
   GSN_REQUIRE(K % 4 == 0, "gsn_linear_spikes: K=%d must be a multiple of 4 (16-byte row alignment)", K);
   GSN_REQUIRE((reinterpret_cast<uintptr_t>(a) & 15) == 0, "gsn_linear_spikes: a must be 16-byte aligned");
-  const int Kmma = (K + 15) / 16 * 16;
-  if (3 * Kmma / 2 + 2 * 64 <= 512)
-    return gsn::launch_linear_tc<64>(a, w, bias, out, out_act, act, M, K, N, sm_budget, gsn::as_stream(stream));
-  if (3 * Kmma / 2 + 2 * 16 <= 512)
-    return gsn::launch_linear_tc<16>(a, w, bias, out, out_act, act, M, K, N, sm_budget, gsn::as_stream(stream));
-  return gsn::fail(GSN_ENOSUP, "gsn_linear_spikes: K=%d does not fit tensor memory (K <= 320)", K);
+  return gsn::dispatch_linear_tc<false>(a, nullptr, w, bias, out, out_act, act, M, K, N, sm_budget,
+                                        gsn::as_stream(stream));
+}
+
+extern "C" int gsn_linear_spike_bits(const uint32_t* a_bits, const float* w, const float* bias, float* out,
+                                     float* out_act, int act, int64_t M, int K, int N, int sm_budget,
+                                     gsn_stream_t stream) {
+  GSN_REQUIRE(a_bits && w && out, "gsn_linear_spike_bits: null pointer");
+  GSN_REQUIRE(M > 0 && K > 0 && N > 0, "gsn_linear_spike_bits: bad shape M=%lld K=%d N=%d", (long long)M, K, N);
+  GSN_REQUIRE(act >= 0 && act <= 3, "gsn_linear_spike_bits: unknown activation %d", act);
+  return gsn::dispatch_linear_tc<true>(nullptr, a_bits, w, bias, out, out_act, act, M, K, N, sm_budget,
+                                       gsn::as_stream(stream));
+}
+
+extern "C" int gsn_pack_spikes(const float* h, uint32_t* bits, int64_t rows, int H, gsn_stream_t stream) {
+  GSN_REQUIRE(h && bits, "gsn_pack_spikes: null pointer");
+  GSN_REQUIRE(rows > 0 && H > 0, "gsn_pack_spikes: bad shape rows=%lld H=%d", (long long)rows, H);
+  const int W = (H + 31) / 32;
+  const long long warps = rows * W;
+  const unsigned blocks = (unsigned)((warps * 32 + 255) / 256);
+  gsn::k_pack_spikes<<<blocks, 256, 0, gsn::as_stream(stream)>>>(h, bits, rows, H, W);
+  GSN_LAUNCH_CHECK("k_pack_spikes");
+  return GSN_OK;
 }

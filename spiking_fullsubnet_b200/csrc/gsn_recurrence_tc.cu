@@ -35,6 +35,7 @@ struct RecTcParams {
   const float* c0;
   float* h_out;         // [T, R, H]
   float* c_out;         // [T, R, H] or null
+  uint32_t* h_bits;     // [T, R, ceil(H/32)] bit-packed spike trace or null (neuron n = bit n%32 of word n/32)
   float* hT;
   float* cT;
   int T, R, H, Kmma;    // Kmma = round_up(H, 16)
@@ -120,6 +121,7 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
   const bool comp = jv && !isg;                    // this thread integrates the membrane of neuron j
   const int gH = SHARED ? H : 2 * H;
   const int KWp = tc_kw_padded(C, WPS);
+  const int Wb = (H + 31) / 32;
 
   uint8_t* sB = smem;
   size_t off = ((size_t)NT * Kmma * 2 + 127) / 128 * 128;
@@ -471,6 +473,8 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
         myw = (lane % CPT) == (i0 + u) ? w : myw;
       }
     }
+    if (p.h_bits && q < WPS && lane < CPT && (int)slice * WPS + q < Wb && row0 + g * CPT + lane < R)
+      p.h_bits[((size_t)t * R + row0 + g * CPT + lane) * Wb + slice * WPS + q] = myw;  // the ballots ARE the packed trace
     const long long q4 = PROF ? clock64() : 0;
     // ---- exchange: ONE asynchronous DSMEM store per sending lane into the staging buffer of a CTA of the
     //      cluster; the bytes are counted on the receiver's mbarrier (no fence, no arrive on this side) ----
@@ -586,13 +590,14 @@ static int launch_nt(const RecTcParams& p_in, int C, cudaStream_t st) {
 int launch_recurrence_tc(const float* xproj, const float* w_hh, const float* bias, const float* bn_scale,
                          const float* bn_shift, const float* h0, const float* c0, float* h_out, float* c_out,
                          float* hT, float* cT, int T, int R, int H, int shared, int sm_budget, void* workspace,
-                         cudaStream_t st) {
+                         uint32_t* h_bits, cudaStream_t st) {
   int dev = 0, sms = 148;
   GSN_CUDA(cudaGetDevice(&dev));
   GSN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   RecTcParams p{};
   p.xproj = xproj; p.w_hh = w_hh; p.bias = bias; p.bn_scale = bn_scale; p.bn_shift = bn_shift; p.h0 = h0; p.c0 = c0;
   p.h_out = h_out; p.c_out = c_out; p.hT = hT; p.cT = cT; p.T = T; p.R = R; p.H = H; p.Kmma = (H + 15) / 16 * 16;
+  p.h_bits = h_bits;
   p.prof = reinterpret_cast<unsigned long long*>(workspace); p.trace = trace_buffer();
   const int C = shared ? (H + 127) / 128 : (H + 63) / 64;
   if (sm_budget > 0 && sm_budget < sms) sms = sm_budget;

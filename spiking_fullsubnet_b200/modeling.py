@@ -113,21 +113,23 @@ def _needs_autograd(module):
     return any(isinstance(m, nn.BatchNorm1d) and m.training for m in module.modules())
 
 
-def _run_layer(cell, x, state, want_c, backend, sm_budget=0, spikes_in=False):
+def _run_layer(cell, x, state, want_c, backend, sm_budget=0, spikes_in=False, bits_in=None, bits_out=None):
+    """bits_in: bit-packed copy of a spike-trace input `x`; bits_out: buffer for the bit-packed copy of the
+    returned trace (ops.spike_bits_buffer) -- what the next spike-input linear reads instead of fp32."""
     if cell.use_bn and cell.batchnorm.training:
         raise RuntimeError("internal error: training-mode BatchNorm reached the inference kernels")
     if not x.is_cuda:
         raise RuntimeError("spiking_fullsubnet_b200 has no CPU path: move the model and input to CUDA")
     x = x.contiguous()
     # (bias joins in the recurrence, in the reference's order; layers >= 1 see the previous layer's spikes)
-    xproj = ops.linear(x, cell.weight_ih.detach(), spikes=spikes_in, sm_budget=sm_budget)
+    xproj = ops.linear(x, cell.weight_ih.detach(), spikes=spikes_in, sm_budget=sm_budget, bits=bits_in)
     a, b = cell.folded_bn()
     h0 = c0 = None
     if state is not None:
         h0, c0 = state[0].contiguous(), state[1].contiguous()
     return ops.layer_recurrence(xproj, cell.weight_hh.detach(), cell.bias_ih.detach(), a, b,
                                 shared=cell.shared_weights, want_c=want_c, h0=h0, c0=c0,
-                                want_state=True, backend=backend, sm_budget=sm_budget)
+                                want_state=True, backend=backend, sm_budget=sm_budget, out_bits=bits_out)
 
 
 class StackedGSU(nn.Module):
@@ -146,18 +148,23 @@ class StackedGSU(nn.Module):
             from . import training
             out, trace = training.run_stack(self, input.contiguous())
             self.last_c = [None] * len(self.layers)
+            self.last_bits = None
             return out, [MemoryState(t[-1], None) for t in trace[1:]], trace
         out = input
         out_states, trace = [], [input]
         self.last_c = []
+        bits = None
         for i, layer in enumerate(self.layers):
             st = None if states is None else states[i]
+            H = layer.cell.hidden_size
+            nbits = ops.spike_bits_buffer(out.shape[:-1], H, out.device) if ops.SPIKE_BITS[0] and H <= 320 else None
             h, c, (hT, cT) = _run_layer(layer.cell, out, st, want_c, self.backend, self.sm_budget,
-                                        spikes_in=i > 0)
+                                        spikes_in=i > 0, bits_in=bits, bits_out=nbits)
             out_states.append(MemoryState(hT, cT))
             trace.append(h)
             self.last_c.append(c)
-            out = h
+            out, bits = h, nbits
+        self.last_bits = bits  # bit-packed copy of `out` for the caller's proj (None when disabled)
         return out, out_states, trace
 
 
@@ -205,7 +212,8 @@ class SequenceModel(nn.Module):
         out, _, trace = self.sequence_model(x, None)
         if isinstance(self.proj, nn.Linear):
             res = ops.linear(out, self.proj.weight.detach(), self.proj.bias.detach(), act=self._act,
-                             spikes=True, sm_budget=self.sequence_model.sm_budget)
+                             spikes=True, sm_budget=self.sequence_model.sm_budget,
+                             bits=getattr(self.sequence_model, "last_bits", None))
             proj, act = res if self._act else (res, res)
         else:
             proj = out
@@ -241,7 +249,7 @@ class _SeqPlan:
         self.L = len(stack.layers)
         f32 = dict(device=device, dtype=torch.float32)
         self.x = torch.empty((T, R, model.input_size), **f32)
-        self.xproj, self.h, self.hs, self.cs, self.bn, self.ws = [], [], [], [], [], []
+        self.xproj, self.h, self.hs, self.cs, self.bn, self.ws, self.hb = [], [], [], [], [], [], []
         for layer in stack.layers:
             cell = layer.cell
             if cell.use_bn and cell.batchnorm.training:
@@ -250,6 +258,7 @@ class _SeqPlan:
             g = 1 if cell.shared_weights else 2
             self.xproj.append(torch.empty((T, R, g * H), **f32))
             self.h.append(torch.empty((T, R, H), **f32))
+            self.hb.append(ops.spike_bits_buffer((T, R), H, device) if ops.SPIKE_BITS[0] and H <= 320 else None)
             self.hs.append(torch.zeros((nchunks + 1, R, H), **f32))
             self.cs.append(torch.zeros((nchunks + 1, R, H), **f32))
             self.bn.append(cell.folded_bn())
@@ -265,8 +274,9 @@ class _SeqPlan:
         """Input-to-hidden product of frames [t0,t1) of layer l (no dependence on the layer's own state)."""
         cell = self.m.sequence_model.layers[l].cell
         inp = self.x[t0:t1] if l == 0 else self.h[l - 1][t0:t1]
+        bits = self.hb[l - 1][t0:t1] if l > 0 and self.hb[l - 1] is not None else None
         ops.linear(inp, cell.weight_ih.detach(), out=self.xproj[l][t0:t1], spikes=l > 0,
-                   sm_budget=self.lin_budget)
+                   sm_budget=self.lin_budget, bits=bits)
 
     def run_rec(self, l, k, t0, t1):
         """Recurrence of frames [t0,t1) of layer l from the state carried out of chunk k-1."""
@@ -275,7 +285,8 @@ class _SeqPlan:
         ops.layer_recurrence(self.xproj[l][t0:t1], cell.weight_hh.detach(), cell.bias_ih.detach(), a, b,
                              shared=cell.shared_weights, h0=self.hs[l][k], c0=self.cs[l][k],
                              out_h=self.h[l][t0:t1], out_hT=self.hs[l][k + 1], out_cT=self.cs[l][k + 1],
-                             backend=self.backend, workspace=self.ws[l], sm_budget=self.sm_budget)
+                             backend=self.backend, workspace=self.ws[l], sm_budget=self.sm_budget,
+                             out_bits=self.hb[l][t0:t1] if self.hb[l] is not None else None)
 
     def run_post(self, k, t0, t1):
         """Output projection (+ activation) of frames [t0,t1)."""
@@ -283,7 +294,7 @@ class _SeqPlan:
         if self.proj is not None:
             ops.linear(self.h[-1][t0:t1], m.proj.weight.detach(), m.proj.bias.detach(), act=m._act,
                        out=self.proj[t0:t1], out_act=self.act[t0:t1] if m._act else None, spikes=True,
-                       sm_budget=self.lin_budget)
+                       sm_budget=self.lin_budget, bits=self.hb[-1][t0:t1] if self.hb[-1] is not None else None)
 
     def outputs(self):
         """(proj_out, activated, all_layer_outputs) exactly as SequenceModel.run_time_major returns them."""
@@ -822,7 +833,7 @@ class _FreezeSequenceModel(nn.Module):
         out, _, trace = self.sequence_model(x, None)
         if int(self.output_size):
             out = ops.linear(out, self.fc_output_layer.weight.detach(), self.fc_output_layer.bias.detach(),
-                             spikes=True)
+                             spikes=True, bits=getattr(self.sequence_model, "last_bits", None))
             trace = trace + [out]
         act = self.activate_function(out) if self.output_activate_function_name else out
         return out, act, trace

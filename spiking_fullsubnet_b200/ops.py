@@ -76,10 +76,30 @@ TC_TRAIN = [True]   # training forward on tcgen05 where supported (False: fp32 C
 TC_LINEAR = [True]  # spike-input linears on tcgen05 (set False to force the fp32 CUDA-core kernel)
 
 
-def linear(a, w, bias=None, act=None, out=None, out_act=None, spikes=False, sm_budget=0):
+SPIKE_BITS = [True]  # recurrences also emit the bit-packed trace and spike-input linears read it (False: fp32 trace)
+
+
+def spike_bits_buffer(shape, H, device):
+    """Bit-packed trace buffer for a [..., H] spike trace: int32 [..., ceil(H/32)] (see gsn_layer_recurrence_bits)."""
+    return torch.empty(tuple(shape) + ((H + 31) // 32,), device=device, dtype=torch.int32)
+
+
+def pack_spikes(h):
+    """fp32 {0,1} trace [..., H] -> bit-packed int32 [..., ceil(H/32)] (gsn_pack_spikes)."""
+    lib, st = _prep(h)
+    H = h.shape[-1]
+    bits = spike_bits_buffer(h.shape[:-1], H, h.device)
+    _lib.check(lib.gsn_pack_spikes(_ptr(h), bits.data_ptr(), h.numel() // H, H, st))
+    LAUNCHES[0] += 1
+    return bits
+
+
+def linear(a, w, bias=None, act=None, out=None, out_act=None, spikes=False, sm_budget=0, bits=None):
     """out[..., N] = a[..., K] @ w[N,K]^T + bias.  Returns out, or (out, act(out)) if act.
     spikes=True promises that `a` holds {0,1} (a spike trace): the product then runs on tcgen05 with the
-    weights as exact bf16x3 planes (gsn_linear_spikes); otherwise fp32 FMA on CUDA cores (gsn_linear_f32)."""
+    weights as exact bf16x3 planes (gsn_linear_spikes); otherwise fp32 FMA on CUDA cores (gsn_linear_f32).
+    bits: the same trace bit-packed (int32 [..., ceil(K/32)], from layer_recurrence(out_bits=...)); when given
+    the tcgen05 kernel reads it instead of `a` (gsn_linear_spike_bits)."""
     lib, st = _prep(a, w, bias, out, out_act)
     K = a.shape[-1]
     N = w.shape[0]
@@ -89,7 +109,12 @@ def linear(a, w, bias=None, act=None, out=None, out_act=None, spikes=False, sm_b
     out = _out(out, a.shape[:-1] + (N,), a)
     code = _ACT[act]
     out_act = _out(out_act, out.shape, a) if code else None
-    if spikes and TC_LINEAR[0] and K % 4 == 0 and K <= 320 and a.data_ptr() % 16 == 0:
+    if bits is not None and TC_LINEAR[0] and K <= 320:
+        if bits.dtype != torch.int32 or not bits.is_contiguous() or bits.numel() != M * ((K + 31) // 32):
+            raise ValueError(f"linear: bits {tuple(bits.shape)} {bits.dtype} does not match a{tuple(a.shape)}")
+        _lib.check(lib.gsn_linear_spike_bits(bits.data_ptr(), _ptr(w), _ptr(bias), _ptr(out), _ptr(out_act), code,
+                                             M, K, N, int(sm_budget), st))
+    elif spikes and TC_LINEAR[0] and K % 4 == 0 and K <= 320 and a.data_ptr() % 16 == 0:
         _lib.check(lib.gsn_linear_spikes(_ptr(a), _ptr(w), _ptr(bias), _ptr(out), _ptr(out_act), code, M, K, N,
                                          int(sm_budget), st))
     else:
@@ -108,8 +133,9 @@ def recurrence_workspace(R, H, shared, backend, device):
 
 def layer_recurrence(xproj, w_hh, bias, bn_scale=None, bn_shift=None, shared=True, want_c=False,
                      h0=None, c0=None, want_state=False, backend="auto", out_h=None, out_c=None, out_hT=None,
-                     out_cT=None, workspace=None, sm_budget=0):
-    """One GSULayer over all frames (ESN:75-81 / 132-153).  xproj [T,R,gH] -> h [T,R,H] (and c, (hT,cT))."""
+                     out_cT=None, workspace=None, sm_budget=0, out_bits=None):
+    """One GSULayer over all frames (ESN:75-81 / 132-153).  xproj [T,R,gH] -> h [T,R,H] (and c, (hT,cT)).
+    out_bits: optional int32 [T,R,ceil(H/32)] buffer that receives the same spike trace bit-packed."""
     lib, st = _prep(xproj, w_hh, bias, bn_scale, bn_shift, h0, c0, out_h, out_c, out_hT, out_cT)
     T, R, gH = xproj.shape
     H = w_hh.shape[1]
@@ -129,9 +155,13 @@ def layer_recurrence(xproj, w_hh, bias, bn_scale=None, bn_shift=None, shared=Tru
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    _lib.check(lib.gsn_layer_recurrence(_ptr(xproj), _ptr(w_hh), _ptr(bias), _ptr(bn_scale), _ptr(bn_shift),
-                                        _ptr(h0), _ptr(c0), _ptr(h), _ptr(c), _ptr(hT), _ptr(cT), T, R, H,
-                                        int(shared), be, int(sm_budget), ws.data_ptr() + off, st))
+    if out_bits is not None and (out_bits.dtype != torch.int32 or not out_bits.is_contiguous()
+                                 or tuple(out_bits.shape) != (T, R, (H + 31) // 32)):
+        raise ValueError(f"layer_recurrence: out_bits {tuple(out_bits.shape)} {out_bits.dtype}")
+    _lib.check(lib.gsn_layer_recurrence_bits(_ptr(xproj), _ptr(w_hh), _ptr(bias), _ptr(bn_scale), _ptr(bn_shift),
+                                             _ptr(h0), _ptr(c0), _ptr(h), _ptr(c), _ptr(hT), _ptr(cT),
+                                             _ptr(out_bits), T, R, H, int(shared), be, int(sm_budget),
+                                             ws.data_ptr() + off, st))
     LAUNCHES[0] += 2  # weight preparation + the recurrence kernel
     LAST_WS[0] = (ws, 0)
     if PROFILE is not None:

@@ -288,6 +288,58 @@ def test_linear_spikes_is_exact(M, K, N):
     assert np.abs(act_tc.cpu().numpy() - np.tanh(ref)).max() <= 1e-5
 
 
+def _pack_np(h):
+    """numpy restatement of the bit-packed trace layout: neuron n = bit n%32 of word n/32."""
+    H = h.shape[-1]
+    W = (H + 31) // 32
+    padded = np.zeros(h.shape[:-1] + (W * 32,), dtype=np.uint64)
+    padded[..., :H] = h != 0
+    words = (padded.reshape(h.shape[:-1] + (W, 32)) << np.arange(32, dtype=np.uint64)).sum(-1)
+    return words.astype(np.uint32)
+
+
+@pytest.mark.parametrize("M,K,N", [(1, 16, 8), (130, 160, 160), (1000, 240, 64), (777, 256, 256), (300, 320, 320),
+                                   (515, 268, 1542), (64, 224, 448), (5000, 160, 24), (333, 38, 40), (70, 250, 96)])
+def test_linear_spike_bits_matches_fp32_trace(M, K, N):
+    """gsn_linear_spike_bits reads the bit-packed trace (gsn_pack_spikes layout) and must give BIT-IDENTICAL
+    results to gsn_linear_spikes on the fp32 trace (same MMAs on the same operands); K need not be a multiple
+    of 4 or 32 here."""
+    rs = np.random.RandomState(M * 7 + K)
+    a = (rs.uniform(size=(M, K)) < 0.4).astype(np.float32)
+    w = rs.uniform(-0.1, 0.1, (N, K)).astype(np.float32)
+    b = rs.uniform(-0.1, 0.1, N).astype(np.float32)
+    bits = ops.pack_spikes(_t(a))
+    assert np.array_equal(bits.cpu().numpy().view(np.uint32), _pack_np(a))
+    out_bits, act_bits = ops.linear(_t(a), _t(w), _t(b), act="sigmoid", spikes=True, bits=bits)
+    ref = a.astype(np.float64) @ w.astype(np.float64).T + b
+    assert np.abs(out_bits.cpu().numpy() - ref).max() <= 2e-6 * np.abs(ref).max()
+    if K % 4 == 0:
+        out_f, act_f = ops.linear(_t(a), _t(w), _t(b), act="sigmoid", spikes=True)
+        assert torch.equal(out_bits, out_f) and torch.equal(act_bits, act_f)
+
+
+@pytest.mark.parametrize("backend", ["simt", "tcgen05", "tcgen05_i8"])
+@pytest.mark.parametrize("T,R,H,shared", [(9, 37, 160, True), (5, 16, 240, True), (7, 70, 72, False),
+                                          (4, 130, 320, True), (6, 33, 100, True)])
+def test_recurrence_bit_packed_trace(T, R, H, shared, backend):
+    """gsn_layer_recurrence_bits: the bit-packed trace equals the fp32 trace packed on the host, for every back
+    end (tcgen05 writes its ballot words, the others pack afterwards)."""
+    rs = np.random.RandomState(T * 100 + R)
+    gH = H if shared else 2 * H
+    s = 1 / np.sqrt(H)
+    xproj = rs.uniform(-1, 1, (T, R, gH)).astype(np.float32)
+    w = rs.uniform(-s, s, (gH, H)).astype(np.float32)
+    b = rs.uniform(-s, s, 2 * H).astype(np.float32)
+    bits = ops.spike_bits_buffer((T, R), H, DEV)
+    bits.fill_(-1)
+    try:
+        h, _, _ = ops.layer_recurrence(_t(xproj), _t(w), _t(b), shared=shared, backend=backend, out_bits=bits)
+    except NotImplementedError:
+        pytest.skip(f"{backend} does not support R={R} H={H} shared={shared}")
+    assert np.array_equal(bits.cpu().numpy().view(np.uint32), _pack_np(h.cpu().numpy()))
+    assert 0.02 < float(h.mean()) < 0.98
+
+
 @pytest.mark.parametrize("name", ["tiny_train_shared_bn", "tiny_train_unshared_nobn"])
 def test_training_step_vs_golden(name):
     """Protocol P4: one training step (train-mode BatchNorm, BPTT with the Triangle surrogate) against the
