@@ -142,15 +142,34 @@ __global__ void __launch_bounds__(256, 1)
   auto convert = [&](long long tile, uint8_t* dst) {
     const long long r0 = tile * NT;
     if (BITS) {
-      for (int i = tid; i < ntask; i += 256) {
-        const int nlo = i & 7, k8 = (i >> 3) % k8n, nhi = (i >> 3) / k8n;
-        const long long row = r0 + nhi * 8 + nlo;
-        const uint32_t b8 = row < M ? (__ldg(a_bits + row * Wb + (k8 >> 2)) >> (8 * (k8 & 3))) & 0xFFu : 0u;
-        uint32_t v[4];
+      // task = (row n, one 32-bit word of its packed trace) -> up to four 16-byte chunks of the operand; all the
+      // words of a thread are loaded before any is expanded (independent loads in flight, not a dependent chain)
+      const int nw = (k8n + 3) / 4;
+      constexpr int MAXW = (NT * 10 + 255) / 256;  // Kmma <= 320: at most 10 words per row
+      uint32_t wd[MAXW];
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-          v[e] = ((b8 >> (2 * e)) & 1u ? 0x3F80u : 0u) | ((b8 >> (2 * e + 1)) & 1u ? 0x3F800000u : 0u);
-        *reinterpret_cast<uint4*>(dst + (uint32_t)(nhi * SBO + k8 * 128 + nlo * 16)) = make_uint4(v[0], v[1], v[2], v[3]);
+      for (int it = 0; it < MAXW; ++it) {
+        const int i = tid + 256 * it;
+        const int nlo = i & 7, wi = (i >> 3) % nw, nhi = (i >> 3) / nw;
+        const long long row = r0 + nhi * 8 + nlo;
+        wd[it] = (i < NT * nw && row < M) ? __ldg(a_bits + row * Wb + wi) : 0u;
+      }
+#pragma unroll
+      for (int it = 0; it < MAXW; ++it) {
+        const int i = tid + 256 * it;
+        if (i >= NT * nw) break;
+        const int nlo = i & 7, wi = (i >> 3) % nw, nhi = (i >> 3) / nw;
+#pragma unroll
+        for (int e4 = 0; e4 < 4; ++e4) {
+          const int k8 = 4 * wi + e4;
+          if (k8 >= k8n) break;
+          const uint32_t b8 = (wd[it] >> (8 * e4)) & 0xFFu;
+          uint32_t v[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            v[e] = ((b8 >> (2 * e)) & 1u ? 0x3F80u : 0u) | ((b8 >> (2 * e + 1)) & 1u ? 0x3F800000u : 0u);
+          *reinterpret_cast<uint4*>(dst + (uint32_t)(nhi * SBO + k8 * 128 + nlo * 16)) = make_uint4(v[0], v[1], v[2], v[3]);
+        }
       }
       return;
     }
@@ -224,33 +243,65 @@ __global__ void __launch_bounds__(256, 1)
     __syncthreads();
     if (warp == 0) issue(0);
   }
+  // development aid: with a trace buffer set, thread 0 of CTA (0,0) accumulates per-phase cycles into its header
+  const bool prof = tb != nullptr && tslot >= 0;
+  unsigned int pc[5] = {0, 0, 0, 0, 0};
   for (long long i = 0; i < my_tiles; ++i) {
     const int cur = (int)(i & 1), nxt = cur ^ 1;
     const long long tile = first + i * P;
+    const long long q0 = prof ? clock64() : 0;
     if (i + 1 < my_tiles) convert(tile + P, nxt ? sB1 : sB0);  // overlaps MMA(i)
+    const long long q1 = prof ? clock64() : 0;
     tc::fence_proxy_async_smem();
     tc::tc_fence_before();
     __syncthreads();
+    const long long q2 = prof ? clock64() : 0;
     if (!tc::mbar_wait(cur ? &bar[1] : &bar[0], (uint32_t)((i >> 1) & 1))) { alive = false; break; }
     tc::tc_fence_after();
-    if (i + 1 < my_tiles && warp == 0) issue(nxt);  // tensor pipe works on tile i+1 during this epilogue
-    // epilogue of tile i: thread = feature j, rows [g*NT/2, +NT/2) of the tile; coalesced over features
+    const long long q3 = prof ? clock64() : 0;
+    // accumulators of tile i -> registers BEFORE the next MMAs are issued: tcgen05.ld issued behind in-flight MMAs
+    // waits for them (measured: 3650 cycles per tile for this epilogue when it ran under the MMAs of tile i+1)
+    uint32_t zr[NT / 16][8];  // the destination registers are only read after tcgen05.wait::ld
+#pragma unroll
+    for (int c8 = 0; c8 < NT / 16; ++c8)
+      tc::tmem_ld8((cur ? tmem_d1 : tmem_d0) + lane_base + g * (NT / 2) + c8 * 8, zr[c8]);
+    tc::tmem_wait_ld();
+    if (i + 1 < my_tiles) {
+      tc::tc_fence_before();
+      __syncthreads();
+      if (warp == 0) issue(nxt);  // the tensor pipe works on tile i+1 while tile i is stored
+    }
+    const long long q4 = prof ? clock64() : 0;
+    // stores of tile i: thread = feature j, rows [g*NT/2, +NT/2) of the tile; coalesced over features.
+    // Everything row-invariant is hoisted: a full half tile is a straight run of stores (no per-row predicate).
     const long long r0 = tile * NT + g * (NT / 2);
+    const long long left = M - r0;
+    if (jv && left > 0) {
+      float* po = out + r0 * N + j;
+      if (left >= NT / 2) {
 #pragma unroll
-    for (int c0 = 0; c0 < NT / 2; c0 += 8) {
-      uint32_t zr[8];
-      tc::tmem_ld8((cur ? tmem_d1 : tmem_d0) + lane_base + g * (NT / 2) + c0, zr);
-      tc::tmem_wait_ld();
+        for (int u = 0; u < NT / 2; ++u) po[(size_t)u * N] = __uint_as_float(zr[u >> 3][u & 7]) + bj;
+      } else {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const long long row = r0 + c0 + u;
-        if (jv && row < M) {
-          const float v = __uint_as_float(zr[u]) + bj;
-          out[row * N + j] = v;
-          if (out_act) out_act[row * N + j] = lin_act(v, act);
-        }
+        for (int u = 0; u < NT / 2; ++u)
+          if (u < (int)left) po[(size_t)u * N] = __uint_as_float(zr[u >> 3][u & 7]) + bj;
+      }
+      if (out_act) {
+        float* pa = out_act + r0 * N + j;
+#pragma unroll
+        for (int u = 0; u < NT / 2; ++u)
+          if (u < left) pa[(size_t)u * N] = lin_act(__uint_as_float(zr[u >> 3][u & 7]) + bj, act);
       }
     }
+    if (prof) {
+      const long long q5 = clock64();
+      pc[0] += (unsigned)(q1 - q0); pc[1] += (unsigned)(q2 - q1); pc[2] += (unsigned)(q3 - q2);
+      pc[3] += (unsigned)(q4 - q3); pc[4] += (unsigned)(q5 - q4);
+    }
+  }
+  if (prof) {  // convert, sync, MMA wait, MMA issue, epilogue, tiles (last traced linear wins)
+    for (int u = 0; u < 5; ++u) tb->pad[u] = pc[u];
+    tb->pad[5] = (unsigned)my_tiles;
   }
   if (!alive) __trap();
   tc::tc_fence_before();

@@ -19,7 +19,9 @@ kernels for the recurrence, differentiable torch ops around it).
 from __future__ import annotations
 
 import math
+import os
 from collections import namedtuple
+
 
 import torch
 import torch.nn as nn
@@ -602,9 +604,10 @@ class SpikingFullSubNet(_GraphedNetwork, nn.Module):
         for p_ in plans_all:
             cell0 = p_.m.sequence_model.layers[0].cell
             demands += [_cluster_ctas(p_.x.shape[1], cell0.hidden_size, cell0.shared_weights)] * p_.L
-        bud = _sm_budgets(demands)
+        bud = _sm_budgets(demands, total=int(os.environ.get("GSN_WF_SM_TOTAL", 148)))
         # SMs left over by the resident recurrence CTAs are what the (persistent) tcgen05 linears can get
         free = max(8, 148 - sum(min(d, b) if b else d for d, b in zip(demands, bud)))
+        free = int(os.environ.get("GSN_WF_LIN_BUDGET", free))
         o_ = 0
         for p_ in plans_all:
             p_.sm_budget = bud[o_]
