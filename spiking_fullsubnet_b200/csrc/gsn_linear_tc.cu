@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(256, 1)
   // weights of my feature -> three exact bf16 planes in TMEM (the two row-half warps split the K range)
   {
     const bool staged = wpitch > 0;
-    if (staged && !tc::mbar_wait(bar_w, 0)) __trap();
+    if (staged && !tc::mbar_wait_cta(bar_w, 0)) __trap();
     const float* srow = wst + (size_t)(q * 32 + lane) * wpitch;
     for (int c0 = 8 * g; c0 < (int)plane_cols; c0 += 16) {
       float wv[16];
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(256, 1)
     tc::tc_fence_before();
     __syncthreads();
     const long long q2 = prof ? clock64() : 0;
-    if (!tc::mbar_wait(cur ? &bar[1] : &bar[0], (uint32_t)((i >> 1) & 1))) { alive = false; break; }
+    if (!tc::mbar_wait_cta(cur ? &bar[1] : &bar[0], (uint32_t)((i >> 1) & 1))) { alive = false; break; }
     tc::tc_fence_after();
     const long long q3 = prof ? clock64() : 0;
     // accumulators of tile i -> registers BEFORE the next MMAs are issued: tcgen05.ld issued behind in-flight MMAs

@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
   // the G warps that share a lane quarter split the K range between them
   {
     const bool staged = p.wpitch > 0;
-    if (staged && !tc::mbar_wait(bar_w, 0)) __trap();
+    if (staged && !tc::mbar_wait_cta(bar_w, 0)) __trap();
     const float* srow = wst + (size_t)tl * p.wpitch;
     for (int c0 = 8 * g; c0 < (int)plane_cols; c0 += 8 * G) {
       float wv[16];
@@ -259,24 +259,20 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
   unsigned int epoch = 0;
   float shift = 0.f;  // one-pass variance is taken around the previous frame's mean
   float c[CPT];
-  uint32_t boff[CPT];      // byte offset of (row, neuron) inside one frame of a [T, R, H] fp32 tensor
-  uint32_t valid = 0;      // bit i: row i of my group exists and my neuron exists
+  // My CPT rows are consecutive, so the valid ones are a PREFIX [0, nv) (nv = 0 when my neuron does not exist) and
+  // the byte offset of (row i, my neuron) inside one frame is boff0 + i * hstride: no per-column offset registers.
+  const int rfirst = row0 + g * CPT;
+  const int nv = comp ? (R - rfirst < CPT ? (R - rfirst > 0 ? R - rfirst : 0) : CPT) : 0;
+  const bool full = nv == CPT;
+  const uint32_t hstride = (uint32_t)H * 4u, xstride = (uint32_t)gH * 4u;
+  const uint32_t boff0 = ((uint32_t)rfirst * (uint32_t)H + (uint32_t)j) * 4u;   // [T, R, H] fp32 tensors
+  const uint32_t xoff0 = ((uint32_t)rfirst * (uint32_t)gH + (uint32_t)j) * 4u;  // xproj [T, R, gH]
 #pragma unroll
-  for (int i = 0; i < CPT; ++i) {
-    const int row = row0 + g * CPT + i;
-    const bool ok = comp && row < R;
-    valid |= ok ? 1u << i : 0u;
-    boff[i] = ok ? ((uint32_t)row * (uint32_t)H + (uint32_t)j) * 4u : 0u;
-    c[i] = (p.c0 && ok) ? *reinterpret_cast<const float*>(reinterpret_cast<const char*>(p.c0) + boff[i]) : 0.f;
-  }
+  for (int i = 0; i < CPT; ++i)
+    c[i] = (p.c0 && i < nv) ? *reinterpret_cast<const float*>(reinterpret_cast<const char*>(p.c0) + boff0 + i * hstride)
+                            : 0.f;
   const size_t frame_bytes = (size_t)R * H * sizeof(float);
   const size_t xframe_bytes = (size_t)R * gH * sizeof(float);
-  uint32_t xoff[CPT];      // byte offset of my forget-gate input projection inside one [R, gH] frame
-#pragma unroll
-  for (int i = 0; i < CPT; ++i) {
-    const int row = row0 + g * CPT + i;
-    xoff[i] = ((valid >> i) & 1u) ? ((uint32_t)row * (uint32_t)gH + (uint32_t)j) * 4u : 0u;
-  }
 
   // spike-bit exchange: lane l < CPT*C of every warp sends word (l % CPT) of its warp to CTA (l / CPT);
   // the remote staging cell and the remote barrier are fixed per frame parity
@@ -306,18 +302,27 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
 
   // trace of frame t (spikes, membrane) -> global, coalesced over neurons
   auto store_frame = [&](int t) {
-    char* hf = reinterpret_cast<char*>(p.h_out) + (size_t)t * frame_bytes;
-    char* cf = p.c_out ? reinterpret_cast<char*>(p.c_out) + (size_t)t * frame_bytes : nullptr;
+    char* hf = reinterpret_cast<char*>(p.h_out) + (size_t)t * frame_bytes + boff0;
+    char* cf = p.c_out ? reinterpret_cast<char*>(p.c_out) + (size_t)t * frame_bytes + boff0 : nullptr;
+    if (full && !TRAIN) {  // the common case: a straight run of stores
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) *reinterpret_cast<float*>(hf + i * hstride) = hval[i];
+      if (cf) {
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) *reinterpret_cast<float*>(cf + i * hstride) = c[i];
+      }
+      return;
+    }
 #pragma unroll
     for (int i = 0; i < CPT; ++i) {
-      if ((valid >> i) & 1u) {
-        *reinterpret_cast<float*>(hf + boff[i]) = hval[i];
-        if (cf) *reinterpret_cast<float*>(cf + boff[i]) = c[i];
+      if (i < nv) {
+        *reinterpret_cast<float*>(hf + i * hstride) = hval[i];
+        if (cf) *reinterpret_cast<float*>(cf + i * hstride) = c[i];
         if (TRAIN && p.f_out) {
-          *reinterpret_cast<float*>(reinterpret_cast<char*>(p.f_out) + (size_t)t * frame_bytes + boff[i]) = fsave[i];
-          *reinterpret_cast<float*>(reinterpret_cast<char*>(p.g_out) + (size_t)t * frame_bytes + boff[i]) = gsave[i];
-          if (batch_stats)
-            *reinterpret_cast<float*>(reinterpret_cast<char*>(p.xhat_out) + (size_t)t * frame_bytes + boff[i]) = xsave[i];
+          const size_t o = (size_t)t * frame_bytes + boff0 + i * hstride;
+          *reinterpret_cast<float*>(reinterpret_cast<char*>(p.f_out) + o) = fsave[i];
+          *reinterpret_cast<float*>(reinterpret_cast<char*>(p.g_out) + o) = gsave[i];
+          if (batch_stats) *reinterpret_cast<float*>(reinterpret_cast<char*>(p.xhat_out) + o) = xsave[i];
         }
       }
     }
@@ -326,12 +331,12 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
   // input projection of one frame -> registers, always fetched ONE FRAME AHEAD of its use
   float xn[CPT], xqn[SHARED ? 1 : CPT];
   auto load_xproj = [&](int t) {
-    const char* xf = reinterpret_cast<const char*>(p.xproj) + (size_t)t * xframe_bytes;
+    const char* xf = reinterpret_cast<const char*>(p.xproj) + (size_t)t * xframe_bytes + xoff0;
 #pragma unroll
     for (int i = 0; i < CPT; ++i) {
-      const bool ok = (valid >> i) & 1u;
-      xn[i] = ok ? __ldg(reinterpret_cast<const float*>(xf + xoff[i])) : 0.f;
-      if (!SHARED) xqn[i] = ok ? __ldg(reinterpret_cast<const float*>(xf + xoff[i]) + H) : 0.f;
+      const bool ok = full || i < nv;
+      xn[i] = ok ? __ldg(reinterpret_cast<const float*>(xf + i * xstride)) : 0.f;
+      if (!SHARED) xqn[i] = ok ? __ldg(reinterpret_cast<const float*>(xf + i * xstride) + H) : 0.f;
     }
   };
   if (PF) load_xproj(0);
@@ -375,7 +380,7 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
       xg_[i] = __fadd_rn(SHARED ? xn[i] : xqn[i], bc);
     }
     if (PF && t + 1 < T) load_xproj(t + 1);  // consumed one frame later: a full frame of latency tolerance
-    if (!tc::mbar_wait(bar_mma, t & 1)) { alive = false; break; }
+    if (!tc::mbar_wait_cta(bar_mma, t & 1)) { alive = false; break; }
     tc::tc_fence_after();
     const long long q3 = PROF ? clock64() : 0;
 
@@ -411,7 +416,7 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int u = 0; u < CH; ++u) {
-          if ((valid >> (i0 + u)) & 1u) {
+          if (i0 + u < nv) {
             const float d = ctil[u] - shift;
             s1 += d;
             s2 += d * d;
@@ -467,7 +472,7 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
         }
         float cn = __fadd_rn(__fmul_rn(ctil[u], bs), bt);
         c[i0 + u] = cn;
-        const bool spike = ((valid >> (i0 + u)) & 1u) && cn >= 0.f;
+        const bool spike = (i0 + u < nv) && cn >= 0.f;
         hval[i0 + u] = spike ? 1.0f : 0.0f;
         const uint32_t w = __ballot_sync(0xffffffffu, spike);
         myw = (lane % CPT) == (i0 + u) ? w : myw;
@@ -480,7 +485,7 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
     //      cluster; the bytes are counted on the receiver's mbarrier (no fence, no arrive on this side) ----
     if (sender) tc::st_async_u32(par ? snd_cell1 : snd_cell0, myw, par ? snd_bar1 : snd_bar0);
     const long long q5 = PROF ? clock64() : 0;
-    if (!tc::mbar_wait(&bar_bits[par], (t >> 1) & 1)) { alive = false; break; }
+    if (!tc::mbar_wait_cta(&bar_bits[par], (t >> 1) & 1)) { alive = false; break; }
     const long long q6 = PROF ? clock64() : 0;
     // ---- rebuild the bf16 B operand (spikes of frame t, all H neurons of my rows) from the bits -------
     {
@@ -514,9 +519,9 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
   }
 #pragma unroll
   for (int i = 0; i < CPT; ++i) {
-    if ((valid >> i) & 1u) {
-      if (p.cT) *reinterpret_cast<float*>(reinterpret_cast<char*>(p.cT) + boff[i]) = c[i];
-      if (p.hT) *reinterpret_cast<float*>(reinterpret_cast<char*>(p.hT) + boff[i]) = hval[i];
+    if (i < nv) {
+      if (p.cT) *reinterpret_cast<float*>(reinterpret_cast<char*>(p.cT) + boff0 + i * hstride) = c[i];
+      if (p.hT) *reinterpret_cast<float*>(reinterpret_cast<char*>(p.hT) + boff0 + i * hstride) = hval[i];
     }
   }
   tc::tc_fence_before();

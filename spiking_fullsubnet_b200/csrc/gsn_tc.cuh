@@ -51,6 +51,25 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, uint32
   return false;
 }
 
+// Same bounded wait with the default (CTA-scope) acquire: for barriers completed by the async proxy -- bulk copies,
+// st.async complete_tx from peer CTAs, tcgen05.commit -- whose data lands in THIS CTA's shared / tensor memory.
+// (The cluster-scope acquire makes the compiler emit CCTL.IVALL, an L1 invalidation, after every successful wait.)
+__device__ __forceinline__ bool mbar_wait_cta(uint64_t* bar, uint32_t parity, uint32_t max_polls = 1u << 22) {
+  const uint32_t a = smem_u32(bar);
+  for (uint32_t i = 0; i < max_polls; ++i) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+    if (ok) return true;
+  }
+  return false;
+}
+
 // ---------------------------------------------------------------- cluster / DSMEM
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

@@ -70,10 +70,10 @@ if __name__ == "__main__":
     print("| size | batch x clip | recurrence backend | ms/step serial graph | ms/step wavefront graph | frames/s (best) | "
           "TFLOP/s (algorithmic) | of tensor roofline |")
     print("|---|---|---|---|---|---|---|---|")
-    model_row("S", 32, 4, 16)      # BASELINE configs[1]
-    model_row("M", 32, 4, 16)
-    model_row("XL", 32, 4, 16)
-    model_row("L", 32, 4, 16)
+    model_row("S", 32, 4, 12)      # BASELINE configs[1]
+    model_row("M", 32, 4, 12)
+    model_row("XL", 32, 4, 12)
+    model_row("L", 32, 4, 12)
     if not quick:
         model_row("L", 64, 10, 16, reps=2)   # BASELINE configs[2]
     print("\nconfig 5: 2-layer GSN stack (input projection + recurrence), K=38, batch 32, T=501, eager launches\n")

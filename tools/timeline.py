@@ -10,11 +10,14 @@ from oracle import synth  # noqa: E402
 from spiking_fullsubnet_b200 import SpikingFullSubNet, _lib  # noqa: E402
 
 chunks = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-cfg = synth.CFG_S
+size = sys.argv[2] if len(sys.argv) > 2 else "S"
+batch = int(sys.argv[3]) if len(sys.argv) > 3 else 32
+frames = int(sys.argv[4]) if len(sys.argv) > 4 else 501
+cfg = synth.CONFIGS[size]
 model = SpikingFullSubNet(**cfg)
 model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in synth.make_params(cfg, 5).items()})
 model = model.eval().cuda()
-mag = torch.from_numpy(synth.make_mag(32, 257, 501, 11)).cuda()
+mag = torch.from_numpy(synth.make_mag(batch, 257, frames, 11)).cuda()
 lib = _lib.load()
 buf = torch.zeros(64 + 32 * 4096, dtype=torch.uint8, device="cuda")
 _lib.check(lib.gsn_trace_set(buf.data_ptr(), buf.numel()))
@@ -29,7 +32,7 @@ raw = buf.cpu().numpy()
 n = int(raw[:4].view(np.uint32)[0])
 rec = raw[64:64 + 32 * n].view(np.dtype([("t0", "<u8"), ("t1", "<u8"), ("kind", "<i4"), ("a", "<i4"), ("b", "<i4"), ("c", "<i4")]))
 t_min = rec["t0"].min()
-names = {1: "linear", 2: "recur", 3: "feat"}
+names = {1: "linear", 2: "recur", 3: "feat", 4: "lin_tc"}
 print(f"{n} traced launches, span {(max(rec['t1'].max(), rec['t0'].max()) - t_min) / 1e3:.1f} us")
 for r in sorted(rec, key=lambda r: r["t0"]):
     dur = (int(r["t1"]) - int(r["t0"])) / 1e3 if r["t1"] else 0
