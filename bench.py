@@ -35,7 +35,7 @@ def parse():
     ap.add_argument("--seconds", type=float, default=4.0)
     ap.add_argument("--backend", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--chunks", type=int, default=16, help="frame chunks of the wavefront schedule (graph mode)")
+    ap.add_argument("--chunks", type=int, default=12, help="frame chunks of the wavefront schedule (graph mode)")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of "
                     "replaying the captured CUDA graph")
     return ap.parse_args()
@@ -259,8 +259,14 @@ def main():
     ops.PROFILE = None
     model.sb_model.concurrent_bands = True
     serial_ms = s0.elapsed_time(s1) / 3.0
-    rec_ms = sum(a.elapsed_time(b) for (_, a, b) in rec) / 3.0
-    rec_flops = sum(f for (f, _, _) in rec) / 3.0
+    rec_ms = sum(a.elapsed_time(b) for (_, a, b, _) in rec) / 3.0
+    rec_flops = sum(f for (f, _, _, _) in rec) / 3.0
+    # latency model of the serial frame chain (SURVEY 8d "Bound"): per launch, measured us per frame against the
+    # tensor-pipe floor of one frame = 3 planes x ceil(H/16) tcgen05.mma at the measured ~42 cycles per 128xNx16
+    # instruction with the A operand in tensor memory (tools/tc_mma_timing.py), at the SM clock sampled above
+    per_launch = {}
+    for (_, a, b, (t_, r_, h_)) in rec:
+        per_launch.setdefault((t_, r_, h_), []).append(a.elapsed_time(b) * 1e3 / t_)
 
     t = torch.tensor([dev_ms, e2e_s], device=dev, dtype=torch.float64)
     if world > 1:
@@ -303,6 +309,18 @@ def main():
                      "share_of_step": rec_ms / serial_ms, "serial_step_ms": serial_ms,
                      "peak_source": peak_src},
     }
+    traffic_file = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if args.size == "S" and B == 32 and abs(args.seconds - 4.0) < 1e-9 and os.path.exists(traffic_file):
+        # dram__bytes_read.sum + dram__bytes_write.sum of the same launches from one `ncu --set full` capture
+        tr = json.load(open(traffic_file))
+        line["roofline"]["traffic"] = tr["dram_bytes_per_step"]
+        line["roofline"]["traffic_source"] = tr["source"]
+    mhz = (line["clocks"]["sm_mhz"] or 1965.0)
+    line["roofline"]["latency_model"] = [
+        {"frames": t_, "rows": r_, "hidden": h_, "us_per_frame": float(np.mean(v)),
+         "mma_floor_us_per_frame": 3 * ((h_ + 15) // 16) * 42 / mhz,
+         "frac_of_mma_floor": 3 * ((h_ + 15) // 16) * 42 / mhz / float(np.mean(v))}
+        for (t_, r_, h_), v in sorted(per_launch.items())]
     if world == 1 and not args.no_cpu_baseline:
         times, cores = time_cpu_port(synth, cfg, B, T, 3, 1)
         line["cpu_baseline"] = {"value": B * T / min(times), "unit": "frames/s", "cores": cores, "kind": "port",

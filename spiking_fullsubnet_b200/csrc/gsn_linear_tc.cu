@@ -217,16 +217,7 @@ __global__ void __launch_bounds__(256, 1)
     if (tc::elect_one()) {
       const uint64_t desc_b0 = tc::make_smem_desc(tc::smem_u32(buf ? sB1 : sB0), 128, SBO);
       const uint32_t td = buf ? tmem_d1 : tmem_d0;
-      uint32_t acc = 0;
-#pragma unroll 1
-      for (int pl = 0; pl < 3; ++pl) {
-        const uint32_t a0 = tmem_a + pl * plane_cols;
-#pragma unroll 2
-        for (int ks = 0; ks < ksteps; ++ks) {
-          tc::mma_ts(td, a0 + ks * 8, desc_b0 + (uint64_t)(ks * 16), idesc, acc);
-          acc = 1;
-        }
-      }
+      tc::mma_planes<3>(ksteps, td, tmem_a, desc_b0, idesc);  // straight-line issue, lo plane first
       tc::mma_commit(buf ? &bar[1] : &bar[0]);
     }
     __syncwarp();

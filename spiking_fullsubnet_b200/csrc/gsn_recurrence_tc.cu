@@ -39,6 +39,7 @@ struct RecTcParams {
   float* hT;
   float* cT;
   int T, R, H, Kmma;    // Kmma = round_up(H, 16)
+  int dbg;              // PROF builds only (GSN_TC_DBG, timing experiments): 1 = no trace stores, 2 = no xproj loads
   int wpitch;           // > 0: stage the CTA's weight rows in shared memory (row pitch in floats), else direct loads
   unsigned long long* prof;  // [8] cycle counters of CTA 0 / thread 0 (workspace), see tools/tc_profile.py
   TraceBuf* trace;
@@ -355,23 +356,15 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
       tc::tc_fence_after();
       if (tc::elect_one()) {
         tc::mbar_arrive_expect_tx(&bar_bits[par], bits_bytes);  // arm this frame's spike-bit exchange
-        uint32_t acc = 0;
-#pragma unroll 1
-        for (int pl = 0; pl < kTcPlanes; ++pl) {
-          const uint32_t a0 = tmem_a + pl * plane_cols;
-#pragma unroll 2
-          for (int ks = 0; ks < ksteps; ++ks) {
-            tc::mma_ts(tmem_d, a0 + ks * 8, desc_b0 + (uint64_t)(ks * 16), idesc, acc);
-            acc = 1;
-          }
-        }
+        // plane 0 = lo first; straight-line issue (see mma_planes_unrolled): ~8 instead of ~45 cycles per MMA
+        tc::mma_planes<kTcPlanes>(ksteps, tmem_d, tmem_a, desc_b0, idesc);
         tc::mma_commit(bar_mma);
       }
       __syncwarp();
     }
     const long long q2 = PROF ? clock64() : 0;
     // ---- work hidden under the MMAs: trace of frame t-1 out, input projection of frame t in ----------
-    if (t > 0) store_frame(t - 1);
+    if (t > 0 && !(PROF && (p.dbg & 1))) store_frame(t - 1);
     float xf_[CPT], xg_[CPT];
     if (!PF) load_xproj(t);
 #pragma unroll
@@ -379,7 +372,7 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
       xf_[i] = __fadd_rn(xn[i], bf);
       xg_[i] = __fadd_rn(SHARED ? xn[i] : xqn[i], bc);
     }
-    if (PF && t + 1 < T) load_xproj(t + 1);  // consumed one frame later: a full frame of latency tolerance
+    if (PF && t + 1 < T && !(PROF && (p.dbg & 2))) load_xproj(t + 1);  // consumed one frame later: a full frame of latency tolerance
     if (!tc::mbar_wait_cta(bar_mma, t & 1)) { alive = false; break; }
     tc::tc_fence_after();
     const long long q3 = PROF ? clock64() : 0;
@@ -608,6 +601,7 @@ int launch_recurrence_tc(const float* xproj, const float* w_hh, const float* bia
   if (sm_budget > 0 && sm_budget < sms) sms = sm_budget;
   const int nt = tc_pick_nt(R, H, shared, sms);
   static const bool prof = getenv("GSN_TC_PROF") != nullptr;  // dev knob: per-phase cycle counters
+  p.dbg = getenv("GSN_TC_DBG") ? atoi(getenv("GSN_TC_DBG")) : 0;
   if (!shared) {
     switch (nt) {
       case 16: return launch_nt<16, 4, false, false>(p, C, st);

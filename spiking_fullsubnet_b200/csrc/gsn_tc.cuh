@@ -210,6 +210,45 @@ __device__ __forceinline__ void mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_
       "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// ---- straight-line MMA issue --------------------------------------------------------------------------------
+// A rolled issue loop (runtime trip count, operands recomputed per iteration) costs ~42-50 cycles per tcgen05.mma
+// on the issuing thread -- 5x the tensor pipe's own 8 cycles for a 128 x 16 x 16 tile (tools/tc_mma_timing.py:
+// 8.5 / 13.6 / 25.4 cycles per MMA at N = 16 / 32 / 64 when every operand is base + immediate).  So the k loop is
+// fully unrolled for a compile-time number of k steps and selected by a switch on the runtime value.
+template <int ACC>
+__device__ __forceinline__ void mma_ts_c(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "n"(ACC)
+      : "memory");
+}
+// D = sum over PLANES planes (plane pl at tmem_a + pl * KS * 8 columns) and KS k steps of A[plane][ks] * B[ks];
+// the first MMA overwrites D
+template <int KS, int PLANES>
+__device__ __forceinline__ void mma_planes_unrolled(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b0,
+                                                    uint32_t idesc) {
+  mma_ts_c<0>(tmem_d, tmem_a, desc_b0, idesc);
+#pragma unroll
+  for (int i = 1; i < KS * PLANES; ++i) {
+    const int pl = i / KS, ks = i % KS;
+    mma_ts_c<1>(tmem_d, tmem_a + (uint32_t)((pl * KS + ks) * 8), desc_b0 + (uint64_t)(ks * 16), idesc);
+  }
+}
+// runtime dispatch: ksteps = Kmma / 16 in [1, 20]  (Kmma <= 320).  Returns false for an unsupported count.
+template <int PLANES>
+__device__ __forceinline__ bool mma_planes(int ksteps, uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b0,
+                                           uint32_t idesc) {
+  switch (ksteps) {
+#define GSN_KS_CASE(n) case n: mma_planes_unrolled<n, PLANES>(tmem_d, tmem_a, desc_b0, idesc); return true;
+    GSN_KS_CASE(1) GSN_KS_CASE(2) GSN_KS_CASE(3) GSN_KS_CASE(4) GSN_KS_CASE(5) GSN_KS_CASE(6) GSN_KS_CASE(7)
+    GSN_KS_CASE(8) GSN_KS_CASE(9) GSN_KS_CASE(10) GSN_KS_CASE(11) GSN_KS_CASE(12) GSN_KS_CASE(13) GSN_KS_CASE(14)
+    GSN_KS_CASE(15) GSN_KS_CASE(16) GSN_KS_CASE(17) GSN_KS_CASE(18) GSN_KS_CASE(19) GSN_KS_CASE(20)
+#undef GSN_KS_CASE
+    default: return false;
+  }
+}
+
 // kind::i8: D(int32)[tmem] (+)= A(int8/uint8)[tmem] * B(int8/uint8)[smem desc], K = 32 per instruction
 __device__ __forceinline__ uint32_t make_idesc_i8(uint32_t M, uint32_t N, bool a_signed, bool b_signed) {
   return (2u << 4) | ((a_signed ? 1u : 0u) << 7) | ((b_signed ? 1u : 0u) << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);

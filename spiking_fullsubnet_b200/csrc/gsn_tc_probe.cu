@@ -139,6 +139,52 @@ __global__ void __launch_bounds__(128) k_tc_mma_timing(long long* out, int N, in
   if (warp == 0) tc::tmem_dealloc<512>(tmem);
 }
 
+// timing probe 2: fully unrolled issue (operands = base + immediates), M = 128 or 64, A in tensor memory
+template <int KS, int MM>
+__global__ void __launch_bounds__(128) k_tc_mma_timing2(long long* out, int N) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  constexpr int K = KS * 16;
+  for (int i = tid; i < N * K / 2; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (tid == 0) {
+    tc::mbar_init(&bar, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc<512>(&tmem_base_slot);
+  tc::tc_fence_before();
+  tc::fence_proxy_async_smem();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+  long long t0 = 0, t1 = 0, t2 = 0;
+  if (warp == 0) {
+    if (tc::elect_one()) {
+      const uint32_t idesc = tc::make_idesc_f16(MM, N, true);
+      const uint64_t db0 = tc::make_smem_desc(tc::smem_u32(smem), 128, 16u * K);
+      const uint32_t ta = tmem + 64;
+      t0 = clock64();
+#pragma unroll
+      for (int pl = 0; pl < 3; ++pl)
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+          asm volatile("tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, 1;" ::"r"(tmem),
+                       "r"(ta + (uint32_t)((pl * KS + ks) * 8)), "l"(db0 + (uint64_t)(ks * 16)), "r"(idesc)
+                       : "memory");
+      tc::mma_commit(&bar);
+      t1 = clock64();
+    }
+    __syncwarp();
+  }
+  tc::mbar_wait(&bar, 0);
+  t2 = clock64();
+  if (tid == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<512>(tmem);
+}
+
 // int8 probe: d[128,N] (int32) = a[128,K] (int8, resident in TMEM: 4 consecutive k per 32-bit column) x
 // b[N,K] (uint8, K-major no-swizzle shared memory: 8 rows x 16 bytes core matrices), K = 32 per instruction.
 __global__ void __launch_bounds__(128)
@@ -229,6 +275,17 @@ extern "C" GSN_API int gsn_tc_mma_timing(long long* out, int N, int K, int reps,
   GSN_CUDA(cudaFuncSetAttribute(gsn::k_tc_mma_timing, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   gsn::k_tc_mma_timing<<<1, 128, smem, gsn::as_stream(stream)>>>(out, N, K, reps, a_in_tmem);
   GSN_LAUNCH_CHECK("k_tc_mma_timing");
+  return GSN_OK;
+}
+
+// undeclared dev symbol (tools/tc_mma_timing.py): variant 0 = K 160 M 128, 1 = K 160 M 64, 2 = K 240 M 128
+extern "C" GSN_API int gsn_tc_mma_timing2(long long* out, int N, int variant, gsn_stream_t stream) {
+  const size_t smem = (size_t)N * 240 * 2 + 1024;
+  cudaStream_t st = gsn::as_stream(stream);
+  if (variant == 0) gsn::k_tc_mma_timing2<10, 128><<<1, 128, smem, st>>>(out, N);
+  else if (variant == 1) gsn::k_tc_mma_timing2<10, 64><<<1, 128, smem, st>>>(out, N);
+  else gsn::k_tc_mma_timing2<15, 128><<<1, 128, smem, st>>>(out, N);
+  GSN_LAUNCH_CHECK("k_tc_mma_timing2");
   return GSN_OK;
 }
 

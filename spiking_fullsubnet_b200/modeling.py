@@ -99,6 +99,21 @@ def _cluster_ctas(rows, H, shared, nt=16):
     return ((rows + nt - 1) // nt) * ((H + 127) // 128 if shared else (H + 63) // 64)
 
 
+def _chunk_bounds(T, nchunks):
+    """Frame ranges of the wavefront schedule: `nchunks` equal chunks.  (GSN_WF_WEIGHTS="1,2,4,..." sets relative
+    chunk lengths instead -- a development knob: tapered schedules with short first / last chunks measured 4-9 %
+    SLOWER than equal chunks on B200, see profiles/r01_schedule_experiments.md.)"""
+    nchunks = max(1, min(nchunks, T))
+    env = os.environ.get("GSN_WF_WEIGHTS")
+    w = [float(v) for v in env.split(",")] if env else [1.0] * nchunks
+    cum, acc = [0], 0.0
+    for v in w:
+        acc += v
+        cum.append(int(round(T * acc / sum(w))))
+    cum[-1] = T
+    return [(a, b) for a, b in zip(cum[:-1], cum[1:]) if b > a]
+
+
 def _sm_budgets(demands, total=148, floor=4):
     """Split the SMs between concurrently running recurrences in proportion to their demand (0 = no cap when
     everything fits at the finest tiling)."""
@@ -579,8 +594,8 @@ class SpikingFullSubNet(_GraphedNetwork, nn.Module):
         (sequence model, layer); meant to be captured into a CUDA graph (see enable_cuda_graph)."""
         dev = mag.device
         B, F, T = mag.shape
-        nchunks = max(1, min(nchunks, T))
-        bounds = [(T * i // nchunks, T * (i + 1) // nchunks) for i in range(nchunks)]
+        bounds = _chunk_bounds(T, nchunks)
+        nchunks = len(bounds)
         main = torch.cuda.current_stream(dev)
         fbm, sbm = self.fb_model, self.sb_model
         rep = (self.n_fft // 2 + 1) // self.fb_input_size

@@ -11,7 +11,7 @@ _ACT = {None: 0, False: 0, "tanh": 1, "sigmoid": 2, "relu": 3}
 _bound_device = [None]
 LAUNCHES = [0]   # number of libgsn_b200 kernels enqueued so far (bench.py reports it)
 LAST_WS = [None]  # workspace of the last recurrence call (tcgen05 backend: 8 cycle counters of CTA 0)
-PROFILE = None   # bench.py sets a list: (algorithmic flops, start event, stop event) per recurrence call
+PROFILE = None   # bench.py sets a list: (algorithmic flops, start event, stop event, (T, R, H)) per recurrence call
 
 
 def _prep(*tensors):
@@ -166,7 +166,7 @@ def layer_recurrence(xproj, w_hh, bias, bn_scale=None, bn_shift=None, shared=Tru
     LAST_WS[0] = (ws, 0)
     if PROFILE is not None:
         e1.record()
-        PROFILE.append((2.0 * T * R * gH * H, e0, e1))
+        PROFILE.append((2.0 * T * R * gH * H, e0, e1, (T, R, H)))
     return h, c, (hT, cT)
 
 

@@ -22,3 +22,14 @@ for K in (160, 256):
             n = 3 * K // 16
             o = out.cpu().tolist()
             print(f"K={K} N={N} a_in_tmem={a_in_tmem}: {n} MMAs, issue {o[0] / n:.1f} cyc/MMA, complete {o[1] / n:.1f} cyc/MMA")
+
+fn2 = lib.gsn_tc_mma_timing2
+fn2.restype = C.c_int
+fn2.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+for variant, name, n in ((0, "K=160 M=128", 30), (1, "K=160 M=64", 30), (2, "K=240 M=128", 45)):
+    for N in (16, 32, 64):
+        for _ in range(2):
+            _lib.check(fn2(out.data_ptr(), N, variant, None))
+            torch.cuda.synchronize()
+        o = out.cpu().tolist()
+        print(f"unrolled issue, {name} N={N}: {n} MMAs, issue {o[0] / n:.1f} cyc/MMA, complete {o[1] / n:.1f} cyc/MMA")
