@@ -125,6 +125,17 @@ GSN_API int gsn_layer_recurrence_bits(const float* xproj, const float* w_hh, con
                          gsn_stream_t stream);
 /* bits[r, w] (W = ceil(H/32) words per row) from an fp32 {0,1} trace h [rows, H]. */
 GSN_API int gsn_pack_spikes(const float* h, uint32_t* bits, int64_t rows, int H, gsn_stream_t stream);
+/* Per-thread launch options for the following calls.  GSN_OPT_PDL != 0: gsn_layer_recurrence(_bits) launches of the
+ * tcgen05 back end are enqueued as PROGRAMMATIC DEPENDENTS of the previous kernel in their stream (CUDA programmatic
+ * dependent launch): the grid may be scheduled while that kernel drains and waits (griddepcontrol.wait) before it
+ * reads anything.  Meant for back-to-back frame chunks of one layer on one stream (the wavefront schedule), where the
+ * previous kernel is the previous chunk; the caller must make sure that kernel does not WRITE this call's weights.  */
+#define GSN_OPT_PDL 1
+/* GSN_OPT_F32_MAX_CTAS = n > 0: gsn_subband_features and gsn_linear_f32 launch at most n CTAs and stride over their
+ * work (same results).  The wavefront schedule uses it so that these short kernels cannot occupy the SMs the
+ * latency-critical recurrence chunks are about to be placed on.  0 = one CTA per tile (default).               */
+#define GSN_OPT_F32_MAX_CTAS 2
+GSN_API int gsn_set_option(int option, int value);
 /* which backend GSN_BACKEND_AUTO resolves to for this shape (GSN_BACKEND_SIMT / _TCGEN05 / _TCGEN05_I8). */
 GSN_API int gsn_layer_recurrence_pick_backend(int R, int H, int shared);
 

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libgsn_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "gsn_b200.h")
 
 GSN_OK, GSN_EINVAL, GSN_ECUDA, GSN_ENOSUP = 0, 1, 2, 3
+OPT_PDL, OPT_F32_MAX_CTAS = 1, 2
 BACKEND_AUTO, BACKEND_SIMT, BACKEND_TCGEN05, BACKEND_TCGEN05_I8 = 0, 1, 2, 3
 BACKENDS = {"auto": BACKEND_AUTO, "simt": BACKEND_SIMT, "tcgen05": BACKEND_TCGEN05, "tcgen05_i8": BACKEND_TCGEN05_I8}
 
@@ -23,6 +24,7 @@ SIGNATURES = {
     "gsn_abi_version": (_i, []),
     "gsn_last_error": (C.c_char_p, []),
     "gsn_bind_device": (_i, [_i]),
+    "gsn_set_option": (_i, [_i, _i]),
     "gsn_device_info": (_i, [C.POINTER(_i)] * 4),
     "gsn_compress_mag": (_i, [_p, _p, _i, _i, _i, _i, _f, _p]),
     "gsn_subband_features": (_i, [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p, _p, _f, _p]),

@@ -13,6 +13,9 @@ char* err_buf() {
 static TraceBuf* g_trace = nullptr;
 TraceBuf* trace_buffer() { return g_trace; }
 
+static thread_local int g_options[4] = {0, 0, 0, 0};
+int launch_option(int option) { return option >= 0 && option < 4 ? g_options[option] : 0; }
+
 int fail(int code, const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -51,6 +54,12 @@ extern "C" int gsn_trace_set(void* device_buffer, size_t bytes) {
   hdr[1] = (unsigned int)((bytes - 64) / sizeof(gsn::TraceRec));
   GSN_CUDA(cudaMemcpy(device_buffer, hdr, sizeof(hdr), cudaMemcpyHostToDevice));
   gsn::g_trace = reinterpret_cast<gsn::TraceBuf*>(device_buffer);
+  return GSN_OK;
+}
+
+extern "C" int gsn_set_option(int option, int value) {
+  GSN_REQUIRE(option == GSN_OPT_PDL || option == GSN_OPT_F32_MAX_CTAS, "gsn_set_option: unknown option %d", option);
+  gsn::g_options[option] = value;
   return GSN_OK;
 }
 

@@ -46,6 +46,7 @@ struct TraceBuf {  // lives in device memory; header then records
   TraceRec rec[1];
 };
 TraceBuf* trace_buffer();  // host side: current buffer or nullptr (gsn_api.cu)
+int launch_option(int option);  // gsn_set_option value of the calling thread (gsn_api.cu)
 
 __device__ __forceinline__ unsigned long long global_ns() {
   unsigned long long t;
@@ -55,6 +56,17 @@ __device__ __forceinline__ unsigned long long global_ns() {
 __device__ __forceinline__ int trace_begin(TraceBuf* tb, int kind, int a, int b, int c) {
   if (tb == nullptr || blockIdx.x != 0 || blockIdx.y != 0 || blockIdx.z != 0 || threadIdx.x != 0 || threadIdx.y != 0)
     return -1;
+  const unsigned int slot = atomicAdd(&tb->count, 1u);
+  if (slot >= tb->capacity) return -1;
+  tb->rec[slot].kind = kind; tb->rec[slot].a = a; tb->rec[slot].b = b; tb->rec[slot].c = c;
+  tb->rec[slot].t1 = 0;
+  tb->rec[slot].t0 = global_ns();
+  return (int)slot;
+}
+// every CTA of a kernel (not only CTA 0) when the capacity field's top bit is set (gsn_trace_set flags: per-CTA)
+__device__ __forceinline__ int trace_begin_cta(TraceBuf* tb, int kind, int a, int b, int c) {
+  if (tb == nullptr || threadIdx.x != 0 || threadIdx.y != 0 || blockIdx.x == 0) return -1;
+  if (!(tb->pad[13] & 1u)) return -1;
   const unsigned int slot = atomicAdd(&tb->count, 1u);
   if (slot >= tb->capacity) return -1;
   tb->rec[slot].kind = kind; tb->rec[slot].a = a; tb->rec[slot].b = b; tb->rec[slot].c = c;

@@ -3,6 +3,8 @@
 //   k_subband_features  : MSF:241-312 gather (+ reflect pad, + tiled full-band output MSF:443) fused with the
 //                         pre-LayerNorm MSF:111-112
 //   k_deepfilter_band   : MSF:315-346 applied straight from the proj output layout MSF:160-167
+#include <stdlib.h>
+
 #include "gsn_common.cuh"
 
 namespace gsn {
@@ -41,67 +43,71 @@ __global__ void __launch_bounds__(256) k_subband_features(
     const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps, TraceBuf* tb) {
   const int tslot = trace_begin(tb, 3, T, B * N, ctr + 2 * nbr + (fb ? ctr : 0));
   trace_end(tb, tslot);  // entry stamp only (warps exit independently)
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int R = B * N;
-  if (warp >= T * R) return;
-  const int t = warp / R, r = warp - t * R;
-  const int b = r / N, n = r - b * N;
   const int k_noisy = ctr + 2 * nbr;
   const int K = k_noisy + (fb ? ctr : 0);
-  const float* cm_row = cm + ((size_t)t * B + b) * f_cm;
-  const float* fb_row = fb ? fb + ((size_t)t * B + b) * f_fb : nullptr;
-  const int base = lo + n * ctr;
-  float v[kMaxPerLane];
-  float sum = 0.f;
-#pragma unroll
-  for (int i = 0; i < kMaxPerLane; ++i) {
-    const int j = lane + 32 * i;
-    v[i] = 0.f;
-    if (j < K) {
-      if (j < k_noisy) {
-        int q = base - nbr + j;
-        q = q < 0 ? -q : q;
-        q = q > f_cm - 1 ? 2 * (f_cm - 1) - q : q;
-        v[i] = cm_row[q];
-      } else {
-        v[i] = fb_row[(base + j - k_noisy) % f_fb];
-      }
-      sum += v[i];
-    }
-    if (32 * (i + 1) >= K) break;
-  }
-  float* out = x + (size_t)warp * K;
-  if (ln_w == nullptr) {
+  // grid-stride over the (t, row) pairs: the launcher may cap the grid so that this kernel cannot flood the SMs
+  // the latency-critical recurrence chunks are waiting for (wavefront schedule)
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; warp < (long long)T * R;
+       warp += nwarps) {
+    const int t = (int)(warp / R), r = (int)(warp - (long long)t * R);
+    const int b = r / N, n = r - b * N;
+    const float* cm_row = cm + ((size_t)t * B + b) * f_cm;
+    const float* fb_row = fb ? fb + ((size_t)t * B + b) * f_fb : nullptr;
+    const int base = lo + n * ctr;
+    float v[kMaxPerLane];
+    float sum = 0.f;
 #pragma unroll
     for (int i = 0; i < kMaxPerLane; ++i) {
       const int j = lane + 32 * i;
-      if (j < K) out[j] = v[i];
+      v[i] = 0.f;
+      if (j < K) {
+        if (j < k_noisy) {
+          int q = base - nbr + j;
+          q = q < 0 ? -q : q;
+          q = q > f_cm - 1 ? 2 * (f_cm - 1) - q : q;
+          v[i] = cm_row[q];
+        } else {
+          v[i] = fb_row[(base + j - k_noisy) % f_fb];
+        }
+        sum += v[i];
+      }
       if (32 * (i + 1) >= K) break;
     }
-    return;
-  }
+    float* out = x + (size_t)warp * K;
+    if (ln_w == nullptr) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float mean = sum / (float)K;
-  float sq = 0.f;
-#pragma unroll
-  for (int i = 0; i < kMaxPerLane; ++i) {
-    const int j = lane + 32 * i;
-    if (j < K) {
-      const float d = v[i] - mean;
-      sq += d * d;
+      for (int i = 0; i < kMaxPerLane; ++i) {
+        const int j = lane + 32 * i;
+        if (j < K) out[j] = v[i];
+        if (32 * (i + 1) >= K) break;
+      }
+      continue;
     }
-    if (32 * (i + 1) >= K) break;
-  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-  const float rstd = 1.0f / sqrtf(sq / (float)K + eps);
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)K;
+    float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < kMaxPerLane; ++i) {
-    const int j = lane + 32 * i;
-    if (j < K) out[j] = (v[i] - mean) * rstd * ln_w[j] + ln_b[j];
-    if (32 * (i + 1) >= K) break;
+    for (int i = 0; i < kMaxPerLane; ++i) {
+      const int j = lane + 32 * i;
+      if (j < K) {
+        const float d = v[i] - mean;
+        sq += d * d;
+      }
+      if (32 * (i + 1) >= K) break;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = 1.0f / sqrtf(sq / (float)K + eps);
+#pragma unroll
+    for (int i = 0; i < kMaxPerLane; ++i) {
+      const int j = lane + 32 * i;
+      if (j < K) out[j] = (v[i] - mean) * rstd * ln_w[j] + ln_b[j];
+      if (32 * (i + 1) >= K) break;
+    }
   }
 }
 
@@ -173,9 +179,15 @@ extern "C" int gsn_subband_features(const float* cm, int f_cm, const float* fb, 
   GSN_REQUIRE(!fb || f_fb > 0, "gsn_subband_features: f_fb");
   GSN_REQUIRE((ln_weight == nullptr) == (ln_bias == nullptr), "gsn_subband_features: ln params");
   const long long warps = (long long)T * B * N;
-  const long long blocks = (warps + 7) / 8;
+  long long blocks = (warps + 7) / 8;
   GSN_REQUIRE(blocks < 2147483647LL, "gsn_subband_features: too many rows");
-  gsn::k_subband_features<<<(unsigned)blocks, 256, 0, gsn::as_stream(stream)>>>(
+  const int cap = gsn::launch_option(GSN_OPT_F32_MAX_CTAS);
+  if (cap > 0 && blocks > cap) blocks = cap;
+  static const int excl_kib = getenv("GSN_F32_EXCL") ? atoi(getenv("GSN_F32_EXCL")) : 0;  // see gsn_linear.cu
+  if (excl_kib > 0)
+    GSN_CUDA(cudaFuncSetAttribute(gsn::k_subband_features, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  excl_kib * 1024));
+  gsn::k_subband_features<<<(unsigned)blocks, 256, (size_t)excl_kib * 1024, gsn::as_stream(stream)>>>(
       cm, f_cm, fb, f_fb, x, T, B, N, lo, ctr, nbr, ln_weight, ln_bias, ln_eps, gsn::trace_buffer());
   GSN_LAUNCH_CHECK("k_subband_features");
   return GSN_OK;

@@ -2,6 +2,8 @@
 // Used for the input-to-hidden product with a REAL-valued operand (layer 0; ESN:141) where plain bf16
 // tensor-core math cannot meet the 1e-3 parity bar, and for proj (MSF:118).
 // 128x64 CTA tile, 16-deep k slabs, 256 threads, 8x4 register tile per thread.
+#include <stdlib.h>
+
 #include "gsn_common.cuh"
 
 namespace gsn {
@@ -27,9 +29,14 @@ __global__ void __launch_bounds__(256, 2)
   const int tslot = trace_begin(tb, 1, (int)M, K, N);
   __shared__ __align__(16) float As[LBK][LBM + 4];
   __shared__ __align__(16) float Ws[LBK][LBN + 4];
-  const long long m0 = (long long)blockIdx.x * LBM;
-  const int n0 = blockIdx.y * LBN;
   const int tid = threadIdx.x;
+  // 1-D grid-stride over the (row tile, column tile) pairs, column tile fastest: the launcher may cap the grid (see
+  // gsn_subband_features) without changing any result
+  const int ny = (N + LBN - 1) / LBN;
+  const long long ntiles = ((M + LBM - 1) / LBM) * ny;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  const long long m0 = (tile / ny) * LBM;
+  const int n0 = (int)(tile % ny) * LBN;
   const int tm = tid >> 4;   // 0..15 -> rows tm*8 .. +7
   const int tn = tid & 15;   // 0..15 -> cols tn*4 .. +3
   float acc[8][4];
@@ -95,6 +102,7 @@ __global__ void __launch_bounds__(256, 2)
       if (out_act) out_act[m * N + n] = apply_act(v, act);
     }
   }
+  }  // tile loop
   trace_end(tb, tslot);
 }
 
@@ -108,10 +116,18 @@ extern "C" int gsn_linear_f32(const float* a, const float* w, const float* bias,
   GSN_REQUIRE(act >= 0 && act <= 3, "gsn_linear_f32: unknown activation %d", act);
   const long long gx = (M + gsn::LBM - 1) / gsn::LBM;
   const int gy = (N + gsn::LBN - 1) / gsn::LBN;
-  GSN_REQUIRE(gx < 2147483647LL && gy <= 65535, "gsn_linear_f32: grid too large");
-  dim3 grid((unsigned)gx, gy);
-  gsn::k_linear_f32<<<grid, 256, 0, gsn::as_stream(stream)>>>(a, w, bias, out, out_act, act, M, K, N,
-                                                             gsn::trace_buffer());
+  long long nblocks = gx * gy;
+  GSN_REQUIRE(nblocks < 2147483647LL, "gsn_linear_f32: grid too large");
+  const int cap = gsn::launch_option(GSN_OPT_F32_MAX_CTAS);
+  if (cap > 0 && nblocks > cap) nblocks = cap;
+  dim3 grid((unsigned)nblocks);
+  // development knob: GSN_F32_EXCL=<KiB> of (unused) dynamic shared memory keeps this kernel off the SMs that hold a
+  // resident tcgen05 recurrence CTA (profiles/r01_schedule_experiments.md)
+  static const int excl_kib = getenv("GSN_F32_EXCL") ? atoi(getenv("GSN_F32_EXCL")) : 0;
+  if (excl_kib > 0)
+    GSN_CUDA(cudaFuncSetAttribute(gsn::k_linear_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, excl_kib * 1024));
+  gsn::k_linear_f32<<<grid, 256, (size_t)excl_kib * 1024, gsn::as_stream(stream)>>>(a, w, bias, out, out_act, act, M,
+                                                                                   K, N, gsn::trace_buffer());
   GSN_LAUNCH_CHECK("k_linear_f32");
   return GSN_OK;
 }

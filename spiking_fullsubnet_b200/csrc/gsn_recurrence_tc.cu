@@ -107,7 +107,8 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
   static_assert(CPT == 4 || CPT == 8 || CPT == 16, "NT / G must be 4, 8 or 16");
   constexpr bool PF = CPT <= 8 || (SHARED && !TRAIN);  // prefetch xproj one frame ahead where registers allow
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int tslot = trace_begin(p.trace, 2, p.T, p.R, p.H);
+  int tslot = trace_begin(p.trace, 2, p.T, p.R, p.H);
+  if (blockIdx.x != 0) tslot = trace_begin_cta(p.trace, 5, (int)blockIdx.x, p.R, p.H);  // per-CTA records (dev aid)
   const long long e0 = PROF ? clock64() : 0;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3;    // TMEM lane quarter this warp may access
@@ -171,6 +172,10 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
     task_dst[it] = i < NT * k8n ? (uint32_t)(nhi * SBO + k8 * 128 + nlo * 16) : 0xFFFFFFFFu;
     task_src[it] = (uint32_t)(n * KWp + (k8 >> 2)) | ((uint32_t)(8 * (k8 & 3)) << 24);
   }
+  // Programmatic dependent launch (GSN_OPT_PDL): this grid may have been scheduled before the previous kernel of its
+  // stream -- the previous frame chunk of the same layer -- has finished; everything it produced (h0, c0) and every
+  // other input is only read after this point.  A no-op for ordinary launches.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   // frame 0: the initial spikes h0 (zeros when null)
 #pragma unroll
   for (int it = 0; it < MAXT; ++it) {
@@ -501,6 +506,9 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_tc(const RecTcParams 
     }
   }
   if (!alive) __trap();  // a broken pipeline fails loudly instead of hanging the device
+  // the next chunk's grid (if it was launched as a programmatic dependent) may be scheduled from here on: its CTAs
+  // are then already queued, ahead of lower-priority work, when this grid's SMs become free
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const long long e4 = PROF ? clock64() : 0;
   if (PROF && p.prof && blockIdx.x == 0 && tid == 0)
     for (int i = 0; i < 8; ++i) p.prof[i] = (unsigned long long)pc[i];
@@ -572,7 +580,7 @@ static int launch_nt(const RecTcParams& p_in, int C, cudaStream_t st) {
   cfg.blockDim = dim3(128 * G);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[3];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = C;
   attr[0].val.clusterDim.y = 1;
@@ -581,6 +589,11 @@ static int launch_nt(const RecTcParams& p_in, int C, cudaStream_t st) {
   attr[1].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = TRAIN ? 2 : 1;
+  if (!TRAIN && launch_option(GSN_OPT_PDL)) {
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
   GSN_CUDA(cudaLaunchKernelEx(&cfg, k_recurrence_tc<NT, G, PROF, SHARED, TRAIN>, p));
   return GSN_OK;
 }

@@ -295,10 +295,20 @@ class _SeqPlan:
         ops.linear(inp, cell.weight_ih.detach(), out=self.xproj[l][t0:t1], spikes=l > 0,
                    sm_budget=self.lin_budget, bits=bits)
 
-    def run_rec(self, l, k, t0, t1):
-        """Recurrence of frames [t0,t1) of layer l from the state carried out of chunk k-1."""
+    def run_rec(self, l, k, t0, t1, pdl=False):
+        """Recurrence of frames [t0,t1) of layer l from the state carried out of chunk k-1.  pdl: enqueue it as a
+        programmatic dependent of the previous kernel of the stream (= chunk k-1 of this layer)."""
         cell = self.m.sequence_model.layers[l].cell
         a, b = self.bn[l]
+        if pdl:
+            ops.set_option(ops.OPT_PDL, 1)
+        try:
+            self._run_rec(cell, a, b, l, k, t0, t1)
+        finally:
+            if pdl:
+                ops.set_option(ops.OPT_PDL, 0)
+
+    def _run_rec(self, cell, a, b, l, k, t0, t1):
         ops.layer_recurrence(self.xproj[l][t0:t1], cell.weight_hh.detach(), cell.bias_ih.detach(), a, b,
                              shared=cell.shared_weights, h0=self.hs[l][k], c0=self.cs[l][k],
                              out_h=self.h[l][t0:t1], out_hT=self.hs[l][k + 1], out_cT=self.cs[l][k + 1],
@@ -346,8 +356,8 @@ def coef_layout(proj, B, N, df, S):
 _BAND_STREAMS = {}
 
 
-def _band_streams(device, n, priority=0):
-    key = (device.index, n, priority)
+def _band_streams(device, n, priority=0, tag=None):
+    key = (device.index, n, priority, tag)
     if key not in _BAND_STREAMS:
         _BAND_STREAMS[key] = [torch.cuda.Stream(device=device, priority=priority) for _ in range(n)]
     return _BAND_STREAMS[key]
@@ -637,14 +647,17 @@ class SpikingFullSubNet(_GraphedNetwork, nn.Module):
         # streams per sequence model: pre[l] (input projections), rec[l] (recurrences), post (proj)
         # (the latency-critical recurrences get high-priority streams so their CTAs are placed first)
         plans = [fbp] + sbps
-        lo_streams = _band_streams(dev, sum(p.L + 1 for p in plans), priority=0)
-        hi_streams = _band_streams(dev, sum(p.L for p in plans), priority=-1)
-        streams = lo_streams + hi_streams
-        groups, o_lo, o_hi = [], 0, 0
-        for p in plans:
-            groups.append((lo_streams[o_lo:o_lo + p.L], hi_streams[o_hi:o_hi + p.L], lo_streams[o_lo + p.L]))
-            o_lo += p.L + 1
-            o_hi += p.L
+        # Priorities (lower = placed first): the full-band model is the head of every dependency chain, so its
+        # recurrences and the linears between them outrank the sub-band recurrences, which outrank the remaining
+        # projections.  GSN_WF_PRIO="fb_rec,fb_lin,sb_rec,sb_lin" overrides (development knob).
+        prio = [int(v) for v in os.environ.get("GSN_WF_PRIO", "-3,-2,-1,0").split(",")]
+        groups, streams = [], []
+        for pi, p in enumerate(plans):
+            p_rec, p_lin = (prio[0], prio[1]) if pi == 0 else (prio[2], prio[3])
+            lin = _band_streams(dev, p.L + 1, priority=p_lin, tag=("wf_lin", pi))
+            rec = _band_streams(dev, p.L, priority=p_rec, tag=("wf_rec", pi))
+            groups.append((lin[:p.L], rec, lin[p.L]))
+            streams += lin + rec
         fork = torch.cuda.Event()
         fork.record(main)
         for st in streams:
@@ -660,6 +673,8 @@ class SpikingFullSubNet(_GraphedNetwork, nn.Module):
                 ev.record(stream)
             return ev
 
+        pdl = os.environ.get("GSN_WF_PDL", "1") != "0"
+
         def run_model(p, group, k, t0, t1, feed, feed_ev):
             """chunk k of one sequence model; `feed` fills p.x[t0:t1] (runs on the layer-0 pre stream)."""
             pre, rec, post = group
@@ -670,10 +685,27 @@ class SpikingFullSubNet(_GraphedNetwork, nn.Module):
                         feed()
                     p.run_pre(l, k, t0, t1)
                 e_pre = staged(pre[l], [feed_ev if l == 0 else ev], do_pre)
-                ev = staged(rec[l], [e_pre], lambda l=l: p.run_rec(l, k, t0, t1))
+                ev = staged(rec[l], [e_pre], lambda l=l: p.run_rec(l, k, t0, t1, pdl=pdl and k > 0))
             return staged(post, [ev], lambda: p.run_post(k, t0, t1))
 
         w_fb, b_fb, e_fb = ln(fbm)
+        # the gather and fp32 projection kernels get a capped grid here (see GSN_OPT_F32_MAX_CTAS in gsn_b200.h)
+        f32_cap = int(os.environ.get("GSN_WF_F32_CTAS", "0"))
+        ops.set_option(ops.OPT_F32_MAX_CTAS, f32_cap)
+        try:
+            self._wavefront_enqueue(bounds, run_model, fbp, sbps, geo, groups, cm, w_fb, b_fb, e_fb, ln)
+        finally:
+            ops.set_option(ops.OPT_F32_MAX_CTAS, 0)
+        for st in streams:
+            done = torch.cuda.Event()
+            done.record(st)
+            main.wait_event(done)
+        _, _, fb_all = fbp.outputs()
+        outs = [p.outputs() for p in sbps]
+        self._keepalive = (cm, fbp, sbps)  # buffers referenced by the captured graph
+        return [o[0] for o in outs], fb_all, [o[2] for o in outs]
+
+    def _wavefront_enqueue(self, bounds, run_model, fbp, sbps, geo, groups, cm, w_fb, b_fb, e_fb, ln):
         for k, (t0, t1) in enumerate(bounds):
             ev_fb = run_model(fbp, groups[0], k, t0, t1,
                               lambda: ops.subband_features(cm[t0:t1], None, 1, 0, self.fb_input_size, 0, w_fb,
@@ -684,14 +716,6 @@ class SpikingFullSubNet(_GraphedNetwork, nn.Module):
                           lambda p=p, N=N, lo=lo, ctr=ctr, nbr=nbr, w_sb=w_sb, b_sb=b_sb, e_sb=e_sb:
                           ops.subband_features(cm[t0:t1], fbp.act[t0:t1], N, lo, ctr, nbr, w_sb, b_sb, e_sb,
                                                out=p.x[t0:t1]), ev_fb)
-        for st in streams:
-            done = torch.cuda.Event()
-            done.record(st)
-            main.wait_event(done)
-        _, _, fb_all = fbp.outputs()
-        outs = [p.outputs() for p in sbps]
-        self._keepalive = (cm, fbp, sbps)  # buffers referenced by the captured graph
-        return [o[0] for o in outs], fb_all, [o[2] for o in outs]
 
     def coefficients(self, mag):
         """Deep-filter coefficient tensors [B, df_i, S, F_i, T, 2] in the reference layout."""

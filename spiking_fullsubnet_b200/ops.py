@@ -37,6 +37,14 @@ def _prep(*tensors):
     return lib, torch.cuda.current_stream(dev).cuda_stream
 
 
+OPT_PDL, OPT_F32_MAX_CTAS = _lib.OPT_PDL, _lib.OPT_F32_MAX_CTAS
+
+
+def set_option(option, value):
+    """gsn_set_option for the calling thread (e.g. OPT_PDL around the recurrence launches of a frame-chunk chain)."""
+    _lib.check(_lib.load().gsn_set_option(int(option), int(value)))
+
+
 def _ptr(t):
     return None if t is None else t.data_ptr()
 
