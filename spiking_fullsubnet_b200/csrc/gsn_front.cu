@@ -35,8 +35,12 @@ __global__ void __launch_bounds__(256) k_compress_mag(const float* __restrict__ 
   }
 }
 
-// one warp per (t, row); lanes stride over the K features (K <= 1024 -> <= 32 per lane)
+// one warp per (t, row); lanes stride over the K features (K <= 1024 -> <= 32 per lane).  MAXPL = features per lane
+// the instantiation can hold: the small ones (K <= 64 / 256) need a third of the registers, so that several of their
+// CTAs fit beside a resident 512-thread recurrence CTA (wavefront schedule); same lane partition and reduction
+// order in all of them, i.e. bit-identical results.
 constexpr int kMaxPerLane = 32;
+template <int MAXPL>
 __global__ void __launch_bounds__(256) k_subband_features(
     const float* __restrict__ cm, int f_cm, const float* __restrict__ fb, int f_fb,
     float* __restrict__ x, int T, int B, int N, int lo, int ctr, int nbr,
@@ -57,10 +61,10 @@ __global__ void __launch_bounds__(256) k_subband_features(
     const float* cm_row = cm + ((size_t)t * B + b) * f_cm;
     const float* fb_row = fb ? fb + ((size_t)t * B + b) * f_fb : nullptr;
     const int base = lo + n * ctr;
-    float v[kMaxPerLane];
+    float v[MAXPL];
     float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxPerLane; ++i) {
+    for (int i = 0; i < MAXPL; ++i) {
       const int j = lane + 32 * i;
       v[i] = 0.f;
       if (j < K) {
@@ -79,7 +83,7 @@ __global__ void __launch_bounds__(256) k_subband_features(
     float* out = x + (size_t)warp * K;
     if (ln_w == nullptr) {
 #pragma unroll
-      for (int i = 0; i < kMaxPerLane; ++i) {
+      for (int i = 0; i < MAXPL; ++i) {
         const int j = lane + 32 * i;
         if (j < K) out[j] = v[i];
         if (32 * (i + 1) >= K) break;
@@ -91,7 +95,7 @@ __global__ void __launch_bounds__(256) k_subband_features(
     const float mean = sum / (float)K;
     float sq = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxPerLane; ++i) {
+    for (int i = 0; i < MAXPL; ++i) {
       const int j = lane + 32 * i;
       if (j < K) {
         const float d = v[i] - mean;
@@ -103,7 +107,7 @@ __global__ void __launch_bounds__(256) k_subband_features(
     for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
     const float rstd = 1.0f / sqrtf(sq / (float)K + eps);
 #pragma unroll
-    for (int i = 0; i < kMaxPerLane; ++i) {
+    for (int i = 0; i < MAXPL; ++i) {
       const int j = lane + 32 * i;
       if (j < K) out[j] = (v[i] - mean) * rstd * ln_w[j] + ln_b[j];
       if (32 * (i + 1) >= K) break;
@@ -183,12 +187,13 @@ extern "C" int gsn_subband_features(const float* cm, int f_cm, const float* fb, 
   GSN_REQUIRE(blocks < 2147483647LL, "gsn_subband_features: too many rows");
   const int cap = gsn::launch_option(GSN_OPT_F32_MAX_CTAS);
   if (cap > 0 && blocks > cap) blocks = cap;
-  static const int excl_kib = getenv("GSN_F32_EXCL") ? atoi(getenv("GSN_F32_EXCL")) : 0;  // see gsn_linear.cu
-  if (excl_kib > 0)
-    GSN_CUDA(cudaFuncSetAttribute(gsn::k_subband_features, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  excl_kib * 1024));
-  gsn::k_subband_features<<<(unsigned)blocks, 256, (size_t)excl_kib * 1024, gsn::as_stream(stream)>>>(
-      cm, f_cm, fb, f_fb, x, T, B, N, lo, ctr, nbr, ln_weight, ln_bias, ln_eps, gsn::trace_buffer());
+  auto launch = [&](auto kern) {
+    kern<<<(unsigned)blocks, 256, 0, gsn::as_stream(stream)>>>(cm, f_cm, fb, f_fb, x, T, B, N, lo, ctr, nbr, ln_weight,
+                                                              ln_bias, ln_eps, gsn::trace_buffer());
+  };
+  if (K <= 64) launch(gsn::k_subband_features<2>);
+  else if (K <= 256) launch(gsn::k_subband_features<8>);
+  else launch(gsn::k_subband_features<gsn::kMaxPerLane>);
   GSN_LAUNCH_CHECK("k_subband_features");
   return GSN_OK;
 }

@@ -22,7 +22,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // Software pipelined: the global loads of k-slab i+1 are in flight (registers) while slab i is multiplied
 // out of shared memory.  <= 96 registers so that a CTA fits beside a resident 512-thread recurrence CTA
 // (wavefront schedule: the projections of chunk k+1 run while the recurrences of chunk k occupy the SMs).
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(320, 2)  // launched with 256 threads; 320 caps ptxas at 96 registers (see above)
     k_linear_f32(const float* __restrict__ a, const float* __restrict__ w,
                  const float* __restrict__ bias, float* __restrict__ out,
                  float* __restrict__ out_act, int act, long long M, int K, int N, TraceBuf* tb) {
@@ -45,27 +45,21 @@ __global__ void __launch_bounds__(256, 2)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  // loader mapping: 16 consecutive threads cover the 16 k of one row (64 contiguous bytes)
+  // loader mapping: 16 consecutive threads cover the 16 k of one row (64 contiguous bytes); one base pointer per
+  // operand + a row count instead of per-row pointers (registers: a CTA must fit beside a recurrence CTA)
   const int lk = tid & 15, lr = tid >> 4;  // lr 0..15
-  const float* ap[LBM / 16];
-  const float* wp[LBN / 16];
-#pragma unroll
-  for (int i = 0; i < LBM / 16; ++i) {
-    const long long m = m0 + lr + 16 * i;
-    ap[i] = m < M ? a + m * K : nullptr;
-  }
-#pragma unroll
-  for (int i = 0; i < LBN / 16; ++i) {
-    const int n = n0 + lr + 16 * i;
-    wp[i] = n < N ? w + (size_t)n * K : nullptr;
-  }
+  const float* abase = a + (m0 + lr) * K;
+  const float* wbase = w + (size_t)(n0 + lr) * K;
+  const int arows = (int)(M - m0 < LBM ? M - m0 : LBM) - lr;  // rows lr + 16 i with 16 i < arows exist
+  const int wrows = (N - n0 < LBN ? N - n0 : LBN) - lr;
   float ra[LBM / 16], rw[LBN / 16];
   auto fetch = [&](int k0) {
     const int k = k0 + lk;
+    const bool kv = k < K;
 #pragma unroll
-    for (int i = 0; i < LBM / 16; ++i) ra[i] = (ap[i] && k < K) ? __ldg(ap[i] + k) : 0.f;
+    for (int i = 0; i < LBM / 16; ++i) ra[i] = (kv && 16 * i < arows) ? __ldg(abase + 16 * i * K + k) : 0.f;
 #pragma unroll
-    for (int i = 0; i < LBN / 16; ++i) rw[i] = (wp[i] && k < K) ? __ldg(wp[i] + k) : 0.f;
+    for (int i = 0; i < LBN / 16; ++i) rw[i] = (kv && 16 * i < wrows) ? __ldg(wbase + 16 * i * K + k) : 0.f;
   };
   fetch(0);
   for (int k0 = 0; k0 < K; k0 += LBK) {
@@ -121,13 +115,8 @@ extern "C" int gsn_linear_f32(const float* a, const float* w, const float* bias,
   const int cap = gsn::launch_option(GSN_OPT_F32_MAX_CTAS);
   if (cap > 0 && nblocks > cap) nblocks = cap;
   dim3 grid((unsigned)nblocks);
-  // development knob: GSN_F32_EXCL=<KiB> of (unused) dynamic shared memory keeps this kernel off the SMs that hold a
-  // resident tcgen05 recurrence CTA (profiles/r01_schedule_experiments.md)
-  static const int excl_kib = getenv("GSN_F32_EXCL") ? atoi(getenv("GSN_F32_EXCL")) : 0;
-  if (excl_kib > 0)
-    GSN_CUDA(cudaFuncSetAttribute(gsn::k_linear_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, excl_kib * 1024));
-  gsn::k_linear_f32<<<grid, 256, (size_t)excl_kib * 1024, gsn::as_stream(stream)>>>(a, w, bias, out, out_act, act, M,
-                                                                                   K, N, gsn::trace_buffer());
+  gsn::k_linear_f32<<<grid, 256, 0, gsn::as_stream(stream)>>>(a, w, bias, out, out_act, act, M, K, N,
+                                                             gsn::trace_buffer());
   GSN_LAUNCH_CHECK("k_linear_f32");
   return GSN_OK;
 }
