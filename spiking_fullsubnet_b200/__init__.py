@@ -7,5 +7,6 @@ Drop-in model classes (select them from a recipe TOML with
 from .modeling import (CirmGSN, GSUCell, GSULayer, MemoryState, Separator, SequenceModel,  # noqa: F401
                        SpikingFullSubNet, StackedGSU, SubbandModel, SubBandSequenceModel,
                        efficient_spiking_neuron)
+from . import losses  # noqa: F401  (freq_MAE / mag_MAE / SISNRLoss of the recipes)
 
 __version__ = "0.1.0"

@@ -40,3 +40,13 @@ def spike_flip_stats(a, b):
 def load_golden_weights(name):
     z = np.load(os.path.join(GOLDEN, name + "_weights.npz"), allow_pickle=False)
     return {k: z[k] for k in z.files}
+
+
+def loss_waveforms(n=2, length=12000, seed=20220815):
+    """Seeded (estimate, clean) waveform pair of the loss fixture (tests/golden/make_golden_loss.py)."""
+    rs = np.random.RandomState(seed)
+    t = np.arange(length) / 16000.0
+    clean = (0.1 * np.sin(2 * np.pi * (200 + 300 * t) * t))[None, :].repeat(n, 0) * rs.uniform(0.5, 1.5, (n, 1))
+    clean = clean.astype(np.float32)
+    est = (clean + 0.03 * rs.standard_normal(clean.shape)).astype(np.float32)
+    return est, clean

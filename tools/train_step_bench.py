@@ -5,8 +5,10 @@ torch DDP (exactly what `accelerator.prepare(model)` sets up in the reference, r
     python tools/train_step_bench.py [--size L] [--batch 32] [--seconds 6] [--steps 3] [--cpu-sample]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/train_step_bench.py ...
 
-Loss: a stand-in with the structure of the recipe's (recipes/.../trainer.py:33-37; the loss functions themselves
-are the "next" row f3): waveform L1 + magnitude L1 on the outputs forward() returns.  Prints ONE JSON line.
+Loss: the recipe's own (recipes/.../trainer.py:33-37): freq_MAE + mag_MAE + 0.001 * (100 - SI-SNR) from
+spiking_fullsubnet_b200.losses (row f3; each 2048-point STFT computed once).  `--loss standin` keeps the earlier
+waveform-L1 + magnitude-L1 stand-in (the rows of profiles/r01_training_step.md before the last one used it).
+Prints ONE JSON line.
 """
 import argparse
 import json
@@ -20,7 +22,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import synth  # noqa: E402  (synthetic weights / inputs only)
-from spiking_fullsubnet_b200 import SpikingFullSubNet  # noqa: E402
+from spiking_fullsubnet_b200 import SpikingFullSubNet, losses  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--size", default="L")
@@ -28,6 +30,7 @@ ap.add_argument("--batch", type=int, default=32, help="clips per GPU")
 ap.add_argument("--seconds", type=float, default=6.0, help="the recipe's training crop (dataloader.py:13)")
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--cpu-sample", action="store_true", help="also time a bounded CPU sample of the same step")
+ap.add_argument("--loss", default="recipe", choices=["recipe", "standin"])
 args = ap.parse_args()
 
 rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
@@ -52,7 +55,10 @@ clean_mag = torch.stft(clean, 512, 128, 512, window=torch.hann_window(512, devic
 def step():
     opt.zero_grad(set_to_none=True)
     enh_y, enh_mag, *_ = net(wave)
-    loss = (enh_y - clean).abs().mean() + (enh_mag - clean_mag).abs().mean()
+    if args.loss == "recipe":
+        loss = losses.ndns_training_loss(enh_y, clean)["loss"]
+    else:
+        loss = (enh_y - clean).abs().mean() + (enh_mag - clean_mag).abs().mean()
     loss.backward()
     opt.step()
     return loss
@@ -77,7 +83,7 @@ if rank == 0:
             "n_gpus": world, "ms_per_step": float(ms), "loss": float(loss.detach()),
             "config": {"workload": f"spiking_fullsubnet-{args.size} training step (fwd + BPTT + AdamW), batch "
                                    f"{args.batch} x {args.seconds:g} s per GPU (T={T}), DDP/NCCL gradient all-reduce",
-                       "global_batch": world * args.batch},
+                       "global_batch": world * args.batch, "loss": args.loss},
             "grad_bytes": int(sum(p.numel() for p in model.parameters()) * 4)}
     if args.cpu_sample:
         from oracle import gsn_oracle_torch as OT
