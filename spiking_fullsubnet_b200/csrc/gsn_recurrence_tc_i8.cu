@@ -257,14 +257,8 @@ __global__ void __launch_bounds__(128 * G, 1) k_recurrence_i8(const RecI8Params 
       tc::tc_fence_after();
       if (tc::elect_one()) {
         tc::mbar_arrive_expect_tx(&bar_bits[par], bits_bytes);  // arm this frame's spike-bit exchange
-#pragma unroll 1
-        for (int pl = 0; pl < NPL; ++pl) {
-          const uint32_t a0 = tmem_a + pl * plane_cols;
-          const uint32_t idesc = pl == NPL - 1 ? idesc_s : idesc_u;
-#pragma unroll 2
-          for (int ks = 0; ks < ksteps; ++ks)
-            tc::mma_i8_ts(tmem_d + pl * NT, a0 + ks * 8, desc_b0 + (uint64_t)(ks * 16), idesc, ks > 0);
-        }
+        // straight-line issue (operands = base + immediate), one int32 accumulator per plane
+        tc::mma_i8_planes<NPL>(ksteps, tmem_d, NT, tmem_a, desc_b0, idesc_u, idesc_s);
         tc::mma_commit(bar_mma);
       }
       __syncwarp();

@@ -261,6 +261,44 @@ __device__ __forceinline__ void mma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint
       "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// straight-line issue for kind::i8 (see mma_planes_unrolled): plane pl accumulates into its OWN int32 accumulator
+// tmem_d + pl * d_stride; the top plane is signed (idesc_s), the others unsigned digits (idesc_u)
+template <int ACC>
+__device__ __forceinline__ void mma_i8_ts_c(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "n"(ACC)
+      : "memory");
+}
+template <int KS, int PLANES>
+__device__ __forceinline__ void mma_i8_planes_unrolled(uint32_t tmem_d, uint32_t d_stride, uint32_t tmem_a,
+                                                       uint64_t desc_b0, uint32_t idesc_u, uint32_t idesc_s) {
+#pragma unroll
+  for (int pl = 0; pl < PLANES; ++pl) {
+    const uint32_t idesc = pl == PLANES - 1 ? idesc_s : idesc_u;
+    mma_i8_ts_c<0>(tmem_d + pl * d_stride, tmem_a + (uint32_t)(pl * KS * 8), desc_b0, idesc);
+#pragma unroll
+    for (int ks = 1; ks < KS; ++ks)
+      mma_i8_ts_c<1>(tmem_d + pl * d_stride, tmem_a + (uint32_t)((pl * KS + ks) * 8), desc_b0 + (uint64_t)(ks * 16),
+                     idesc);
+  }
+}
+// runtime dispatch: ksteps = Kmma / 32 in [1, 16]  (Kmma <= 512)
+template <int PLANES>
+__device__ __forceinline__ bool mma_i8_planes(int ksteps, uint32_t tmem_d, uint32_t d_stride, uint32_t tmem_a,
+                                              uint64_t desc_b0, uint32_t idesc_u, uint32_t idesc_s) {
+  switch (ksteps) {
+#define GSN_KS_CASE(n) \
+  case n: mma_i8_planes_unrolled<n, PLANES>(tmem_d, d_stride, tmem_a, desc_b0, idesc_u, idesc_s); return true;
+    GSN_KS_CASE(1) GSN_KS_CASE(2) GSN_KS_CASE(3) GSN_KS_CASE(4) GSN_KS_CASE(5) GSN_KS_CASE(6) GSN_KS_CASE(7)
+    GSN_KS_CASE(8) GSN_KS_CASE(9) GSN_KS_CASE(10) GSN_KS_CASE(11) GSN_KS_CASE(12) GSN_KS_CASE(13) GSN_KS_CASE(14)
+    GSN_KS_CASE(15) GSN_KS_CASE(16)
+#undef GSN_KS_CASE
+    default: return false;
+  }
+}
+
 // all previously issued MMAs of this thread arrive (once) on `bar` when complete
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))

@@ -123,3 +123,39 @@ def test_sync_free_istft_matches_torch_istft():
         spec = _stft(x, n, h, n) * (1 + 0.1 * torch.randn(2, n // 2 + 1, 1 + L // h))
         a, b = _istft(spec, n, h, n, L), _istft_nosync(spec, n, h, n, L)
         assert a.shape == b.shape and float((a - b).abs().max() / a.abs().max()) < 2e-6
+
+
+def test_launch_options_validate_without_gpu():
+    """gsn_set_option: known options are accepted (and reset), unknown ones are GSN_EINVAL with a message."""
+    lib = _lib.load()
+    for opt in (_lib.OPT_PDL, _lib.OPT_F32_MAX_CTAS):
+        assert lib.gsn_set_option(opt, 1) == _lib.GSN_OK
+        assert lib.gsn_set_option(opt, 0) == _lib.GSN_OK
+    rc = lib.gsn_set_option(99, 1)
+    assert rc == _lib.GSN_EINVAL and b"unknown option" in lib.gsn_last_error()
+    rc = lib.gsn_pack_spikes(None, None, 1, 1, None)
+    assert rc == _lib.GSN_EINVAL
+    rc = lib.gsn_linear_spike_bits(None, None, None, None, None, 0, 1, 16, 16, 0, None)
+    assert rc == _lib.GSN_EINVAL
+
+
+def test_wavefront_chunk_bounds_cover_all_frames(monkeypatch):
+    """Frame chunks of the wavefront schedule: contiguous, non-empty, cover [0, T) exactly; more chunks than
+    frames collapses to one frame per chunk; GSN_WF_WEIGHTS reshapes them without losing frames."""
+    from spiking_fullsubnet_b200.modeling import _chunk_bounds
+    monkeypatch.delenv("GSN_WF_WEIGHTS", raising=False)
+    for T, n in [(501, 12), (501, 1), (126, 16), (5, 12), (1251, 16), (1, 3)]:
+        b = _chunk_bounds(T, n)
+        assert b[0][0] == 0 and b[-1][1] == T and len(b) == min(n, T)
+        assert all(a1 == b0 for (_, a1), (b0, _) in zip(b[:-1], b[1:])) and all(hi > lo for lo, hi in b)
+        assert max(hi - lo for lo, hi in b) - min(hi - lo for lo, hi in b) <= 1
+    monkeypatch.setenv("GSN_WF_WEIGHTS", "1,2,4,2,1")
+    b = _chunk_bounds(501, 12)
+    assert len(b) == 5 and b[0][0] == 0 and b[-1][1] == 501 and (b[2][1] - b[2][0]) > 3 * (b[0][1] - b[0][0])
+
+
+def test_spike_bits_layout_helpers_on_cpu():
+    """ops.spike_bits_buffer sizes the packed trace as ceil(H/32) int32 words per row."""
+    from spiking_fullsubnet_b200 import ops
+    for H, W in [(16, 1), (32, 1), (33, 2), (160, 5), (240, 8), (320, 10)]:
+        assert tuple(ops.spike_bits_buffer((7, 3), H, "cpu").shape) == (7, 3, W)
