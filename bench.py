@@ -262,8 +262,9 @@ def main():
     rec_ms = sum(a.elapsed_time(b) for (_, a, b, _) in rec) / 3.0
     rec_flops = sum(f for (f, _, _, _) in rec) / 3.0
     # latency model of the serial frame chain (SURVEY 8d "Bound"): per launch, measured us per frame against the
-    # tensor-pipe floor of one frame = 3 planes x ceil(H/16) tcgen05.mma at the measured ~42 cycles per 128xNx16
-    # instruction with the A operand in tensor memory (tools/tc_mma_timing.py), at the SM clock sampled above
+    # tensor-pipe time of one frame = 3 planes x ceil(H/16) tcgen05.mma at 14.6 cycles per 128x16x16 instruction
+    # (A operand in tensor memory, straight-line issue, measured in isolation by tools/tc_mma_timing.py), at the SM
+    # clock sampled above: the rest of the frame is the dependent epilogue / spike exchange / operand rebuild
     per_launch = {}
     for (_, a, b, (t_, r_, h_)) in rec:
         per_launch.setdefault((t_, r_, h_), []).append(a.elapsed_time(b) * 1e3 / t_)
@@ -318,8 +319,8 @@ def main():
     mhz = (line["clocks"]["sm_mhz"] or 1965.0)
     line["roofline"]["latency_model"] = [
         {"frames": t_, "rows": r_, "hidden": h_, "us_per_frame": float(np.mean(v)),
-         "mma_floor_us_per_frame": 3 * ((h_ + 15) // 16) * 42 / mhz,
-         "frac_of_mma_floor": 3 * ((h_ + 15) // 16) * 42 / mhz / float(np.mean(v))}
+         "mma_us_per_frame": 3 * ((h_ + 15) // 16) * 14.6 / mhz,
+         "tensor_pipe_share_of_frame": 3 * ((h_ + 15) // 16) * 14.6 / mhz / float(np.mean(v))}
         for (t_, r_, h_), v in sorted(per_launch.items())]
     if world == 1 and not args.no_cpu_baseline:
         times, cores = time_cpu_port(synth, cfg, B, T, 3, 1)
