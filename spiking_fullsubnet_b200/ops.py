@@ -170,7 +170,11 @@ def layer_recurrence(xproj, w_hh, bias, bn_scale=None, bn_shift=None, shared=Tru
                                              _ptr(h0), _ptr(c0), _ptr(h), _ptr(c), _ptr(hT), _ptr(cT),
                                              _ptr(out_bits), T, R, H, int(shared), be, int(sm_budget),
                                              ws.data_ptr() + off, st))
-    LAUNCHES[0] += 2  # weight preparation + the recurrence kernel
+    # kernels enqueued: tcgen05 = the recurrence kernel alone (it also writes the packed trace); SIMT = weight
+    # transpose + recurrence; SIMT / int8 pack the trace with one more launch when it is requested
+    resolved = be if be != _lib.BACKEND_AUTO else lib.gsn_layer_recurrence_pick_backend(R, H, int(shared))
+    LAUNCHES[0] += (2 if resolved == _lib.BACKEND_SIMT else 1) + \
+        (1 if out_bits is not None and resolved != _lib.BACKEND_TCGEN05 else 0)
     LAST_WS[0] = (ws, 0)
     if PROFILE is not None:
         e1.record()
