@@ -136,6 +136,10 @@ GSN_API int gsn_pack_spikes(const float* h, uint32_t* bits, int64_t rows, int H,
  * latency-critical recurrence chunks are about to be placed on.  0 = one CTA per tile (default).               */
 #define GSN_OPT_F32_MAX_CTAS 2
 GSN_API int gsn_set_option(int option, int value);
+/* Row tile NT (rows per thread-block cluster: 16, 32 or 64) the tcgen05 back ends use for this shape and SM budget
+ * (0 for the SIMT back end / unsupported shapes): what gsn_layer_recurrence(_bits) will launch.  Parity tests use it
+ * to make sure every tile instantiation is exercised.                                                        */
+GSN_API int gsn_layer_recurrence_tile(int R, int H, int shared, int backend, int sm_budget);
 /* which backend GSN_BACKEND_AUTO resolves to for this shape (GSN_BACKEND_SIMT / _TCGEN05 / _TCGEN05_I8). */
 GSN_API int gsn_layer_recurrence_pick_backend(int R, int H, int shared);
 

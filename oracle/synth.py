@@ -133,6 +133,13 @@ CFG_ZOO_S = dict(sr=16000, fdrc=0.5, n_fft=512, fb_freqs=64, hop_length=128, win
                  norm_type="offline_laplace_norm", shared_weights=True, bn=True)
 
 
+# model_zoo/intel_ndns/spike_fsb/baseline_l/config__2023_07_27--22_13_36.toml [model_g.args] (surface B, zoo "L")
+CFG_ZOO_L = dict(CFG_ZOO_S, fb_hidden_size=320, sb_hidden_size=256, freq_cutoffs=[32, 128, 192],
+                 sb_df_orders=[5, 3, 1, 1], sb_num_center_freqs=[2, 4, 32, 64],
+                 sb_num_neighbor_freqs=[15, 15, 15, 15], fb_num_center_freqs=[2, 4, 32, 64],
+                 fb_num_neighbor_freqs=[0, 0, 0, 0])
+
+
 def tiny_cfg_b(**over):
     """Structurally complete surface-B (`Separator`) config, small enough for golden traces."""
     cfg = dict(sr=16000, fdrc=0.5, n_fft=64, fb_freqs=8, hop_length=16, win_length=64, num_freqs=32,

@@ -42,6 +42,7 @@ SIGNATURES = {
     "gsn_layer_train_forward_tc": (_i, [_p] * 13 + [_i] * 4 + [_f, _f, _i, _p, _p]),
     "gsn_layer_train_backward": (_i, [_p] * 13 + [_i] * 5 + [_f, _p, _p]),
     "gsn_layer_recurrence_pick_backend": (_i, [_i, _i, _i]),
+    "gsn_layer_recurrence_tile": (_i, [_i, _i, _i, _i, _i]),
     "gsn_deepfilter_band": (_i, [_p] * 5 + [_i] * 9 + [_p]),
     "gsn_trace_set": (_i, [_p, _sz]),
     "gsn_tc_selftest": (_i, [_p] * 4 + [_i] * 5 + [_p]),

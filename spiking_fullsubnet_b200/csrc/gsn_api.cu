@@ -35,6 +35,8 @@ int launch_recurrence_tc(const float*, const float*, const float*, const float*,
                          void*, uint32_t*, cudaStream_t);
 size_t recurrence_tc_workspace(int R, int H, int shared);
 bool recurrence_tc_supported(int R, int H, int shared);
+int recurrence_tc_tile(int R, int H, int shared, int sms);
+int recurrence_i8_tile(int R, int H, int shared, int sms);
 // gsn_recurrence_tc_i8.cu
 int launch_recurrence_i8(const float*, const float*, const float*, const float*, const float*,
                          const float*, const float*, float*, float*, float*, float*, int, int, int, int, int,
@@ -84,6 +86,16 @@ extern "C" int gsn_layer_recurrence_pick_backend(int R, int H, int shared) {
   if (gsn::recurrence_tc_supported(R, H, shared)) return GSN_BACKEND_TCGEN05;
   if (gsn::recurrence_i8_supported(R, H, shared)) return GSN_BACKEND_TCGEN05_I8;
   return GSN_BACKEND_SIMT;
+}
+
+extern "C" int gsn_layer_recurrence_tile(int R, int H, int shared, int backend, int sm_budget) {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (sm_budget > 0 && sm_budget < sms) sms = sm_budget;
+  if (backend == GSN_BACKEND_AUTO) backend = gsn_layer_recurrence_pick_backend(R, H, shared);
+  if (backend == GSN_BACKEND_TCGEN05) return gsn::recurrence_tc_tile(R, H, shared, sms);
+  if (backend == GSN_BACKEND_TCGEN05_I8) return gsn::recurrence_i8_tile(R, H, shared, sms);
+  return 0;
 }
 
 extern "C" size_t gsn_layer_recurrence_workspace_bytes(int R, int H, int shared, int backend) {

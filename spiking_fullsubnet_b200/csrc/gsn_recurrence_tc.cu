@@ -557,6 +557,8 @@ bool recurrence_tc_supported(int R, int H, int shared) {
   return tc_pick_nt(R, H, shared, 148) > 0;
 }
 
+int recurrence_tc_tile(int R, int H, int shared, int sms) { return tc_pick_nt(R, H, shared, sms); }
+
 size_t recurrence_tc_workspace(int, int, int) { return 256; }
 
 template <int NT, int G, bool PROF, bool SHARED, bool TRAIN = false>

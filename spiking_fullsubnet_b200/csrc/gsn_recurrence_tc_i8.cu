@@ -396,6 +396,8 @@ static int i8_pick_nt(int R, int H, int shared, int sm_count) {
   return best;
 }
 
+int recurrence_i8_tile(int R, int H, int shared, int sms) { return i8_pick_nt(R, H, shared, sms); }
+
 bool recurrence_i8_supported(int R, int H, int shared) {
   if (R <= 0 || H < 16) return false;
   const int C = shared ? (H + 127) / 128 : (H + 63) / 64;

@@ -182,6 +182,11 @@ def layer_recurrence(xproj, w_hh, bias, bn_scale=None, bn_shift=None, shared=Tru
     return h, c, (hT, cT)
 
 
+def recurrence_tile(R, H, shared, backend="auto", sm_budget=0):
+    """Rows per cluster (16 / 32 / 64) the tcgen05 back ends will use for this shape and SM budget (0: SIMT)."""
+    return _lib.load().gsn_layer_recurrence_tile(R, H, int(shared), _lib.BACKENDS[backend], int(sm_budget))
+
+
 def pick_backend(R, H, shared):
     return {1: "simt", 2: "tcgen05", 3: "tcgen05_i8"}[_lib.load().gsn_layer_recurrence_pick_backend(R, H, int(shared))]
 

@@ -141,6 +141,91 @@ def run_surface_b(name, cfg, params, seed, batch, num_samples, store_weights=Fal
     print(name, {k: (v.shape if hasattr(v, "shape") else v) for k, v in d.items() if k != "cfg"})
 
 
+def _flip_frac(all_a, all_b):
+    """fraction of differing spikes between two all_layer_outputs structures (layers 1..L of every model)."""
+    flips = total = 0
+    for a, b in zip(all_a, all_b):
+        flips += int((a != b).sum())
+        total += a.numel()
+    return flips, total
+
+
+def _spike_layers(fb_all, sb_all, L=2):
+    return [fb_all[1 + l] for l in range(L)] + [al[1 + l] for al in sb_all for l in range(L)]
+
+
+def _coef_rel(ca, cb):
+    return max(float((a - b).abs().max() / (b.abs().max() + 1e-30)) for a, b in zip(ca, cb))
+
+
+SNAP = 32
+
+
+def run_long(name, surface, cfg, params, seed, batch, num_samples, coef_tail=0, weights_file=None):
+    """Free-running parity fixture at BASELINE sizes (T = 501 / 1 251): full bit-packed spike traces, coefficient
+    tensors (all frames, or the last `coef_tail` frames -- chaos grows with T, so the tail is the telling part),
+    the enhanced waveform, and the REFERENCE'S OWN NOISE FLOOR measured in the same run: the reference against
+    itself with the input scaled by 1 + 1e-6 (SURVEY 8c protocol P3) -- spike-flip fraction and coefficient
+    max|delta| / max|ref|.  surface: "A" (SpikingFullSubNet) or "B" (Separator)."""
+    from oracle import run_reference as RR
+    torch.manual_seed(0)
+    model = (RR.build_surface_a if surface == "A" else RR.build_surface_b)(cfg, params)
+    net = RR.network_a if surface == "A" else RR.network_b
+    wave = synth.make_wave(batch, num_samples, seed + 1)
+    x = torch.from_numpy(wave)
+    with torch.no_grad():
+        mag = model.stft(x)[0]
+        enh_y, enh_mag, fb_all, sb_all = model(x)
+        # membrane snapshots every SNAP frames (state after frames SNAP-1, 2*SNAP-1, ...) for the block
+        # teacher-forced protocol: the CUDA recurrence restarts from the reference's own (h, c) every SNAP frames
+        snaps, counters, hooks = {}, {}, []
+        cell_types = tuple(c.GSUCell for c in (RR.load().ESN, sys.modules.get("efficient_spiking_neuron"))
+                           if c is not None and hasattr(c, "GSUCell"))
+
+        def mk(key):
+            def hook(_m, _inp, out):
+                t = counters.get(key, 0)
+                counters[key] = t + 1
+                if (t + 1) % SNAP == 0:
+                    snaps.setdefault(key, []).append(out[1][1].detach().numpy().copy())
+            return hook
+
+        for n_, m_ in model.named_modules():
+            if isinstance(m_, cell_types):
+                tag = "fb" if n_.startswith("fb_model") else "sb" + n_.split("sb_models.")[1].split(".")[0]
+                hooks.append(m_.register_forward_hook(mk(f"{tag}_c{n_.split('layers.')[1].split('.')[0]}")))
+        coefs, fb2, sb2 = net(model, mag, cfg)
+        for h_ in hooks:
+            h_.remove()
+        assert _flip_frac(_spike_layers(fb_all, sb_all), _spike_layers(fb2, sb2))[0] == 0  # run-to-run deterministic
+        # noise floor: the reference against itself under input scalings within +-2e-6 (worst of four)
+        flips, total, floor_coef = 0, 1, 0.0
+        for eps in (1e-6, -1e-6, 2e-6, -2e-6):
+            coefs_n, fb_n, sb_n = net(model, mag * (1.0 + eps), cfg)
+            f_, total = _flip_frac(_spike_layers(fb_n, sb_n), _spike_layers(fb_all, sb_all))
+            flips = max(flips, f_)
+            floor_coef = max(floor_coef, _coef_rel(coefs_n, coefs))
+    d = {"cfg": json.dumps(cfg), "seed": seed, "surface": surface, "wave": wave, "mag": mag.numpy(), "enh_y": enh_y.numpy(),
+         "floor_flips": flips, "floor_total": total, "floor_coef_rel": floor_coef,
+         "coef_tail": coef_tail, "snap": SNAP}
+    for k, v in snaps.items():
+        d[k] = np.stack(v)
+    T = mag.shape[-1]
+    t0 = T - coef_tail if coef_tail else 0
+    for i, c in enumerate(coefs):  # A: [B,df,S,F,T,2]; B: [B,df,F,T,2]
+        d[f"coef{i}"] = c[..., t0:, :].contiguous().numpy()
+    for l in range(2):
+        d[f"fb_h{l}"] = pack(fb_all[1 + l])
+    for i, al in enumerate(sb_all):
+        for l in range(2):
+            d[f"sb{i}_h{l}"] = pack(al[1 + l])
+    if weights_file:
+        d["weights_file"] = weights_file
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
+    print(name, f"T={T} floor: {flips}/{total} flips ({flips / total:.2e}), coef rel {d['floor_coef_rel']:.2e}",
+          {k: (v.shape if hasattr(v, "shape") else v) for k, v in d.items() if k not in ("cfg", "wave", "mag")})
+
+
 def run_train(name, cfg, seed, batch, num_samples):
     """One TRAINING step of surface A on the reference: train-mode BatchNorm (batch statistics per frame,
     running-stat updates) and autograd BPTT through the Triangle surrogate (ESN:84-101)."""
@@ -195,8 +280,28 @@ def run_cirm(name, cfg, seed, batch, num_samples):
     print(name, {k: (v.shape if hasattr(v, "shape") else v) for k, v in d.items() if k != "cfg"})
 
 
+def main_long():
+    """BASELINE config-2 / config-3 sized fixtures: zoo-S and zoo-L `Separator` at 2 clips x 4 s
+    (T = 501) and 1 clip x 10 s (T = 1 251), surface-A S (random init) at 2 x 4 s."""
+    zoo_s = torch.load(REF + "/model_zoo/intel_ndns/spike_fsb/baseline_s/checkpoints/best/pytorch_model.bin",
+                       map_location="cpu")
+    zoo_l = torch.load(REF + "/model_zoo/intel_ndns/spike_fsb/baseline_l/checkpoints/best/pytorch_model.bin",
+                       map_location="cpu")
+    ps = {k: v.numpy() for k, v in zoo_s.items()}
+    pl = {k: v.numpy() for k, v in zoo_l.items()}
+    np.savez_compressed(os.path.join(HERE, "zoo_l_weights.npz"), **pl)
+    run_long("zoo_s_2x4s", "B", synth.CFG_ZOO_S, ps, 201, 2, 64000, weights_file="zoo_s_1s_weights")
+    run_long("zoo_s_1x10s", "B", synth.CFG_ZOO_S, ps, 202, 1, 160000, coef_tail=128, weights_file="zoo_s_1s_weights")
+    run_long("zoo_l_2x4s", "B", synth.CFG_ZOO_L, pl, 203, 2, 64000, coef_tail=128, weights_file="zoo_l_weights")
+    run_long("zoo_l_1x10s", "B", synth.CFG_ZOO_L, pl, 204, 1, 160000, coef_tail=64, weights_file="zoo_l_weights")
+    run_long("cfgS_2x4s", "A", synth.CFG_S, synth.make_params(synth.CFG_S, 5), 205, 2, 64000)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
+    if len(sys.argv) > 1 and sys.argv[1] == "long":
+        main_long()
+        sys.exit(0)
     # tiny structural variants with per-step membrane traces (teacher-forced protocol P1)
     run_surface_a("tiny_shared_bn", synth.tiny_cfg(), 101, 2, 16 * 39, True)
     run_surface_a("tiny_unshared_nobn", synth.tiny_cfg(shared_weights=False, bn=False,

@@ -534,3 +534,133 @@ def test_layer_training_large_rows_vs_torch_autograd():
         ref = p64[k].grad
         err = float((p.grad.double() - ref).abs().max() / (ref.abs().max() + 1e-12))
         assert err < 1e-3, (k, err)
+
+
+# ---- BASELINE-sized parity (VERDICT r01 "close the parity holes") ---------------------------------------------------
+from tests.helpers import LONG, assert_long, block_forced_check, compare_long, load_long, record_parity  # noqa: E402
+
+
+def _long_model(g, backend="auto"):
+    from spiking_fullsubnet_b200 import Separator
+    cls = SpikingFullSubNet if g["surface"] == "A" else Separator
+    m = cls(**g["cfg"])
+    m.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in g["params"].items()}, strict=True)
+    return m.eval().to(DEV).set_backend(backend)
+
+
+@pytest.mark.parametrize("name", LONG)
+def test_long_free_running_vs_reference(name):
+    """Free-running parity with the REFERENCE at BASELINE sizes: T = 501 (config 2) and T = 1 251 (config 3) frames,
+    surface-A S (the bench's weights), trained zoo-S and zoo-L checkpoints.  Bounds: tests.helpers.assert_long (the
+    reference's own noise floor); counts go to gpurun_out/parity_counts.json -> profiles/."""
+    g = load_long(name)
+    m = _long_model(g)
+    with torch.no_grad():
+        coefs, fb_all, sb_all = m.coefficients(_t(g["mag"]))
+    st = compare_long(g, coefs, fb_all, sb_all)
+    print(name, st)
+    record_parity(f"free_running/{name}", st)
+    assert_long(st, name)
+
+
+def _gpu_run_layer(backend, nt_want, tiles_seen):
+    def run_layer(inp, w_ih, w_hh, bias, bn, shared, h0, c0):
+        a = b = None
+        if bn is not None:
+            inv = 1.0 / np.sqrt(bn["running_var"] + np.float32(1e-5))
+            al = (inv * bn["weight"]).astype(np.float32)
+            a, b = _t(al), _t((bn["bias"] - bn["running_mean"] * al).astype(np.float32))
+        x = _t(inp)
+        spikes = bool(((inp == 0) | (inp == 1)).all())
+        xproj = ops.linear(x, _t(w_ih), spikes=spikes)
+        _, R, _ = inp.shape
+        H = w_hh.shape[1]
+        # SM budget that makes the tile picker choose `nt_want` rows per cluster (or the largest tile that fits TMEM)
+        C = (H + 127) // 128 if shared else (H + 63) // 64
+        budget = 0
+        if nt_want > 16:
+            budget = max(1, ((R + nt_want // 2 - 1) // (nt_want // 2)) * C - 1)
+        tiles_seen.add(ops.recurrence_tile(R, H, shared, backend, budget))
+        h, _, _ = ops.layer_recurrence(xproj, _t(w_hh), _t(bias), a, b, shared=shared, h0=_t(h0), c0=_t(c0),
+                                       backend=backend, sm_budget=budget)
+        return h.cpu().numpy()
+    return run_layer
+
+
+@pytest.mark.parametrize("nt", [16, 32, 64])
+@pytest.mark.parametrize("backend", ["tcgen05", "tcgen05_i8"])
+@pytest.mark.parametrize("name", ["zoo_s_2x4s", "zoo_l_2x4s", "zoo_l_1x10s"])
+def test_block_teacher_forced_tiles_vs_reference(name, backend, nt):
+    """Every row tile (NT = 16 / 32 / 64) of both tcgen05 back ends against the REFERENCE with TRAINED weights at
+    H = 160 / 240 / 256 / 320 over T = 501 / 1 251 frames: the recurrence restarts from the reference's state every
+    32 frames (tests.helpers.block_forced_check), all blocks in one launch (rows' = blocks x rows: up to 1 872
+    rows), layer by layer with the reference's own layer inputs.  Bound: < 1e-4 of all spikes (the numpy oracle under
+    the same protocol: 8e-6 on zoo-L)."""
+    g = load_long(name)
+    m = _long_model(g)
+    with torch.no_grad():
+        _, fb_all, sb_all = m.coefficients(_t(g["mag"]))
+    xs = {"fb": fb_all[0].cpu().numpy()}
+    xs.update({f"sb{i}": al[0].cpu().numpy() for i, al in enumerate(sb_all)})
+    tiles = set()
+    try:
+        st = block_forced_check(g, xs, _gpu_run_layer(backend, nt, tiles))
+    except NotImplementedError:
+        pytest.skip(f"{backend} does not support a shape of {name}")
+    st["tiles_used"] = sorted(tiles)
+    print(name, backend, nt, st)
+    record_parity(f"block_forced/{name}/{backend}/nt{nt}", st)
+    assert max(tiles) == nt or nt == 64, f"tile picker never chose NT={nt}: {tiles}"
+    assert st["flips"] / st["total"] < 1e-4, st
+
+
+@pytest.mark.parametrize("R,H,shared,backend", [(1536, 256, True, "tcgen05"), (4096, 256, True, "tcgen05"),
+                                                (4096, 320, True, "tcgen05"), (1536, 224, False, "tcgen05"),
+                                                (4096, 256, True, "tcgen05_i8"), (2048, 448, True, "tcgen05_i8")])
+def test_large_row_tiles_vs_oracle(R, H, shared, backend):
+    """The row counts of BASELINE config 3 (L at batch 64: R = 1 024 / 1 536; 4 096 for the config-5 sweep): with the
+    whole device as budget the picker leaves NT = 16 (R = 1 536 -> 32, R = 4 096 -> 64 at H = 256); two-layer stack
+    against the numpy oracle, every spike."""
+    from spiking_fullsubnet_b200 import efficient_spiking_neuron
+    rs = np.random.RandomState(R + H)
+    T, K, L = 12, 38, 2
+    p = synth._seq_model_params(rs, "m.", K, H, L, 0, shared, True, False)
+    stack = efficient_spiking_neuron(K, H, L, shared_weights=shared, bn=True)
+    stack.load_state_dict({k[len("m.sequence_model."):]: torch.from_numpy(np.array(v)) for k, v in p.items()})
+    stack = stack.eval().to(DEV)
+    stack.backend = backend
+    nt = ops.recurrence_tile(R, H, shared, backend, 0)
+    x = rs.standard_normal((T, R, K)).astype(np.float32)
+    try:
+        with torch.no_grad():
+            out, states, trace = stack(_t(x), None, want_c=True)
+    except NotImplementedError:
+        pytest.skip(f"{backend} does not support R={R} H={H}")
+    _, ref_trace, ref_c = O.gsn_stack_forward(x, p, "m.sequence_model.", L, shared, return_c=True)
+    worst = 0.0
+    for l in range(L):
+        got = trace[1 + l].cpu().numpy()
+        diff = got != ref_trace[1 + l]
+        if diff.any():  # only legitimate where the oracle's membrane potential sits on the threshold
+            first = int(np.argmax(diff.reshape(T, -1).any(axis=1)))
+            bad = diff[first]
+            assert np.abs(ref_c[l][first][bad]).max() < 1e-5, f"NT={nt} layer {l}: flip away from the threshold"
+            break
+        worst = max(worst, float(np.abs(stack.last_c[l].cpu().numpy() - ref_c[l]).max()))
+    record_parity(f"large_rows/R{R}_H{H}_{'sh' if shared else 'un'}_{backend}", {"nt": nt, "max_c_err": worst})
+    assert nt > 16, f"expected a coarse row tile for R={R}, got NT={nt}"
+    assert worst < 1e-4
+
+
+def test_wavefront_graph_matches_eager_at_full_size_S():
+    """The schedule bench.py times (CUDA graph, 12-chunk frame wavefront, programmatic dependent launches) against the
+    eager launch sequence at BASELINE config-2 size (S, batch 32 x 4 s, T = 501): bit-identical coefficients."""
+    cfg = synth.CFG_S
+    m = _model(cfg, synth.make_params(cfg, 5))
+    mag = _t(synth.make_mag(32, 257, 501, 11))
+    with torch.no_grad():
+        eager = [p.clone() for p in m.network(mag)[0]]
+        m.enable_cuda_graph(True, frame_chunks=12)
+        for _ in range(2):
+            out = m.network(mag)[0]
+            assert all(torch.equal(a, b) for a, b in zip(out, eager))
