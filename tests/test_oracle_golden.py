@@ -198,3 +198,21 @@ def test_numpy_oracle_block_teacher_forced_at_T501(name):
     st = block_forced_check(g, xs, run_layer)
     print(name, st)
     assert st["flips"] / st["total"] < 1e-4, st
+
+
+@pytest.mark.parametrize("name", ["cfgS_2x4s", "zoo_l_2x4s"])
+def test_numpy_oracle_first_divergence_sits_on_the_threshold(name):
+    """The free-running numpy oracle leaves the reference (if at all) only at neurons whose reference membrane potential
+    is within 1e-5 of the threshold, and its coefficients agree to 1e-4 before that (tests.helpers.divergence_audit)."""
+    from tests.helpers import coef_rel_before_divergence, divergence_audit, load_long, reference_membrane
+    g = load_long(name)
+    if g["surface"] == "A":
+        coefs, fb_all, sb_all = O.spiking_fullsubnet_network(g["mag"], g["params"], g["cfg"])
+    else:
+        coefs, fb_all, sb_all = O.separator_network(g["mag"], g["params"], g["cfg"])
+    c_hat, _ = reference_membrane(g)
+    st, div = divergence_audit(g, c_hat, fb_all, sb_all)
+    st["coef_rel_before_divergence"] = coef_rel_before_divergence(g, coefs, div)
+    print(name, st)
+    assert st["bad_root_flips"] == 0, st
+    assert st["coef_rel_before_divergence"] < 1e-4, st
