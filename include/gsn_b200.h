@@ -123,6 +123,33 @@ GSN_API int gsn_layer_recurrence_bits(const float* xproj, const float* w_hh, con
                          const float* c0, float* h_out, float* c_out, float* hT, float* cT, uint32_t* h_bits,
                          int T, int R, int H, int shared, int backend, int sm_budget, void* workspace,
                          gsn_stream_t stream);
+/* ---- streaming recurrence (gsn_recurrence_stream.cu): StackedGSU.forward ESN:50-62 as a frame-granular pipeline ---
+ * One persistent, warp-specialised tcgen05 launch runs GSULayer.forward (ESN:75-81) of one layer for all T frames
+ * from a ZERO initial state (MSF:100-106), shared gate weights only, and is chained to concurrently running producer /
+ * consumer kernels through per-frame counters in global memory:
+ *   - input, one of
+ *       xproj [T,R,H]               input projection without bias (layer 0 / wide layers), staged by bulk copies, or
+ *       in_bits [T,R,ceil(K_in/32)] bit-packed spikes of the layer below + w_ih [H,K_in]: the input-to-hidden product
+ *                                   runs inside the kernel (both weight matrices resident in tensor memory; needs
+ *                                   3*ceil16(H)/2 + 3*ceil16(K_in)/2 + 2*NT <= 512 columns, e.g. H = K_in = 160);
+ *   - in_cnt [T] (may be NULL): frame t of the input may be read once in_cnt[t] >= in_target (acquire);
+ *   - h_bits [T,R,ceil(H/32)]: the spike trace, bit-packed (always); h_out / c_out [T,R,H] fp32 optional (NULL);
+ *     hT / cT [R,H] optional;
+ *   - out_cnt [T] (may be NULL): every CTA adds 1 to out_cnt[t] (release) when its part of frame t (h_bits, h_out,
+ *     c_out) is globally visible; the frame is complete at gsn_recurrence_stream_ctas(...);
+ *   - spike_count (may be NULL): += number of spikes emitted (firing-rate numerator of SynOps, metric.py:303-340).
+ * Results are bit-identical to gsn_layer_recurrence(TCGEN05) fed by gsn_linear_spike_bits / the same xproj.
+ * Counters must be zeroed by the caller before the first producer starts.  workspace may be NULL.               */
+GSN_API int gsn_recurrence_stream(const float* xproj, const uint32_t* in_bits, const float* w_ih, int K_in,
+                                  const float* w_hh, const float* bias, const float* bn_scale, const float* bn_shift,
+                                  uint32_t* h_bits, float* h_out, float* c_out, float* hT, float* cT,
+                                  const unsigned int* in_cnt, unsigned int in_target, unsigned int* out_cnt,
+                                  unsigned long long* spike_count, int T, int R, int H, int sm_budget,
+                                  void* workspace, gsn_stream_t stream);
+/* Row tile (16 / 32 / 64; 0 = unsupported) and number of CTAs (= out_cnt target) of that launch. */
+GSN_API int gsn_recurrence_stream_tile(int R, int H, int K_in, int fused, int sm_budget);
+GSN_API int gsn_recurrence_stream_ctas(int R, int H, int K_in, int fused, int sm_budget);
+
 /* bits[r, w] (W = ceil(H/32) words per row) from an fp32 {0,1} trace h [rows, H]. */
 GSN_API int gsn_pack_spikes(const float* h, uint32_t* bits, int64_t rows, int H, gsn_stream_t stream);
 /* Per-thread launch options for the following calls.  GSN_OPT_PDL != 0: gsn_layer_recurrence(_bits) launches of the

@@ -34,6 +34,9 @@ SIGNATURES = {
     "gsn_layer_recurrence": (_i, [_p] * 11 + [_i] * 6 + [_p, _p]),
     "gsn_layer_recurrence_bits": (_i, [_p] * 12 + [_i] * 6 + [_p, _p]),
     "gsn_pack_spikes": (_i, [_p, _p, _i64, _i, _p]),
+    "gsn_recurrence_stream": (_i, [_p, _p, _p, _i] + [_p] * 9 + [_p, C.c_uint, _p, _p] + [_i] * 4 + [_p, _p]),
+    "gsn_recurrence_stream_tile": (_i, [_i] * 5),
+    "gsn_recurrence_stream_ctas": (_i, [_i] * 5),
     "gsn_linear_spike_bits": (_i, [_p, _p, _p, _p, _p, _i, _i64, _i, _i, _i, _p]),
     "gsn_layer_train_workspace_bytes": (_sz, [_i, _i, _i]),
     "gsn_layer_train_forward": (_i, [_p] * 13 + [_i] * 5 + [_f, _f, _p, _p]),

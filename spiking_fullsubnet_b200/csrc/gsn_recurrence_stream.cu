@@ -1,0 +1,695 @@
+// Streaming tcgen05 recurrence: GSULayer.forward ESN:75-81 over GSUCell.forward ESN:132-153 as ONE persistent,
+// warp-specialised launch per (sequence model, layer) for all T frames, chained to its producers / consumers through
+// per-frame counters in global memory instead of kernel boundaries (StackedGSU.forward ESN:50-62 and the
+// full-band -> sub-band hand-over MSF:441-447 become a frame-granular pipeline of co-resident kernels).
+//
+// Same arithmetic and decomposition as gsn_recurrence_tc.cu (cluster = one tile of NT rows, CTA s = neurons
+// [128 s, 128 s + 128), recurrent weights as three exact bf16 planes stationary in tensor memory, spikes exchanged as
+// ballot words over DSMEM); what changes is everything around the MMAs:
+//   * warp roles: 16 epilogue warps (thread = neuron x 4 row groups), one MMA-issue warp (highest warp of its
+//     scheduler, so its tcgen05.mma stream is never queued behind epilogue instructions), one loader warp, one
+//     publisher warp.  All hand-overs are mbarriers; there is no __syncthreads in the frame loop;
+//   * FUSED (layers >= 1): the input-to-hidden product W_ih . h^{l-1}_t runs in the SAME kernel: W_ih sits in tensor
+//     memory next to W_hh (H <= 160), the loader warp expands the previous layer's bit-packed spikes of frame t+1 into
+//     a second B operand while frame t is in flight, and the issue warp queues those MMAs behind the recurrent ones of
+//     frame t, off the critical path.  xproj of layers >= 1 never exists in HBM.  The product lands in its own
+//     accumulator and joins as (xproj + bias) + z exactly like the unfused path: bit-identical results;
+//   * !FUSED (layer 0 / wide layers): the loader warp stages xproj[t+1..t+RX] tiles in shared memory with bulk
+//     asynchronous copies (TMA unit, one per row) counted on an mbarrier: no per-thread global loads in the loop;
+//   * the spike trace leaves the kernel bit-packed only (the ballot words); the fp32 [T,R,H] trace the reference
+//     returns is optional (strict outputs);
+//   * in_cnt / out_cnt: the loader polls in_cnt[t] (acquire) before it touches frame t of its input; the publisher
+//     adds 1 to out_cnt[t] (release) once every epilogue warp's stores of frame t are done.
+#include <stdlib.h>
+
+#include "gsn_common.cuh"
+#include "gsn_tc.cuh"
+
+namespace gsn {
+
+struct RecStreamParams {
+  const float* xproj;        // !FUSED: [T, R, H]
+  const uint32_t* in_bits;   // FUSED: [T, R, Wi] bit-packed spikes of the layer below, Wi = ceil(K_in / 32)
+  const float* w_ih;         // FUSED: [H, K_in]
+  const float* w_hh;         // [H, H]
+  const float* bias;         // [2H]
+  const float* bn_scale;     // [H] or null
+  const float* bn_shift;
+  uint32_t* h_bits;          // [T, R, Wb]
+  float* h_out;              // [T, R, H] or null
+  float* c_out;              // [T, R, H] or null
+  float* hT;                 // [R, H] or null
+  float* cT;
+  const unsigned int* in_cnt;   // [T] or null: frame t of the input is complete when in_cnt[t] >= in_target
+  unsigned int in_target;
+  unsigned int* out_cnt;        // [T] or null: += 1 per CTA when its part of frame t is globally visible
+  unsigned long long* spike_count;  // or null: += number of spikes emitted by this launch (SynOps accounting)
+  unsigned long long* prof;     // PROF builds: cycle counters
+  int T, R, H, Kmma;
+  int K_in, Kin_mma;
+  int wpitch, wpitch_in;
+  TraceBuf* trace;
+};
+
+constexpr uint32_t kStTmemCols = 512;
+constexpr int kStPlanes = 3;
+constexpr int kEpiWarps = 16;
+constexpr int kIssueWarp = 16, kLoadWarp = 17, kPubWarp = 18;
+constexpr int kStThreads = 19 * 32;
+constexpr int kRI = 4;        // ring depth of the fused input operand
+constexpr int kPubRing = 4;
+constexpr uint32_t kOneBf = 0x3F80u;
+
+template <int NT>
+struct StCfg {
+  static constexpr int RX = NT <= 16 ? 4 : (NT <= 32 ? 3 : 2);  // ring depth of the staged xproj tiles
+};
+
+__host__ __device__ inline int st_kw_padded(int C) { return 4 * C + 1; }
+
+// shared-memory carve-up (bytes); everything is a function of (NT, Kmma, Kin_mma, C, FUSED)
+struct StLayout {
+  size_t sB, bits, ring, bars, stage, total;
+};
+template <int NT, bool FUSED>
+__host__ __device__ inline StLayout st_layout(int Kmma, int Kin_mma, int C, int wpitch_max) {
+  StLayout L;
+  size_t off = 0;
+  L.sB = off;
+  off += ((size_t)NT * Kmma * 2 + 127) / 128 * 128;
+  L.bits = off;
+  off += ((size_t)2 * NT * st_kw_padded(C) * 4 + 127) / 128 * 128;
+  L.ring = off;
+  if (FUSED) off += (size_t)kRI * (((size_t)NT * Kin_mma * 2 + 127) / 128 * 128);
+  else off += (size_t)StCfg<NT>::RX * NT * 128 * 4;
+  L.bars = off;
+  off += 256;
+  L.stage = off;  // weight staging (prologue only)
+  off += (size_t)128 * wpitch_max * 4;
+  L.total = (off + 127) / 128 * 128;
+  return L;
+}
+
+__device__ __forceinline__ void st_split3(float w, uint32_t& hi, uint32_t& mid, uint32_t& lo) {
+  const uint32_t wb = __float_as_uint(w);
+  hi = wb >> 16;
+  const float r1 = w - __uint_as_float(wb & 0xFFFF0000u);
+  const uint32_t r1b = __float_as_uint(r1);
+  mid = r1b >> 16;
+  const float r2 = r1 - __uint_as_float(r1b & 0xFFFF0000u);
+  lo = __float_as_uint(r2) >> 16;
+}
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add(unsigned int* p, unsigned int v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// bounded poll of a global counter (another, concurrently running kernel is the producer)
+__device__ __forceinline__ bool wait_counter(const unsigned int* p, unsigned int target) {
+  for (unsigned int i = 0; i < (1u << 23); ++i) {
+    if (ld_acquire_u32(p) >= target) return true;
+    __nanosleep(40);
+  }
+  return false;
+}
+
+// 128 weight rows (this CTA's neuron slice) -> three exact bf16 planes in tensor memory (lane = neuron).
+// Rows are staged in shared memory with one bulk copy per row when aligned, else read directly.
+__device__ __forceinline__ void st_weights_to_tmem(const float* w, int ld, int K, int Kmma, int first_row, int nrows,
+                                                   float* wst, int wpitch, uint64_t* bar_w, uint32_t bar_parity,
+                                                   uint32_t tmem_a, int warp, int lane, bool epi) {
+  const int q = warp & 3, g = warp >> 2, tl = q * 32 + lane;
+  const bool rv = tl < nrows;
+  const float* wrow = w + (size_t)(first_row + (rv ? tl : 0)) * ld;
+  const bool staged = wpitch > 0;
+  if (staged) {
+    if (warp == 0 && lane == 0) tc::mbar_arrive_expect_tx(bar_w, (uint32_t)nrows * (uint32_t)K * 4u);
+    __syncthreads();
+    if (epi && g == 0 && rv) tc::bulk_g2s(wst + (size_t)tl * wpitch, wrow, (uint32_t)K * 4u, bar_w);
+    if (epi && !tc::mbar_wait_cta(bar_w, bar_parity)) __trap();
+  }
+  if (epi) {
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const uint32_t plane_cols = Kmma / 2;
+    const float* srow = wst + (size_t)tl * wpitch;
+    for (int c0 = 8 * g; c0 < (int)plane_cols; c0 += 8 * 4) {
+      float wv[16];
+      if (staged) {
+#pragma unroll
+        for (int v4 = 0; v4 < 4; ++v4) {
+          const int k = 2 * c0 + 4 * v4;
+          const float4 x = (rv && k < K) ? *reinterpret_cast<const float4*>(srow + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+          wv[4 * v4 + 0] = x.x; wv[4 * v4 + 1] = x.y; wv[4 * v4 + 2] = x.z; wv[4 * v4 + 3] = x.w;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int k = 2 * c0 + e;
+          wv[e] = (rv && k < K) ? __ldg(wrow + k) : 0.f;
+        }
+      }
+      uint32_t vh[8], vm[8], vl[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        uint32_t h2[2], m2[2], l2[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) st_split3(wv[2 * u + e], h2[e], m2[e], l2[e]);
+        vh[u] = h2[0] | (h2[1] << 16);
+        vm[u] = m2[0] | (m2[1] << 16);
+        vl[u] = l2[0] | (l2[1] << 16);
+      }
+      tc::tmem_st8(tmem_a + lane_base + 0 * plane_cols + c0, vl);  // plane 0 = lo (issued first)
+      tc::tmem_st8(tmem_a + lane_base + 1 * plane_cols + c0, vm);
+      tc::tmem_st8(tmem_a + lane_base + 2 * plane_cols + c0, vh);
+    }
+    tc::tmem_wait_st();
+  }
+  __syncthreads();  // the staging area may be reused
+}
+
+template <int NT, bool FUSED, bool PROF>
+__global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecStreamParams p) {
+  constexpr int CPT = NT / 4;                       // rows per epilogue thread
+  constexpr int CH = CPT < 8 ? CPT : 8;
+  constexpr int RX = StCfg<NT>::RX;
+  constexpr int MAXT = (NT * 40 + 511) / 512;       // operand rebuild tasks per epilogue thread (Kmma <= 320)
+  static_assert(CPT == 4 || CPT == 8 || CPT == 16, "NT must be 16, 32 or 64");
+  extern __shared__ __align__(1024) uint8_t smem[];
+  int tslot = trace_begin(p.trace, 2, p.T, p.R, p.H);
+  // warp index through a shuffle: tells the compiler it is warp-uniform, so the role branches below are uniform
+  // control flow and the MMA-issue code may live in uniform registers (CUTLASS's canonical_warp_idx_sync trick)
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  const bool epi = warp < kEpiWarps;
+  const int q = warp & 3, g = (warp >> 2) & 3;
+  const uint32_t C = tc::cluster_nctarank(), slice = tc::cluster_ctarank();
+  const int row0 = (blockIdx.x / C) * NT;
+  const int H = p.H, R = p.R, T = p.T, Kmma = p.Kmma;
+  const int tl = q * 32 + lane;
+  const int j = slice * 128 + tl;
+  const bool comp = epi && j < H;
+  const int KWp = st_kw_padded(C);
+  const int Wb = (H + 31) / 32;
+  const int Wi = FUSED ? (p.K_in + 31) / 32 : 0;
+  const int wp_max = p.wpitch > p.wpitch_in ? p.wpitch : p.wpitch_in;
+  const StLayout L = st_layout<NT, FUSED>(Kmma, p.Kin_mma, (int)C, wp_max);
+
+  uint8_t* sB = smem + L.sB;
+  uint32_t* bits = reinterpret_cast<uint32_t*>(smem + L.bits);  // [2][NT][KWp]
+  uint8_t* ring = smem + L.ring;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
+  uint64_t* bar_w = bars + 0;
+  uint64_t* bar_mma = bars + 1;
+  uint64_t* bar_B = bars + 2;
+  uint64_t* bar_bits = bars + 3;       // [2]
+  uint64_t* bar_in_full = bars + 5;    // [4] FUSED: operand of frame tt ready; else xproj tile landed (tx)
+  uint64_t* bar_in_free = bars + 9;    // [4]
+  uint64_t* bar_dih_full = bars + 13;
+  uint64_t* bar_dih_free = bars + 14;
+  uint64_t* bar_pub = bars + 15;       // [kPubRing]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  volatile int* pub_done = reinterpret_cast<volatile int*>(bars + 21);
+  float* wst = reinterpret_cast<float*>(smem + L.stage);
+  constexpr int RING_IN = FUSED ? kRI : RX;
+
+  if (tid == 0) {
+    tc::mbar_init(bar_w, 1);
+    tc::mbar_init(bar_mma, 1);
+    tc::mbar_init(bar_B, kEpiWarps);
+    tc::mbar_init(&bar_bits[0], 1);
+    tc::mbar_init(&bar_bits[1], 1);
+    for (int i = 0; i < 4; ++i) {
+      tc::mbar_init(&bar_in_full[i], 1);
+      tc::mbar_init(&bar_in_free[i], FUSED ? 1 : kEpiWarps);
+    }
+    tc::mbar_init(bar_dih_full, 1);
+    tc::mbar_init(bar_dih_free, kEpiWarps);
+    for (int i = 0; i < kPubRing; ++i) tc::mbar_init(&bar_pub[i], kEpiWarps);
+    *pub_done = 0;
+    tc::fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc<kStTmemCols>(tmem_slot);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+  const uint32_t tmem_dhh = tmem;
+  const uint32_t tmem_dih = tmem + NT;
+  const uint32_t tmem_ahh = tmem + (FUSED ? 2 * NT : NT);
+  const uint32_t tmem_aih = tmem_ahh + kStPlanes * (Kmma / 2);
+
+  // ---- prologue: weights -> tensor memory; hh operand of frame 0 = zeros -----------------------------------------
+  {
+    const int first = (int)slice * 128;
+    const int nrows = H - first < 128 ? H - first : 128;
+    st_weights_to_tmem(p.w_hh, H, H, Kmma, first, nrows, wst, p.wpitch, bar_w, 0, tmem_ahh, warp, lane, epi);
+    if (FUSED)
+      st_weights_to_tmem(p.w_ih, p.K_in, p.K_in, p.Kin_mma, first, nrows, wst, p.wpitch_in, bar_w, p.wpitch > 0 ? 1 : 0,
+                         tmem_aih, warp, lane, epi);
+  }
+  const uint32_t SBO = 16u * Kmma;
+  const int k8n = Kmma / 8;
+  uint32_t task_dst[MAXT], task_src[MAXT];
+  if (epi) {
+#pragma unroll
+    for (int it = 0; it < MAXT; ++it) {
+      const int i = tid + 512 * it;
+      const int nlo = i & 7, k8 = (i >> 3) % k8n, nhi = (i >> 3) / k8n;
+      const int n = nhi * 8 + nlo;
+      task_dst[it] = i < NT * k8n ? (uint32_t)(nhi * SBO + k8 * 128 + nlo * 16) : 0xFFFFFFFFu;
+      task_src[it] = (uint32_t)(n * KWp + (k8 >> 2)) | ((uint32_t)(8 * (k8 & 3)) << 24);
+      if (task_dst[it] != 0xFFFFFFFFu) *reinterpret_cast<uint4*>(sB + task_dst[it]) = make_uint4(0, 0, 0, 0);
+    }
+    tc::fence_proxy_async_smem();
+  }
+
+  const int jj = comp ? j : 0;
+  const float bf = p.bias[jj], bc = p.bias[H + jj];
+  const float bs = p.bn_scale ? p.bn_scale[jj] : 1.0f;
+  const float bt = p.bn_shift ? p.bn_shift[jj] : 0.0f;
+  const int rfirst = row0 + g * CPT;
+  const int nv = comp ? (R - rfirst < CPT ? (R - rfirst > 0 ? R - rfirst : 0) : CPT) : 0;
+  const uint32_t hstride = (uint32_t)H * 4u;
+  const uint32_t boff0 = ((uint32_t)rfirst * (uint32_t)H + (uint32_t)j) * 4u;
+  const size_t frame_bytes = (size_t)R * H * sizeof(float);
+
+  uint32_t snd_cell0 = 0, snd_cell1 = 0, snd_bar0 = 0, snd_bar1 = 0;
+  const bool sender = epi && lane < CPT * (int)C;
+  if (sender) {
+    const int i = lane % CPT;
+    const uint32_t r = lane / CPT;
+    snd_cell0 = tc::map_to_rank(bits + ((size_t)0 * NT + g * CPT + i) * KWp + slice * 4 + q, r);
+    snd_cell1 = tc::map_to_rank(bits + ((size_t)1 * NT + g * CPT + i) * KWp + slice * 4 + q, r);
+    snd_bar0 = tc::map_to_rank(&bar_bits[0], r);
+    snd_bar1 = tc::map_to_rank(&bar_bits[1], r);
+  }
+  // every barrier of the cluster is initialised (and the frame-0 operand written) before anybody stores remotely
+  tc::tc_fence_before();
+  tc::cluster_sync_all();
+  tc::tc_fence_after();
+
+  const uint32_t idesc = tc::make_idesc_f16(128, NT, true);
+  const uint32_t bits_bytes = (uint32_t)NT * 4u * C * 4u;
+  const int ksteps = Kmma / 16;
+  bool alive = true;
+
+  if (warp == kIssueWarp) {
+    // =============================== MMA issue warp ===============================
+    // The whole warp runs the loop and the barrier waits; only the tcgen05.mma / commit instructions sit in a small
+    // elect.sync region, so the compiler keeps their operands in uniform registers (base + immediate).  With the loop
+    // itself inside a single-thread region every MMA issue cost ~55 cycles of R2UR traffic.
+    const bool leader = tc::elect_one();
+    const uint64_t desc_b0 = tc::make_smem_desc(tc::smem_u32(sB), 128, SBO);
+    const uint32_t ih_slot_bytes = (uint32_t)(((size_t)NT * p.Kin_mma * 2 + 127) / 128 * 128);
+    const int ksteps_in = FUSED ? p.Kin_mma / 16 : 0;
+    auto issue_ih = [&](int tt) {  // input-to-hidden product of frame tt -> D_ih
+      const int slot = tt % kRI;
+      if (!tc::mbar_wait_cta(&bar_in_full[slot], (uint32_t)((tt / kRI) & 1))) __trap();
+      if (tt > 0 && !tc::mbar_wait_cta(bar_dih_free, (uint32_t)((tt - 1) & 1))) __trap();
+      tc::tc_fence_after();
+      const uint64_t db = tc::make_smem_desc(tc::smem_u32(ring + (size_t)slot * ih_slot_bytes), 128, 16u * p.Kin_mma);
+      if (leader) {
+        tc::mma_planes<kStPlanes>(ksteps_in, tmem_dih, tmem_aih, db, idesc);
+        tc::mma_commit(&bar_in_free[slot]);
+        tc::mma_commit(bar_dih_full);
+      }
+      __syncwarp();
+    };
+    if (FUSED) issue_ih(0);
+    long long ic[3] = {0, 0, 0};
+    for (int t = 0; t < T; ++t) {
+      const long long i0 = PROF ? clock64() : 0;
+      if (!tc::mbar_wait_cta(bar_B, (uint32_t)(t & 1))) __trap();
+      tc::tc_fence_after();
+      const long long i1 = PROF ? clock64() : 0;
+      if (leader) {
+        tc::mbar_arrive_expect_tx(&bar_bits[t & 1], bits_bytes);  // arm this frame's spike-bit exchange
+        tc::mma_planes<kStPlanes>(ksteps, tmem_dhh, tmem_ahh, desc_b0, idesc);
+        tc::mma_commit(bar_mma);
+      }
+      __syncwarp();
+      const long long i2 = PROF ? clock64() : 0;
+      if (FUSED && t + 1 < T) issue_ih(t + 1);
+      if (PROF) { ic[0] += i1 - i0; ic[1] += i2 - i1; ic[2] += clock64() - i2; }
+    }
+    if (PROF && p.prof && blockIdx.x == 0 && leader)
+      for (int i = 0; i < 3; ++i) p.prof[8 + i] = (unsigned long long)ic[i];
+  } else if (warp == kLoadWarp) {
+    // =============================== loader warp ===============================
+    if (FUSED) {
+      const uint32_t slot_bytes = (uint32_t)(((size_t)NT * p.Kin_mma * 2 + 127) / 128 * 128);
+      const uint32_t SBOi = 16u * p.Kin_mma;
+      const int k8i = p.Kin_mma / 8;
+      const int nw = (k8i + 3) / 4;                 // words per row that carry operand columns
+      constexpr int MAXW = (NT * 10 + 31) / 32;      // K_in <= 320
+      for (int tt = 0; tt < T; ++tt) {
+        const int slot = tt % kRI;
+        if (tt >= kRI && !tc::mbar_wait_cta(&bar_in_free[slot], (uint32_t)(((tt / kRI) - 1) & 1))) { alive = false; break; }
+        if (p.in_cnt) {
+          bool ok = true;
+          if (lane == 0) ok = wait_counter(p.in_cnt + tt, p.in_target);
+          ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
+          if (!ok) { alive = false; break; }
+        }
+        uint8_t* dst = ring + (size_t)slot * slot_bytes;
+        uint32_t wd[MAXW];
+#pragma unroll
+        for (int it = 0; it < MAXW; ++it) {
+          const int i = lane + 32 * it;
+          const int nlo = i & 7, wi = (i >> 3) % nw, nhi = (i >> 3) / nw;
+          const int row = row0 + nhi * 8 + nlo;
+          wd[it] = (i < NT * nw && row < R && wi < Wi) ? ld_cg_u32(p.in_bits + ((size_t)tt * R + row) * Wi + wi) : 0u;
+        }
+#pragma unroll
+        for (int it = 0; it < MAXW; ++it) {
+          const int i = lane + 32 * it;
+          if (i >= NT * nw) break;
+          const int nlo = i & 7, wi = (i >> 3) % nw, nhi = (i >> 3) / nw;
+#pragma unroll
+          for (int e4 = 0; e4 < 4; ++e4) {
+            const int k8 = 4 * wi + e4;
+            if (k8 >= k8i) break;
+            const uint32_t b8 = (wd[it] >> (8 * e4)) & 0xFFu;
+            uint32_t v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              v[e] = ((b8 >> (2 * e)) & 1u ? kOneBf : 0u) | ((b8 >> (2 * e + 1)) & 1u ? (kOneBf << 16) : 0u);
+            *reinterpret_cast<uint4*>(dst + (uint32_t)(nhi * SBOi + k8 * 128 + nlo * 16)) = make_uint4(v[0], v[1], v[2], v[3]);
+          }
+        }
+        tc::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&bar_in_full[slot]);
+      }
+    } else {
+      const int first = (int)slice * 128;
+      const int ncols = H - first < 128 ? H - first : 128;
+      const uint32_t row_bytes = (uint32_t)ncols * 4u;
+      const int nrows = R - row0 < NT ? R - row0 : NT;
+      const bool bulk_ok = (H % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.xproj) & 15) == 0);
+      for (int tt = 0; tt < T; ++tt) {
+        const int slot = tt % RX;
+        if (tt >= RX && !tc::mbar_wait_cta(&bar_in_free[slot], (uint32_t)(((tt / RX) - 1) & 1))) { alive = false; break; }
+        if (p.in_cnt) {
+          bool ok = true;
+          if (lane == 0) ok = wait_counter(p.in_cnt + tt, p.in_target);
+          ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
+          if (!ok) { alive = false; break; }
+          asm volatile("fence.proxy.async;" ::: "memory");  // the bulk copies below read what the producer wrote
+        }
+        float* xs = reinterpret_cast<float*>(ring) + (size_t)slot * NT * 128;
+        const float* src = p.xproj + ((size_t)tt * R + row0) * H + first;
+        if (bulk_ok) {
+          if (lane == 0) tc::mbar_arrive_expect_tx(&bar_in_full[slot], (uint32_t)nrows * row_bytes);
+          __syncwarp();
+          for (int r = lane; r < nrows; r += 32)
+            tc::bulk_g2s(xs + (size_t)r * 128, src + (size_t)r * H, row_bytes, &bar_in_full[slot]);
+        } else {
+          for (int i = lane; i < nrows * ncols; i += 32) {
+            const int r = i / ncols, cix = i - r * ncols;
+            xs[r * 128 + cix] = __uint_as_float(ld_cg_u32(reinterpret_cast<const uint32_t*>(src + (size_t)r * H + cix)));
+          }
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&bar_in_full[slot]);
+        }
+      }
+    }
+    if (!alive) __trap();
+  } else if (warp == kPubWarp) {
+    // =============================== publisher warp ===============================
+    if (lane == 0 && p.out_cnt != nullptr) {
+      for (int t = 0; t < T; ++t) {
+        if (!tc::mbar_wait_cta(&bar_pub[t % kPubRing], (uint32_t)((t / kPubRing) & 1))) { alive = false; break; }
+        __threadfence();
+        red_release_add(p.out_cnt + t, 1u);
+        *pub_done = t + 1;
+      }
+      if (!alive) __trap();
+    }
+    __syncwarp();
+  } else {
+    // =============================== epilogue warps ===============================
+    float c[CPT], hval[CPT];
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) { c[i] = 0.f; hval[i] = 0.f; }
+    unsigned int nspk = 0;
+    // frame-0 operand is in place (zeros)
+    __syncwarp();
+    if (lane == 0) tc::mbar_arrive(bar_B);
+    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int t = 0; t < T; ++t) {
+      const int par = t & 1;
+      const long long q0 = PROF ? clock64() : 0;
+      // ---- input projection of frame t -> registers (under the recurrent MMAs) ----
+      float xn[CPT];
+      if (FUSED) {
+        if (!tc::mbar_wait_cta(bar_dih_full, (uint32_t)par)) { alive = false; break; }
+        tc::tc_fence_after();
+#pragma unroll
+        for (int i0 = 0; i0 < CPT; i0 += CH) {
+          uint32_t zr[CH];
+          tc::tmem_ld<CH>(tmem_dih + lane_base + g * CPT + i0, zr);
+          tc::tmem_wait_ld();
+#pragma unroll
+          for (int u = 0; u < CH; ++u) xn[i0 + u] = __uint_as_float(zr[u]);
+        }
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(bar_dih_free);
+      } else {
+        const int slot = t % RX;
+        if (!tc::mbar_wait_cta(&bar_in_full[slot], (uint32_t)((t / RX) & 1))) { alive = false; break; }
+        const float* xs = reinterpret_cast<const float*>(ring) + (size_t)slot * NT * 128 + (size_t)(g * CPT) * 128 + tl;
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) xn[i] = i < nv ? xs[i * 128] : 0.f;
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&bar_in_free[slot]);
+      }
+      float xf_[CPT], xg_[CPT];
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) {  // reference order: (x W_ih^T + bias) + h W_hh^T   (ESN:140-145)
+        xf_[i] = __fadd_rn(xn[i], bf);
+        xg_[i] = __fadd_rn(xn[i], bc);
+      }
+      const long long q1 = PROF ? clock64() : 0;
+      if (!tc::mbar_wait_cta(bar_mma, (uint32_t)par)) { alive = false; break; }
+      tc::tc_fence_after();
+      const long long q2 = PROF ? clock64() : 0;
+      // ---- leak / BatchNorm / threshold; spikes -> one bit each ----
+      uint32_t myw = 0;
+#pragma unroll
+      for (int i0 = 0; i0 < CPT; i0 += CH) {
+        uint32_t zr[CH];
+        tc::tmem_ld<CH>(tmem_dhh + lane_base + g * CPT + i0, zr);
+        tc::tmem_wait_ld();
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+          const float z = __uint_as_float(zr[u]);
+          const float sg = sigmoid_f32(__fadd_rn(xf_[i0 + u], z));
+          const float gh = __fadd_rn(xg_[i0 + u], z);
+          const float ctil = __fadd_rn(__fmul_rn(sg, c[i0 + u]), __fmul_rn(__fsub_rn(1.0f, sg), gh));
+          const float cn = __fadd_rn(__fmul_rn(ctil, bs), bt);
+          c[i0 + u] = cn;
+          const bool spike = (i0 + u < nv) && cn >= 0.f;
+          hval[i0 + u] = spike ? 1.0f : 0.0f;
+          const uint32_t w = __ballot_sync(0xffffffffu, spike);
+          myw = (lane % CPT) == (i0 + u) ? w : myw;
+        }
+      }
+      tc::tc_fence_before();
+      const long long q3 = PROF ? clock64() : 0;
+      // ---- exchange first (critical path), then the trace ----
+      if (sender) tc::st_async_u32(par ? snd_cell1 : snd_cell0, myw, par ? snd_bar1 : snd_bar0);
+      if (lane < CPT) {
+        const int row = row0 + g * CPT + lane;
+        if ((int)slice * 4 + q < Wb && row < R) p.h_bits[((size_t)t * R + row) * Wb + slice * 4 + q] = myw;
+        nspk += __popc(myw);
+      }
+      if (p.h_out) {
+        char* hf = reinterpret_cast<char*>(p.h_out) + (size_t)t * frame_bytes + boff0;
+#pragma unroll
+        for (int i = 0; i < CPT; ++i)
+          if (i < nv) *reinterpret_cast<float*>(hf + i * hstride) = hval[i];
+      }
+      if (p.c_out) {
+        char* cf = reinterpret_cast<char*>(p.c_out) + (size_t)t * frame_bytes + boff0;
+#pragma unroll
+        for (int i = 0; i < CPT; ++i)
+          if (i < nv) *reinterpret_cast<float*>(cf + i * hstride) = c[i];
+      }
+      if (p.out_cnt) {
+        __syncwarp();
+        if (lane == 0) {
+          if (t >= kPubRing) {  // never run a whole ring ahead of the publisher (mbarrier phases would alias)
+            unsigned int spins = 0;
+            while (*pub_done < t - kPubRing + 1) {
+              if (++spins > (1u << 24)) { alive = false; break; }
+            }
+          }
+          tc::mbar_arrive(&bar_pub[t % kPubRing]);
+        }
+      }
+      const long long q4 = PROF ? clock64() : 0;
+      if (t + 1 < T) {
+        if (!tc::mbar_wait_cta(&bar_bits[par], (uint32_t)((t >> 1) & 1))) { alive = false; break; }
+        const long long q5 = PROF ? clock64() : 0;
+        // ---- rebuild the bf16 hh operand (spikes of frame t, all H neurons of my rows) from the bits ----
+        const uint32_t* src = bits + (size_t)par * NT * KWp;
+#pragma unroll
+        for (int it = 0; it < MAXT; ++it) {
+          if (task_dst[it] == 0xFFFFFFFFu) continue;
+          const uint32_t b8 = (src[task_src[it] & 0xFFFFFFu] >> (task_src[it] >> 24)) & 0xFFu;
+          uint32_t v[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            v[e] = ((b8 >> (2 * e)) & 1u ? kOneBf : 0u) | ((b8 >> (2 * e + 1)) & 1u ? (kOneBf << 16) : 0u);
+          *reinterpret_cast<uint4*>(sB + task_dst[it]) = make_uint4(v[0], v[1], v[2], v[3]);
+        }
+        tc::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(bar_B);
+        if (PROF) {
+          const long long q6 = clock64();
+          pc[4] += q5 - q4; pc[5] += q6 - q5;
+        }
+      }
+      if (PROF) { pc[0] += q1 - q0; pc[1] += q2 - q1; pc[2] += q3 - q2; pc[3] += q4 - q3; }
+    }
+    if (!__all_sync(0xffffffffu, alive)) __trap();
+    if (PROF && p.prof && blockIdx.x == 0 && tid == 0)
+      for (int i = 0; i < 8; ++i) p.prof[i] = (unsigned long long)pc[i];
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+      if (i < nv) {
+        if (p.cT) *reinterpret_cast<float*>(reinterpret_cast<char*>(p.cT) + boff0 + i * hstride) = c[i];
+        if (p.hT) *reinterpret_cast<float*>(reinterpret_cast<char*>(p.hT) + boff0 + i * hstride) = hval[i];
+      }
+    }
+    if (p.spike_count && lane < CPT && nspk) atomicAdd(p.spike_count, (unsigned long long)nspk);
+  }
+  tc::tc_fence_before();
+  tc::cluster_sync_all();  // nobody leaves while a peer may still store into its staging buffer
+  if (warp == 0) tc::tmem_dealloc<kStTmemCols>(tmem);
+  trace_end(p.trace, tslot);
+}
+
+// ------------------------------------------------------------------------------------------------
+static inline int st_wpitch(int K) { return ((K / 4) & 1) ? K : K + 4; }
+
+bool recurrence_stream_fused_fits(int H, int K_in, int nt) {
+  const int Kmma = (H + 15) / 16 * 16, Kin = (K_in + 15) / 16 * 16;
+  return 2 * nt + kStPlanes * (Kmma / 2) + kStPlanes * (Kin / 2) <= (int)kStTmemCols && K_in <= 320;
+}
+
+int recurrence_stream_tile(int R, int H, int K_in, int fused, int sms) {
+  const int C = (H + 127) / 128;
+  const int Kmma = (H + 15) / 16 * 16;
+  int best = 0;
+  for (int nt : {16, 32, 64}) {
+    if (fused ? !recurrence_stream_fused_fits(H, K_in, nt) : (nt + kStPlanes * (Kmma / 2) > (int)kStTmemCols)) break;
+    if ((nt / 4) * C > 32) break;
+    best = nt;
+    if ((long long)((R + nt - 1) / nt) * C <= sms) break;
+  }
+  return best;
+}
+
+template <int NT, bool FUSED>
+static int launch_stream(RecStreamParams p, int C, cudaStream_t st) {
+  p.wpitch = 0;
+  p.wpitch_in = 0;
+  if (p.H % 4 == 0 && (reinterpret_cast<uintptr_t>(p.w_hh) & 15) == 0) p.wpitch = st_wpitch(p.H);
+  if (FUSED && p.K_in % 4 == 0 && (reinterpret_cast<uintptr_t>(p.w_ih) & 15) == 0) p.wpitch_in = st_wpitch(p.K_in);
+  auto layout = [&]() {
+    return st_layout<NT, FUSED>(p.Kmma, p.Kin_mma, C, p.wpitch > p.wpitch_in ? p.wpitch : p.wpitch_in);
+  };
+  if (layout().total > tc::kMaxDynamicSmem) {  // no room for the staging area: read the weights directly
+    p.wpitch = 0;
+    p.wpitch_in = 0;
+  }
+  size_t smem = layout().total;
+  if (smem > tc::kMaxDynamicSmem) return fail(GSN_ENOSUP, "gsn_recurrence_stream: shared memory (%zu B) exceeded", smem);
+  if (smem < tc::kTmemExclusiveSmem) smem = tc::kTmemExclusiveSmem;
+  static const bool prof = getenv("GSN_TC_PROF") != nullptr;
+  auto kern = prof ? k_recurrence_stream<NT, FUSED, true> : k_recurrence_stream<NT, FUSED, false>;
+  GSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(((p.R + NT - 1) / NT) * C));
+  cfg.blockDim = dim3(kStThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  GSN_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+  return GSN_OK;
+}
+
+}  // namespace gsn
+
+extern "C" int gsn_recurrence_stream_tile(int R, int H, int K_in, int fused, int sm_budget) {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (sm_budget > 0 && sm_budget < sms) sms = sm_budget;
+  if (H < 16 || (H + 127) / 128 > 8) return 0;
+  return gsn::recurrence_stream_tile(R, H, K_in, fused, sms);
+}
+
+extern "C" int gsn_recurrence_stream_ctas(int R, int H, int K_in, int fused, int sm_budget) {
+  const int nt = gsn_recurrence_stream_tile(R, H, K_in, fused, sm_budget);
+  return nt ? ((R + nt - 1) / nt) * ((H + 127) / 128) : 0;
+}
+
+extern "C" int gsn_recurrence_stream(const float* xproj, const uint32_t* in_bits, const float* w_ih, int K_in,
+                                     const float* w_hh, const float* bias, const float* bn_scale,
+                                     const float* bn_shift, uint32_t* h_bits, float* h_out, float* c_out, float* hT,
+                                     float* cT, const unsigned int* in_cnt, unsigned int in_target,
+                                     unsigned int* out_cnt, unsigned long long* spike_count, int T, int R, int H,
+                                     int sm_budget, void* workspace, gsn_stream_t stream) {
+  using namespace gsn;
+  const bool fused = in_bits != nullptr;
+  GSN_REQUIRE(w_hh && bias && h_bits, "gsn_recurrence_stream: null pointer");
+  GSN_REQUIRE((xproj != nullptr) != fused, "gsn_recurrence_stream: pass either xproj or (in_bits, w_ih)");
+  GSN_REQUIRE(!fused || (w_ih && K_in > 0), "gsn_recurrence_stream: fused input needs w_ih and K_in");
+  GSN_REQUIRE(T > 0 && R > 0 && H >= 16, "gsn_recurrence_stream: bad shape T=%d R=%d H=%d", T, R, H);
+  GSN_REQUIRE((bn_scale == nullptr) == (bn_shift == nullptr), "gsn_recurrence_stream: bn params");
+  const int nt = gsn_recurrence_stream_tile(R, H, K_in, fused ? 1 : 0, sm_budget);
+  if (nt == 0)
+    return fail(GSN_ENOSUP, "gsn_recurrence_stream: H=%d K_in=%d fused=%d does not fit tensor memory", H, K_in,
+                (int)fused);
+  RecStreamParams p{};
+  p.xproj = xproj; p.in_bits = in_bits; p.w_ih = w_ih; p.w_hh = w_hh; p.bias = bias; p.bn_scale = bn_scale;
+  p.bn_shift = bn_shift; p.h_bits = h_bits; p.h_out = h_out; p.c_out = c_out; p.hT = hT; p.cT = cT;
+  p.in_cnt = in_cnt; p.in_target = in_target; p.out_cnt = out_cnt; p.spike_count = spike_count;
+  p.prof = reinterpret_cast<unsigned long long*>(workspace);
+  p.T = T; p.R = R; p.H = H; p.Kmma = (H + 15) / 16 * 16;
+  p.K_in = fused ? K_in : 0; p.Kin_mma = fused ? (K_in + 15) / 16 * 16 : 0;
+  p.trace = trace_buffer();
+  const int C = (H + 127) / 128;
+  cudaStream_t st = as_stream(stream);
+  if (fused) {
+    switch (nt) {
+      case 16: return launch_stream<16, true>(p, C, st);
+      case 32: return launch_stream<32, true>(p, C, st);
+      default: return launch_stream<64, true>(p, C, st);
+    }
+  }
+  switch (nt) {
+    case 16: return launch_stream<16, false>(p, C, st);
+    case 32: return launch_stream<32, false>(p, C, st);
+    default: return launch_stream<64, false>(p, C, st);
+  }
+}

@@ -187,6 +187,60 @@ def recurrence_tile(R, H, shared, backend="auto", sm_budget=0):
     return _lib.load().gsn_layer_recurrence_tile(R, H, int(shared), _lib.BACKENDS[backend], int(sm_budget))
 
 
+def unpack_spikes(bits, H):
+    """bit-packed trace int32 [..., ceil(H/32)] -> fp32 {0,1} [..., H] (inverse of pack_spikes; torch ops, used only
+    when a caller asks for the reference-shaped fp32 trace of a streamed layer)."""
+    sh = torch.arange(32, device=bits.device, dtype=torch.int32)
+    b = (bits.unsqueeze(-1) >> sh) & 1
+    return b.reshape(bits.shape[:-1] + (bits.shape[-1] * 32,))[..., :H].to(torch.float32)
+
+
+def frame_counters(T, device, n=1):
+    """n zeroed per-frame counter arrays [n, T] (uint32 as int32) for the streaming pipeline."""
+    return torch.zeros((n, T), device=device, dtype=torch.int32)
+
+
+def stream_ctas(R, H, K_in=0, fused=False, sm_budget=0):
+    """CTAs of a gsn_recurrence_stream launch = value its out counters reach when a frame is complete (0: unsupported)."""
+    return _lib.load().gsn_recurrence_stream_ctas(R, H, int(K_in), int(bool(fused)), int(sm_budget))
+
+
+def recurrence_stream(w_hh, bias, bn_scale=None, bn_shift=None, xproj=None, in_bits=None, w_ih=None, out_bits=None,
+                      out_h=None, out_c=None, out_hT=None, out_cT=None, in_cnt=None, in_target=0, out_cnt=None,
+                      spike_count=None, sm_budget=0, workspace=None):
+    """One GSULayer over all frames as a persistent streaming launch (gsn_recurrence_stream): zero initial state,
+    shared gate weights.  Input: xproj [T,R,H] OR (in_bits [T,R,ceil(K/32)] int32, w_ih [H,K]) for the fused
+    input-to-hidden product.  Returns the bit-packed spike trace int32 [T,R,ceil(H/32)]."""
+    lib, st = _prep(w_hh, bias, bn_scale, bn_shift, xproj, w_ih, out_h, out_c, out_hT, out_cT)
+    H = w_hh.shape[1]
+    if w_hh.shape[0] != H or bias.numel() != 2 * H:
+        raise ValueError("recurrence_stream: shared gate weights only (w_hh [H,H], bias [2H])")
+    if (xproj is None) == (in_bits is None):
+        raise ValueError("recurrence_stream: pass either xproj or (in_bits, w_ih)")
+    if xproj is not None:
+        T, R, _ = xproj.shape
+        K_in = 0
+    else:
+        T, R, Wi = in_bits.shape
+        K_in = w_ih.shape[1]
+        if in_bits.dtype != torch.int32 or not in_bits.is_contiguous() or Wi != (K_in + 31) // 32 or w_ih.shape[0] != H:
+            raise ValueError("recurrence_stream: in_bits / w_ih shapes")
+    Wb = (H + 31) // 32
+    if out_bits is None:
+        out_bits = torch.empty((T, R, Wb), device=w_hh.device, dtype=torch.int32)
+    elif out_bits.dtype != torch.int32 or not out_bits.is_contiguous() or tuple(out_bits.shape) != (T, R, Wb):
+        raise ValueError("recurrence_stream: out_bits")
+    for cnt in (in_cnt, out_cnt):
+        if cnt is not None and (cnt.dtype != torch.int32 or cnt.numel() != T or not cnt.is_contiguous()):
+            raise ValueError("recurrence_stream: counters must be contiguous int32 [T]")
+    _lib.check(lib.gsn_recurrence_stream(
+        _ptr(xproj), _ptr(in_bits), _ptr(w_ih), int(K_in), _ptr(w_hh), _ptr(bias), _ptr(bn_scale), _ptr(bn_shift),
+        out_bits.data_ptr(), _ptr(out_h), _ptr(out_c), _ptr(out_hT), _ptr(out_cT), _ptr(in_cnt), int(in_target),
+        _ptr(out_cnt), _ptr(spike_count), T, R, H, int(sm_budget), _ptr(workspace), st))
+    LAUNCHES[0] += 1
+    return out_bits
+
+
 def pick_backend(R, H, shared):
     return {1: "simt", 2: "tcgen05", 3: "tcgen05_i8"}[_lib.load().gsn_layer_recurrence_pick_backend(R, H, int(shared))]
 
