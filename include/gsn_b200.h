@@ -150,6 +150,29 @@ GSN_API int gsn_recurrence_stream(const float* xproj, const uint32_t* in_bits, c
 GSN_API int gsn_recurrence_stream_tile(int R, int H, int K_in, int fused, int sm_budget);
 GSN_API int gsn_recurrence_stream_ctas(int R, int H, int K_in, int fused, int sm_budget);
 
+/* gsn_linear_spike_bits as a stage of the streaming pipeline: a_bits [T*R, ceil(K/32)] is produced frame by frame by
+ * a concurrently running gsn_recurrence_stream; the persistent kernel waits for in_cnt[t] >= in_target before it reads
+ * frame t and adds the rows it has written to out_cnt[t] per 128-feature slice (frame complete at R * ceil(N/128)).
+ * `ctas` persistent CTAs in total (>= ceil(N/128)).  Either counter array may be NULL.  Same results.          */
+GSN_API int gsn_linear_spike_bits_stream(const uint32_t* a_bits, const float* w, const float* bias, float* out,
+                                         float* out_act, int act, int T, int R, int K, int N, int ctas,
+                                         const unsigned int* in_cnt, unsigned int in_target, unsigned int* out_cnt,
+                                         gsn_stream_t stream);
+
+/* Streaming front end of one sequence model (gsn_pre_stream.cu): gsn_subband_features (same gather, same LayerNorm
+ * arithmetic: x is bit-identical) fused with the layer-0 input-to-hidden product xproj[t, r, :] = x[t, r, :] @ w_ih^T
+ * (ESN:141; no bias) on tcgen05: both operands as three exact bf16 planes, 8 of the 9 plane pairs accumulated in fp32
+ * (fp32-faithful; not bit-identical to gsn_linear_f32).  Persistent; walks the [T*R] rows in order.
+ *   in_cnt [T] (may be NULL): `fb` of frame t may be read once in_cnt[t] >= in_target;
+ *   out_cnt [T] (may be NULL): += rows written per (row tile, 128-feature slice); frame t of xproj is complete at
+ *   R * ceil(H/128).  x_out [T,R,K] (may be NULL) receives the normalised input (all_layer_outputs[0]).
+ * ctas_per_slice: persistent CTAs per 128-feature slice.  K <= 288.                                             */
+GSN_API int gsn_pre_stream_supported(int K, int H);
+GSN_API int gsn_pre_stream(const float* cm, int f_cm, const float* fb, int f_fb, const float* ln_weight,
+                           const float* ln_bias, float ln_eps, const float* w_ih, float* x_out, float* xproj,
+                           const unsigned int* in_cnt, unsigned int in_target, unsigned int* out_cnt, int T, int B,
+                           int N, int lo, int ctr, int nbr, int H, int ctas_per_slice, gsn_stream_t stream);
+
 /* bits[r, w] (W = ceil(H/32) words per row) from an fp32 {0,1} trace h [rows, H]. */
 GSN_API int gsn_pack_spikes(const float* h, uint32_t* bits, int64_t rows, int H, gsn_stream_t stream);
 /* Per-thread launch options for the following calls.  GSN_OPT_PDL != 0: gsn_layer_recurrence(_bits) launches of the

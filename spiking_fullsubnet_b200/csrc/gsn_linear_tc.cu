@@ -46,7 +46,8 @@ template <int NT, bool BITS>
 __global__ void __launch_bounds__(256, 1)
     k_linear_tc(const float* __restrict__ a, const uint32_t* __restrict__ a_bits, const float* __restrict__ w,
                 const float* __restrict__ bias, float* __restrict__ out, float* __restrict__ out_act, int act,
-                long long M, int K, int N, int Kmma, int wpitch, TraceBuf* tb) {
+                long long M, int K, int N, int Kmma, int wpitch, TraceBuf* tb, const unsigned int* in_cnt,
+                unsigned int in_target, unsigned int* out_cnt, int Rf) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tslot = trace_begin(tb, 4, (int)M, K, N);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -139,8 +140,27 @@ __global__ void __launch_bounds__(256, 1)
   const int ntask = NT * k8n;
   constexpr int UNR = 4;
   const int Wb = (K + 31) / 32;  // words per row of the bit-packed trace
+  // streaming use (in_cnt / out_cnt, Rf = rows per frame): `a_bits` is produced frame by frame by a concurrently
+  // running recurrence kernel -- wait for the frames a tile touches, read them past the L1, publish what was written
   auto convert = [&](long long tile, uint8_t* dst) {
     const long long r0 = tile * NT;
+    if (in_cnt) {
+      if (tid == 0) {
+        long long rl = r0 + NT - 1;
+        if (rl >= M) rl = M - 1;
+        for (long long t = r0 / Rf; t <= rl / Rf; ++t) {
+          unsigned int polls = 0;
+          while (true) {
+            unsigned int v;
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(in_cnt + t) : "memory");
+            if (v >= in_target) break;
+            if (++polls > (1u << 23)) __trap();
+            __nanosleep(40);
+          }
+        }
+      }
+      __syncthreads();
+    }
     if (BITS) {
       // task = (row n, one 32-bit word of its packed trace) -> up to four 16-byte chunks of the operand; all the
       // words of a thread are loaded before any is expanded (independent loads in flight, not a dependent chain)
@@ -152,7 +172,12 @@ __global__ void __launch_bounds__(256, 1)
         const int i = tid + 256 * it;
         const int nlo = i & 7, wi = (i >> 3) % nw, nhi = (i >> 3) / nw;
         const long long row = r0 + nhi * 8 + nlo;
-        wd[it] = (i < NT * nw && row < M) ? __ldg(a_bits + row * Wb + wi) : 0u;
+        uint32_t wv_ = 0u;
+        if (i < NT * nw && row < M) {
+          if (in_cnt) asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(wv_) : "l"(a_bits + row * Wb + wi) : "memory");
+          else wv_ = __ldg(a_bits + row * Wb + wi);
+        }
+        wd[it] = wv_;
       }
 #pragma unroll
       for (int it = 0; it < MAXW; ++it) {
@@ -284,6 +309,20 @@ __global__ void __launch_bounds__(256, 1)
           if (u < left) pa[(size_t)u * N] = lin_act(__uint_as_float(zr[u >> 3][u & 7]) + bj, act);
       }
     }
+    if (out_cnt) {
+      __syncthreads();  // every thread's stores of this tile are issued
+      if (tid == 0) {
+        __threadfence();
+        const long long ra = tile * NT;
+        long long rb = ra + NT;
+        if (rb > M) rb = M;
+        for (long long t = ra / Rf; t * Rf < rb; ++t) {
+          const long long lo_ = t * Rf > ra ? t * Rf : ra, hi_ = (t + 1) * Rf < rb ? (t + 1) * Rf : rb;
+          asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(out_cnt + t), "r"((unsigned int)(hi_ - lo_))
+                       : "memory");
+        }
+      }
+    }
     if (prof) {
       const long long q5 = clock64();
       pc[0] += (unsigned)(q1 - q0); pc[1] += (unsigned)(q2 - q1); pc[2] += (unsigned)(q3 - q2);
@@ -303,7 +342,9 @@ __global__ void __launch_bounds__(256, 1)
 
 template <int NT, bool BITS>
 static int launch_linear_tc(const float* a, const uint32_t* a_bits, const float* w, const float* bias, float* out,
-                            float* out_act, int act, long long M, int K, int N, int sm_budget, cudaStream_t st) {
+                            float* out_act, int act, long long M, int K, int N, int sm_budget, cudaStream_t st,
+                            const unsigned int* in_cnt = nullptr, unsigned int in_target = 0,
+                            unsigned int* out_cnt = nullptr, int Rf = 1) {
   const int Kmma = (K + 15) / 16 * 16;
   const size_t b2 = 2 * (((size_t)NT * Kmma * 2 + 127) / 128 * 128);
   // weight rows staged through shared memory with bulk copies when they are 16-byte aligned
@@ -328,19 +369,23 @@ static int launch_linear_tc(const float* a, const uint32_t* a_bits, const float*
   if (P > ntiles) P = ntiles;
   dim3 grid((unsigned)slices, (unsigned)P);
   k_linear_tc<NT, BITS><<<grid, 256, smem, st>>>(a, a_bits, w, bias, out, out_act, act, M, K, N, Kmma, wpitch,
-                                                 trace_buffer());
+                                                 trace_buffer(), in_cnt, in_target, out_cnt, Rf);
   GSN_LAUNCH_CHECK("k_linear_tc");
   return GSN_OK;
 }
 
 template <bool BITS>
 static int dispatch_linear_tc(const float* a, const uint32_t* a_bits, const float* w, const float* bias, float* out,
-                              float* out_act, int act, long long M, int K, int N, int sm_budget, cudaStream_t st) {
+                              float* out_act, int act, long long M, int K, int N, int sm_budget, cudaStream_t st,
+                              const unsigned int* in_cnt = nullptr, unsigned int in_target = 0,
+                              unsigned int* out_cnt = nullptr, int Rf = 1) {
   const int Kmma = (K + 15) / 16 * 16;
   if (3 * Kmma / 2 + 2 * 64 <= 512)
-    return launch_linear_tc<64, BITS>(a, a_bits, w, bias, out, out_act, act, M, K, N, sm_budget, st);
+    return launch_linear_tc<64, BITS>(a, a_bits, w, bias, out, out_act, act, M, K, N, sm_budget, st, in_cnt,
+                                      in_target, out_cnt, Rf);
   if (3 * Kmma / 2 + 2 * 16 <= 512)
-    return launch_linear_tc<16, BITS>(a, a_bits, w, bias, out, out_act, act, M, K, N, sm_budget, st);
+    return launch_linear_tc<16, BITS>(a, a_bits, w, bias, out, out_act, act, M, K, N, sm_budget, st, in_cnt,
+                                      in_target, out_cnt, Rf);
   return fail(GSN_ENOSUP, "gsn_linear_spikes: K=%d does not fit tensor memory (K <= 320)", K);
 }
 
@@ -377,6 +422,17 @@ extern "C" int gsn_linear_spike_bits(const uint32_t* a_bits, const float* w, con
   GSN_REQUIRE(act >= 0 && act <= 3, "gsn_linear_spike_bits: unknown activation %d", act);
   return gsn::dispatch_linear_tc<true>(nullptr, a_bits, w, bias, out, out_act, act, M, K, N, sm_budget,
                                        gsn::as_stream(stream));
+}
+
+extern "C" int gsn_linear_spike_bits_stream(const uint32_t* a_bits, const float* w, const float* bias, float* out,
+                                            float* out_act, int act, int T, int R, int K, int N, int ctas,
+                                            const unsigned int* in_cnt, unsigned int in_target,
+                                            unsigned int* out_cnt, gsn_stream_t stream) {
+  GSN_REQUIRE(a_bits && w && out, "gsn_linear_spike_bits_stream: null pointer");
+  GSN_REQUIRE(T > 0 && R > 0 && K > 0 && N > 0, "gsn_linear_spike_bits_stream: bad shape");
+  GSN_REQUIRE(act >= 0 && act <= 3, "gsn_linear_spike_bits_stream: unknown activation %d", act);
+  return gsn::dispatch_linear_tc<true>(nullptr, a_bits, w, bias, out, out_act, act, (long long)T * R, K, N,
+                                       ctas < 1 ? 1 : ctas, gsn::as_stream(stream), in_cnt, in_target, out_cnt, R);
 }
 
 extern "C" int gsn_pack_spikes(const float* h, uint32_t* bits, int64_t rows, int H, gsn_stream_t stream) {

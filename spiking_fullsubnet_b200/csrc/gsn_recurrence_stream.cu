@@ -442,6 +442,14 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
 #pragma unroll
     for (int i = 0; i < CPT; ++i) { c[i] = 0.f; hval[i] = 0.f; }
     unsigned int nspk = 0;
+    // running output pointers of this thread
+    const int hb_row = row0 + g * CPT + lane;
+    const bool hb_ok = lane < CPT && (int)slice * 4 + q < Wb && hb_row < R;
+    uint32_t* hb_ptr = p.h_bits + (size_t)(hb_ok ? hb_row : 0) * Wb + (hb_ok ? slice * 4 + q : 0);
+    const size_t hb_step = (size_t)R * Wb;
+    const bool do_h = p.h_out != nullptr, do_c = p.c_out != nullptr, do_pub = p.out_cnt != nullptr;
+    char* h_ptr = reinterpret_cast<char*>(p.h_out) + boff0;
+    char* c_ptr = reinterpret_cast<char*>(p.c_out) + boff0;
     // frame-0 operand is in place (zeros)
     __syncwarp();
     if (lane == 0) tc::mbar_arrive(bar_B);
@@ -507,32 +515,32 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
       }
       tc::tc_fence_before();
       const long long q3 = PROF ? clock64() : 0;
-      // ---- exchange first (critical path), then the trace ----
+      // ---- exchange first (critical path), then the trace (running pointers: no per-frame address arithmetic) ----
       if (sender) tc::st_async_u32(par ? snd_cell1 : snd_cell0, myw, par ? snd_bar1 : snd_bar0);
       if (lane < CPT) {
-        const int row = row0 + g * CPT + lane;
-        if ((int)slice * 4 + q < Wb && row < R) p.h_bits[((size_t)t * R + row) * Wb + slice * 4 + q] = myw;
+        if (hb_ok) *hb_ptr = myw;
+        hb_ptr += hb_step;
         nspk += __popc(myw);
       }
-      if (p.h_out) {
-        char* hf = reinterpret_cast<char*>(p.h_out) + (size_t)t * frame_bytes + boff0;
+      if (do_h) {
 #pragma unroll
         for (int i = 0; i < CPT; ++i)
-          if (i < nv) *reinterpret_cast<float*>(hf + i * hstride) = hval[i];
+          if (i < nv) *reinterpret_cast<float*>(h_ptr + i * hstride) = hval[i];
+        h_ptr += frame_bytes;
       }
-      if (p.c_out) {
-        char* cf = reinterpret_cast<char*>(p.c_out) + (size_t)t * frame_bytes + boff0;
+      if (do_c) {
 #pragma unroll
         for (int i = 0; i < CPT; ++i)
-          if (i < nv) *reinterpret_cast<float*>(cf + i * hstride) = c[i];
+          if (i < nv) *reinterpret_cast<float*>(c_ptr + i * hstride) = c[i];
+        c_ptr += frame_bytes;
       }
-      if (p.out_cnt) {
+      if (do_pub) {
         __syncwarp();
         if (lane == 0) {
           if (t >= kPubRing) {  // never run a whole ring ahead of the publisher (mbarrier phases would alias)
             unsigned int spins = 0;
             while (*pub_done < t - kPubRing + 1) {
-              if (++spins > (1u << 24)) { alive = false; break; }
+              if (++spins > (1u << 24)) __trap();
             }
           }
           tc::mbar_arrive(&bar_pub[t % kPubRing]);

@@ -241,6 +241,42 @@ def recurrence_stream(w_hh, bias, bn_scale=None, bn_shift=None, xproj=None, in_b
     return out_bits
 
 
+def pre_stream(cm, fb, N, lo, ctr, nbr, w_ih, ln_weight=None, ln_bias=None, eps=1e-5, out_x=None, out_xproj=None,
+               in_cnt=None, in_target=0, out_cnt=None, ctas_per_slice=1):
+    """Streaming gather + LayerNorm + layer-0 input projection on tcgen05 (gsn_pre_stream).  Returns xproj [T,B*N,H]."""
+    lib, st = _prep(cm, fb, w_ih, ln_weight, ln_bias, out_x, out_xproj)
+    T, B, f_cm = cm.shape
+    K = ctr + 2 * nbr + (ctr if fb is not None else 0)
+    H = w_ih.shape[0]
+    if w_ih.shape[1] != K:
+        raise ValueError(f"pre_stream: w_ih{tuple(w_ih.shape)} vs K={K}")
+    xproj = _out(out_xproj, (T, B * N, H), cm)
+    if out_x is not None and tuple(out_x.shape) != (T, B * N, K):
+        raise ValueError("pre_stream: out_x shape")
+    _lib.check(lib.gsn_pre_stream(_ptr(cm), f_cm, _ptr(fb), fb.shape[2] if fb is not None else 0, _ptr(ln_weight),
+                                  _ptr(ln_bias), float(eps), _ptr(w_ih), _ptr(out_x), _ptr(xproj), _ptr(in_cnt),
+                                  int(in_target), _ptr(out_cnt), T, B, N, lo, ctr, nbr, H, int(ctas_per_slice), st))
+    LAUNCHES[0] += 1
+    return xproj
+
+
+def linear_bits_stream(bits, w, bias=None, act=None, out=None, out_act=None, ctas=1, in_cnt=None, in_target=0,
+                       out_cnt=None):
+    """out[T,R,N] = spikes(bits [T,R,ceil(K/32)]) @ w[N,K]^T + bias as a streaming stage (gsn_linear_spike_bits_stream)."""
+    lib, st = _prep(w, bias, out, out_act)
+    T, R, Wk = bits.shape
+    N, K = w.shape
+    if bits.dtype != torch.int32 or not bits.is_contiguous() or Wk != (K + 31) // 32:
+        raise ValueError("linear_bits_stream: bits shape")
+    out = _out(out, (T, R, N), w)
+    code = _ACT[act]
+    out_act = _out(out_act, out.shape, w) if code else None
+    _lib.check(lib.gsn_linear_spike_bits_stream(bits.data_ptr(), _ptr(w), _ptr(bias), _ptr(out), _ptr(out_act), code,
+                                                T, R, K, N, int(ctas), _ptr(in_cnt), int(in_target), _ptr(out_cnt), st))
+    LAUNCHES[0] += 1
+    return (out, out_act) if code else out
+
+
 def pick_backend(R, H, shared):
     return {1: "simt", 2: "tcgen05", 3: "tcgen05_i8"}[_lib.load().gsn_layer_recurrence_pick_backend(R, H, int(shared))]
 
