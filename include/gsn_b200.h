@@ -131,7 +131,11 @@ GSN_API int gsn_layer_recurrence_bits(const float* xproj, const float* w_hh, con
  *       xproj [T,R,H]               input projection without bias (layer 0 / wide layers), staged by bulk copies, or
  *       in_bits [T,R,ceil(K_in/32)] bit-packed spikes of the layer below + w_ih [H,K_in]: the input-to-hidden product
  *                                   runs inside the kernel (both weight matrices resident in tensor memory; needs
- *                                   3*ceil16(H)/2 + 3*ceil16(K_in)/2 + 2*NT <= 512 columns, e.g. H = K_in = 160);
+ *                                   3*ceil16(H)/2 + 3*ceil16(K_in)/2 + 2*NT <= 512 columns, e.g. H = K_in = 160), or
+ *       in_planes                   REAL-valued layer-0 input as the bf16x3 operand images gsn_xplanes_stream writes
+ *                                   (row tile = gsn_recurrence_stream_tile(.., fused = 1, ..)) + w_ih [H,K_in]: the
+ *                                   product x_t . w_ih^T (ESN:141) runs inside the kernel too (8 of the 9 plane pairs,
+ *                                   fp32-faithful), one bulk copy per frame; same tensor-memory condition, K_in <= 256;
  *   - in_cnt [T] (may be NULL): frame t of the input may be read once in_cnt[t] >= in_target (acquire);
  *   - h_bits [T,R,ceil(H/32)]: the spike trace, bit-packed (always); h_out / c_out [T,R,H] fp32 optional (NULL);
  *     hT / cT [R,H] optional;
@@ -140,12 +144,17 @@ GSN_API int gsn_layer_recurrence_bits(const float* xproj, const float* w_hh, con
  *   - spike_count (may be NULL): += number of spikes emitted (firing-rate numerator of SynOps, metric.py:303-340).
  * Results are bit-identical to gsn_layer_recurrence(TCGEN05) fed by gsn_linear_spike_bits / the same xproj.
  * Counters must be zeroed by the caller before the first producer starts.  workspace may be NULL.               */
-GSN_API int gsn_recurrence_stream(const float* xproj, const uint32_t* in_bits, const float* w_ih, int K_in,
-                                  const float* w_hh, const float* bias, const float* bn_scale, const float* bn_shift,
-                                  uint32_t* h_bits, float* h_out, float* c_out, float* hT, float* cT,
-                                  const unsigned int* in_cnt, unsigned int in_target, unsigned int* out_cnt,
-                                  unsigned long long* spike_count, int T, int R, int H, int sm_budget,
-                                  void* workspace, gsn_stream_t stream);
+GSN_API int gsn_recurrence_stream(const float* xproj, const uint32_t* in_bits, const void* in_planes,
+                                  const float* w_ih, int K_in, const float* w_hh, const float* bias,
+                                  const float* bn_scale, const float* bn_shift, uint32_t* h_bits, float* h_out,
+                                  float* c_out, float* hT, float* cT, const unsigned int* in_cnt,
+                                  unsigned int in_target, unsigned int* out_cnt, unsigned long long* spike_count,
+                                  int T, int R, int H, int sm_budget, void* workspace, gsn_stream_t stream);
+/* Loads every kernel of the streaming pipeline into the context.  The pipeline's kernels spin on counters their
+ * producers advance, and with lazy module loading the first launch of a kernel synchronises with running kernels:
+ * call once per process and device BEFORE the first pipeline launch (a spinning consumer would otherwise wait for a
+ * producer that cannot be loaded, and trap on its wall-clock bound). */
+GSN_API int gsn_stream_preload(void);
 /* Row tile (16 / 32 / 64; 0 = unsupported) and number of CTAs (= out_cnt target) of that launch. */
 GSN_API int gsn_recurrence_stream_tile(int R, int H, int K_in, int fused, int sm_budget);
 GSN_API int gsn_recurrence_stream_ctas(int R, int H, int K_in, int fused, int sm_budget);
@@ -159,14 +168,27 @@ GSN_API int gsn_linear_spike_bits_stream(const uint32_t* a_bits, const float* w,
                                          const unsigned int* in_cnt, unsigned int in_target, unsigned int* out_cnt,
                                          gsn_stream_t stream);
 
-/* Streaming front end of one sequence model (gsn_pre_stream.cu): gsn_subband_features (same gather, same LayerNorm
- * arithmetic: x is bit-identical) fused with the layer-0 input-to-hidden product xproj[t, r, :] = x[t, r, :] @ w_ih^T
+/* Streaming front end for the fused layer-0 recurrence (gsn_xplanes_stream.cu): the gather of gsn_subband_features +
+ * LayerNorm + truncation split x = hi + mid + lo into three bf16 planes, written as the tcgen05 B-operand images
+ * xop[t][tile][plane lo,mid,hi][nt rows x ceil16(K), K-major 8x16-byte core matrices] that gsn_recurrence_stream
+ * (in_planes) fetches with one bulk copy per frame.  CUDA cores only; `ctas` persistent CTAs.  xop must hold
+ * gsn_xplanes_bytes(T, R, K, nt) bytes, 128-byte aligned, and be ZEROED once by the caller (padding rows of the last
+ * tile).  in_cnt / in_target as below; out_cnt[t] += rows written (frame complete at R = B*N).  K <= 256.       */
+GSN_API size_t gsn_xplanes_bytes(int T, int R, int K, int nt);
+GSN_API int gsn_xplanes_stream(const float* cm, int f_cm, const float* fb, int f_fb, const float* ln_weight,
+                               const float* ln_bias, float ln_eps, float* x_out, void* xop,
+                               const unsigned int* in_cnt, unsigned int in_target, unsigned int* out_cnt, int T,
+                               int B, int N, int lo, int ctr, int nbr, int nt, int ctas, gsn_stream_t stream);
+
+/* Streaming front end of one sequence model as a separate tensor-core stage (gsn_stage_stream.cu; used when the fused
+ * layer-0 recurrence does not fit tensor memory): the same gather + LayerNorm (x within 2e-6 of gsn_subband_features)
+ * fused with the layer-0 input-to-hidden product xproj[t, r, :] = x[t, r, :] @ w_ih^T
  * (ESN:141; no bias) on tcgen05: both operands as three exact bf16 planes, 8 of the 9 plane pairs accumulated in fp32
  * (fp32-faithful; not bit-identical to gsn_linear_f32).  Persistent; walks the [T*R] rows in order.
  *   in_cnt [T] (may be NULL): `fb` of frame t may be read once in_cnt[t] >= in_target;
  *   out_cnt [T] (may be NULL): += rows written per (row tile, 128-feature slice); frame t of xproj is complete at
  *   R * ceil(H/128).  x_out [T,R,K] (may be NULL) receives the normalised input (all_layer_outputs[0]).
- * ctas_per_slice: persistent CTAs per 128-feature slice.  K <= 288.                                             */
+ * ctas_per_slice: persistent CTAs per 128-feature slice.  K <= 256.                                             */
 GSN_API int gsn_pre_stream_supported(int K, int H);
 GSN_API int gsn_pre_stream(const float* cm, int f_cm, const float* fb, int f_fb, const float* ln_weight,
                            const float* ln_bias, float ln_eps, const float* w_ih, float* x_out, float* xproj,

@@ -424,17 +424,6 @@ extern "C" int gsn_linear_spike_bits(const uint32_t* a_bits, const float* w, con
                                        gsn::as_stream(stream));
 }
 
-extern "C" int gsn_linear_spike_bits_stream(const uint32_t* a_bits, const float* w, const float* bias, float* out,
-                                            float* out_act, int act, int T, int R, int K, int N, int ctas,
-                                            const unsigned int* in_cnt, unsigned int in_target,
-                                            unsigned int* out_cnt, gsn_stream_t stream) {
-  GSN_REQUIRE(a_bits && w && out, "gsn_linear_spike_bits_stream: null pointer");
-  GSN_REQUIRE(T > 0 && R > 0 && K > 0 && N > 0, "gsn_linear_spike_bits_stream: bad shape");
-  GSN_REQUIRE(act >= 0 && act <= 3, "gsn_linear_spike_bits_stream: unknown activation %d", act);
-  return gsn::dispatch_linear_tc<true>(nullptr, a_bits, w, bias, out, out_act, act, (long long)T * R, K, N,
-                                       ctas < 1 ? 1 : ctas, gsn::as_stream(stream), in_cnt, in_target, out_cnt, R);
-}
-
 extern "C" int gsn_pack_spikes(const float* h, uint32_t* bits, int64_t rows, int H, gsn_stream_t stream) {
   GSN_REQUIRE(h && bits, "gsn_pack_spikes: null pointer");
   GSN_REQUIRE(rows > 0 && H > 0, "gsn_pack_spikes: bad shape rows=%lld H=%d", (long long)rows, H);

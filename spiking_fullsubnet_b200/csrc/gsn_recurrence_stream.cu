@@ -6,9 +6,8 @@
 // Same arithmetic and decomposition as gsn_recurrence_tc.cu (cluster = one tile of NT rows, CTA s = neurons
 // [128 s, 128 s + 128), recurrent weights as three exact bf16 planes stationary in tensor memory, spikes exchanged as
 // ballot words over DSMEM); what changes is everything around the MMAs:
-//   * warp roles: 16 epilogue warps (thread = neuron x 4 row groups), one MMA-issue warp (highest warp of its
-//     scheduler, so its tcgen05.mma stream is never queued behind epilogue instructions), one loader warp, one
-//     publisher warp.  All hand-overs are mbarriers; there is no __syncthreads in the frame loop;
+//   * warp roles: 16 epilogue warps (thread = neuron x 4 row groups), one MMA-issue warp, one loader warp, two
+//     publisher warps.  All hand-overs are mbarriers; there is no __syncthreads in the frame loop;
 //   * FUSED (layers >= 1): the input-to-hidden product W_ih . h^{l-1}_t runs in the SAME kernel: W_ih sits in tensor
 //     memory next to W_hh (H <= 160), the loader warp expands the previous layer's bit-packed spikes of frame t+1 into
 //     a second B operand while frame t is in flight, and the issue warp queues those MMAs behind the recurrent ones of
@@ -29,7 +28,8 @@ namespace gsn {
 
 struct RecStreamParams {
   const float* xproj;        // !FUSED: [T, R, H]
-  const uint32_t* in_bits;   // FUSED: [T, R, Wi] bit-packed spikes of the layer below, Wi = ceil(K_in / 32)
+  const uint32_t* in_bits;   // IN_BITS: [T, R, Wi] bit-packed spikes of the layer below, Wi = ceil(K_in / 32)
+  const uint8_t* in_planes;  // IN_PLANES: operand images of gsn_xplanes_stream, [T][tiles][3][NT x Kin_mma] bf16
   const float* w_ih;         // FUSED: [H, K_in]
   const float* w_hh;         // [H, H]
   const float* bias;         // [2H]
@@ -42,6 +42,7 @@ struct RecStreamParams {
   float* cT;
   const unsigned int* in_cnt;   // [T] or null: frame t of the input is complete when in_cnt[t] >= in_target
   unsigned int in_target;
+  unsigned int poll_ns;         // back-off between two polls of in_cnt
   unsigned int* out_cnt;        // [T] or null: += 1 per CTA when its part of frame t is globally visible
   unsigned long long* spike_count;  // or null: += number of spikes emitted by this launch (SynOps accounting)
   unsigned long long* prof;     // PROF builds: cycle counters
@@ -54,8 +55,9 @@ struct RecStreamParams {
 constexpr uint32_t kStTmemCols = 512;
 constexpr int kStPlanes = 3;
 constexpr int kEpiWarps = 16;
-constexpr int kIssueWarp = 16, kLoadWarp = 17, kPubWarp = 18;
-constexpr int kStThreads = 19 * 32;
+constexpr int kIssueWarp = 16, kLoadWarp = 17, kPubWarp = 18;  // publishers: warps 18 .. 18 + kPubWarps - 1
+constexpr int kPubWarps = 2;
+constexpr int kStThreads = (kPubWarp + kPubWarps) * 32;
 constexpr int kRI = 4;        // ring depth of the fused input operand
 constexpr int kPubRing = 4;
 constexpr uint32_t kOneBf = 0x3F80u;
@@ -71,8 +73,10 @@ __host__ __device__ inline int st_kw_padded(int C) { return 4 * C + 1; }
 struct StLayout {
   size_t sB, bits, ring, bars, stage, total;
 };
-template <int NT, bool FUSED>
+enum { kInXproj = 0, kInBits = 1, kInPlanes = 2 };
+template <int NT, int IN>
 __host__ __device__ inline StLayout st_layout(int Kmma, int Kin_mma, int C, int wpitch_max) {
+  constexpr bool FUSED = IN != kInXproj;
   StLayout L;
   size_t off = 0;
   L.sB = off;
@@ -80,7 +84,7 @@ __host__ __device__ inline StLayout st_layout(int Kmma, int Kin_mma, int C, int 
   L.bits = off;
   off += ((size_t)2 * NT * st_kw_padded(C) * 4 + 127) / 128 * 128;
   L.ring = off;
-  if (FUSED) off += (size_t)kRI * (((size_t)NT * Kin_mma * 2 + 127) / 128 * 128);
+  if (FUSED) off += (size_t)kRI * (IN == kInPlanes ? 3 : 1) * (((size_t)NT * Kin_mma * 2 + 127) / 128 * 128);
   else off += (size_t)StCfg<NT>::RX * NT * 128 * 4;
   L.bars = off;
   off += 256;
@@ -113,13 +117,26 @@ __device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) {
   asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// bounded poll of a global counter (another, concurrently running kernel is the producer)
-__device__ __forceinline__ bool wait_counter(const unsigned int* p, unsigned int target) {
-  for (unsigned int i = 0; i < (1u << 23); ++i) {
-    if (ld_acquire_u32(p) >= target) return true;
-    __nanosleep(40);
+// Frame counters of a concurrently running producer kernel.  Frames [0, ready) are known complete; one call polls the
+// 32 frames from `ready` on (one acquire load per lane, in parallel) and advances `ready` over the complete prefix.
+// block: repeat until frame `need` is complete (bounded; false on timeout).  An acquire poll costs an L2 round trip, so
+// callers issue the loads of the frame they already own first and poll ahead under them.
+__device__ __forceinline__ bool poll_frames(const unsigned int* cnt, unsigned int target, int T, int& ready, int need,
+                                            bool block, unsigned int ns, int lane) {
+  unsigned long long t0 = 0;
+  for (unsigned int spins = 0;; ++spins) {
+    const int t = ready + lane;
+    const bool ok = t < T && ld_acquire_u32(cnt + t) >= target;
+    const unsigned int m = __ballot_sync(0xffffffffu, ok);
+    ready += m == 0xffffffffu ? 32 : __ffs(~m) - 1;
+    if (ready > need || !block) return true;
+    if ((spins & 0x3FFu) == 0x3FFu) {  // wall-clock bound: the producer kernel may start late (lazy module loading)
+      const unsigned long long now = tc::wait_clock_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > tc::kWaitTimeoutNs) return false;
+    }
+    __nanosleep(ns);
   }
-  return false;
 }
 
 // 128 weight rows (this CTA's neuron slice) -> three exact bf16 planes in tensor memory (lane = neuron).
@@ -176,8 +193,9 @@ __device__ __forceinline__ void st_weights_to_tmem(const float* w, int ld, int K
   __syncthreads();  // the staging area may be reused
 }
 
-template <int NT, bool FUSED, bool PROF>
+template <int NT, int IN, bool PROF>
 __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecStreamParams p) {
+  constexpr bool FUSED = IN != kInXproj;  // the input-to-hidden product runs in this kernel
   constexpr int CPT = NT / 4;                       // rows per epilogue thread
   constexpr int CH = CPT < 8 ? CPT : 8;
   constexpr int RX = StCfg<NT>::RX;
@@ -200,7 +218,7 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
   const int Wb = (H + 31) / 32;
   const int Wi = FUSED ? (p.K_in + 31) / 32 : 0;
   const int wp_max = p.wpitch > p.wpitch_in ? p.wpitch : p.wpitch_in;
-  const StLayout L = st_layout<NT, FUSED>(Kmma, p.Kin_mma, (int)C, wp_max);
+  const StLayout L = st_layout<NT, IN>(Kmma, p.Kin_mma, (int)C, wp_max);
 
   uint8_t* sB = smem + L.sB;
   uint32_t* bits = reinterpret_cast<uint32_t*>(smem + L.bits);  // [2][NT][KWp]
@@ -233,7 +251,8 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
     tc::mbar_init(bar_dih_full, 1);
     tc::mbar_init(bar_dih_free, kEpiWarps);
     for (int i = 0; i < kPubRing; ++i) tc::mbar_init(&bar_pub[i], kEpiWarps);
-    *pub_done = 0;
+    pub_done[0] = 0;
+    pub_done[1] = 0;
     tc::fence_mbar_init();
   }
   if (warp == 0) tc::tmem_alloc<kStTmemCols>(tmem_slot);
@@ -309,7 +328,7 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
     // itself inside a single-thread region every MMA issue cost ~55 cycles of R2UR traffic.
     const bool leader = tc::elect_one();
     const uint64_t desc_b0 = tc::make_smem_desc(tc::smem_u32(sB), 128, SBO);
-    const uint32_t ih_slot_bytes = (uint32_t)(((size_t)NT * p.Kin_mma * 2 + 127) / 128 * 128);
+    const uint32_t ih_slot_bytes = (uint32_t)((IN == kInPlanes ? 3 : 1) * (((size_t)NT * p.Kin_mma * 2 + 127) / 128 * 128));
     const int ksteps_in = FUSED ? p.Kin_mma / 16 : 0;
     auto issue_ih = [&](int tt) {  // input-to-hidden product of frame tt -> D_ih
       const int slot = tt % kRI;
@@ -318,7 +337,8 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
       tc::tc_fence_after();
       const uint64_t db = tc::make_smem_desc(tc::smem_u32(ring + (size_t)slot * ih_slot_bytes), 128, 16u * p.Kin_mma);
       if (leader) {
-        tc::mma_planes<kStPlanes>(ksteps_in, tmem_dih, tmem_aih, db, idesc);
+        if (IN == kInPlanes) tc::mma_pairs<NT>(ksteps_in, tmem_dih, tmem_aih, db, idesc);  // real-valued input: 8 pairs
+        else tc::mma_planes<kStPlanes>(ksteps_in, tmem_dih, tmem_aih, db, idesc);
         tc::mma_commit(&bar_in_free[slot]);
         tc::mma_commit(bar_dih_full);
       }
@@ -345,7 +365,26 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
       for (int i = 0; i < 3; ++i) p.prof[8 + i] = (unsigned long long)ic[i];
   } else if (warp == kLoadWarp) {
     // =============================== loader warp ===============================
-    if (FUSED) {
+    int ready = 0;  // frames [0, ready) of the input are known complete
+    if (IN == kInPlanes) {
+      // one bulk copy per frame: the three operand planes of this row tile, already in the B-operand layout
+      const uint32_t blk_bytes = 3u * (uint32_t)NT * (uint32_t)p.Kin_mma * 2u;
+      const int ntiles = (R + NT - 1) / NT, tile = blockIdx.x / C;
+      for (int tt = 0; tt < T; ++tt) {
+        const int slot = tt % kRI;
+        if (tt >= kRI && !tc::mbar_wait_cta(&bar_in_free[slot], (uint32_t)(((tt / kRI) - 1) & 1))) { alive = false; break; }
+        if (p.in_cnt && ready <= tt) {
+          if (!poll_frames(p.in_cnt, p.in_target, T, ready, tt, true, p.poll_ns, lane)) { alive = false; break; }
+          asm volatile("fence.proxy.async;" ::: "memory");  // the bulk copy below reads what the producer wrote
+        }
+        if (lane == 0) {
+          tc::mbar_arrive_expect_tx(&bar_in_full[slot], blk_bytes);
+          tc::bulk_g2s(ring + (size_t)slot * blk_bytes, p.in_planes + ((size_t)tt * ntiles + tile) * blk_bytes, blk_bytes,
+                       &bar_in_full[slot]);
+        }
+        __syncwarp();
+      }
+    } else if (FUSED) {
       const uint32_t slot_bytes = (uint32_t)(((size_t)NT * p.Kin_mma * 2 + 127) / 128 * 128);
       const uint32_t SBOi = 16u * p.Kin_mma;
       const int k8i = p.Kin_mma / 8;
@@ -354,11 +393,9 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
       for (int tt = 0; tt < T; ++tt) {
         const int slot = tt % kRI;
         if (tt >= kRI && !tc::mbar_wait_cta(&bar_in_free[slot], (uint32_t)(((tt / kRI) - 1) & 1))) { alive = false; break; }
-        if (p.in_cnt) {
-          bool ok = true;
-          if (lane == 0) ok = wait_counter(p.in_cnt + tt, p.in_target);
-          ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
-          if (!ok) { alive = false; break; }
+        if (p.in_cnt && ready <= tt && !poll_frames(p.in_cnt, p.in_target, T, ready, tt, true, p.poll_ns, lane)) {
+          alive = false;
+          break;
         }
         uint8_t* dst = ring + (size_t)slot * slot_bytes;
         uint32_t wd[MAXW];
@@ -369,6 +406,8 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
           const int row = row0 + nhi * 8 + nlo;
           wd[it] = (i < NT * nw && row < R && wi < Wi) ? ld_cg_u32(p.in_bits + ((size_t)tt * R + row) * Wi + wi) : 0u;
         }
+        // poll ahead while the words of frame tt are in flight
+        if (p.in_cnt && ready <= tt + 1 && tt + 1 < T) poll_frames(p.in_cnt, p.in_target, T, ready, tt + 1, false, 0, lane);
 #pragma unroll
         for (int it = 0; it < MAXW; ++it) {
           const int i = lane + 32 * it;
@@ -399,11 +438,8 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
       for (int tt = 0; tt < T; ++tt) {
         const int slot = tt % RX;
         if (tt >= RX && !tc::mbar_wait_cta(&bar_in_free[slot], (uint32_t)(((tt / RX) - 1) & 1))) { alive = false; break; }
-        if (p.in_cnt) {
-          bool ok = true;
-          if (lane == 0) ok = wait_counter(p.in_cnt + tt, p.in_target);
-          ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
-          if (!ok) { alive = false; break; }
+        if (p.in_cnt && ready <= tt) {
+          if (!poll_frames(p.in_cnt, p.in_target, T, ready, tt, true, p.poll_ns, lane)) { alive = false; break; }
           asm volatile("fence.proxy.async;" ::: "memory");  // the bulk copies below read what the producer wrote
         }
         float* xs = reinterpret_cast<float*>(ring) + (size_t)slot * NT * 128;
@@ -424,14 +460,18 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
       }
     }
     if (!alive) __trap();
-  } else if (warp == kPubWarp) {
-    // =============================== publisher warp ===============================
+  } else if (warp >= kPubWarp) {
+    // =============================== publisher warps ===============================
+    // One gpu-scope release per frame costs an L2 round trip (about a frame time): the frames alternate between the
+    // publisher warps so that two releases are in flight, and neither sits on the epilogue's path.
     if (lane == 0 && p.out_cnt != nullptr) {
-      for (int t = 0; t < T; ++t) {
+      const int pw = warp - kPubWarp;
+      for (int t = pw; t < T; t += kPubWarps) {
         if (!tc::mbar_wait_cta(&bar_pub[t % kPubRing], (uint32_t)((t / kPubRing) & 1))) { alive = false; break; }
-        __threadfence();
-        red_release_add(p.out_cnt + t, 1u);
-        *pub_done = t + 1;
+        // the epilogue warps' stores of frame t were observed through the mbarrier: fence + relaxed add = release
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p.out_cnt + t), "r"(1u) : "memory");
+        pub_done[pw] = t + 1;
       }
       if (!alive) __trap();
     }
@@ -539,7 +579,7 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
         if (lane == 0) {
           if (t >= kPubRing) {  // never run a whole ring ahead of the publisher (mbarrier phases would alias)
             unsigned int spins = 0;
-            while (*pub_done < t - kPubRing + 1) {
+            while (pub_done[t % kPubWarps] < t - kPubRing + 1) {
               if (++spins > (1u << 24)) __trap();
             }
           }
@@ -611,14 +651,15 @@ int recurrence_stream_tile(int R, int H, int K_in, int fused, int sms) {
   return best;
 }
 
-template <int NT, bool FUSED>
+template <int NT, int IN>
 static int launch_stream(RecStreamParams p, int C, cudaStream_t st) {
+  constexpr bool FUSED = IN != kInXproj;
   p.wpitch = 0;
   p.wpitch_in = 0;
   if (p.H % 4 == 0 && (reinterpret_cast<uintptr_t>(p.w_hh) & 15) == 0) p.wpitch = st_wpitch(p.H);
   if (FUSED && p.K_in % 4 == 0 && (reinterpret_cast<uintptr_t>(p.w_ih) & 15) == 0) p.wpitch_in = st_wpitch(p.K_in);
   auto layout = [&]() {
-    return st_layout<NT, FUSED>(p.Kmma, p.Kin_mma, C, p.wpitch > p.wpitch_in ? p.wpitch : p.wpitch_in);
+    return st_layout<NT, IN>(p.Kmma, p.Kin_mma, C, p.wpitch > p.wpitch_in ? p.wpitch : p.wpitch_in);
   };
   if (layout().total > tc::kMaxDynamicSmem) {  // no room for the staging area: read the weights directly
     p.wpitch = 0;
@@ -628,7 +669,7 @@ static int launch_stream(RecStreamParams p, int C, cudaStream_t st) {
   if (smem > tc::kMaxDynamicSmem) return fail(GSN_ENOSUP, "gsn_recurrence_stream: shared memory (%zu B) exceeded", smem);
   if (smem < tc::kTmemExclusiveSmem) smem = tc::kTmemExclusiveSmem;
   static const bool prof = getenv("GSN_TC_PROF") != nullptr;
-  auto kern = prof ? k_recurrence_stream<NT, FUSED, true> : k_recurrence_stream<NT, FUSED, false>;
+  auto kern = prof ? k_recurrence_stream<NT, IN, true> : k_recurrence_stream<NT, IN, false>;
   GSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(((p.R + NT - 1) / NT) * C));
@@ -648,6 +689,19 @@ static int launch_stream(RecStreamParams p, int C, cudaStream_t st) {
 
 }  // namespace gsn
 
+namespace gsn {
+// force the (lazily loaded) kernels into the context: see gsn_stream_preload
+int preload_recurrence_stream() {
+  cudaFuncAttributes a;
+#define GSN_PRE(NT, IN) GSN_CUDA(cudaFuncGetAttributes(&a, k_recurrence_stream<NT, IN, false>));
+  GSN_PRE(16, kInXproj) GSN_PRE(32, kInXproj) GSN_PRE(64, kInXproj)
+  GSN_PRE(16, kInBits) GSN_PRE(32, kInBits) GSN_PRE(64, kInBits)
+  GSN_PRE(16, kInPlanes) GSN_PRE(32, kInPlanes) GSN_PRE(64, kInPlanes)
+#undef GSN_PRE
+  return GSN_OK;
+}
+}  // namespace gsn
+
 extern "C" int gsn_recurrence_stream_tile(int R, int H, int K_in, int fused, int sm_budget) {
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -661,17 +715,21 @@ extern "C" int gsn_recurrence_stream_ctas(int R, int H, int K_in, int fused, int
   return nt ? ((R + nt - 1) / nt) * ((H + 127) / 128) : 0;
 }
 
-extern "C" int gsn_recurrence_stream(const float* xproj, const uint32_t* in_bits, const float* w_ih, int K_in,
-                                     const float* w_hh, const float* bias, const float* bn_scale,
-                                     const float* bn_shift, uint32_t* h_bits, float* h_out, float* c_out, float* hT,
-                                     float* cT, const unsigned int* in_cnt, unsigned int in_target,
-                                     unsigned int* out_cnt, unsigned long long* spike_count, int T, int R, int H,
-                                     int sm_budget, void* workspace, gsn_stream_t stream) {
+extern "C" int gsn_recurrence_stream(const float* xproj, const uint32_t* in_bits, const void* in_planes,
+                                     const float* w_ih, int K_in, const float* w_hh, const float* bias,
+                                     const float* bn_scale, const float* bn_shift, uint32_t* h_bits, float* h_out,
+                                     float* c_out, float* hT, float* cT, const unsigned int* in_cnt,
+                                     unsigned int in_target, unsigned int* out_cnt, unsigned long long* spike_count,
+                                     int T, int R, int H, int sm_budget, void* workspace, gsn_stream_t stream) {
   using namespace gsn;
-  const bool fused = in_bits != nullptr;
+  const int in_mode = in_bits != nullptr ? kInBits : (in_planes != nullptr ? kInPlanes : kInXproj);
+  const bool fused = in_mode != kInXproj;
   GSN_REQUIRE(w_hh && bias && h_bits, "gsn_recurrence_stream: null pointer");
-  GSN_REQUIRE((xproj != nullptr) != fused, "gsn_recurrence_stream: pass either xproj or (in_bits, w_ih)");
+  GSN_REQUIRE((xproj != nullptr) + (in_bits != nullptr) + (in_planes != nullptr) == 1,
+              "gsn_recurrence_stream: pass exactly one of xproj, (in_bits, w_ih), (in_planes, w_ih)");
   GSN_REQUIRE(!fused || (w_ih && K_in > 0), "gsn_recurrence_stream: fused input needs w_ih and K_in");
+  GSN_REQUIRE(in_mode != kInPlanes || (K_in <= 256 && (reinterpret_cast<uintptr_t>(in_planes) & 15) == 0),
+              "gsn_recurrence_stream: in_planes needs K_in <= 256 and 16-byte alignment");
   GSN_REQUIRE(T > 0 && R > 0 && H >= 16, "gsn_recurrence_stream: bad shape T=%d R=%d H=%d", T, R, H);
   GSN_REQUIRE((bn_scale == nullptr) == (bn_shift == nullptr), "gsn_recurrence_stream: bn params");
   const int nt = gsn_recurrence_stream_tile(R, H, K_in, fused ? 1 : 0, sm_budget);
@@ -679,25 +737,26 @@ extern "C" int gsn_recurrence_stream(const float* xproj, const uint32_t* in_bits
     return fail(GSN_ENOSUP, "gsn_recurrence_stream: H=%d K_in=%d fused=%d does not fit tensor memory", H, K_in,
                 (int)fused);
   RecStreamParams p{};
-  p.xproj = xproj; p.in_bits = in_bits; p.w_ih = w_ih; p.w_hh = w_hh; p.bias = bias; p.bn_scale = bn_scale;
+  p.xproj = xproj; p.in_bits = in_bits; p.in_planes = static_cast<const uint8_t*>(in_planes); p.w_ih = w_ih;
+  p.w_hh = w_hh; p.bias = bias; p.bn_scale = bn_scale;
   p.bn_shift = bn_shift; p.h_bits = h_bits; p.h_out = h_out; p.c_out = c_out; p.hT = hT; p.cT = cT;
   p.in_cnt = in_cnt; p.in_target = in_target; p.out_cnt = out_cnt; p.spike_count = spike_count;
+  static const unsigned int poll_ns = getenv("GSN_POLL_NS") ? (unsigned int)atoi(getenv("GSN_POLL_NS")) : 100u;
+  p.poll_ns = poll_ns;
   p.prof = reinterpret_cast<unsigned long long*>(workspace);
   p.T = T; p.R = R; p.H = H; p.Kmma = (H + 15) / 16 * 16;
   p.K_in = fused ? K_in : 0; p.Kin_mma = fused ? (K_in + 15) / 16 * 16 : 0;
   p.trace = trace_buffer();
   const int C = (H + 127) / 128;
   cudaStream_t st = as_stream(stream);
-  if (fused) {
-    switch (nt) {
-      case 16: return launch_stream<16, true>(p, C, st);
-      case 32: return launch_stream<32, true>(p, C, st);
-      default: return launch_stream<64, true>(p, C, st);
-    }
+#define GSN_ST_DISPATCH(MODE)                                   \
+  switch (nt) {                                                 \
+    case 16: return launch_stream<16, MODE>(p, C, st);          \
+    case 32: return launch_stream<32, MODE>(p, C, st);          \
+    default: return launch_stream<64, MODE>(p, C, st);          \
   }
-  switch (nt) {
-    case 16: return launch_stream<16, false>(p, C, st);
-    case 32: return launch_stream<32, false>(p, C, st);
-    default: return launch_stream<64, false>(p, C, st);
-  }
+  if (in_mode == kInBits) { GSN_ST_DISPATCH(kInBits) }
+  if (in_mode == kInPlanes) { GSN_ST_DISPATCH(kInPlanes) }
+  GSN_ST_DISPATCH(kInXproj)
+#undef GSN_ST_DISPATCH
 }

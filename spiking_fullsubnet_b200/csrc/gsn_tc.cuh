@@ -34,10 +34,19 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
-// bounded spin: returns false on timeout so that a broken pipeline cannot hang the GPU box
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, uint32_t max_polls = 1u << 22) {
+// Bounded spin: returns false on timeout so that a broken pipeline cannot hang the GPU box.  The bound is wall-clock
+// (kWaitTimeoutNs of %globaltimer, checked every 64 Ki failed polls): kernels of the streaming pipeline legitimately wait
+// for producer kernels whose launch may be delayed by tens of milliseconds (lazy module loading on first use).
+constexpr unsigned long long kWaitTimeoutNs = 4000000000ull;
+__device__ __forceinline__ unsigned long long wait_clock_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
-  for (uint32_t i = 0; i < max_polls; ++i) {
+  unsigned long long t0 = 0;
+  for (uint32_t i = 0;; ++i) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -47,16 +56,21 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, uint32
         : "r"(a), "r"(parity)
         : "memory");
     if (ok) return true;
+    if ((i & 0xFFFFu) == 0xFFFFu) {
+      const unsigned long long now = wait_clock_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > kWaitTimeoutNs) return false;
+    }
   }
-  return false;
 }
 
 // Same bounded wait with the default (CTA-scope) acquire: for barriers completed by the async proxy -- bulk copies,
 // st.async complete_tx from peer CTAs, tcgen05.commit -- whose data lands in THIS CTA's shared / tensor memory.
 // (The cluster-scope acquire makes the compiler emit CCTL.IVALL, an L1 invalidation, after every successful wait.)
-__device__ __forceinline__ bool mbar_wait_cta(uint64_t* bar, uint32_t parity, uint32_t max_polls = 1u << 22) {
+__device__ __forceinline__ bool mbar_wait_cta(uint64_t* bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
-  for (uint32_t i = 0; i < max_polls; ++i) {
+  unsigned long long t0 = 0;
+  for (uint32_t i = 0;; ++i) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -66,8 +80,12 @@ __device__ __forceinline__ bool mbar_wait_cta(uint64_t* bar, uint32_t parity, ui
         : "r"(a), "r"(parity)
         : "memory");
     if (ok) return true;
+    if ((i & 0xFFFFu) == 0xFFFFu) {
+      const unsigned long long now = wait_clock_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > kWaitTimeoutNs) return false;
+    }
   }
-  return false;
 }
 
 // ---------------------------------------------------------------- cluster / DSMEM
@@ -244,6 +262,33 @@ __device__ __forceinline__ bool mma_planes(int ksteps, uint32_t tmem_d, uint32_t
     GSN_KS_CASE(1) GSN_KS_CASE(2) GSN_KS_CASE(3) GSN_KS_CASE(4) GSN_KS_CASE(5) GSN_KS_CASE(6) GSN_KS_CASE(7)
     GSN_KS_CASE(8) GSN_KS_CASE(9) GSN_KS_CASE(10) GSN_KS_CASE(11) GSN_KS_CASE(12) GSN_KS_CASE(13) GSN_KS_CASE(14)
     GSN_KS_CASE(15) GSN_KS_CASE(16) GSN_KS_CASE(17) GSN_KS_CASE(18) GSN_KS_CASE(19) GSN_KS_CASE(20)
+#undef GSN_KS_CASE
+    default: return false;
+  }
+}
+
+// ---- bf16x3 x bf16x3 ("both operands real"): 8 of the 9 plane pairs x KS k steps, smallest terms first (lo x lo,
+// <= 2^-32 |w||x|, is dropped).  w plane pw at tmem_a + (pw*KS + ks)*8 columns, x plane px at desc_b0 + px*PB + ks*16
+// (PB = plane bytes >> 4 = NT*KS*2).  Plane index: 0 = lo, 1 = mid, 2 = hi.  The first MMA overwrites D.
+template <int KS, int PB>
+__device__ __forceinline__ void mma_pairs_unrolled(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b0, uint32_t idesc) {
+  constexpr int PW[8] = {0, 1, 0, 2, 1, 1, 2, 2};
+  constexpr int PX[8] = {1, 0, 2, 0, 1, 2, 1, 2};
+  mma_ts_c<0>(tmem_d, tmem_a + (uint32_t)((PW[0] * KS) * 8), desc_b0 + (uint64_t)(PX[0] * PB), idesc);
+#pragma unroll
+  for (int i = 1; i < 8 * KS; ++i) {
+    const int term = i / KS, ks = i % KS;
+    mma_ts_c<1>(tmem_d, tmem_a + (uint32_t)((PW[term] * KS + ks) * 8), desc_b0 + (uint64_t)(PX[term] * PB + ks * 16),
+                idesc);
+  }
+}
+template <int NT>
+__device__ __forceinline__ bool mma_pairs(int ksteps, uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b0, uint32_t idesc) {
+  switch (ksteps) {
+#define GSN_KS_CASE(n) case n: mma_pairs_unrolled<n, NT * n * 2>(tmem_d, tmem_a, desc_b0, idesc); return true;
+    GSN_KS_CASE(1) GSN_KS_CASE(2) GSN_KS_CASE(3) GSN_KS_CASE(4) GSN_KS_CASE(5) GSN_KS_CASE(6) GSN_KS_CASE(7)
+    GSN_KS_CASE(8) GSN_KS_CASE(9) GSN_KS_CASE(10) GSN_KS_CASE(11) GSN_KS_CASE(12) GSN_KS_CASE(13) GSN_KS_CASE(14)
+    GSN_KS_CASE(15) GSN_KS_CASE(16)
 #undef GSN_KS_CASE
     default: return false;
   }

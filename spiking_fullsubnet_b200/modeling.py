@@ -63,8 +63,11 @@ class GSUCell(nn.Module):
         if not self.use_bn:
             return None, None
         bn = self.batchnorm
+        # the training kernels update the running statistics through raw pointers (no _version bump) but always advance
+        # num_batches_tracked (training.GSNLayerFn), so its version is part of the key
+        nbt = bn.num_batches_tracked
         key = (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version,
-               bn.weight.data_ptr(), bn.running_var.data_ptr())
+               nbt._version if nbt is not None else 0, bn.weight.data_ptr(), bn.running_var.data_ptr())
         capturing = bn.weight.is_cuda and torch.cuda.is_current_stream_capturing()
         if capturing or self._bn_cache is None or self._bn_cache[0] != key:
             with torch.no_grad():
@@ -92,6 +95,11 @@ class GSULayer(nn.Module):
         """input [T,R,K] -> (h [T,R,H], final state) (ESN:75-81) -- one kernel, no Python time loop."""
         h, _, (hT, cT) = _run_layer(self.cell, input, state, want_c=False, backend="auto")
         return h, MemoryState(hT, cT)
+
+
+def _lib_supported_pre(K, H):
+    from . import _lib
+    return bool(_lib.load().gsn_pre_stream_supported(int(K), int(H)))
 
 
 def _cluster_ctas(rows, H, shared, nt=16):
@@ -250,6 +258,34 @@ class SequenceModel(nn.Module):
         x = ops.subband_features(cm, None, 1, 0, K, 0, lnw, lnb, eps)
         _, act, all_out = self.run_time_major(x)
         return act.permute(1, 2, 0), all_out
+
+
+class LazyOutputs(list):
+    """all_layer_outputs of a streamed sequence model: same positions as the reference's list ([x_norm, h1..hL,
+    proj_out], MSF:115-125), but the fp32 [T,R,.] tensors nobody may ever read (SynOps accounting is their only
+    consumer, audiozen/metric.py:303-327) are produced on first access from what the kernels actually wrote
+    (bit-packed spike traces; the gather is re-run for x_norm)."""
+
+    def __init__(self, thunks):
+        super().__init__(thunks)
+
+    def _resolve(self, i):
+        v = list.__getitem__(self, i)
+        if callable(v):
+            v = v()
+            list.__setitem__(self, i, v)
+        return v
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self._resolve(k) for k in range(*i.indices(len(self)))]
+        return self._resolve(i if i >= 0 else len(self) + i)
+
+    def __iter__(self):
+        return (self._resolve(k) for k in range(len(self)))
+
+    def __add__(self, other):
+        return list(self) + list(other)
 
 
 class _SeqPlan:
@@ -507,6 +543,10 @@ class _GraphedNetwork:
         if torch.cuda.is_current_stream_capturing():
             return self._network_sched(mag) if self.use_cuda_graph else self._network(mag)
         if not self.use_cuda_graph:
+            if getattr(self, "streaming", False):
+                res = self._network_stream(mag)
+                if res is not None:
+                    return res
             return self._network(mag)
         graphs = self.__dict__.setdefault("_graphs", {})
         key = ("network", tuple(mag.shape), mag.device.index)
@@ -581,7 +621,12 @@ class SpikingFullSubNet(_GraphedNetwork, nn.Module):
         return projs, fb_all, sb_all
 
     def _network_sched(self, mag):
-        """The schedule a captured graph replays: frame-chunked wavefront when it applies, else band streams."""
+        """The schedule a captured graph replays: the streaming pipeline when enabled and co-resident, else the
+        frame-chunked wavefront when it applies, else band streams."""
+        if self.streaming:
+            res = self._network_stream(mag)
+            if res is not None:
+                return res
         if self.frame_chunks > 1 and self._fits_wavefront(mag.shape[0]):
             return self._network_wavefront(mag, self.frame_chunks)
         return self._network(mag)
@@ -716,6 +761,246 @@ class SpikingFullSubNet(_GraphedNetwork, nn.Module):
                           lambda p=p, N=N, lo=lo, ctr=ctr, nbr=nbr, w_sb=w_sb, b_sb=b_sb, e_sb=e_sb:
                           ops.subband_features(cm[t0:t1], fbp.act[t0:t1], N, lo, ctr, nbr, w_sb, b_sb, e_sb,
                                                out=p.x[t0:t1]), ev_fb)
+
+    # ---- streaming schedule: every stage of every sequence model is ONE persistent kernel for all T frames, chained
+    #      to its producers through per-frame counters (gsn_recurrence_stream / gsn_pre_stream /
+    #      gsn_linear_spike_bits_stream); ~20 launches per step, no xproj of layers >= 1, bit-packed traces only.
+    streaming = False
+    strict_outputs = False
+
+    def enable_streaming(self, flag=True, strict_outputs=False):
+        """Run the hot path as the frame-granular streaming pipeline where it fits on the device (else the previous
+        schedules).  strict_outputs=True also materialises the reference-shaped fp32 traces inside the kernels."""
+        self.streaming = bool(flag)
+        self.strict_outputs = bool(strict_outputs)
+        self._graphs = {}
+        return self
+
+    def _stream_models(self, B):
+        sb = self.sb_model
+        out = [dict(m=self.fb_model, R=B, N=1, lo=0, ctr=self.fb_input_size, nbr=0, fb=False)]
+        for i, m in enumerate(sb.sb_models):
+            lo, hi, ctr = sb.freq_cutoffs[i], sb.freq_cutoffs[i + 1], sb.center_freq_sizes[i]
+            if (hi - lo) % ctr != 0:
+                raise ValueError(f"Number of frequency bins must be divisible by the center frequency."
+                                 f"GOT: ctr_freq={ctr}, upper_cutoff_freq={hi}, lower_cutoff_freq={lo}")
+            N = (hi - lo) // ctr
+            out.append(dict(m=m, R=B * N, N=N, lo=lo, ctr=ctr, nbr=sb.neighbor_freq_sizes[i], fb=True))
+        return out
+
+    # cost model of the helper stages (measured on B200, tools/stream_stage_timing.py / stream_fused0_check.py):
+    #   gsn_xplanes_stream: (0.009 + 0.00028 Kmma) us per row per CTA;
+    #   tcgen05 stages: ~75 cycles per MMA at 64-row tiles (3 planes for spike inputs, 8 plane pairs for real inputs)
+    _STREAM_TARGET_US = 1.0   # helper stages must be faster than the recurrences' frame time (1.2 - 1.3 us)
+
+    @staticmethod
+    def _xplanes_ctas(R, K, target):
+        kmma = (K + 15) // 16 * 16
+        return max(1, int(math.ceil(R * (0.009 + 0.00028 * kmma) / target)))
+
+    @staticmethod
+    def _stage_ctas(R, K, passes, target):
+        kmma = (K + 15) // 16 * 16
+        us = (R / 64.0) * passes * (kmma // 16) * 75.0 / 1965.0
+        return max(1, int(math.ceil(us / target)))
+
+    def _stream_plan(self, B, sm_total=None):
+        """Stage list with CTA counts, or None when the pipeline cannot be co-resident (all kernels spin on each
+        other's counters, so every CTA of every stage must be resident at once: one CTA per SM)."""
+        if sm_total is None:
+            sm_total = int(os.environ.get("GSN_STREAM_SMS", "146"))
+        target = float(os.environ.get("GSN_STREAM_TARGET_US", self._STREAM_TARGET_US))
+        models = self._stream_models(B)
+        helpers = 0
+        for d in models:
+            m = d["m"]
+            cells = [l.cell for l in m.sequence_model.layers]
+            if any(not c.shared_weights for c in cells) or any(c.use_bn and c.batchnorm.training for c in cells):
+                return None
+            H, K, R = m.hidden_size, m.input_size, d["R"]
+            if not isinstance(m.proj, nn.Linear) or m.proj_size > 2048 or H > 320 or K > 256:
+                return None
+            C = (H + 127) // 128
+            d["C"] = C
+            d["fused0"] = ops.stream_ctas(R, H, K, True) > 0
+            d["layers"] = [dict(fused=(l > 0 and ops.stream_ctas(R, H, H, True) > 0)) for l in range(len(cells))]
+            if d["fused0"]:
+                d["pre_p"] = self._xplanes_ctas(R, K, target)
+                helpers += d["pre_p"]
+            else:
+                if not _lib_supported_pre(K, H):
+                    return None
+                d["pre_p"] = self._stage_ctas(R, K, 8, target)
+                helpers += C * d["pre_p"]
+            d["lin_p"] = self._stage_ctas(R, H, 3, target)
+            d["proj_p"] = self._stage_ctas(R, H, 3, target)
+            helpers += sum(0 if (ly["fused"] or i == 0) else C * d["lin_p"] for i, ly in enumerate(d["layers"]))
+            helpers += ((m.proj_size + 127) // 128) * d["proj_p"]
+        # only with the finest row tile: 32- and 64-row frames cost 2.9 / 5.1 us, the chunked wavefront is faster there
+        nt = 16
+        rec = sum(((d["R"] + nt - 1) // nt) * d["C"] * len(d["layers"]) for d in models)
+        if rec + helpers > sm_total:
+            return None
+        for d in models:
+            d["nt"] = nt
+        return models
+
+    def _network_stream(self, mag):
+        dev = mag.device
+        B, F, T = mag.shape
+        models = self._stream_plan(B)
+        if models is None:
+            return None
+        fbm = self.fb_model
+        rep = (self.n_fft // 2 + 1) // self.fb_input_size
+        if rep * fbm.proj_size < F - 1:
+            raise ValueError(f"full-band output ({fbm.proj_size} bins x {rep}) does not cover {F - 1} bins")
+        strict = self.strict_outputs
+        ops.stream_preload(dev)
+        main = torch.cuda.current_stream(dev)
+        cm = ops.compress_mag(mag.contiguous(), F - 1, self.fdrc)
+        f32 = dict(device=dev, dtype=torch.float32)
+        ncnt = sum(2 + 2 * len(d["layers"]) for d in models)
+        counters = ops.frame_counters(T, dev, ncnt)
+        nxt = iter(range(ncnt))
+        streams = _band_streams(dev, ncnt, priority=0, tag="stream_pipeline")
+        st_it = iter(streams)
+        # operand-image buffers of the fused layer-0 path: zero-filled ONCE (padding rows), on the main stream and
+        # before the fork, then reused by every call of this shape
+        keep = self.__dict__.setdefault("_xop_cache", {})
+        for mi, d in enumerate(models):
+            if d["fused0"]:
+                m = d["m"]
+                budget = ((d["R"] + d["nt"] - 1) // d["nt"]) * d["C"]
+                nt0 = ops.stream_tile(d["R"], m.hidden_size, m.input_size, True, budget)
+                key = (mi, T, d["R"], m.input_size, nt0, dev.index)
+                if key not in keep:
+                    keep[key] = ops.xplanes_buffer(T, d["R"], m.input_size, nt0, dev)
+                d["xop"], d["nt0"] = keep[key], nt0
+        # folded BatchNorm affines are (re)computed by torch kernels on the main stream while a graph is captured: they
+        # must precede the fork too.  `hold` keeps every buffer of this call alive until the next one, so that the
+        # caching allocator cannot hand a block to a later allocation while a concurrently running stage still uses it
+        hold = []
+        for d in models:
+            d["bn"] = [l.cell.folded_bn() for l in d["m"].sequence_model.layers]
+            hold.append(d["bn"])
+        fork = torch.cuda.Event()
+        fork.record(main)
+        used = []
+
+        def on_stream(fn):
+            stq = next(st_it)
+            stq.wait_event(fork)
+            with torch.cuda.stream(stq):
+                fn()
+            used.append(stq)
+
+        def ln(m):
+            if not m.use_pre_layer_norm:
+                return None, None, 1e-5
+            return m.pre_layer_norm.weight.detach(), m.pre_layer_norm.bias.detach(), m.pre_layer_norm.eps
+
+        fb_cnt = None
+        fb_target = 0
+        fb_act = None
+        results = []
+        # The recurrences (thread-block clusters) are enqueued before the helper stages of their model so that cluster
+        # placement is not fragmented by single-CTA kernels; consumers spin on their producers' frame counters.
+        for mi, d in enumerate(models):
+            m, R = d["m"], d["R"]
+            H, K, C = m.hidden_size, m.input_size, d["C"]
+            cells = [l.cell for l in m.sequence_model.layers]
+            nt = d["nt"]
+            budget = ((R + nt - 1) // nt) * C  # makes the tile picker choose nt
+            w_ln, b_ln, e_ln = ln(m)
+            x_out = torch.empty((T, R, K), **f32) if strict else None
+            geo = (d["N"], d["lo"], d["ctr"], d["nbr"])
+            fbt = fb_act if d["fb"] else None
+            c_pre = counters[next(nxt)]
+            pre_in = dict(in_cnt=fb_cnt if d["fb"] else None, in_target=fb_target)
+            w_ih0 = cells[0].weight_ih.detach()
+            if d["fused0"]:
+                xop, nt0 = d["xop"], d["nt0"]
+                xproj = None
+                pre = (lambda geo=geo, fbt=fbt, nt0=nt0, xop=xop, w_ln=w_ln, b_ln=b_ln, e_ln=e_ln, x_out=x_out, c_pre=c_pre,
+                       pre_in=pre_in, d=d: ops.xplanes_stream(cm, fbt, *geo, nt0, xop, w_ln, b_ln, e_ln, out_x=x_out,
+                                                               out_cnt=c_pre, ctas=d["pre_p"], **pre_in))
+                pre_target = R
+            else:
+                xop = None
+                xproj = torch.empty((T, R, H), **f32)
+                hold.append(xproj)
+                pre = (lambda geo=geo, fbt=fbt, w_ih0=w_ih0, xproj=xproj, w_ln=w_ln, b_ln=b_ln, e_ln=e_ln, x_out=x_out,
+                       c_pre=c_pre, pre_in=pre_in, d=d: ops.pre_stream(cm, fbt, *geo, w_ih0, w_ln, b_ln, e_ln, out_x=x_out,
+                                                                       out_xproj=xproj, out_cnt=c_pre,
+                                                                       ctas_per_slice=d["pre_p"], **pre_in))
+                pre_target = R * C
+            in_cnt, in_target = c_pre, pre_target
+            bits_prev = None
+            bits_all, h_all = [], []
+            helpers = [pre]
+            for l, (cell, ly) in enumerate(zip(cells, d["layers"])):
+                a, b = d["bn"][l]
+                bits = ops.spike_bits_buffer((T, R), H, dev)
+                h_out = torch.empty((T, R, H), **f32) if strict else None
+                c_out = counters[next(nxt)]
+                kw = dict(out_bits=bits, out_h=h_out, out_cnt=c_out, sm_budget=budget, in_cnt=in_cnt, in_target=in_target)
+                w_hh, bias = cell.weight_hh.detach(), cell.bias_ih.detach()
+                fused = ly["fused"] or (l == 0 and d["fused0"])
+                if l == 0 and d["fused0"]:
+                    on_stream(lambda w_hh=w_hh, bias=bias, a=a, b=b, kw=kw, xop=xop, w_ih0=w_ih0, R=R:
+                              ops.recurrence_stream(w_hh, bias, a, b, in_planes=xop, w_ih=w_ih0, frames_rows=(T, R), **kw))
+                elif l == 0:
+                    on_stream(lambda w_hh=w_hh, bias=bias, a=a, b=b, kw=kw, xp=xproj:
+                              ops.recurrence_stream(w_hh, bias, a, b, xproj=xp, **kw))
+                elif ly["fused"]:
+                    on_stream(lambda w_hh=w_hh, bias=bias, a=a, b=b, kw=kw, bp=bits_prev, w=cell.weight_ih.detach():
+                              ops.recurrence_stream(w_hh, bias, a, b, in_bits=bp, w_ih=w, **kw))
+                else:
+                    xp = torch.empty((T, R, H), **f32)
+                    hold.append(xp)
+                    c_lin = counters[next(nxt)]
+                    helpers.append(lambda w=cell.weight_ih.detach(), bp=bits_prev, xp=xp, ic=in_cnt, it=in_target,
+                                   c_lin=c_lin, d=d: ops.linear_bits_stream(bp, w, out=xp, ctas=C * d["lin_p"], in_cnt=ic,
+                                                                            in_target=it, out_cnt=c_lin))
+                    kw.update(in_cnt=c_lin, in_target=R * C)
+                    on_stream(lambda w_hh=w_hh, bias=bias, a=a, b=b, kw=kw, xp=xp:
+                              ops.recurrence_stream(w_hh, bias, a, b, xproj=xp, **kw))
+                in_cnt, in_target = c_out, ops.stream_ctas(R, H, (K if l == 0 else H) if fused else 0, fused, budget)
+                bits_prev = bits
+                bits_all.append(bits)
+                h_all.append(h_out)
+            P = m.proj_size
+            proj = torch.empty((T, R, P), **f32)
+            act = torch.empty_like(proj) if m._act else proj
+            hold.append(act)
+            c_proj = counters[next(nxt)]
+            pslices = (P + 127) // 128
+            helpers.append(lambda m=m, bp=bits_prev, proj=proj, act=act, ic=in_cnt, it=in_target, c_proj=c_proj, d=d:
+                           ops.linear_bits_stream(bp, m.proj.weight.detach(), m.proj.bias.detach(), act=m._act, out=proj,
+                                                  out_act=act if m._act else None, ctas=pslices * d["proj_p"], in_cnt=ic,
+                                                  in_target=it, out_cnt=c_proj))
+            for fn in helpers:
+                on_stream(fn)
+            if not d["fb"]:
+                fb_cnt, fb_target, fb_act = c_proj, R * pslices, act
+
+            # all_layer_outputs in the reference's positions; fp32 traces on demand unless strict
+            def lazy_x(geo=geo, fbt=fbt, w_ln=w_ln, b_ln=b_ln, e_ln=e_ln):
+                return ops.subband_features(cm, fbt, geo[0], geo[1], geo[2], geo[3], w_ln, b_ln, e_ln)
+
+            entries = [x_out if strict else lazy_x]
+            for bits, h_out in zip(bits_all, h_all):
+                entries.append(h_out if strict else (lambda bits=bits, H=H: ops.unpack_spikes(bits, H)))
+            entries.append(proj)
+            results.append((proj, LazyOutputs(entries), bits_all))
+        for stq in used:
+            done = torch.cuda.Event()
+            done.record(stq)
+            main.wait_event(done)
+        self._keepalive = (cm, counters, results, hold)
+        self.last_spike_bits = [r[2] for r in results]
+        return [r[0] for r in results[1:]], results[0][1], [r[1] for r in results[1:]]
 
     def coefficients(self, mag):
         """Deep-filter coefficient tensors [B, df_i, S, F_i, T, 2] in the reference layout."""

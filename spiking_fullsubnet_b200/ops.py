@@ -200,6 +200,24 @@ def frame_counters(T, device, n=1):
     return torch.zeros((n, T), device=device, dtype=torch.int32)
 
 
+_PRELOADED = set()
+
+
+def stream_preload(device):
+    """Load the streaming pipeline's kernels on `device` (once): see gsn_stream_preload."""
+    idx = torch.device(device).index
+    idx = torch.cuda.current_device() if idx is None else idx
+    if idx not in _PRELOADED:
+        with torch.cuda.device(idx):
+            _lib.check(_lib.load().gsn_stream_preload())
+        _PRELOADED.add(idx)
+
+
+def stream_tile(R, H, K_in=0, fused=False, sm_budget=0):
+    """Row tile (16 / 32 / 64; 0: unsupported) a gsn_recurrence_stream launch of this shape uses."""
+    return _lib.load().gsn_recurrence_stream_tile(R, H, int(K_in), int(bool(fused)), int(sm_budget))
+
+
 def stream_ctas(R, H, K_in=0, fused=False, sm_budget=0):
     """CTAs of a gsn_recurrence_stream launch = value its out counters reach when a frame is complete (0: unsupported)."""
     return _lib.load().gsn_recurrence_stream_ctas(R, H, int(K_in), int(bool(fused)), int(sm_budget))
@@ -207,24 +225,32 @@ def stream_ctas(R, H, K_in=0, fused=False, sm_budget=0):
 
 def recurrence_stream(w_hh, bias, bn_scale=None, bn_shift=None, xproj=None, in_bits=None, w_ih=None, out_bits=None,
                       out_h=None, out_c=None, out_hT=None, out_cT=None, in_cnt=None, in_target=0, out_cnt=None,
-                      spike_count=None, sm_budget=0, workspace=None):
+                      spike_count=None, sm_budget=0, workspace=None, in_planes=None, frames_rows=None):
     """One GSULayer over all frames as a persistent streaming launch (gsn_recurrence_stream): zero initial state,
-    shared gate weights.  Input: xproj [T,R,H] OR (in_bits [T,R,ceil(K/32)] int32, w_ih [H,K]) for the fused
-    input-to-hidden product.  Returns the bit-packed spike trace int32 [T,R,ceil(H/32)]."""
+    shared gate weights.  Input: xproj [T,R,H], OR (in_bits [T,R,ceil(K/32)] int32, w_ih [H,K]) for the fused
+    spike-input product, OR (in_planes = the operand images of `xplanes_stream`, w_ih [H,K], frames_rows = (T, R)) for
+    the fused real-input product of layer 0.  Returns the bit-packed spike trace int32 [T,R,ceil(H/32)]."""
     lib, st = _prep(w_hh, bias, bn_scale, bn_shift, xproj, w_ih, out_h, out_c, out_hT, out_cT)
     H = w_hh.shape[1]
     if w_hh.shape[0] != H or bias.numel() != 2 * H:
         raise ValueError("recurrence_stream: shared gate weights only (w_hh [H,H], bias [2H])")
-    if (xproj is None) == (in_bits is None):
-        raise ValueError("recurrence_stream: pass either xproj or (in_bits, w_ih)")
+    if (xproj is not None) + (in_bits is not None) + (in_planes is not None) != 1:
+        raise ValueError("recurrence_stream: pass exactly one of xproj, (in_bits, w_ih), (in_planes, w_ih)")
     if xproj is not None:
         T, R, _ = xproj.shape
         K_in = 0
-    else:
+    elif in_bits is not None:
         T, R, Wi = in_bits.shape
         K_in = w_ih.shape[1]
         if in_bits.dtype != torch.int32 or not in_bits.is_contiguous() or Wi != (K_in + 31) // 32 or w_ih.shape[0] != H:
             raise ValueError("recurrence_stream: in_bits / w_ih shapes")
+    else:
+        T, R = frames_rows
+        K_in = w_ih.shape[1]
+        nt = lib.gsn_recurrence_stream_tile(R, H, K_in, 1, int(sm_budget))
+        if w_ih.shape[0] != H or nt == 0 or in_planes.numel() * in_planes.element_size() < lib.gsn_xplanes_bytes(
+                T, R, K_in, nt):
+            raise ValueError("recurrence_stream: in_planes / w_ih shapes")
     Wb = (H + 31) // 32
     if out_bits is None:
         out_bits = torch.empty((T, R, Wb), device=w_hh.device, dtype=torch.int32)
@@ -234,11 +260,37 @@ def recurrence_stream(w_hh, bias, bn_scale=None, bn_shift=None, xproj=None, in_b
         if cnt is not None and (cnt.dtype != torch.int32 or cnt.numel() != T or not cnt.is_contiguous()):
             raise ValueError("recurrence_stream: counters must be contiguous int32 [T]")
     _lib.check(lib.gsn_recurrence_stream(
-        _ptr(xproj), _ptr(in_bits), _ptr(w_ih), int(K_in), _ptr(w_hh), _ptr(bias), _ptr(bn_scale), _ptr(bn_shift),
-        out_bits.data_ptr(), _ptr(out_h), _ptr(out_c), _ptr(out_hT), _ptr(out_cT), _ptr(in_cnt), int(in_target),
-        _ptr(out_cnt), _ptr(spike_count), T, R, H, int(sm_budget), _ptr(workspace), st))
+        _ptr(xproj), _ptr(in_bits), _ptr(in_planes), _ptr(w_ih), int(K_in), _ptr(w_hh), _ptr(bias), _ptr(bn_scale),
+        _ptr(bn_shift), out_bits.data_ptr(), _ptr(out_h), _ptr(out_c), _ptr(out_hT), _ptr(out_cT), _ptr(in_cnt),
+        int(in_target), _ptr(out_cnt), _ptr(spike_count), T, R, H, int(sm_budget), _ptr(workspace), st))
     LAUNCHES[0] += 1
     return out_bits
+
+
+def xplanes_buffer(T, R, K, nt, device):
+    """Zeroed operand-image buffer of `xplanes_stream` (uint8, 128-byte aligned by the caching allocator)."""
+    n = _lib.load().gsn_xplanes_bytes(int(T), int(R), int(K), int(nt))
+    if n == 0:
+        raise ValueError(f"xplanes_buffer: bad shape T={T} R={R} K={K} nt={nt}")
+    return torch.zeros(n, device=device, dtype=torch.uint8)
+
+
+def xplanes_stream(cm, fb, N, lo, ctr, nbr, nt, xop, ln_weight=None, ln_bias=None, eps=1e-5, out_x=None, in_cnt=None,
+                   in_target=0, out_cnt=None, ctas=1):
+    """Streaming gather + LayerNorm + bf16x3 split of a sequence model's layer-0 input into the B-operand images the
+    fused layer-0 recurrence reads (gsn_xplanes_stream).  `xop` from `xplanes_buffer` (same nt)."""
+    lib, st = _prep(cm, fb, ln_weight, ln_bias, out_x)
+    T, B, f_cm = cm.shape
+    K = ctr + 2 * nbr + (ctr if fb is not None else 0)
+    if xop.dtype != torch.uint8 or xop.numel() < lib.gsn_xplanes_bytes(T, B * N, K, nt) or xop.device != cm.device:
+        raise ValueError("xplanes_stream: xop buffer")
+    if out_x is not None and tuple(out_x.shape) != (T, B * N, K):
+        raise ValueError("xplanes_stream: out_x shape")
+    _lib.check(lib.gsn_xplanes_stream(_ptr(cm), f_cm, _ptr(fb), fb.shape[2] if fb is not None else 0, _ptr(ln_weight),
+                                      _ptr(ln_bias), float(eps), _ptr(out_x), xop.data_ptr(), _ptr(in_cnt),
+                                      int(in_target), _ptr(out_cnt), T, B, N, lo, ctr, nbr, int(nt), int(ctas), st))
+    LAUNCHES[0] += 1
+    return xop
 
 
 def pre_stream(cm, fb, N, lo, ctr, nbr, w_ih, ln_weight=None, ln_bias=None, eps=1e-5, out_x=None, out_xproj=None,

@@ -244,10 +244,13 @@ def layer0_inputs_from_reference(g):
 def reference_membrane(g):
     """c_hat[f"{tag}_{l}"] [T,R,H]: the reference's membrane potentials reconstructed by the numpy oracle under the
     block teacher-forced protocol (restart from the fixture's snapshots every SNAP frames, reference spikes as layer
-    inputs): equal to the reference's own values to ~1e-7 except inside the few blocks where the oracle itself flips."""
+    inputs): equal to the reference's own values to ~1e-7 except inside the few blocks where the oracle itself flips.
+    The returned stats also carry "noise_abs_c": the largest |c| at which the numpy fp32 oracle ITSELF first leaves the
+    reference inside a block -- the distance from the threshold at which two independent fp32 implementations of this
+    model (trained weights: folded BatchNorm scales up to ~10^2) can disagree about a spike."""
     from oracle import gsn_oracle as O
     c_hat = {}
-    order = []
+    order, order_h = [], []
 
     def run_layer(inp, w_ih, w_hh, bias, bn, shared, h0, c0):
         hs, cs = [], []
@@ -257,19 +260,37 @@ def reference_membrane(g):
             hs.append(h)
             cs.append(c)
         order.append(np.stack(cs))
-        return np.stack(hs)
+        order_h.append(np.stack(hs))
+        return order_h[-1]
 
     st = block_forced_check(g, layer0_inputs_from_reference(g), run_layer)
     snap = int(g["snap"])
     k = 0
+    noise = 0.0
     for tag, _, H in _models_of(g["cfg"]):
         for l in range(2):
-            cs = order[k]
+            cs, hs = order[k], order_h[k]
             k += 1
-            T = unpack(g[f"{tag}_h{l}"], H).shape[0]
+            href = unpack(g[f"{tag}_h{l}"], H)
+            T = href.shape[0]
             R = cs.shape[1] // ((T + snap - 1) // snap)
             nb = cs.shape[1] // R
             c_hat[f"{tag}_{l}"] = cs.reshape(snap, nb, R, H).transpose(1, 0, 2, 3).reshape(nb * snap, R, H)[:T]
+            hb = hs.reshape(snap, nb, R, H).transpose(1, 0, 2, 3).reshape(nb * snap, R, H)[:T]
+            d = hb != href
+            if d.any():
+                pad = np.zeros((nb * snap, R, H), dtype=bool)
+                pad[:T] = d
+                blk = pad.reshape(nb, snap, R, H)
+                anyrow = blk.any(axis=3)                                   # [nb, snap, R]
+                first = anyrow.argmax(axis=1)                              # [nb, R] first flipped frame of the block
+                cb = np.zeros((nb * snap, R, H), dtype=np.float32)
+                cb[:T] = c_hat[f"{tag}_{l}"]
+                cb = cb.reshape(nb, snap, R, H)
+                for b, r in zip(*np.nonzero(anyrow.any(axis=1))):
+                    t = first[b, r]
+                    noise = max(noise, float(np.abs(cb[b, t, r][blk[b, t, r]]).max()))
+    st["noise_abs_c"] = noise
     return c_hat, st
 
 
@@ -310,6 +331,10 @@ def divergence_audit(g, c_hat, fb_all, sb_all, thr=1e-5):
                 out["root_flips"] += int(d.sum())
                 out["bad_root_flips"] += int((cabs >= thr).sum())
                 out["worst_root_abs_c"] = max(out["worst_root_abs_c"], float(cabs.max()))
+                if (cabs >= thr).any():
+                    out.setdefault("bad_roots", []).append(
+                        {"model": tag, "layer": l, "row": int(r), "frame": int(t), "limit": int(min(lim, 10 ** 9)),
+                         "abs_c": [float(v) for v in cabs[cabs >= thr][:4]]})
         first = np.minimum(np.minimum(t0, t1), limit)
         out["rows"] += R
         out["rows_diverged"] += int((first < T).sum())
@@ -322,6 +347,11 @@ def divergence_audit(g, c_hat, fb_all, sb_all, thr=1e-5):
         R = _np(sb_all[i][1]).shape[1]
         N = R // B
         lim = np.repeat(div["fb"], N)
+        if str(g.get("surface", "A")) == "B":
+            # surface B normalises the full-band part of the sub-band input by its mean over ALL frames of the utterance
+            # (offline_laplace_norm, model_low_freq.py:146-171): a full-band divergence at frame t moves the sub-band
+            # input of EVERY frame by ~1e-4 relative, so it excuses the utterance's sub-band rows from frame 0 on
+            lim = np.where(lim < T, 0, lim)
         lim = np.where(lim >= T, 10 ** 9, lim)
         first, _ = audit(f"sb{i}", cfg["sb_hidden_size"], sb_all[i], lim)
         div[f"sb{i}"] = np.minimum(first, T)
