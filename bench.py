@@ -38,6 +38,9 @@ def parse():
     ap.add_argument("--chunks", type=int, default=12, help="frame chunks of the wavefront schedule (graph mode)")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of "
                     "replaying the captured CUDA graph")
+    ap.add_argument("--schedule", default="auto", choices=["auto", "stream", "wavefront"],
+                    help="auto/stream: frame-granular streaming pipeline of persistent kernels where it is co-resident "
+                         "(else the frame-chunked wavefront); wavefront: round-1 schedule")
     return ap.parse_args()
 
 
@@ -200,6 +203,14 @@ def main():
     model = SpikingFullSubNet(**cfg)
     model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in params.items()}, strict=True)
     model = model.eval().to(dev).set_backend(args.backend)
+    streaming = False
+    if args.schedule != "wavefront" and args.backend in ("auto", "tcgen05"):
+        model.enable_streaming(True)
+        streaming = model._stream_plan(B) is not None
+        if not streaming:
+            if args.schedule == "stream":
+                raise SystemExit(f"--schedule stream: size {args.size} batch {B} is not co-resident on this device")
+            model.enable_streaming(False)
     mag = torch.from_numpy(synth.make_mag(B, 257, T, 11 + rank)).to(dev)
     wave_host = torch.from_numpy(synth.make_wave(B, L, 21 + rank)).pin_memory()
     out_host = torch.empty((B, L), dtype=torch.float32).pin_memory()
@@ -282,33 +293,75 @@ def main():
     sampler.stop_flag = True
     sampler.join()
 
-    # per-kernel timing of the dominant kernel (the recurrence), live, with CUDA events on its stream
-    # (sub-band streams serialised for this pass so each launch is timed alone; `share_of_step` is the
-    # kernel's share of that serial step)
+    # per-kernel timing of the dominant kernel (the recurrence), live, with CUDA events on its stream, every launch
+    # timed ALONE (`share_of_step` is the kernel's share of the serial step, i.e. of the sum of all launches run one
+    # after the other)
     model.enable_cuda_graph(False)
-    model.sb_model.concurrent_bands = False
-    step()
-    torch.cuda.synchronize()
-    ops.PROFILE = []
-    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s0.record()
-    for _ in range(3):
-        step()
-    s1.record()
-    torch.cuda.synchronize()
-    rec = ops.PROFILE
-    ops.PROFILE = None
-    model.sb_model.concurrent_bands = True
-    serial_ms = s0.elapsed_time(s1) / 3.0
-    rec_ms = sum(a.elapsed_time(b) for (_, a, b, _) in rec) / 3.0
-    rec_flops = sum(f for (f, _, _, _) in rec) / 3.0
-    # latency model of the serial frame chain (SURVEY 8d "Bound"): per launch, measured us per frame against the
-    # tensor-pipe time of one frame = 3 planes x ceil(H/16) tcgen05.mma at 14.6 cycles per 128x16x16 instruction
-    # (A operand in tensor memory, straight-line issue, measured in isolation by tools/tc_mma_timing.py), at the SM
-    # clock sampled above: the rest of the frame is the dependent epilogue / spike exchange / operand rebuild
     per_launch = {}
-    for (_, a, b, (t_, r_, h_)) in rec:
-        per_launch.setdefault((t_, r_, h_), []).append(a.elapsed_time(b) * 1e3 / t_)
+    if streaming:
+        # streaming schedule: the persistent recurrence kernels normally overlap for the whole step; here each one is
+        # relaunched without counters on inputs the step has left complete
+        model.record_stream_launches = True
+        step()
+        torch.cuda.synchronize()
+        model.record_stream_launches = False
+        recs = model.stream_launches
+        model.enable_streaming(False)
+        model.sb_model.concurrent_bands = False
+        step()
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(3):
+            step()
+        s1.record()
+        torch.cuda.synchronize()
+        model.sb_model.concurrent_bands = True
+        serial_ms = s0.elapsed_time(s1) / 3.0
+        rec_ms = rec_flops = 0.0
+        for r in recs:
+            def one(r=r):
+                ops.recurrence_stream(r["w_hh"], r["bias"], r["a"], r["b"], out_bits=r["out_bits"],
+                                      sm_budget=r["budget"], **r["ins"])
+            one()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(3):
+                a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a_.record()
+                one()
+                b_.record()
+                torch.cuda.synchronize()
+                ts.append(a_.elapsed_time(b_))
+            ms = float(np.mean(ts))
+            rec_ms += ms
+            rec_flops += r["flops"]
+            per_launch.setdefault((r["T"], r["R"], r["H"], r["K_in"], r["layer"] > 0), []).append(ms * 1e3 / r["T"])
+        serial_ms = max(serial_ms, rec_ms)
+        model.enable_streaming(True)
+    else:
+        model.sb_model.concurrent_bands = False
+        step()
+        torch.cuda.synchronize()
+        ops.PROFILE = []
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(3):
+            step()
+        s1.record()
+        torch.cuda.synchronize()
+        rec = ops.PROFILE
+        ops.PROFILE = None
+        model.sb_model.concurrent_bands = True
+        serial_ms = s0.elapsed_time(s1) / 3.0
+        rec_ms = sum(a.elapsed_time(b) for (_, a, b, _) in rec) / 3.0
+        rec_flops = sum(f for (f, _, _, _) in rec) / 3.0
+        for (_, a, b, (t_, r_, h_)) in rec:
+            per_launch.setdefault((t_, r_, h_, 0, False), []).append(a.elapsed_time(b) * 1e3 / t_)
+    # latency model of the serial frame chain (SURVEY 8d "Bound"): per launch, measured us per frame against the
+    # tensor-pipe time of one frame = 3 planes x ceil(H/16) recurrent tcgen05.mma (+ the fused input product: 3 planes
+    # for spike inputs, 8 / 6 plane pairs for the real-valued layer-0 input) at ~17 cycles per 128x16x16 instruction
+    # with the A operand in tensor memory (measured inside the kernel: 30 MMAs complete 520 cycles after issue)
 
     t = torch.tensor([dev_ms, e2e_s], device=dev, dtype=torch.float64)
     if world > 1:
@@ -335,9 +388,11 @@ def main():
         "data": "synthetic",
         "config": dict(wl, l2="flushed between timed iterations (256 MiB write)",
                        recurrence_backends=backends,
-                       launch=f"CUDA graph replay of the step, frame-chunked wavefront ({args.chunks} chunks, one "
-                              f"stream per model x layer)" if not args.no_graph
-                       else "eager enqueue from Python"),
+                       launch=("eager enqueue from Python" if args.no_graph else "CUDA graph replay of the step") +
+                              (", streaming pipeline: every (model, layer) recurrence and helper stage is ONE persistent "
+                               "kernel for all frames, chained through per-frame counters; layer-0 and layer >= 1 input "
+                               "products fused into the recurrences" if streaming else
+                               f", frame-chunked wavefront ({args.chunks} chunks, one stream per model x layer)")),
         "clocks": sampler.summary(),
         "e2e": {"value": world * B * T * args.steps / e2e_s, "unit": "frames/s",
                 "h2d_bytes_per_step": int(wave_host.numel() * 4), "d2h_bytes_per_step": int(out_host.numel() * 4),
@@ -346,23 +401,35 @@ def main():
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
                      "frac": achieved / tf_peak if tf_peak else None, "traffic": None,
-                     "kernel": "GSN recurrence (all layers of all sequence models of one step)",
+                     "kernel": "GSN recurrence (all layers of all sequence models of one step" + (", input products fused)" if streaming else ")"),
                      "algorithmic_flops_per_step": rec_flops, "kernel_ms_per_step": rec_ms,
                      "share_of_step": rec_ms / serial_ms, "serial_step_ms": serial_ms,
                      "peak_source": peak_src},
     }
-    traffic_file = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
-    if args.size == "S" and B == 32 and abs(args.seconds - 4.0) < 1e-9 and os.path.exists(traffic_file):
-        # dram__bytes_read.sum + dram__bytes_write.sum of the same launches from one `ncu --set full` capture
+    # dram__bytes_read.sum + dram__bytes_write.sum of the recurrence launches from one `ncu --set full` capture of THIS
+    # schedule (tools/ncu_traffic.py writes the file with the schedule / shape it was taken on; anything else -> null)
+    traffic_file = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+    if os.path.exists(traffic_file):
         tr = json.load(open(traffic_file))
-        line["roofline"]["traffic"] = tr["dram_bytes_per_step"]
-        line["roofline"]["traffic_source"] = tr["source"]
+        if (tr.get("size"), tr.get("batch"), tr.get("frames"), tr.get("schedule")) == \
+                (args.size, B, T, "stream" if streaming else "wavefront"):
+            line["roofline"]["traffic"] = tr["dram_bytes_per_step"]
+            line["roofline"]["traffic_source"] = tr["source"]
     mhz = (line["clocks"]["sm_mhz"] or 1965.0)
+
+    def mma_per_frame(h_, k_in, spikes_in):
+        n = 3 * ((h_ + 15) // 16)
+        if k_in:
+            ks = (k_in + 15) // 16
+            n += (3 if spikes_in else (6 if ks >= 8 else 8)) * ks
+        return n
+
     line["roofline"]["latency_model"] = [
-        {"frames": t_, "rows": r_, "hidden": h_, "us_per_frame": float(np.mean(v)),
-         "mma_us_per_frame": 3 * ((h_ + 15) // 16) * 14.6 / mhz,
-         "tensor_pipe_share_of_frame": 3 * ((h_ + 15) // 16) * 14.6 / mhz / float(np.mean(v))}
-        for (t_, r_, h_), v in sorted(per_launch.items())]
+        {"frames": t_, "rows": r_, "hidden": h_, "fused_input": k_, "us_per_frame": float(np.mean(v)),
+         "mma_per_frame": mma_per_frame(h_, k_, sp_),
+         "mma_us_per_frame": mma_per_frame(h_, k_, sp_) * 17.0 / mhz,
+         "tensor_pipe_share_of_frame": mma_per_frame(h_, k_, sp_) * 17.0 / mhz / float(np.mean(v))}
+        for (t_, r_, h_, k_, sp_), v in sorted(per_launch.items())]
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_leg(synth, cfg, B, T, 3, 1)[1]
     print(json.dumps(line))

@@ -43,6 +43,7 @@ struct RecStreamParams {
   const unsigned int* in_cnt;   // [T] or null: frame t of the input is complete when in_cnt[t] >= in_target
   unsigned int in_target;
   unsigned int poll_ns;         // back-off between two polls of in_cnt
+  int direct;                   // epilogue warps write the bf16 hh operand of the next frame straight into every CTA
   unsigned int* out_cnt;        // [T] or null: += 1 per CTA when its part of frame t is globally visible
   unsigned long long* spike_count;  // or null: += number of spikes emitted by this launch (SynOps accounting)
   unsigned long long* prof;     // PROF builds: cycle counters
@@ -61,6 +62,11 @@ constexpr int kStThreads = (kPubWarp + kPubWarps) * 32;
 constexpr int kRI = 4;        // ring depth of the fused input operand
 constexpr int kPubRing = 4;
 constexpr uint32_t kOneBf = 0x3F80u;
+// Fused real-input product: the recurrence CTA's tensor pipe has room for about 60 extra MMAs per frame next to the 30-45
+// recurrent ones (each costs ~25 cycles at 16-row tiles).  From K_in > 112 on (8 k steps: 64 / 80 MMAs with 8 pairs)
+// the two smallest plane pairs (lo x mid, mid x lo: together <= 2^-23 |w||x|, the rounding level of an fp32 product) are
+// dropped so that the layer keeps the frame rate of the others.
+constexpr int kWidePairsKsteps = 8;
 
 template <int NT>
 struct StCfg {
@@ -75,12 +81,12 @@ struct StLayout {
 };
 enum { kInXproj = 0, kInBits = 1, kInPlanes = 2 };
 template <int NT, int IN>
-__host__ __device__ inline StLayout st_layout(int Kmma, int Kin_mma, int C, int wpitch_max) {
+__host__ __device__ inline StLayout st_layout(int Kmma, int Kin_mma, int C, int wpitch_max, bool direct) {
   constexpr bool FUSED = IN != kInXproj;
   StLayout L;
   size_t off = 0;
   L.sB = off;
-  off += ((size_t)NT * Kmma * 2 + 127) / 128 * 128;
+  off += (direct ? 2 : 1) * (((size_t)NT * Kmma * 2 + 127) / 128 * 128);  // direct: one operand buffer per frame parity
   L.bits = off;
   off += ((size_t)2 * NT * st_kw_padded(C) * 4 + 127) / 128 * 128;
   L.ring = off;
@@ -203,6 +209,8 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
   static_assert(CPT == 4 || CPT == 8 || CPT == 16, "NT must be 16, 32 or 64");
   extern __shared__ __align__(1024) uint8_t smem[];
   int tslot = trace_begin(p.trace, 2, p.T, p.R, p.H);
+  const long long prof_c0 = PROF ? clock64() : 0;
+  const unsigned long long prof_t0 = PROF ? global_ns() : 0;
   // warp index through a shuffle: tells the compiler it is warp-uniform, so the role branches below are uniform
   // control flow and the MMA-issue code may live in uniform registers (CUTLASS's canonical_warp_idx_sync trick)
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
@@ -218,7 +226,8 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
   const int Wb = (H + 31) / 32;
   const int Wi = FUSED ? (p.K_in + 31) / 32 : 0;
   const int wp_max = p.wpitch > p.wpitch_in ? p.wpitch : p.wpitch_in;
-  const StLayout L = st_layout<NT, IN>(Kmma, p.Kin_mma, (int)C, wp_max);
+  const bool direct = p.direct != 0;
+  const StLayout L = st_layout<NT, IN>(Kmma, p.Kin_mma, (int)C, wp_max, direct);
 
   uint8_t* sB = smem + L.sB;
   uint32_t* bits = reinterpret_cast<uint32_t*>(smem + L.bits);  // [2][NT][KWp]
@@ -242,8 +251,9 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
     tc::mbar_init(bar_w, 1);
     tc::mbar_init(bar_mma, 1);
     tc::mbar_init(bar_B, kEpiWarps);
-    tc::mbar_init(&bar_bits[0], 1);
-    tc::mbar_init(&bar_bits[1], 1);
+    // direct mode: + one arrival per epilogue warp (its chunks for THIS CTA are plain shared-memory stores)
+    tc::mbar_init(&bar_bits[0], p.direct ? 1 + kEpiWarps : 1);
+    tc::mbar_init(&bar_bits[1], p.direct ? 1 + kEpiWarps : 1);
     for (int i = 0; i < 4; ++i) {
       tc::mbar_init(&bar_in_full[i], 1);
       tc::mbar_init(&bar_in_free[i], FUSED ? 1 : kEpiWarps);
@@ -311,6 +321,14 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
     snd_bar0 = tc::map_to_rank(&bar_bits[0], r);
     snd_bar1 = tc::map_to_rank(&bar_bits[1], r);
   }
+  // direct mode: lane = (destination CTA of a pair, one of the warp's 16 operand chunks = (row i, 8 neurons)); the chunk
+  // goes to byte dir_off of the destination's operand buffer of the NEXT frame's parity
+  const uint32_t sB_bytes = (uint32_t)(((size_t)NT * Kmma * 2 + 127) / 128 * 128);
+  const int dir_i = (lane & 15) >> 2, dir_sub = lane & 3;
+  const int dir_k8 = (int)slice * 16 + q * 4 + dir_sub;
+  const int dir_n = g * CPT + dir_i;
+  const uint32_t dir_off = (uint32_t)((dir_n >> 3) * SBO + dir_k8 * 128 + (dir_n & 7) * 16);
+  const bool dir_ok = epi && CPT == 4 && dir_k8 < Kmma / 8;
   // every barrier of the cluster is initialised (and the frame-0 operand written) before anybody stores remotely
   tc::tc_fence_before();
   tc::cluster_sync_all();
@@ -328,6 +346,10 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
     // itself inside a single-thread region every MMA issue cost ~55 cycles of R2UR traffic.
     const bool leader = tc::elect_one();
     const uint64_t desc_b0 = tc::make_smem_desc(tc::smem_u32(sB), 128, SBO);
+    const uint64_t desc_b1 = tc::make_smem_desc(tc::smem_u32(sB + sB_bytes), 128, SBO);
+    // bytes of the next frame's operand that arrive as st.async from the OTHER CTAs of the cluster
+    const int own_k8 = Kmma / 8 - (int)slice * 16 < 16 ? Kmma / 8 - (int)slice * 16 : 16;
+    const uint32_t op_bytes = (uint32_t)NT * 16u * (uint32_t)(Kmma / 8 - (own_k8 > 0 ? own_k8 : 0));
     const uint32_t ih_slot_bytes = (uint32_t)((IN == kInPlanes ? 3 : 1) * (((size_t)NT * p.Kin_mma * 2 + 127) / 128 * 128));
     const int ksteps_in = FUSED ? p.Kin_mma / 16 : 0;
     auto issue_ih = [&](int tt) {  // input-to-hidden product of frame tt -> D_ih
@@ -337,7 +359,10 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
       tc::tc_fence_after();
       const uint64_t db = tc::make_smem_desc(tc::smem_u32(ring + (size_t)slot * ih_slot_bytes), 128, 16u * p.Kin_mma);
       if (leader) {
-        if (IN == kInPlanes) tc::mma_pairs<NT>(ksteps_in, tmem_dih, tmem_aih, db, idesc);  // real-valued input: 8 pairs
+        if (IN == kInPlanes) {  // real-valued input: 8 plane pairs; 6 for wide inputs (see kWidePairsKsteps)
+          if (ksteps_in >= kWidePairsKsteps) tc::mma_pairs<NT, 6>(ksteps_in, tmem_dih, tmem_aih, db, idesc);
+          else tc::mma_pairs<NT, 8>(ksteps_in, tmem_dih, tmem_aih, db, idesc);
+        }
         else tc::mma_planes<kStPlanes>(ksteps_in, tmem_dih, tmem_aih, db, idesc);
         tc::mma_commit(&bar_in_free[slot]);
         tc::mma_commit(bar_dih_full);
@@ -348,12 +373,23 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
     long long ic[3] = {0, 0, 0};
     for (int t = 0; t < T; ++t) {
       const long long i0 = PROF ? clock64() : 0;
-      if (!tc::mbar_wait_cta(bar_B, (uint32_t)(t & 1))) __trap();
+      if (direct) {
+        // operand of frame t (buffer t&1) = st.async stores of every epilogue warp of the cluster, counted in bytes
+        if (t > 0 && !tc::mbar_wait_cta(&bar_bits[t & 1], (uint32_t)(((t - 1) >> 1) & 1))) __trap();
+        tc::fence_proxy_async_smem();
+      } else if (!tc::mbar_wait_cta(bar_B, (uint32_t)(t & 1))) {
+        __trap();
+      }
       tc::tc_fence_after();
       const long long i1 = PROF ? clock64() : 0;
       if (leader) {
-        tc::mbar_arrive_expect_tx(&bar_bits[t & 1], bits_bytes);  // arm this frame's spike-bit exchange
-        tc::mma_planes<kStPlanes>(ksteps, tmem_dhh, tmem_ahh, desc_b0, idesc);
+        if (direct) {
+          if (t + 1 < T) tc::mbar_arrive_expect_tx(&bar_bits[(t + 1) & 1], op_bytes);  // arm the next frame's operand
+          tc::mma_planes<kStPlanes>(ksteps, tmem_dhh, tmem_ahh, (t & 1) ? desc_b1 : desc_b0, idesc);
+        } else {
+          tc::mbar_arrive_expect_tx(&bar_bits[t & 1], bits_bytes);  // arm this frame's spike-bit exchange
+          tc::mma_planes<kStPlanes>(ksteps, tmem_dhh, tmem_ahh, desc_b0, idesc);
+        }
         tc::mma_commit(bar_mma);
       }
       __syncwarp();
@@ -492,7 +528,7 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
     char* c_ptr = reinterpret_cast<char*>(p.c_out) + boff0;
     // frame-0 operand is in place (zeros)
     __syncwarp();
-    if (lane == 0) tc::mbar_arrive(bar_B);
+    if (lane == 0 && !direct) tc::mbar_arrive(bar_B);
     long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int t = 0; t < T; ++t) {
       const int par = t & 1;
@@ -556,7 +592,37 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
       tc::tc_fence_before();
       const long long q3 = PROF ? clock64() : 0;
       // ---- exchange first (critical path), then the trace (running pointers: no per-frame address arithmetic) ----
-      if (sender) tc::st_async_u32(par ? snd_cell1 : snd_cell0, myw, par ? snd_bar1 : snd_bar0);
+      if (direct) {
+        if (t + 1 < T) {
+          // my warp's 32 neurons x 4 rows as sixteen 16-byte operand chunks, to every CTA of the cluster
+          const uint32_t wrow = __shfl_sync(0xffffffffu, myw, dir_i);
+          const uint32_t b8 = (wrow >> (8 * dir_sub)) & 0xFFu;
+          uint32_t v[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            v[e] = ((b8 >> (2 * e)) & 1u ? kOneBf : 0u) | ((b8 >> (2 * e + 1)) & 1u ? (kOneBf << 16) : 0u);
+          const uint32_t local = tc::smem_u32(sB + (par ? 0u : sB_bytes)) + dir_off;  // buffer (t+1)&1
+          const uint32_t lbar = tc::smem_u32(&bar_bits[par ^ 1]);
+          // The chunk for this CTA is a plain store (the st.async path takes ~1.4 cycles per 16-byte packet: 512
+          // packets per frame would cost more than the bit exchange it replaces), made visible to the tensor core's
+          // proxy and announced with one arrival per warp; the remote chunks follow as st.async, counted in bytes on
+          // the peer's barrier (issued after the proxy fence, which would otherwise wait for them)
+          if (dir_ok && (slice & 1u) == (uint32_t)(lane >> 4))
+            *reinterpret_cast<uint4*>(sB + (par ? 0u : sB_bytes) + dir_off) = make_uint4(v[0], v[1], v[2], v[3]);
+          tc::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&bar_bits[par ^ 1]);
+          if (PROF) pc[6] += clock64() - q3;
+          for (uint32_t r0 = 0; r0 < C; r0 += 2) {
+            const uint32_t r = r0 + (lane >> 4);
+            if (dir_ok && r < C && r != slice)
+              tc::st_async_v4(tc::map_shared_rank(local, r), v, tc::map_shared_rank(lbar, r));
+          }
+          if (PROF) pc[7] += clock64() - q3;
+        }
+      } else if (sender) {
+        tc::st_async_u32(par ? snd_cell1 : snd_cell0, myw, par ? snd_bar1 : snd_bar0);
+      }
       if (lane < CPT) {
         if (hb_ok) *hb_ptr = myw;
         hb_ptr += hb_step;
@@ -587,7 +653,7 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
         }
       }
       const long long q4 = PROF ? clock64() : 0;
-      if (t + 1 < T) {
+      if (t + 1 < T && !direct) {
         if (!tc::mbar_wait_cta(&bar_bits[par], (uint32_t)((t >> 1) & 1))) { alive = false; break; }
         const long long q5 = PROF ? clock64() : 0;
         // ---- rebuild the bf16 hh operand (spikes of frame t, all H neurons of my rows) from the bits ----
@@ -627,6 +693,10 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
   tc::tc_fence_before();
   tc::cluster_sync_all();  // nobody leaves while a peer may still store into its staging buffer
   if (warp == 0) tc::tmem_dealloc<kStTmemCols>(tmem);
+  if (PROF && p.prof && blockIdx.x == 0 && threadIdx.x == 0) {  // SM cycles and nanoseconds of the whole launch
+    p.prof[12] = (unsigned long long)(clock64() - prof_c0);
+    p.prof[13] = global_ns() - prof_t0;
+  }
   trace_end(p.trace, tslot);
 }
 
@@ -659,7 +729,7 @@ static int launch_stream(RecStreamParams p, int C, cudaStream_t st) {
   if (p.H % 4 == 0 && (reinterpret_cast<uintptr_t>(p.w_hh) & 15) == 0) p.wpitch = st_wpitch(p.H);
   if (FUSED && p.K_in % 4 == 0 && (reinterpret_cast<uintptr_t>(p.w_ih) & 15) == 0) p.wpitch_in = st_wpitch(p.K_in);
   auto layout = [&]() {
-    return st_layout<NT, IN>(p.Kmma, p.Kin_mma, C, p.wpitch > p.wpitch_in ? p.wpitch : p.wpitch_in);
+    return st_layout<NT, IN>(p.Kmma, p.Kin_mma, C, p.wpitch > p.wpitch_in ? p.wpitch : p.wpitch_in, p.direct != 0);
   };
   if (layout().total > tc::kMaxDynamicSmem) {  // no room for the staging area: read the weights directly
     p.wpitch = 0;
@@ -743,6 +813,8 @@ extern "C" int gsn_recurrence_stream(const float* xproj, const uint32_t* in_bits
   p.in_cnt = in_cnt; p.in_target = in_target; p.out_cnt = out_cnt; p.spike_count = spike_count;
   static const unsigned int poll_ns = getenv("GSN_POLL_NS") ? (unsigned int)atoi(getenv("GSN_POLL_NS")) : 100u;
   p.poll_ns = poll_ns;
+  static const int direct = getenv("GSN_STREAM_DIRECT") ? atoi(getenv("GSN_STREAM_DIRECT")) : 1;
+  p.direct = (direct != 0 && nt == 16) ? 1 : 0;
   p.prof = reinterpret_cast<unsigned long long*>(workspace);
   p.T = T; p.R = R; p.H = H; p.Kmma = (H + 15) / 16 * 16;
   p.K_in = fused ? K_in : 0; p.Kin_mma = fused ? (K_in + 15) / 16 * 16 : 0;

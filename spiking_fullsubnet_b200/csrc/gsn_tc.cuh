@@ -118,6 +118,18 @@ __device__ __forceinline__ void st_async_u32(uint32_t remote_addr, uint32_t v, u
                "r"(v), "r"(remote_bar)
                : "memory");
 }
+// 16-byte variant, and mapa on an already converted shared-window address
+__device__ __forceinline__ void st_async_v4(uint32_t remote_addr, const uint32_t (&v)[4], uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+                   remote_addr),
+               "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(remote_bar)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t map_shared_rank(uint32_t local_shared_addr, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_shared_addr), "r"(rank));
+  return remote;
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t leader;
   asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(leader));
@@ -267,25 +279,28 @@ __device__ __forceinline__ bool mma_planes(int ksteps, uint32_t tmem_d, uint32_t
   }
 }
 
-// ---- bf16x3 x bf16x3 ("both operands real"): 8 of the 9 plane pairs x KS k steps, smallest terms first (lo x lo,
-// <= 2^-32 |w||x|, is dropped).  w plane pw at tmem_a + (pw*KS + ks)*8 columns, x plane px at desc_b0 + px*PB + ks*16
-// (PB = plane bytes >> 4 = NT*KS*2).  Plane index: 0 = lo, 1 = mid, 2 = hi.  The first MMA overwrites D.
-template <int KS, int PB>
+// ---- bf16x3 x bf16x3 ("both operands real"): PAIRS of the 9 plane pairs x KS k steps, smallest terms first.
+// PAIRS = 8 drops only lo x lo (<= 2^-32 |w||x|); PAIRS = 6 also drops lo x mid and mid x lo (<= 2^-23 |w||x| together:
+// the rounding level of an fp32 product).  w plane pw at tmem_a + (pw*KS + ks)*8 columns, x plane px at
+// desc_b0 + px*PB + ks*16 (PB = plane bytes >> 4 = NT*KS*2).  Plane index: 0 = lo, 1 = mid, 2 = hi.  The first MMA
+// overwrites D.
+template <int KS, int PB, int PAIRS>
 __device__ __forceinline__ void mma_pairs_unrolled(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b0, uint32_t idesc) {
   constexpr int PW[8] = {0, 1, 0, 2, 1, 1, 2, 2};
   constexpr int PX[8] = {1, 0, 2, 0, 1, 2, 1, 2};
-  mma_ts_c<0>(tmem_d, tmem_a + (uint32_t)((PW[0] * KS) * 8), desc_b0 + (uint64_t)(PX[0] * PB), idesc);
+  constexpr int T0 = 8 - PAIRS;
+  mma_ts_c<0>(tmem_d, tmem_a + (uint32_t)((PW[T0] * KS) * 8), desc_b0 + (uint64_t)(PX[T0] * PB), idesc);
 #pragma unroll
-  for (int i = 1; i < 8 * KS; ++i) {
+  for (int i = T0 * KS + 1; i < 8 * KS; ++i) {
     const int term = i / KS, ks = i % KS;
     mma_ts_c<1>(tmem_d, tmem_a + (uint32_t)((PW[term] * KS + ks) * 8), desc_b0 + (uint64_t)(PX[term] * PB + ks * 16),
                 idesc);
   }
 }
-template <int NT>
+template <int NT, int PAIRS = 8>
 __device__ __forceinline__ bool mma_pairs(int ksteps, uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b0, uint32_t idesc) {
   switch (ksteps) {
-#define GSN_KS_CASE(n) case n: mma_pairs_unrolled<n, NT * n * 2>(tmem_d, tmem_a, desc_b0, idesc); return true;
+#define GSN_KS_CASE(n) case n: mma_pairs_unrolled<n, NT * n * 2, PAIRS>(tmem_d, tmem_a, desc_b0, idesc); return true;
     GSN_KS_CASE(1) GSN_KS_CASE(2) GSN_KS_CASE(3) GSN_KS_CASE(4) GSN_KS_CASE(5) GSN_KS_CASE(6) GSN_KS_CASE(7)
     GSN_KS_CASE(8) GSN_KS_CASE(9) GSN_KS_CASE(10) GSN_KS_CASE(11) GSN_KS_CASE(12) GSN_KS_CASE(13) GSN_KS_CASE(14)
     GSN_KS_CASE(15) GSN_KS_CASE(16)

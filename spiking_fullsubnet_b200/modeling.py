@@ -68,15 +68,20 @@ class GSUCell(nn.Module):
         nbt = bn.num_batches_tracked
         key = (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version,
                nbt._version if nbt is not None else 0, bn.weight.data_ptr(), bn.running_var.data_ptr())
-        capturing = bn.weight.is_cuda and torch.cuda.is_current_stream_capturing()
-        if capturing or self._bn_cache is None or self._bn_cache[0] != key:
+        if self._bn_cache is None or self._bn_cache[0] != key:
             with torch.no_grad():
                 invstd = 1.0 / torch.sqrt(bn.running_var + bn.eps)
                 alpha = (invstd * bn.weight).contiguous()
                 beta = (bn.bias - bn.running_mean * alpha).contiguous()
-            if capturing:  # the fold becomes part of the CUDA graph, so replays see updated statistics
-                return alpha, beta
-            self._bn_cache = (key, alpha, beta)
+            old = self._bn_cache
+            if old is not None and old[1].shape == alpha.shape and old[1].device == alpha.device:
+                # refresh IN PLACE: captured CUDA graphs hold these two tensors (network() calls refresh_folded_bn
+                # before every replay, so replays see updated parameters / statistics without re-capturing)
+                old[1].copy_(alpha)
+                old[2].copy_(beta)
+                self._bn_cache = (key, old[1], old[2])
+            else:
+                self._bn_cache = (key, alpha, beta)
         return self._bn_cache[1], self._bn_cache[2]
 
     def forward(self, input, state):
@@ -537,6 +542,14 @@ class _GraphedNetwork:
     def _network_sched(self, mag):
         return self._network(mag)
 
+    def refresh_folded_bn(self):
+        """Bring the cached eval-BatchNorm affines of every cell up to date (in place: captured graphs read them)."""
+        cells = self.__dict__.get("_gsu_cells")
+        if cells is None:
+            cells = self.__dict__["_gsu_cells"] = [m for m in self.modules() if isinstance(m, GSUCell) and m.use_bn]
+        for c in cells:
+            c.folded_bn()
+
     def network(self, mag):
         if not mag.is_cuda:
             raise RuntimeError("spiking_fullsubnet_b200 has no CPU path: move the model and input to CUDA")
@@ -562,6 +575,7 @@ class _GraphedNetwork:
                     static_out = self._network_sched(static_in)
             entry = graphs[key] = (graph, static_in, static_out)
         graph, static_in, static_out = entry
+        self.refresh_folded_bn()
         static_in.copy_(mag)
         graph.replay()
         return static_out
@@ -904,6 +918,7 @@ class SpikingFullSubNet(_GraphedNetwork, nn.Module):
         fb_target = 0
         fb_act = None
         results = []
+        record = [] if self.__dict__.get("record_stream_launches") else None
         # The recurrences (thread-block clusters) are enqueued before the helper stages of their model so that cluster
         # placement is not fragmented by single-CTA kernels; consumers spin on their producers' frame counters.
         for mi, d in enumerate(models):
@@ -947,10 +962,20 @@ class SpikingFullSubNet(_GraphedNetwork, nn.Module):
                 kw = dict(out_bits=bits, out_h=h_out, out_cnt=c_out, sm_budget=budget, in_cnt=in_cnt, in_target=in_target)
                 w_hh, bias = cell.weight_hh.detach(), cell.bias_ih.detach()
                 fused = ly["fused"] or (l == 0 and d["fused0"])
+                if record is not None:
+                    # the same launch without counters (its inputs are complete once this step has run): timed alone
+                    kin = (K if l == 0 else H) if fused else 0
+                    ins = (dict(in_planes=xop, w_ih=w_ih0, frames_rows=(T, R)) if (l == 0 and d["fused0"]) else
+                           dict(in_bits=bits_prev, w_ih=cell.weight_ih.detach()) if ly["fused"] else None)
+                    record.append(dict(model=mi, layer=l, T=T, R=R, H=H, K_in=kin, fused=fused,
+                                       flops=2.0 * T * R * H * (H + kin), w_hh=w_hh, bias=bias, a=a, b=b, ins=ins,
+                                       out_bits=bits, budget=budget))
                 if l == 0 and d["fused0"]:
                     on_stream(lambda w_hh=w_hh, bias=bias, a=a, b=b, kw=kw, xop=xop, w_ih0=w_ih0, R=R:
                               ops.recurrence_stream(w_hh, bias, a, b, in_planes=xop, w_ih=w_ih0, frames_rows=(T, R), **kw))
                 elif l == 0:
+                    if record is not None:
+                        record[-1]["ins"] = dict(xproj=xproj)
                     on_stream(lambda w_hh=w_hh, bias=bias, a=a, b=b, kw=kw, xp=xproj:
                               ops.recurrence_stream(w_hh, bias, a, b, xproj=xp, **kw))
                 elif ly["fused"]:
@@ -964,6 +989,8 @@ class SpikingFullSubNet(_GraphedNetwork, nn.Module):
                                    c_lin=c_lin, d=d: ops.linear_bits_stream(bp, w, out=xp, ctas=C * d["lin_p"], in_cnt=ic,
                                                                             in_target=it, out_cnt=c_lin))
                     kw.update(in_cnt=c_lin, in_target=R * C)
+                    if record is not None:
+                        record[-1]["ins"] = dict(xproj=xp)
                     on_stream(lambda w_hh=w_hh, bias=bias, a=a, b=b, kw=kw, xp=xp:
                               ops.recurrence_stream(w_hh, bias, a, b, xproj=xp, **kw))
                 in_cnt, in_target = c_out, ops.stream_ctas(R, H, (K if l == 0 else H) if fused else 0, fused, budget)
@@ -998,6 +1025,8 @@ class SpikingFullSubNet(_GraphedNetwork, nn.Module):
             done = torch.cuda.Event()
             done.record(stq)
             main.wait_event(done)
+        if record is not None:
+            self.stream_launches = record
         self._keepalive = (cm, counters, results, hold)
         self.last_spike_bits = [r[2] for r in results]
         return [r[0] for r in results[1:]], results[0][1], [r[1] for r in results[1:]]

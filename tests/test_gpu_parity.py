@@ -554,16 +554,18 @@ def test_long_free_running_vs_reference(name):
     surface-A S (the bench's weights), trained zoo-S and zoo-L checkpoints.  fp32 threshold chaos makes the raw flip
     count a heavy-tailed quantity (tests/helpers.py, divergence audit), so the pass/fail statements are:
     (1) every row trajectory leaves the reference -- if at all -- only through neurons whose reference membrane
-    potential is within 1e-5 of the threshold; (2) until then the coefficients agree to 1e-4 of max|ref| (north star:
+    potential is within 1e-5 of the threshold, or within 8 x the drift between an fp32 and an fp64 evaluation of that
+    neuron under the reference's own spike history (tests.helpers.membrane_noise: the trained zoo-L recursion is
+    expanding, a f > 1, and that drift reaches 1e-2 by frame 431 with identical spikes); (2) until then the coefficients agree to 1e-4 of max|ref| (north star:
     1e-3).  Raw counts, the reference's own 1 +- 2e-6 noise floor and the audit go to gpurun_out/parity_counts.json."""
-    from tests.helpers import coef_rel_before_divergence, divergence_audit, reference_membrane
+    from tests.helpers import coef_rel_before_divergence, divergence_audit, membrane_noise, reference_membrane
     g = load_long(name)
     m = _long_model(g)
     with torch.no_grad():
         coefs, fb_all, sb_all = m.coefficients(_t(g["mag"]))
     st = compare_long(g, coefs, fb_all, sb_all)
     c_hat, _ = reference_membrane(g)
-    audit, div = divergence_audit(g, c_hat, fb_all, sb_all)
+    audit, div = divergence_audit(g, c_hat, fb_all, sb_all, noise=membrane_noise(g))
     audit["coef_rel_before_divergence"] = coef_rel_before_divergence(g, coefs, div)
     st.update(audit)
     print(name, st)

@@ -10,7 +10,7 @@ os.environ.setdefault("GSN_TC_PROF", "1")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from spiking_fullsubnet_b200 import ops  # noqa: E402
 
-EPI = ["input(wait+ld)", "mma_wait", "ld+math+ballot", "send+trace", "bits_wait", "expand+arrive"]
+EPI = ["input(wait+ld)", "mma_wait", "ld+math+ballot", "send+trace", "bits_wait", "expand+arrive", "(send: local+fence+arrive)", "(send: +st.async)"]
 ISS = ["wait_B", "issue_hh", "issue_ih(+waits)"]
 
 
@@ -37,8 +37,9 @@ def run(R, H, T, fused):
     pr = ws.cpu().numpy()
     ms = e0.elapsed_time(e1)
     print(f"R={R} H={H} T={T} fused={fused}: {ms * 1e3 / T:.2f} us/frame; epilogue cycles/frame:",
-          {n: round(float(v) / T, 1) for n, v in zip(EPI, pr[:6])}, "sum", round(float(pr[:6].sum()) / T, 1),
-          "| issuer:", {n: round(float(v) / T, 1) for n, v in zip(ISS, pr[8:11])})
+          {n: round(float(v) / T, 1) for n, v in zip(EPI, pr[:8])}, "sum", round(float(pr[:6].sum()) / T, 1),
+          "| issuer:", {n: round(float(v) / T, 1) for n, v in zip(ISS, pr[8:11])},
+          f"| launch: {int(pr[12])} cycles in {int(pr[13])} ns = {float(pr[12]) / max(1.0, float(pr[13])):.3f} GHz")
 
 
 if __name__ == "__main__":

@@ -23,6 +23,8 @@ buf = torch.zeros(64 + 32 * 16384, dtype=torch.uint8, device="cuda")
 _lib.check(lib.gsn_trace_set(buf.data_ptr(), buf.numel()))
 if os.environ.get("GSN_TRACE_ALL_CTAS"):  # header word 15 bit 0: one record per recurrence CTA (kind 5)
     buf[60:64] = torch.tensor([1, 0, 0, 0], dtype=torch.uint8, device="cuda")
+if os.environ.get("GSN_TIMELINE_STREAM"):
+    model.enable_streaming(True)
 model.enable_cuda_graph(True, frame_chunks=chunks)
 with torch.no_grad():
     model.network(mag)  # capture (+ warm-up)
@@ -34,7 +36,7 @@ raw = buf.cpu().numpy()
 n = int(raw[:4].view(np.uint32)[0])
 rec = raw[64:64 + 32 * n].view(np.dtype([("t0", "<u8"), ("t1", "<u8"), ("kind", "<i4"), ("a", "<i4"), ("b", "<i4"), ("c", "<i4")]))
 t_min = rec["t0"].min()
-names = {1: "linear", 2: "recur", 3: "feat", 4: "lin_tc", 5: "rcta"}
+names = {1: "linear", 2: "recur", 3: "feat", 4: "lin_tc", 5: "rcta", 6: "pre", 7: "xplane"}
 print(f"{n} traced launches, span {(max(rec['t1'].max(), rec['t0'].max()) - t_min) / 1e3:.1f} us")
 for r in sorted(rec, key=lambda r: r["t0"]):
     dur = (int(r["t1"]) - int(r["t0"])) / 1e3 if r["t1"] else 0
