@@ -321,8 +321,9 @@ def main():
         rec_ms = rec_flops = 0.0
         for r in recs:
             def one(r=r):
+                # (out_cnt: the ring-buffered operand images of a fused layer 0 require the back-pressure counters)
                 ops.recurrence_stream(r["w_hh"], r["bias"], r["a"], r["b"], out_bits=r["out_bits"],
-                                      sm_budget=r["budget"], **r["ins"])
+                                      sm_budget=r["budget"], out_cnt=r["out_cnt"], **r["ins"])
             one()
             torch.cuda.synchronize()
             ts = []

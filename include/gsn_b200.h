@@ -136,6 +136,9 @@ GSN_API int gsn_layer_recurrence_bits(const float* xproj, const float* w_hh, con
  *                                   (row tile = gsn_recurrence_stream_tile(.., fused = 1, ..)) + w_ih [H,K_in]: the
  *                                   product x_t . w_ih^T (ESN:141) runs inside the kernel too (8 of the 9 plane pairs,
  *                                   fp32-faithful), one bulk copy per frame; same tensor-memory condition, K_in <= 256;
+ *                                   planes_ring = frames the image buffer holds (frame t in slot t % planes_ring;
+ *                                   <= 0 or >= T: one slot per frame; a shorter ring needs out_cnt, which the
+ *                                   producer reads as back-pressure);
  *   - in_cnt [T] (may be NULL): frame t of the input may be read once in_cnt[t] >= in_target (acquire);
  *   - h_bits [T,R,ceil(H/32)]: the spike trace, bit-packed (always); h_out / c_out [T,R,H] fp32 optional (NULL);
  *     hT / cT [R,H] optional;
@@ -145,7 +148,7 @@ GSN_API int gsn_layer_recurrence_bits(const float* xproj, const float* w_hh, con
  * Results are bit-identical to gsn_layer_recurrence(TCGEN05) fed by gsn_linear_spike_bits / the same xproj.
  * Counters must be zeroed by the caller before the first producer starts.  workspace may be NULL.               */
 GSN_API int gsn_recurrence_stream(const float* xproj, const uint32_t* in_bits, const void* in_planes,
-                                  const float* w_ih, int K_in, const float* w_hh, const float* bias,
+                                  int planes_ring, const float* w_ih, int K_in, const float* w_hh, const float* bias,
                                   const float* bn_scale, const float* bn_shift, uint32_t* h_bits, float* h_out,
                                   float* c_out, float* hT, float* cT, const unsigned int* in_cnt,
                                   unsigned int in_target, unsigned int* out_cnt, unsigned long long* spike_count,
@@ -175,10 +178,14 @@ GSN_API int gsn_linear_spike_bits_stream(const uint32_t* a_bits, const float* w,
  * gsn_xplanes_bytes(T, R, K, nt) bytes, 128-byte aligned, and be ZEROED once by the caller (padding rows of the last
  * tile).  in_cnt / in_target as below; out_cnt[t] += rows written (frame complete at R = B*N).  K <= 256.       */
 GSN_API size_t gsn_xplanes_bytes(int T, int R, int K, int nt);
+/* ring: frames the buffer holds (gsn_xplanes_bytes(ring, ...) bytes; <= 0 or >= T: T).  With a ring shorter than T the
+ * images stay L2-resident instead of making a DRAM round trip; frame t then waits for bp_cnt[t - ring] >= bp_target
+ * (bp_cnt = the out_cnt of the consuming gsn_recurrence_stream, bp_target = its CTA count). */
 GSN_API int gsn_xplanes_stream(const float* cm, int f_cm, const float* fb, int f_fb, const float* ln_weight,
-                               const float* ln_bias, float ln_eps, float* x_out, void* xop,
-                               const unsigned int* in_cnt, unsigned int in_target, unsigned int* out_cnt, int T,
-                               int B, int N, int lo, int ctr, int nbr, int nt, int ctas, gsn_stream_t stream);
+                               const float* ln_bias, float ln_eps, float* x_out, void* xop, int ring,
+                               const unsigned int* in_cnt, unsigned int in_target, unsigned int* out_cnt,
+                               const unsigned int* bp_cnt, unsigned int bp_target, int T, int B, int N, int lo,
+                               int ctr, int nbr, int nt, int ctas, gsn_stream_t stream);
 
 /* Streaming front end of one sequence model as a separate tensor-core stage (gsn_stage_stream.cu; used when the fused
  * layer-0 recurrence does not fit tensor memory): the same gather + LayerNorm (x within 2e-6 of gsn_subband_features)

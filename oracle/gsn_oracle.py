@@ -264,14 +264,26 @@ def offline_laplace_norm(x):
     return (x / (mu + x.dtype.type(EPSILON))).astype(x.dtype)
 
 
+def cumulative_laplace_norm(x):
+    """recipes/intel_ndns/spiking_fullsubnet_freeze_phase/model_low_freq_count_time.py:173-204 on [..., K, T]: every
+    leading index is divided by the mean of its own K x (t+1) entries up to frame t."""
+    K, T = x.shape[-2], x.shape[-1]
+    cum = np.cumsum(x.sum(axis=-2, dtype=x.dtype), axis=-1, dtype=x.dtype)            # [..., T]
+    count = np.arange(K, K * T + 1, K, dtype=x.dtype)
+    return (x / ((cum / count)[..., None, :] + x.dtype.type(EPSILON))).astype(x.dtype)
+
+
 def separator_network(mag, params, cfg, dtype=np.float32):
-    """MLF:574-586: mag [B, n_fft//2+1, T] -> (coef list [B,df,F_i,T,2], fb_all, sb_all), offline laplace norm."""
-    assert cfg["norm_type"] == "offline_laplace_norm"
+    """MLF:574-586: mag [B, n_fft//2+1, T] -> (coef list [B,df,F_i,T,2], fb_all, sb_all); offline laplace norm, or the
+    cumulative one of the count_time variant."""
+    assert cfg["norm_type"] in ("offline_laplace_norm", "cumulative_laplace_norm")
     shared = cfg.get("shared_weights", False)
     B = mag.shape[0]
     cm = compress_mag(mag, cfg["fdrc"], dtype)[:, :-1, :]
     nf = cm.shape[1]
-    fb_in = offline_laplace_norm(np.ascontiguousarray(cm[:, : cfg["fb_freqs"], :]))
+    cumulative = cfg["norm_type"] == "cumulative_laplace_norm"
+    fb_raw = np.ascontiguousarray(cm[:, : cfg["fb_freqs"], :])
+    fb_in = cumulative_laplace_norm(fb_raw) if cumulative else offline_laplace_norm(fb_raw)
     act = {"Tanh": "tanh", "ReLU": "relu"}.get(cfg.get("fb_output_activate_function") or None)
     fb_out, fb_all = sequence_model_forward(fb_in, params, "fb_model.", 2, shared, act, dtype,
                                             proj="fc_output_layer")
@@ -281,7 +293,10 @@ def separator_network(mag, params, cfg, dtype=np.float32):
     for i, (ctr, nbr, df) in enumerate(zip(cfg["sb_num_center_freqs"], cfg["sb_num_neighbor_freqs"],
                                            cfg["sb_df_orders"])):
         x = subband_inputs(cm, fb_tiled, cuts[i], cuts[i + 1], ctr, nbr)  # [B*N, K, T]
-        x = offline_laplace_norm(x.reshape(B, -1)).reshape(x.shape)  # MLF:475 over (N, 1, K, T) jointly
+        if cumulative:
+            x = cumulative_laplace_norm(x)                               # count_time :173-204: per (b, n) row
+        else:
+            x = offline_laplace_norm(x.reshape(B, -1)).reshape(x.shape)  # MLF:475 over (N, 1, K, T) jointly
         sact = {"Tanh": "tanh", "ReLU": "relu"}.get(cfg.get("sb_output_activate_function") or None)
         out, all_out = sequence_model_forward(x, params, f"sb_model.sb_models.{i}.", 2, shared, sact, dtype,
                                               proj="fc_output_layer")

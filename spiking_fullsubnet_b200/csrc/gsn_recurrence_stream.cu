@@ -29,7 +29,8 @@ namespace gsn {
 struct RecStreamParams {
   const float* xproj;        // !FUSED: [T, R, H]
   const uint32_t* in_bits;   // IN_BITS: [T, R, Wi] bit-packed spikes of the layer below, Wi = ceil(K_in / 32)
-  const uint8_t* in_planes;  // IN_PLANES: operand images of gsn_xplanes_stream, [T][tiles][3][NT x Kin_mma] bf16
+  const uint8_t* in_planes;  // IN_PLANES: operand images of gsn_xplanes_stream, [ring][tiles][3][NT x Kin_mma] bf16
+  int planes_ring;           // frames the image buffer holds (frame t in slot t % planes_ring)
   const float* w_ih;         // FUSED: [H, K_in]
   const float* w_hh;         // [H, H]
   const float* bias;         // [2H]
@@ -43,6 +44,7 @@ struct RecStreamParams {
   const unsigned int* in_cnt;   // [T] or null: frame t of the input is complete when in_cnt[t] >= in_target
   unsigned int in_target;
   unsigned int poll_ns;         // back-off between two polls of in_cnt
+  int pub_nofence;              // TIMING EXPERIMENT ONLY (GSN_PUB_NOFENCE=1): publish without the release fence
   int direct;                   // epilogue warps write the bf16 hh operand of the next frame straight into every CTA
   unsigned int* out_cnt;        // [T] or null: += 1 per CTA when its part of frame t is globally visible
   unsigned long long* spike_count;  // or null: += number of spikes emitted by this launch (SynOps accounting)
@@ -209,7 +211,7 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
   static_assert(CPT == 4 || CPT == 8 || CPT == 16, "NT must be 16, 32 or 64");
   extern __shared__ __align__(1024) uint8_t smem[];
   int tslot = trace_begin(p.trace, 2, p.T, p.R, p.H);
-  const long long prof_c0 = PROF ? clock64() : 0;
+  const long long prof_c0 = (PROF || tslot >= 0) ? clock64() : 0;
   const unsigned long long prof_t0 = PROF ? global_ns() : 0;
   // warp index through a shuffle: tells the compiler it is warp-uniform, so the role branches below are uniform
   // control flow and the MMA-issue code may live in uniform registers (CUTLASS's canonical_warp_idx_sync trick)
@@ -415,7 +417,7 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
         }
         if (lane == 0) {
           tc::mbar_arrive_expect_tx(&bar_in_full[slot], blk_bytes);
-          tc::bulk_g2s(ring + (size_t)slot * blk_bytes, p.in_planes + ((size_t)tt * ntiles + tile) * blk_bytes, blk_bytes,
+          tc::bulk_g2s(ring + (size_t)slot * blk_bytes, p.in_planes + ((size_t)(tt % p.planes_ring) * ntiles + tile) * blk_bytes, blk_bytes,
                        &bar_in_full[slot]);
         }
         __syncwarp();
@@ -505,7 +507,7 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
       for (int t = pw; t < T; t += kPubWarps) {
         if (!tc::mbar_wait_cta(&bar_pub[t % kPubRing], (uint32_t)((t / kPubRing) & 1))) { alive = false; break; }
         // the epilogue warps' stores of frame t were observed through the mbarrier: fence + relaxed add = release
-        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        if (!p.pub_nofence) asm volatile("fence.acq_rel.gpu;" ::: "memory");
         asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p.out_cnt + t), "r"(1u) : "memory");
         pub_done[pw] = t + 1;
       }
@@ -698,6 +700,7 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
     p.prof[13] = global_ns() - prof_t0;
   }
   trace_end(p.trace, tslot);
+  if (tslot >= 0) p.trace->rec[tslot].c = (int)((clock64() - prof_c0) >> 10);  // SM kilo-cycles of the launch (tools/timeline.py)
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -786,7 +789,7 @@ extern "C" int gsn_recurrence_stream_ctas(int R, int H, int K_in, int fused, int
 }
 
 extern "C" int gsn_recurrence_stream(const float* xproj, const uint32_t* in_bits, const void* in_planes,
-                                     const float* w_ih, int K_in, const float* w_hh, const float* bias,
+                                     int planes_ring, const float* w_ih, int K_in, const float* w_hh, const float* bias,
                                      const float* bn_scale, const float* bn_shift, uint32_t* h_bits, float* h_out,
                                      float* c_out, float* hT, float* cT, const unsigned int* in_cnt,
                                      unsigned int in_target, unsigned int* out_cnt, unsigned long long* spike_count,
@@ -808,6 +811,9 @@ extern "C" int gsn_recurrence_stream(const float* xproj, const uint32_t* in_bits
                 (int)fused);
   RecStreamParams p{};
   p.xproj = xproj; p.in_bits = in_bits; p.in_planes = static_cast<const uint8_t*>(in_planes); p.w_ih = w_ih;
+  p.planes_ring = (planes_ring <= 0 || planes_ring > T) ? T : planes_ring;
+  GSN_REQUIRE(in_mode != kInPlanes || p.planes_ring == T || out_cnt != nullptr,
+              "gsn_recurrence_stream: a ring shorter than T needs out_cnt (the producer's back-pressure)");
   p.w_hh = w_hh; p.bias = bias; p.bn_scale = bn_scale;
   p.bn_shift = bn_shift; p.h_bits = h_bits; p.h_out = h_out; p.c_out = c_out; p.hT = hT; p.cT = cT;
   p.in_cnt = in_cnt; p.in_target = in_target; p.out_cnt = out_cnt; p.spike_count = spike_count;
@@ -815,6 +821,8 @@ extern "C" int gsn_recurrence_stream(const float* xproj, const uint32_t* in_bits
   p.poll_ns = poll_ns;
   static const int direct = getenv("GSN_STREAM_DIRECT") ? atoi(getenv("GSN_STREAM_DIRECT")) : 1;
   p.direct = (direct != 0 && nt == 16) ? 1 : 0;
+  static const int nofence = getenv("GSN_PUB_NOFENCE") ? atoi(getenv("GSN_PUB_NOFENCE")) : 0;
+  p.pub_nofence = nofence;
   p.prof = reinterpret_cast<unsigned long long*>(workspace);
   p.T = T; p.R = R; p.H = H; p.Kmma = (H + 15) / 16 * 16;
   p.K_in = fused ? K_in : 0; p.Kin_mma = fused ? (K_in + 15) / 16 * 16 : 0;

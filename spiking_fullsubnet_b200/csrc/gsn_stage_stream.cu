@@ -28,6 +28,8 @@
 //                      the two warps (a release costs an L2 round trip: it must neither sit on the epilogue's path
 //                      nor be serialised tile after tile).
 // All hand-overs are mbarriers; there is no __syncthreads in the tile loop.
+#include <stdlib.h>
+
 #include "gsn_common.cuh"
 #include "gsn_tc.cuh"
 
@@ -56,6 +58,7 @@ struct StageParams {
   int T, R, K, Kmma, Nout;
   int wpitch, ns;
   int pitch;  // GATHER: scratch row pitch in floats (>= Kmma, pitch % 8 == 4)
+  unsigned int poll_ns;
   TraceBuf* trace;
 };
 
@@ -94,7 +97,7 @@ __device__ __forceinline__ uint32_t sg_ld_cg(const void* p) {
 // Frame counters of a concurrently running producer kernel: frames [0, ready) are known complete; polls the 32 frames
 // from `ready` on (one acquire load per lane) until frame `need` is complete.  Bounded: false on timeout.
 __device__ __forceinline__ bool sg_poll_frames(const unsigned int* cnt, unsigned int target, int T, int& ready, int need,
-                                               int lane) {
+                                               int lane, unsigned int ns) {
   unsigned long long t0 = 0;
   for (unsigned int spins = 0;; ++spins) {
     const int t = ready + lane;
@@ -112,7 +115,7 @@ __device__ __forceinline__ bool sg_poll_frames(const unsigned int* cnt, unsigned
       if (t0 == 0) t0 = now;
       else if (now - t0 > tc::kWaitTimeoutNs) return false;
     }
-    __nanosleep(100);
+    __nanosleep(ns);
   }
 }
 
@@ -313,7 +316,7 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_stage_stream(const StageParam
       if (p.in_cnt != nullptr) {
         const int ml = m0 + NT - 1 < M ? m0 + NT - 1 : M - 1;
         const int t_hi = ml / R;
-        if (ready <= t_hi && !sg_poll_frames(p.in_cnt, p.in_target, p.T, ready, t_hi, lane)) __trap();
+        if (ready <= t_hi && !sg_poll_frames(p.in_cnt, p.in_target, p.T, ready, t_hi, lane, p.poll_ns)) __trap();
       }
       if (MODE == kStageBits) {
         // task = (row, one 32-bit word of its packed trace) -> up to four 16-byte operand chunks; lanes run over the
@@ -554,6 +557,8 @@ static int launch_stage(StageParams p, int ctas_per_slice, cudaStream_t st) {
   if (ns > kSgMaxStages) ns = kSgMaxStages;
   if (ns < 2) return fail(GSN_ENOSUP, "gsn stage stream: K=%d does not fit shared memory", p.K);
   p.ns = ns;
+  static const unsigned int poll_ns = getenv("GSN_POLL_NS") ? (unsigned int)atoi(getenv("GSN_POLL_NS")) : 100u;
+  p.poll_ns = poll_ns;
   const size_t ring = (size_t)ns * stage;
   size_t smem = ((ring > wst ? ring : wst) + 127) / 128 * 128 + extra + (per_stage - stage) * ns;
   if (smem < tc::kTmemExclusiveSmem) smem = tc::kTmemExclusiveSmem;

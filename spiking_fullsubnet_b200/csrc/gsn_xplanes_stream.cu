@@ -15,6 +15,8 @@
 // words, does the LayerNorm (two shuffles per reduction), the split, and three 16-byte stores per chunk (8 lanes fill
 // one 128-byte core matrix).  The publisher issues one gpu-scope release per round of units and adds the rows done to
 // out_cnt[t] (frame complete at R).
+#include <stdlib.h>
+
 #include "gsn_common.cuh"
 #include "gsn_tc.cuh"
 
@@ -33,8 +35,12 @@ struct XpParams {
   const unsigned int* in_cnt;  // [T] or null
   unsigned int in_target;
   unsigned int* out_cnt;       // [T] or null: += rows
+  const unsigned int* bp_cnt;  // [T] or null: the consumer's frame counters (back-pressure of the ring)
+  unsigned int bp_target;
+  int ring;                    // frames the operand-image buffer holds (slot = t % ring); >= T: no reuse
   int T, B, N, lo, ctr, nbr, f_cm, f_fb, K, Kmma, R, nt, pitch;
   float eps;
+  unsigned int poll_ns;
   TraceBuf* trace;
 };
 
@@ -49,7 +55,7 @@ __device__ __forceinline__ uint32_t xp_ld_cg(const void* p) {
 }
 
 __device__ __forceinline__ bool xp_poll_frames(const unsigned int* cnt, unsigned int target, int T, int& ready, int need,
-                                               int lane) {
+                                               int lane, unsigned int ns) {
   unsigned long long t0 = 0;
   for (unsigned int spins = 0;; ++spins) {
     const int t = ready + lane;
@@ -67,7 +73,7 @@ __device__ __forceinline__ bool xp_poll_frames(const unsigned int* cnt, unsigned
       if (t0 == 0) t0 = now;
       else if (now - t0 > tc::kWaitTimeoutNs) return false;
     }
-    __nanosleep(100);
+    __nanosleep(ns);
   }
 }
 
@@ -148,13 +154,17 @@ __global__ void __launch_bounds__(kXpThreads, 1) k_xplanes_stream(const XpParams
       g_base[i] = (g_noisy[i] || p.fb == nullptr) ? p.cm : p.fb;
     }
     const int lo_mod = p.f_fb > 0 ? p.lo % p.f_fb : 0;
-    int ready = 0;  // frames [0, ready) of the input are known complete
+    int ready = 0;     // frames [0, ready) of the input are known complete
+    int ready_bp = 0;  // frames [0, ready_bp) have been consumed downstream (their ring slots are free)
     for (long long k = 0; k < rounds; ++k) {
       const long long u = k * per_round + (long long)blockIdx.x * kXpWorkers + warp;
       if (u < total) {
         const int t = (int)(u / G), g = (int)(u - (long long)t * G);
         const int r0 = g * 8;
-        if (p.in_cnt != nullptr && ready <= t && !xp_poll_frames(p.in_cnt, p.in_target, p.T, ready, t, lane)) __trap();
+        if (p.in_cnt != nullptr && ready <= t && !xp_poll_frames(p.in_cnt, p.in_target, p.T, ready, t, lane, p.poll_ns)) __trap();
+        // ring reuse: slot t % ring still holds frame t - ring until the consumer has finished that frame
+        if (p.bp_cnt != nullptr && t >= p.ring && ready_bp <= t - p.ring &&
+            !xp_poll_frames(p.bp_cnt, p.bp_target, p.T, ready_bp, t - p.ring, lane, p.poll_ns)) __trap();
         {
           // (1) raw features, lanes over the features; rows walk (b, ns) without a division per row
           int rb = r0 / p.N, rn = r0 - rb * p.N;
@@ -242,7 +252,7 @@ __global__ void __launch_bounds__(kXpThreads, 1) k_xplanes_stream(const XpParams
         }
         float* xo = (p.x_out != nullptr && rv) ? p.x_out + ((size_t)t * R + r) * K : nullptr;
         const int tile = r / NT, n = r - tile * NT;  // row tile of the recurrence and the row inside it
-        uint8_t* blk = p.xop + ((size_t)t * ntiles + tile) * 3 * plane_bytes + (size_t)(n >> 3) * SBO + (n & 7) * 16;
+        uint8_t* blk = p.xop + ((size_t)(t % p.ring) * ntiles + tile) * 3 * plane_bytes + (size_t)(n >> 3) * SBO + (n & 7) * 16;
 #pragma unroll
         for (int jc = 0; jc < J; ++jc) {
           const int ch = cg + 4 * jc;
@@ -288,6 +298,8 @@ __global__ void __launch_bounds__(kXpThreads, 1) k_xplanes_stream(const XpParams
 template <int J>
 static int launch_xplanes(XpParams p, int ctas, cudaStream_t st) {
   p.pitch = p.Kmma + 4;  // Kmma % 16 == 0, so pitch % 8 == 4: conflict-free 16-byte reads by 8 consecutive rows
+  static const unsigned int poll_ns = getenv("GSN_POLL_NS") ? (unsigned int)atoi(getenv("GSN_POLL_NS")) : 100u;
+  p.poll_ns = poll_ns;
   const size_t smem = ((size_t)2 * p.Kmma + (size_t)kXpWorkers * 8 * p.pitch) * 4 + 2 * kXpRing * 8 + 64;
   if (smem > tc::kMaxDynamicSmem) return fail(GSN_ENOSUP, "gsn_xplanes_stream: K=%d does not fit shared memory", p.K);
   GSN_CUDA(cudaFuncSetAttribute(k_xplanes_stream<J>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -327,9 +339,10 @@ extern "C" size_t gsn_xplanes_bytes(int T, int R, int K, int nt) {
 }
 
 extern "C" int gsn_xplanes_stream(const float* cm, int f_cm, const float* fb, int f_fb, const float* ln_weight,
-                                  const float* ln_bias, float ln_eps, float* x_out, void* xop,
-                                  const unsigned int* in_cnt, unsigned int in_target, unsigned int* out_cnt, int T,
-                                  int B, int N, int lo, int ctr, int nbr, int nt, int ctas, gsn_stream_t stream) {
+                                  const float* ln_bias, float ln_eps, float* x_out, void* xop, int ring,
+                                  const unsigned int* in_cnt, unsigned int in_target, unsigned int* out_cnt,
+                                  const unsigned int* bp_cnt, unsigned int bp_target, int T, int B, int N, int lo,
+                                  int ctr, int nbr, int nt, int ctas, gsn_stream_t stream) {
   using namespace gsn;
   GSN_REQUIRE(cm && xop, "gsn_xplanes_stream: null pointer");
   GSN_REQUIRE(T > 0 && B > 0 && N > 0 && ctr > 0 && nbr >= 0 && lo >= 0, "gsn_xplanes_stream: bad shape");
@@ -343,12 +356,20 @@ extern "C" int gsn_xplanes_stream(const float* cm, int f_cm, const float* fb, in
   GSN_REQUIRE(!fb || (f_fb > 0 && ctr <= f_fb), "gsn_xplanes_stream: f_fb=%d must be >= ctr=%d", f_fb, ctr);
   GSN_REQUIRE((long long)T * B * (f_cm > f_fb ? f_cm : f_fb) < (1ll << 31), "gsn_xplanes_stream: inputs too large");
   GSN_REQUIRE((ln_weight == nullptr) == (ln_bias == nullptr), "gsn_xplanes_stream: ln params");
+  if (ring <= 0 || ring > T) ring = T;
+  GSN_REQUIRE(ring == T || bp_cnt != nullptr, "gsn_xplanes_stream: a ring shorter than T needs the consumer's counters");
   XpParams p{};
   p.cm = cm; p.fb = fb; p.ln_w = ln_weight; p.ln_b = ln_bias; p.x_out = x_out; p.xop = static_cast<uint8_t*>(xop);
   p.in_cnt = in_cnt; p.in_target = in_target; p.out_cnt = out_cnt;
+  p.bp_cnt = ring < T ? bp_cnt : nullptr; p.bp_target = bp_target; p.ring = ring;
   p.T = T; p.B = B; p.N = N; p.lo = lo; p.ctr = ctr; p.nbr = nbr; p.f_cm = f_cm; p.f_fb = f_fb;
   p.K = K; p.Kmma = (K + 15) / 16 * 16; p.R = B * N; p.nt = nt; p.eps = ln_eps; p.trace = trace_buffer();
   cudaStream_t st = as_stream(stream);
+  // the ring must hold every frame the grid can have in flight (two rounds of units)
+  const int G = (p.R + 7) / 8;
+  const long long n_ctas = ctas < 1 ? 1 : ctas;
+  GSN_REQUIRE(ring == T || (long long)ring * G >= 2 * n_ctas * kXpWorkers + G,
+              "gsn_xplanes_stream: ring=%d frames is too short for %lld CTAs", ring, n_ctas);
   if (p.Kmma <= 64) return launch_xplanes<2>(p, ctas, st);
   if (p.Kmma <= 96) return launch_xplanes<3>(p, ctas, st);
   if (p.Kmma <= 160) return launch_xplanes<5>(p, ctas, st);

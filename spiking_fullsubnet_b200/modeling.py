@@ -86,6 +86,11 @@ class GSUCell(nn.Module):
 
     def forward(self, input, state):
         """One frame (ESN:132-153): input [R,K], state (h [R,H], c [R,H]) -> (h, (h, c))."""
+        if _needs_autograd(self):
+            _autograd_zero_state_only(state, "GSUCell.forward")
+            from . import training
+            h = training.run_cell_layer(self, input.unsqueeze(0).contiguous())
+            return h[0], MemoryState(h[0], None)
         h, c, (hT, cT) = _run_layer(self, input.unsqueeze(0).contiguous(), state, want_c=False,
                                     backend="auto")
         return hT, MemoryState(hT, cT)
@@ -98,6 +103,11 @@ class GSULayer(nn.Module):
 
     def forward(self, input, state):
         """input [T,R,K] -> (h [T,R,H], final state) (ESN:75-81) -- one kernel, no Python time loop."""
+        if _needs_autograd(self):
+            _autograd_zero_state_only(state, "GSULayer.forward")
+            from . import training
+            h = training.run_cell_layer(self.cell, input.contiguous())
+            return h, MemoryState(h[-1], None)
         h, _, (hT, cT) = _run_layer(self.cell, input, state, want_c=False, backend="auto")
         return h, MemoryState(hT, cT)
 
@@ -133,6 +143,17 @@ def _sm_budgets(demands, total=148, floor=4):
     if sum(demands) <= total:
         return [0] * len(demands)
     return [max(floor, int(total * d / sum(demands))) for d in demands]
+
+
+def _autograd_zero_state_only(state, who):
+    """The autograd kernels (training.GSNLayerFn) start every sequence from a zero state, which is what every caller
+    of the reference passes (MSF:100-106).  Anything else must not be silently ignored."""
+    if state is None:
+        return
+    h, c = state[0], state[1]
+    if (h is not None and bool((h != 0).any())) or (c is not None and bool((c != 0).any())):
+        raise NotImplementedError(f"{who}: a non-zero initial state is not supported on the autograd (training) path; "
+                                  f"call it under torch.no_grad() with eval-mode BatchNorm, or start from zeros")
 
 
 def _needs_autograd(module):
@@ -176,6 +197,8 @@ class StackedGSU(nn.Module):
         if _needs_autograd(self):
             # training path: zero initial state (what every caller of the reference passes, MSF:100-106)
             from . import training
+            for st in (states or []):
+                _autograd_zero_state_only(st, "StackedGSU.forward")
             out, trace = training.run_stack(self, input.contiguous())
             self.last_c = [None] * len(self.layers)
             self.last_bits = None
@@ -257,6 +280,11 @@ class SequenceModel(nn.Module):
             raise RuntimeError("spiking_fullsubnet_b200 has no CPU path: move the model and input to CUDA")
         R, K, T = input.shape
         cm = input.permute(2, 0, 1).contiguous()  # 'b f t -> t b f'
+        if _needs_autograd(self):  # differentiable LayerNorm / projections, autograd recurrence kernels
+            from . import training
+            x = self.pre_layer_norm(cm) if self.use_pre_layer_norm else cm
+            act, all_out = training.run_sequence_model(self, x.contiguous())
+            return act.permute(1, 2, 0), all_out
         lnw = self.pre_layer_norm.weight.detach() if self.use_pre_layer_norm else None
         lnb = self.pre_layer_norm.bias.detach() if self.use_pre_layer_norm else None
         eps = self.pre_layer_norm.eps if self.use_pre_layer_norm else 1e-5
@@ -422,6 +450,9 @@ class SubbandModel(nn.Module):
     def run_time_major(self, cm, fb):
         """cm [T,B,F] compressed magnitude, fb [T,B,f_fb] full-band output (tiled by index) ->
         list of proj outputs [T, B*N_i, P_i] and the per-band all_layer_outputs (MSF:216-263)."""
+        if _needs_autograd(self):  # differentiable gather / LayerNorm / projections, autograd recurrence kernels
+            from . import training
+            return training.run_subband_model(self, cm, fb)
         T, B, F = cm.shape
         for i in range(len(self.sb_models)):
             lo, hi, ctr = self.freq_cutoffs[i], self.freq_cutoffs[i + 1], self.center_freq_sizes[i]
@@ -806,6 +837,7 @@ class SpikingFullSubNet(_GraphedNetwork, nn.Module):
     #   gsn_xplanes_stream: (0.009 + 0.00028 Kmma) us per row per CTA;
     #   tcgen05 stages: ~75 cycles per MMA at 64-row tiles (3 planes for spike inputs, 8 plane pairs for real inputs)
     _STREAM_TARGET_US = 1.0   # helper stages must be faster than the recurrences' frame time (1.2 - 1.3 us)
+    _XOP_RING = 64            # frames of layer-0 operand images kept (ring; S: 64 x 202 KB = 13 MB, L2-resident)
 
     @staticmethod
     def _xplanes_ctas(R, K, target):
@@ -887,10 +919,13 @@ class SpikingFullSubNet(_GraphedNetwork, nn.Module):
                 m = d["m"]
                 budget = ((d["R"] + d["nt"] - 1) // d["nt"]) * d["C"]
                 nt0 = ops.stream_tile(d["R"], m.hidden_size, m.input_size, True, budget)
-                key = (mi, T, d["R"], m.input_size, nt0, dev.index)
+                # a RING of frames (the layer-0 recurrence's out counters are the producer's back-pressure): the images
+                # are consumed microseconds after they are written and never need to reach DRAM
+                ring = min(T, int(os.environ.get("GSN_XOP_RING", self._XOP_RING)))
+                key = (mi, ring, d["R"], m.input_size, nt0, dev.index)
                 if key not in keep:
-                    keep[key] = ops.xplanes_buffer(T, d["R"], m.input_size, nt0, dev)
-                d["xop"], d["nt0"] = keep[key], nt0
+                    keep[key] = ops.xplanes_buffer(ring, d["R"], m.input_size, nt0, dev)
+                d["xop"], d["nt0"], d["ring"] = keep[key], nt0, ring
         # folded BatchNorm affines are (re)computed by torch kernels on the main stream while a graph is captured: they
         # must precede the fork too.  `hold` keeps every buffer of this call alive until the next one, so that the
         # caching allocator cannot hand a block to a later allocation while a concurrently running stage still uses it
@@ -932,14 +967,16 @@ class SpikingFullSubNet(_GraphedNetwork, nn.Module):
             geo = (d["N"], d["lo"], d["ctr"], d["nbr"])
             fbt = fb_act if d["fb"] else None
             c_pre = counters[next(nxt)]
+            c_l0 = counters[next(nxt)]  # out counters of the layer-0 recurrence
             pre_in = dict(in_cnt=fb_cnt if d["fb"] else None, in_target=fb_target)
             w_ih0 = cells[0].weight_ih.detach()
             if d["fused0"]:
                 xop, nt0 = d["xop"], d["nt0"]
                 xproj = None
+                bp = dict(ring=d["ring"], bp_cnt=c_l0, bp_target=ops.stream_ctas(R, H, K, True, budget))
                 pre = (lambda geo=geo, fbt=fbt, nt0=nt0, xop=xop, w_ln=w_ln, b_ln=b_ln, e_ln=e_ln, x_out=x_out, c_pre=c_pre,
-                       pre_in=pre_in, d=d: ops.xplanes_stream(cm, fbt, *geo, nt0, xop, w_ln, b_ln, e_ln, out_x=x_out,
-                                                               out_cnt=c_pre, ctas=d["pre_p"], **pre_in))
+                       pre_in=pre_in, d=d, bp=bp: ops.xplanes_stream(cm, fbt, *geo, nt0, xop, w_ln, b_ln, e_ln, out_x=x_out,
+                                                                      out_cnt=c_pre, ctas=d["pre_p"], **pre_in, **bp))
                 pre_target = R
             else:
                 xop = None
@@ -958,21 +995,22 @@ class SpikingFullSubNet(_GraphedNetwork, nn.Module):
                 a, b = d["bn"][l]
                 bits = ops.spike_bits_buffer((T, R), H, dev)
                 h_out = torch.empty((T, R, H), **f32) if strict else None
-                c_out = counters[next(nxt)]
+                c_out = c_l0 if l == 0 else counters[next(nxt)]
                 kw = dict(out_bits=bits, out_h=h_out, out_cnt=c_out, sm_budget=budget, in_cnt=in_cnt, in_target=in_target)
                 w_hh, bias = cell.weight_hh.detach(), cell.bias_ih.detach()
                 fused = ly["fused"] or (l == 0 and d["fused0"])
                 if record is not None:
                     # the same launch without counters (its inputs are complete once this step has run): timed alone
                     kin = (K if l == 0 else H) if fused else 0
-                    ins = (dict(in_planes=xop, w_ih=w_ih0, frames_rows=(T, R)) if (l == 0 and d["fused0"]) else
+                    ins = (dict(in_planes=xop, w_ih=w_ih0, frames_rows=(T, R), planes_ring=d["ring"]) if (l == 0 and d["fused0"]) else
                            dict(in_bits=bits_prev, w_ih=cell.weight_ih.detach()) if ly["fused"] else None)
                     record.append(dict(model=mi, layer=l, T=T, R=R, H=H, K_in=kin, fused=fused,
                                        flops=2.0 * T * R * H * (H + kin), w_hh=w_hh, bias=bias, a=a, b=b, ins=ins,
-                                       out_bits=bits, budget=budget))
+                                       out_bits=bits, budget=budget, out_cnt=c_out))
                 if l == 0 and d["fused0"]:
-                    on_stream(lambda w_hh=w_hh, bias=bias, a=a, b=b, kw=kw, xop=xop, w_ih0=w_ih0, R=R:
-                              ops.recurrence_stream(w_hh, bias, a, b, in_planes=xop, w_ih=w_ih0, frames_rows=(T, R), **kw))
+                    on_stream(lambda w_hh=w_hh, bias=bias, a=a, b=b, kw=kw, xop=xop, w_ih0=w_ih0, R=R, ring=d["ring"]:
+                              ops.recurrence_stream(w_hh, bias, a, b, in_planes=xop, w_ih=w_ih0, frames_rows=(T, R),
+                                                    planes_ring=ring, **kw))
                 elif l == 0:
                     if record is not None:
                         record[-1]["ins"] = dict(xproj=xproj)
@@ -1222,9 +1260,13 @@ def _utterance_norm(x, B, norm_type):
         std = v.permute(1, 0, 2).reshape(B, -1).std(dim=1).view(1, B, 1)
         return ((v - mu) / (std + EPSILON)).view_as(x)
     if norm_type == "cumulative_laplace_norm":
-        raise NotImplementedError(
-            "cumulative_laplace_norm: the reference itself fails on the 5-D sub-band input "
-            "(model_low_freq.py:181, SURVEY 7.3-7); the zoo checkpoints use offline_laplace_norm")
+        # model_low_freq_count_time.py:173-204 (the variant of the recipe directory that accepts the 5-D sub-band
+        # input; model_low_freq.py:181 unpacks four dims and fails on it): every row [B*N] is divided by the mean of
+        # ITS OWN K features over the frames 0..t -- causal, so the sub-band models can follow the full-band one
+        K = x.shape[2]
+        cum = torch.cumsum(x.sum(dim=2), dim=0)                                        # [T, R]
+        count = torch.arange(K, K * T + 1, K, dtype=x.dtype, device=x.device).view(T, 1)
+        return x / ((cum / count).unsqueeze(-1) + EPSILON)
     raise NotImplementedError("You must set up a type of Norm. e.g. offline_laplace_norm, "
                               "cumulative_laplace_norm, forgetting_norm, etc.")
 

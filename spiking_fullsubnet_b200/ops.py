@@ -225,7 +225,7 @@ def stream_ctas(R, H, K_in=0, fused=False, sm_budget=0):
 
 def recurrence_stream(w_hh, bias, bn_scale=None, bn_shift=None, xproj=None, in_bits=None, w_ih=None, out_bits=None,
                       out_h=None, out_c=None, out_hT=None, out_cT=None, in_cnt=None, in_target=0, out_cnt=None,
-                      spike_count=None, sm_budget=0, workspace=None, in_planes=None, frames_rows=None):
+                      spike_count=None, sm_budget=0, workspace=None, in_planes=None, frames_rows=None, planes_ring=0):
     """One GSULayer over all frames as a persistent streaming launch (gsn_recurrence_stream): zero initial state,
     shared gate weights.  Input: xproj [T,R,H], OR (in_bits [T,R,ceil(K/32)] int32, w_ih [H,K]) for the fused
     spike-input product, OR (in_planes = the operand images of `xplanes_stream`, w_ih [H,K], frames_rows = (T, R)) for
@@ -248,8 +248,9 @@ def recurrence_stream(w_hh, bias, bn_scale=None, bn_shift=None, xproj=None, in_b
         T, R = frames_rows
         K_in = w_ih.shape[1]
         nt = lib.gsn_recurrence_stream_tile(R, H, K_in, 1, int(sm_budget))
+        ring = T if (planes_ring <= 0 or planes_ring > T) else int(planes_ring)
         if w_ih.shape[0] != H or nt == 0 or in_planes.numel() * in_planes.element_size() < lib.gsn_xplanes_bytes(
-                T, R, K_in, nt):
+                ring, R, K_in, nt):
             raise ValueError("recurrence_stream: in_planes / w_ih shapes")
     Wb = (H + 31) // 32
     if out_bits is None:
@@ -260,7 +261,8 @@ def recurrence_stream(w_hh, bias, bn_scale=None, bn_shift=None, xproj=None, in_b
         if cnt is not None and (cnt.dtype != torch.int32 or cnt.numel() != T or not cnt.is_contiguous()):
             raise ValueError("recurrence_stream: counters must be contiguous int32 [T]")
     _lib.check(lib.gsn_recurrence_stream(
-        _ptr(xproj), _ptr(in_bits), _ptr(in_planes), _ptr(w_ih), int(K_in), _ptr(w_hh), _ptr(bias), _ptr(bn_scale),
+        _ptr(xproj), _ptr(in_bits), _ptr(in_planes), int(planes_ring), _ptr(w_ih), int(K_in), _ptr(w_hh), _ptr(bias),
+        _ptr(bn_scale),
         _ptr(bn_shift), out_bits.data_ptr(), _ptr(out_h), _ptr(out_c), _ptr(out_hT), _ptr(out_cT), _ptr(in_cnt),
         int(in_target), _ptr(out_cnt), _ptr(spike_count), T, R, H, int(sm_budget), _ptr(workspace), st))
     LAUNCHES[0] += 1
@@ -268,7 +270,8 @@ def recurrence_stream(w_hh, bias, bn_scale=None, bn_shift=None, xproj=None, in_b
 
 
 def xplanes_buffer(T, R, K, nt, device):
-    """Zeroed operand-image buffer of `xplanes_stream` (uint8, 128-byte aligned by the caching allocator)."""
+    """Zeroed operand-image buffer of `xplanes_stream` for T frames (or a ring of T frames; uint8, 128-byte aligned by
+    the caching allocator)."""
     n = _lib.load().gsn_xplanes_bytes(int(T), int(R), int(K), int(nt))
     if n == 0:
         raise ValueError(f"xplanes_buffer: bad shape T={T} R={R} K={K} nt={nt}")
@@ -276,19 +279,21 @@ def xplanes_buffer(T, R, K, nt, device):
 
 
 def xplanes_stream(cm, fb, N, lo, ctr, nbr, nt, xop, ln_weight=None, ln_bias=None, eps=1e-5, out_x=None, in_cnt=None,
-                   in_target=0, out_cnt=None, ctas=1):
+                   in_target=0, out_cnt=None, ctas=1, ring=0, bp_cnt=None, bp_target=0):
     """Streaming gather + LayerNorm + bf16x3 split of a sequence model's layer-0 input into the B-operand images the
     fused layer-0 recurrence reads (gsn_xplanes_stream).  `xop` from `xplanes_buffer` (same nt)."""
     lib, st = _prep(cm, fb, ln_weight, ln_bias, out_x)
     T, B, f_cm = cm.shape
     K = ctr + 2 * nbr + (ctr if fb is not None else 0)
-    if xop.dtype != torch.uint8 or xop.numel() < lib.gsn_xplanes_bytes(T, B * N, K, nt) or xop.device != cm.device:
+    frames = T if (ring <= 0 or ring > T) else int(ring)
+    if xop.dtype != torch.uint8 or xop.numel() < lib.gsn_xplanes_bytes(frames, B * N, K, nt) or xop.device != cm.device:
         raise ValueError("xplanes_stream: xop buffer")
     if out_x is not None and tuple(out_x.shape) != (T, B * N, K):
         raise ValueError("xplanes_stream: out_x shape")
     _lib.check(lib.gsn_xplanes_stream(_ptr(cm), f_cm, _ptr(fb), fb.shape[2] if fb is not None else 0, _ptr(ln_weight),
-                                      _ptr(ln_bias), float(eps), _ptr(out_x), xop.data_ptr(), _ptr(in_cnt),
-                                      int(in_target), _ptr(out_cnt), T, B, N, lo, ctr, nbr, int(nt), int(ctas), st))
+                                      _ptr(ln_bias), float(eps), _ptr(out_x), xop.data_ptr(), int(ring), _ptr(in_cnt),
+                                      int(in_target), _ptr(out_cnt), _ptr(bp_cnt), int(bp_target), T, B, N, lo, ctr,
+                                      nbr, int(nt), int(ctas), st))
     LAUNCHES[0] += 1
     return xop
 

@@ -72,6 +72,13 @@ def unfold_index(lo, hi, ctr, nbr, num_freqs, device):
     return q
 
 
+def run_cell_layer(cell, x):
+    """One GSULayer (ESN:75-81) with autograd from a zero state: x [T,R,K] -> h [T,R,H]."""
+    bn = cell.batchnorm if cell.use_bn else None
+    return GSNLayerFn.apply(F.linear(x, cell.weight_ih), cell.weight_hh, cell.bias_ih,
+                            bn.weight if bn is not None else None, bn.bias if bn is not None else None, cell)
+
+
 def run_stack(stack, x):
     """StackedGSU.forward (ESN:50-62) with autograd: x [T,R,K] -> (out, all_layer_output)."""
     trace = [x]
@@ -142,6 +149,28 @@ def _tensors(obj):
             yield from _tensors(o)
 
 
+def run_subband_model(sbm, cm, fb_act):
+    """SubbandModel (MSF:216-263) with autograd on time-major tensors: cm [T,B,F] compressed magnitude, fb_act
+    [T,B,f_fb] full-band output (tiled by index, MSF:443) -> (activated outputs [T, B*N_i, P_i], all_layer_outputs)."""
+    T, B, Fq = cm.shape
+
+    def band(i, m):
+        lo, hi = sbm.freq_cutoffs[i], sbm.freq_cutoffs[i + 1]
+        ctr, nbr = sbm.center_freq_sizes[i], sbm.neighbor_freq_sizes[i]
+        qi = unfold_index(lo, hi, ctr, nbr, Fq, cm.device)          # [N, ctr+2nbr]
+        qf = unfold_index(lo, hi, ctr, 0, Fq, cm.device) % fb_act.shape[2]  # tiled full-band output (MSF:443)
+        N = qi.shape[0]
+        xb = torch.cat([cm[:, :, qi], fb_act[:, :, qf]], dim=-1).reshape(T, B * N, -1)
+        if m.use_pre_layer_norm:
+            xb = m.pre_layer_norm(xb)
+        return run_sequence_model(m, xb.contiguous())
+
+    # the sub-band models are independent: one stream each, forward AND backward (autograd replays every
+    # backward node on the stream of its forward), so their latency-bound recurrence kernels overlap
+    res = _fork_join(cm.device, [lambda i=i, m=m: band(i, m) for i, m in enumerate(sbm.sb_models)])
+    return [r[0] for r in res], [r[1] for r in res]
+
+
 def spiking_fullsubnet_forward(model, wave):
     """SpikingFullSubNet.forward (MSF:415-474) on the autograd path."""
     from .modeling import _istft, _stft, coef_layout
@@ -155,28 +184,9 @@ def spiking_fullsubnet_forward(model, wave):
     if fbm.use_pre_layer_norm:
         x = fbm.pre_layer_norm(x)
     fb_act, fb_all = run_sequence_model(fbm, x.contiguous())
-    sbm = model.sb_model
-    T = cm.shape[0]
     S = model.num_spks
-    coefs, sb_all = [], []
-
-    def band(i, m):
-        lo, hi = sbm.freq_cutoffs[i], sbm.freq_cutoffs[i + 1]
-        ctr, nbr = sbm.center_freq_sizes[i], sbm.neighbor_freq_sizes[i]
-        qi = unfold_index(lo, hi, ctr, nbr, Fq, cm.device)          # [N, ctr+2nbr]
-        qf = unfold_index(lo, hi, ctr, 0, Fq, cm.device) % fb_act.shape[2]  # tiled full-band output (MSF:443)
-        N = qi.shape[0]
-        xb = torch.cat([cm[:, :, qi], fb_act[:, :, qf]], dim=-1).reshape(T, B * N, -1)
-        if m.use_pre_layer_norm:
-            xb = m.pre_layer_norm(xb)
-        act, trace = run_sequence_model(m, xb.contiguous())
-        return coef_layout(act, B, N, sbm.df_orders[i], S), trace
-
-    # the sub-band models are independent: one stream each, forward AND backward (autograd replays every
-    # backward node on the stream of its forward), so their latency-bound recurrence kernels overlap
-    for c, tr in _fork_join(cm.device, [lambda i=i, m=m: band(i, m) for i, m in enumerate(sbm.sb_models)]):
-        coefs.append(c)
-        sb_all.append(tr)
+    acts, sb_all = run_subband_model(model.sb_model, cm, fb_act)
+    coefs = [coef_layout(a, B, a.shape[1] // B, d, S) for a, d in zip(acts, model.sb_model.df_orders)]
     enh, lo = [], 0
     for coef, order in zip(coefs, model.df_orders):
         nf = coef.shape[3]

@@ -109,9 +109,11 @@ def run_surface_a(name, cfg, seed, batch, num_samples, with_c):
     print(name, {k: (v.shape if hasattr(v, "shape") else v) for k, v in d.items() if k != "cfg"})
 
 
-def run_surface_b(name, cfg, params, seed, batch, num_samples, store_weights=False):
-    """Surface B `Separator` (recipes/.../model_low_freq.py:485-618)."""
-    import model_low_freq as MLF  # noqa: E402  (reference module, imported from the recipe directory)
+def run_surface_b(name, cfg, params, seed, batch, num_samples, store_weights=False, module="model_low_freq"):
+    """Surface B `Separator` (recipes/.../model_low_freq.py:485-618).  module="model_low_freq_count_time" is the
+    variant of the same recipe directory whose cumulative_laplace_norm accepts the 5-D sub-band input (:173-204)."""
+    import importlib
+    MLF = importlib.import_module(module)  # reference module, imported from the recipe directory
     torch.manual_seed(0)
     model = MLF.Separator(**cfg)
     load_params(model, params)
@@ -317,6 +319,9 @@ if __name__ == "__main__":
     # surface B: tiny structural fixture + the TRAINED model-zoo S checkpoint on a 1 s clip (protocol P3)
     cfgb = synth.tiny_cfg_b()
     run_surface_b("tiny_surface_b", cfgb, synth.make_params_b(cfgb, 105), 105, 2, 16 * 33)
+    cfgc = synth.tiny_cfg_b(norm_type="cumulative_laplace_norm")  # recipes .../baseline_{s,l}.toml:63 select this norm
+    run_surface_b("tiny_surface_b_cumnorm", cfgc, synth.make_params_b(cfgc, 107), 107, 2, 16 * 33,
+                  module="model_low_freq_count_time")
     zoo = torch.load(REF + "/model_zoo/intel_ndns/spike_fsb/baseline_s/checkpoints/best/pytorch_model.bin",
                      map_location="cpu")
     run_surface_b("zoo_s_1s", synth.CFG_ZOO_S, {k: v.numpy() for k, v in zoo.items()}, 106, 2, 16000,

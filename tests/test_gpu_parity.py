@@ -232,7 +232,7 @@ def test_cuda_graph_replay_matches_eager():
 
 
 @pytest.mark.parametrize("backend", BACKENDS)
-@pytest.mark.parametrize("name", ["tiny_surface_b", "zoo_s_1s"])
+@pytest.mark.parametrize("name", ["tiny_surface_b", "tiny_surface_b_cumnorm", "zoo_s_1s"])
 def test_surface_b_vs_golden(name, backend):
     """Surface B `Separator`: tiny fixture and the TRAINED model-zoo S checkpoint (loads strict=True).
     Trained weights are chaotic (protocol P3): spike flips are bounded by the reference's own
@@ -678,3 +678,48 @@ def test_wavefront_graph_matches_eager_at_full_size_S():
         for _ in range(2):
             out = m.network(mag)[0]
             assert all(torch.equal(a, b) for a, b in zip(out, eager))
+
+
+def test_exported_submodules_are_autograd_safe():
+    """The drop-in sub-modules (SequenceModel / SubbandModel / GSULayer / GSUCell) route to the autograd kernels when
+    gradients are recorded: outputs carry a grad_fn, EVERY parameter (pre-LayerNorm and proj included) receives a
+    gradient, eval-mode results equal the inference kernels', and a non-zero initial state is refused instead of being
+    silently ignored."""
+    from spiking_fullsubnet_b200.modeling import GSUCell, GSULayer, SequenceModel, SubbandModel
+    torch.manual_seed(0)
+    sm = SequenceModel(input_size=12, hidden_size=40, num_layers=2, sequence_model="GSN", proj_size=6,
+                       shared_weights=True, output_activate_function="tanh", bn=True, use_pre_layer_norm=True).to(DEV)
+    x = torch.randn(5, 12, 30, device=DEV)
+    sm.train()
+    out, all_out = sm(x)
+    assert out.grad_fn is not None and out.shape == (5, 6, 30) and len(all_out) == 4
+    out.square().mean().backward()
+    missing = [n for n, p in sm.named_parameters() if p.grad is None or not torch.isfinite(p.grad).all()]
+    assert not missing, f"no gradient for {missing}"
+    sm.eval()
+    with torch.no_grad():
+        ref, _ = sm(x)
+    out_eval, _ = sm(x)  # eval BatchNorm, gradients on: autograd kernels with running statistics
+    assert out_eval.grad_fn is not None
+    # (F.linear / cuBLAS vs the fp32 FFMA kernel: a near-threshold spike may flip and move a few outputs)
+    assert float(((out_eval - ref).abs() > 1e-4).float().mean()) < 0.02
+
+    sb = SubbandModel(freq_cutoffs=[0, 8, 24, 32], center_freq_sizes=[2, 4, 8], neighbor_freq_sizes=[3, 3, 3],
+                      df_orders=[3, 2, 1], num_spks=1, hidden_size=40, num_layers=2, shared_weights=True,
+                      sequence_model="GSN", bn=True, use_pre_layer_norm=True).to(DEV).train()
+    noisy = torch.rand(2, 1, 32, 20, device=DEV)
+    fbo = torch.randn(2, 1, 32, 20, device=DEV)
+    coefs, traces = sb(noisy, fbo)
+    assert all(c.grad_fn is not None for c in coefs) and len(traces) == 3
+    sum(c.square().mean() for c in coefs).backward()
+    missing = [n for n, p in sb.named_parameters() if p.grad is None]
+    assert not missing, f"no gradient for {missing}"
+
+    layer = GSULayer(GSUCell, 12, 40, True, True).to(DEV).train()
+    xin = torch.randn(7, 5, 12, device=DEV)
+    h, st = layer(xin, None)
+    assert h.grad_fn is not None and h.shape == (7, 5, 40)
+    with pytest.raises(NotImplementedError):
+        layer(xin, (torch.ones(5, 40, device=DEV), torch.zeros(5, 40, device=DEV)))
+    h1, _ = layer.cell(xin[0], (torch.zeros(5, 40, device=DEV), torch.zeros(5, 40, device=DEV)))
+    assert h1.grad_fn is not None and h1.shape == (5, 40)

@@ -118,7 +118,7 @@ def test_deepfilter_and_backward_consistency():
     assert abs(y[1, 0, f, t] - want) < 1e-12
 
 
-@pytest.mark.parametrize("name", ["tiny_surface_b", "zoo_s_1s"])
+@pytest.mark.parametrize("name", ["tiny_surface_b", "tiny_surface_b_cumnorm", "zoo_s_1s"])
 def test_surface_b_network(name):
     """Surface B (`Separator`, offline laplace norm); `zoo_s_1s` uses the TRAINED model-zoo S checkpoint.
     With trained weights the path is chaotic: numpy-vs-MKL summation order may flip a
