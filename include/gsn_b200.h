@@ -123,6 +123,28 @@ GSN_API int gsn_layer_recurrence_bits(const float* xproj, const float* w_hh, con
                          const float* c0, float* h_out, float* c_out, float* hT, float* cT, uint32_t* h_bits,
                          int T, int R, int H, int shared, int backend, int sm_budget, void* workspace,
                          gsn_stream_t stream);
+/* ---- spectral front / back end on the COMPLEX STFT (gsn_spectral.cu; interleaved re/im as torch.stft returns it) ----
+ * gsn_compress_spec   : cm[t, b, f] = |spec[b, f, t]|^fdrc for f < f_keep (MSF:434-436 + "b f t -> t b f", MSF:108);
+ *                       spec_ri [B, F, T, 2].  Same result as torch.abs + gsn_compress_mag without the |stft| tensor.
+ * gsn_deepfilter_spec : gsn_deepfilter_band with complex in / complex out: out_ri [B, S, F_out, T, 2]; layout 0 = proj
+ *                       features ordered (c fc df s) (MSF:160-167), 1 = (c df s fc) (cirm_gsn, CGN:230).
+ * gsn_spec_passthrough: out[b, s, f, t] = spec[b, f, t] for f in [f_lo, F): the bins no band filters (MSF:461-468).
+ * time_major != 0     : the spectra are [B, T, F] / [B, S, T, F_out] -- the layout cuFFT reads and writes (torch.stft
+ *                       returns a transposed VIEW of it), so the whole forward() runs without a transpose copy.
+ * gsn_overlap_add     : synthesis half of torch.istft(center=True) (audio_feature.py:297-347): frames [B, T, n_fft] =
+ *                       inverse real FFT of every frame (unwindowed), window [n_fft]; y[b, s] = sum over the frames
+ *                       covering sample s + n_fft/2 of frame * window, divided by the overlap-added squared window;
+ *                       samples past the last frame are zero.  y [B, length].                                    */
+GSN_API int gsn_compress_spec(const float* spec_ri, float* cm, int B, int F, int f_keep, int T, float fdrc,
+                              int time_major, gsn_stream_t stream);
+GSN_API int gsn_deepfilter_spec(const float* proj, const float* spec_ri, float* out_ri, int T, int B, int N, int ctr,
+                                int df, int S, int lo, int F, int F_out, int layout, int time_major,
+                                gsn_stream_t stream);
+GSN_API int gsn_spec_passthrough(const float* spec_ri, float* out_ri, int T, int B, int S, int f_lo, int F, int F_out,
+                                 int time_major, gsn_stream_t stream);
+GSN_API int gsn_overlap_add(const float* frames, const float* window, float* y, int B, int T, int n_fft, int hop,
+                            int length, gsn_stream_t stream);
+
 /* ---- streaming recurrence (gsn_recurrence_stream.cu): StackedGSU.forward ESN:50-62 as a frame-granular pipeline ---
  * One persistent, warp-specialised tcgen05 launch runs GSULayer.forward (ESN:75-81) of one layer for all T frames
  * from a ZERO initial state (MSF:100-106), shared gate weights only, and is chained to concurrently running producer /

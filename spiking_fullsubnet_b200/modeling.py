@@ -554,6 +554,40 @@ def _istft_nosync(spec, n_fft, hop, win, length):
     return out
 
 
+_HANN = {}
+
+
+def _empty_spec_like(cmp, S):
+    """Uninitialised enhanced spectrum [B,S,F,T] in the layout of `cmp` [B,F,T] (torch.stft's result is a transposed
+    view of cuFFT's [B,T,F]: keeping that layout end to end avoids every transpose copy up to the inverse FFT)."""
+    B, F, T = cmp.shape
+    if cmp.is_contiguous():
+        return torch.empty((B, S, F, T), dtype=cmp.dtype, device=cmp.device)
+    return torch.empty((B, S, T, F), dtype=cmp.dtype, device=cmp.device).transpose(2, 3)
+
+
+def _merge_speakers(enh):
+    """[B,S,F,T] -> [B*S,F,T] without a copy in either layout."""
+    B, S, F, T = enh.shape
+    if enh.is_contiguous():
+        return enh.reshape(B * S, F, T)
+    return enh.transpose(2, 3).reshape(B * S, T, F).transpose(1, 2)
+
+
+def _istft_fused(spec, n_fft, hop, win, length):
+    """torch.istft(center=True, hann window, normalized=False), asynchronous and graph-capturable: cuFFT inverse real
+    FFT of every frame, then ONE kernel (gsn_overlap_add) for synthesis window, overlap-add, division by the
+    overlap-added squared window and removal of the centre padding (audio_feature.py:297-347).
+    spec complex [B,F,T] -> [B,length]."""
+    assert win == n_fft, "win_length != n_fft is not used by any recipe"
+    key = (n_fft, spec.device.index)
+    window = _HANN.get(key)
+    if window is None:
+        window = _HANN[key] = torch.hann_window(n_fft, device=spec.device)
+    frames = torch.fft.irfft(spec.transpose(1, 2), n=n_fft, dim=-1).contiguous()      # [B,T,n_fft]; no copy when time-major
+    return ops.overlap_add(frames, window, hop, length)
+
+
 class _GraphedNetwork:
     """CUDA-graph replay of `network()` for the drop-in models: `_network(mag)` is the eager launch sequence,
     `_network_sched(mag)` what gets captured (subclasses may substitute a different schedule)."""
@@ -593,10 +627,10 @@ class _GraphedNetwork:
                     return res
             return self._network(mag)
         graphs = self.__dict__.setdefault("_graphs", {})
-        key = ("network", tuple(mag.shape), mag.device.index)
+        key = ("network", tuple(mag.shape), mag.dtype, mag.device.index)
         entry = graphs.get(key)
         if entry is None:
-            static_in = torch.empty_like(mag, memory_format=torch.contiguous_format)
+            static_in = torch.empty_like(mag)  # keeps the strides (a complex STFT may be time-major, ops._spec_layout)
             static_in.copy_(mag)
             with torch.no_grad():
                 self._network(static_in)  # warm-up outside the capture (lazy CUDA initialisation)
@@ -650,7 +684,7 @@ class SpikingFullSubNet(_GraphedNetwork, nn.Module):
     # network(mag [B, n_fft//2+1, T]) -> (projs: list of [T, B*N_i, P_i], fb_all, sb_all); see _GraphedNetwork.
     def _network(self, mag):
         F = mag.shape[1]
-        cm = ops.compress_mag(mag.contiguous(), F - 1, self.fdrc)  # drops the last bin, MSF:436
+        cm = ops.compress_mag(mag if mag.is_complex() else mag.contiguous(), F - 1, self.fdrc)  # drops the last bin, MSF:436
         fbm = self.fb_model
         lnw = fbm.pre_layer_norm.weight.detach() if fbm.use_pre_layer_norm else None
         lnb = fbm.pre_layer_norm.bias.detach() if fbm.use_pre_layer_norm else None
@@ -701,7 +735,7 @@ class SpikingFullSubNet(_GraphedNetwork, nn.Module):
         rep = (self.n_fft // 2 + 1) // self.fb_input_size
         if rep * fbm.proj_size < F - 1 and isinstance(fbm.proj, nn.Linear):
             raise ValueError(f"full-band output ({fbm.proj_size} bins x {rep}) does not cover {F - 1} bins")
-        cm = ops.compress_mag(mag.contiguous(), F - 1, self.fdrc)
+        cm = ops.compress_mag(mag if mag.is_complex() else mag.contiguous(), F - 1, self.fdrc)
         backend = fbm.sequence_model.backend
         fbp = _SeqPlan(fbm, T, B, nchunks, dev, backend)
         geo, sbps = [], []
@@ -904,7 +938,7 @@ class SpikingFullSubNet(_GraphedNetwork, nn.Module):
         strict = self.strict_outputs
         ops.stream_preload(dev)
         main = torch.cuda.current_stream(dev)
-        cm = ops.compress_mag(mag.contiguous(), F - 1, self.fdrc)
+        cm = ops.compress_mag(mag if mag.is_complex() else mag.contiguous(), F - 1, self.fdrc)
         f32 = dict(device=dev, dtype=torch.float32)
         ncnt = sum(2 + 2 * len(d["layers"]) for d in models)
         counters = ops.frame_counters(T, dev, ncnt)
@@ -1110,29 +1144,28 @@ class SpikingFullSubNet(_GraphedNetwork, nn.Module):
         """enh complex [B,S,F,T] -> the reference's return tuple (iSTFT, MSF:463-474)."""
         B, S, F, T = enh.shape
         if S > 1:
-            y = _istft_nosync(enh.reshape(B * S, F, T), self.n_fft, self.hop_length, self.win_length, L)
+            y = _istft_fused(_merge_speakers(enh), self.n_fft, self.hop_length, self.win_length, L)
             return y.reshape(B, S, L), fb_all, sb_all
         enh = enh[:, 0]
-        return _istft_nosync(enh, self.n_fft, self.hop_length, self.win_length, L), enh.abs(), fb_all, sb_all
+        return _istft_fused(enh, self.n_fft, self.hop_length, self.win_length, L), enh.abs(), fb_all, sb_all
 
     def _forward_spec(self, input):
+        """STFT -> network -> deep filter, all on the complex spectrum (no |stft| / real / imag / repeat /
+        torch.complex passes: gsn_compress_spec, gsn_deepfilter_spec, gsn_spec_passthrough)."""
         B, L = input.shape
-        cmp = _stft(input, self.n_fft, self.hop_length, self.win_length)  # [B,F,T] complex
-        mag = cmp.abs().contiguous()
-        projs, fb_all, sb_all = self.network(mag)
+        cmp = _stft(input, self.n_fft, self.hop_length, self.win_length)  # [B,F,T] complex, time-major view
+        projs, fb_all, sb_all = self.network(cmp)
         F, T = cmp.shape[1], cmp.shape[2]
         S = self.num_spks
-        sre, sim = cmp.real.contiguous(), cmp.imag.contiguous()
-        # start from the noisy spectrum so un-filtered bins (Nyquist) pass through (MSF:461-468)
-        ore = sre.unsqueeze(1).repeat(1, S, 1, 1)
-        oim = sim.unsqueeze(1).repeat(1, S, 1, 1)
+        enh = _empty_spec_like(cmp, S)
         cuts, ctrs = self.sb_model.freq_cutoffs, self.sb_model.center_freq_sizes
         lo = 0
         for i, p in enumerate(projs):
             n = (cuts[i + 1] - cuts[i]) // ctrs[i]
-            ops.deepfilter_band(p, sre, sim, ore, oim, n, ctrs[i], self.df_orders[i], S, lo)
+            ops.deepfilter_spec(p, cmp, enh, n, ctrs[i], self.df_orders[i], S, lo)
             lo += n * ctrs[i]
-        return torch.complex(ore, oim), fb_all, sb_all
+        ops.spec_passthrough(cmp, enh, lo)  # un-filtered bins (Nyquist) pass through (MSF:461-468)
+        return enh, fb_all, sb_all
 
 
 class CirmGSN(_GraphedNetwork, nn.Module):
@@ -1153,7 +1186,7 @@ class CirmGSN(_GraphedNetwork, nn.Module):
     def _network(self, mag):
         """mag [B,F,T] -> (activated proj [T,B,P], all_layer_outputs)."""
         fbm = self.fb_model
-        cm = ops.compress_mag(mag.contiguous(), mag.shape[1], self.fdrc)
+        cm = ops.compress_mag(mag if mag.is_complex() else mag.contiguous(), mag.shape[1], self.fdrc)
         lnw = fbm.pre_layer_norm.weight.detach() if fbm.use_pre_layer_norm else None
         lnb = fbm.pre_layer_norm.bias.detach() if fbm.use_pre_layer_norm else None
         x = ops.subband_features(cm, None, 1, 0, self.fb_input_size, 0, lnw, lnb,
@@ -1178,18 +1211,16 @@ class CirmGSN(_GraphedNetwork, nn.Module):
             return training.cirm_gsn_forward(self, input)
         B, L = input.shape
         cmp = _stft(input, self.n_fft, self.hop_length, self.win_length)
-        coef, all_out = self.coefficients(cmp.abs().contiguous())  # [B,d,S,F,T,2]
-        cc = torch.complex(coef[..., 0], coef[..., 1])
-        d = self.df_order
-        pad = torch.nn.functional.pad(cmp, (d - 1, 0))
-        T = cmp.shape[2]
-        enh = sum(pad[:, None, :, k:k + T] * cc[:, k] for k in range(d))  # [B,S,F,T]
-        if self.num_spks > 1:
-            y = _istft(enh.reshape(B * self.num_spks, *enh.shape[2:]), self.n_fft, self.hop_length,
-                       self.win_length, L)
-            return y.reshape(B, self.num_spks, L), all_out
+        act, all_out = self.network(cmp)  # activated proj [T,B,P], features (c d s f) (CGN:230)
+        F, T = cmp.shape[1], cmp.shape[2]
+        S = self.num_spks
+        enh = _empty_spec_like(cmp, S)
+        ops.deepfilter_spec(act.contiguous(), cmp, enh, 1, F, self.df_order, S, 0, layout=1)  # CGN:128, 233
+        if S > 1:
+            y = _istft_fused(_merge_speakers(enh), self.n_fft, self.hop_length, self.win_length, L)
+            return y.reshape(B, S, L), all_out
         enh = enh[:, 0]
-        return _istft(enh, self.n_fft, self.hop_length, self.win_length, L), enh.abs()
+        return _istft_fused(enh, self.n_fft, self.hop_length, self.win_length, L), enh.abs()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -1350,7 +1381,7 @@ class Separator(_GraphedNetwork, nn.Module):
         """mag [B, n_fft//2+1, T] -> (sub-band fc outputs: list of [T, B*N_i, P_i], fb_all, sb_all)
         (model_low_freq.py:574-586)."""
         B, F, T = mag.shape
-        cm = ops.compress_mag(mag.contiguous(), F - 1, self.fdrc)
+        cm = ops.compress_mag(mag if mag.is_complex() else mag.contiguous(), F - 1, self.fdrc)
         x = ops.subband_features(cm, None, 1, 0, self.fb_freqs, 0)
         x = _utterance_norm(x, B, self.norm_type).contiguous()
         _, fb_act, fb_all = self.fb_model.run_time_major(x)
@@ -1379,16 +1410,16 @@ class Separator(_GraphedNetwork, nn.Module):
             return training.separator_forward(self, noisy_y)
         B, L = noisy_y.shape
         cmp = _stft(noisy_y, self.n_fft, self.hop_length, self.win_length)
-        projs, fb_all, sb_all = self.network(cmp.abs().contiguous())
-        sre, sim = cmp.real.contiguous(), cmp.imag.contiguous()
-        ore, oim = sre.unsqueeze(1).clone(), sim.unsqueeze(1).clone()
+        projs, fb_all, sb_all = self.network(cmp)
+        F, T = cmp.shape[1], cmp.shape[2]
+        enh = _empty_spec_like(cmp, 1)
         lo = 0
-        for i, (p, (a, b)) in enumerate(zip(projs, self.sb_model.band_edges(cmp.shape[1] - 1))):
+        for i, (p, (a, b)) in enumerate(zip(projs, self.sb_model.band_edges(F - 1))):
             ctr = self.sb_model.sb_num_center_freqs[i]
             n = (b - a) // ctr
-            ops.deepfilter_band(p.contiguous(), sre, sim, ore, oim, n, ctr, self.sb_df_orders[i], 1, lo)
+            ops.deepfilter_spec(p.contiguous(), cmp, enh, n, ctr, self.sb_df_orders[i], 1, lo)
             lo += n * ctr
-        enh = torch.complex(ore[:, 0], oim[:, 0])
-        y = torch.istft(enh, self.n_fft, self.hop_length, self.win_length,
-                        window=torch.hann_window(self.win_length, device=noisy_y.device), length=L)
+        ops.spec_passthrough(cmp, enh, lo)
+        enh = enh[:, 0]
+        y = _istft_fused(enh, self.n_fft, self.hop_length, self.win_length, L)  # asynchronous, graph-capturable
         return y, enh.abs(), fb_all, sb_all

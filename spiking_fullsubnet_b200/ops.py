@@ -31,10 +31,16 @@ def _prep(*tensors):
         elif t.device != dev:
             raise ValueError("tensors on different devices")
     lib = _lib.load()
-    if _bound_device[0] != dev.index:
-        _lib.check(lib.gsn_bind_device(dev.index))
-        _bound_device[0] = dev.index
+    _bind(dev)
     return lib, torch.cuda.current_stream(dev).cuda_stream
+
+
+def _bind(dev):
+    """The library launches on the calling thread's CURRENT CUDA device (SM count, tensor-memory planning, stream
+    handles belong to it).  No cache: the current device is per-thread state that torch.cuda.set_device / device
+    context managers change behind our back, so it is compared on every call and re-bound when it differs."""
+    if torch.cuda.current_device() != dev.index:
+        _lib.check(_lib.load().gsn_bind_device(dev.index))
 
 
 OPT_PDL, OPT_F32_MAX_CTAS = _lib.OPT_PDL, _lib.OPT_F32_MAX_CTAS
@@ -49,14 +55,76 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
+def _spec_layout(z, what):
+    """0: contiguous [.., F, T]; 1: time-major (a transposed view of contiguous [.., T, F], which is what torch.stft
+    returns and what cuFFT reads and writes)."""
+    if z.dtype != torch.complex64 or not z.is_cuda:
+        raise ValueError(f"{what}: expected a CUDA complex64 tensor")
+    if z.is_contiguous():
+        return 0
+    if z.transpose(-1, -2).is_contiguous():
+        return 1
+    raise ValueError(f"{what}: spectrum must be contiguous as [.., F, T] or as [.., T, F]")
+
+
 def compress_mag(mag, f_keep, fdrc):
-    """mag [B,F,T] -> cm [T,B,f_keep] = mag**fdrc (MSF:434-436, time-major)."""
+    """mag [B,F,T] (or the complex STFT itself, in either layout of `_spec_layout`) -> cm [T,B,f_keep] = |.|**fdrc
+    (MSF:434-436, time-major)."""
+    if mag.is_complex():
+        tm = _spec_layout(mag, "compress_mag")
+        lib = _lib.load()
+        _bind(mag.device)
+        st = torch.cuda.current_stream(mag.device).cuda_stream
+        B, F, T = mag.shape
+        cm = torch.empty((T, B, f_keep), device=mag.device, dtype=torch.float32)
+        _lib.check(lib.gsn_compress_spec(mag.data_ptr(), _ptr(cm), B, F, f_keep, T, float(fdrc), tm, st))
+        LAUNCHES[0] += 1
+        return cm
     lib, st = _prep(mag)
     B, F, T = mag.shape
     cm = torch.empty((T, B, f_keep), device=mag.device, dtype=torch.float32)
     _lib.check(lib.gsn_compress_mag(_ptr(mag), _ptr(cm), B, F, f_keep, T, float(fdrc), st))
     LAUNCHES[0] += 1
     return cm
+
+
+def deepfilter_spec(proj, spec, out, N, ctr, df, S, lo, layout=0):
+    """Deep filter of one band (MSF:315-346) from its proj output, complex in / complex out: spec [B,F,T] complex64,
+    out [B,S,F_out,T] complex64 (bins [lo, lo + N*ctr) are written), both in the same layout of `_spec_layout`.
+    layout 0: proj features (c fc df s), MSF:160-167; 1: (c df s fc), cirm_gsn CGN:230."""
+    lib, st = _prep(proj)
+    tm = _spec_layout(spec, "deepfilter_spec")
+    if _spec_layout(out, "deepfilter_spec") != tm or out.device != proj.device or spec.device != proj.device:
+        raise ValueError("deepfilter_spec: spec and out must share layout and device")
+    T = proj.shape[0]
+    B, F, _ = spec.shape
+    _lib.check(lib.gsn_deepfilter_spec(_ptr(proj), spec.data_ptr(), out.data_ptr(), T, B, N, ctr, df, S, lo, F,
+                                       out.shape[2], int(layout), tm, st))
+    LAUNCHES[0] += 1
+
+
+def spec_passthrough(spec, out, f_lo):
+    """out[b, s, f, :] = spec[b, f, :] for f >= f_lo (the bins no band filters, MSF:461-468)."""
+    tm = _spec_layout(spec, "spec_passthrough")
+    if _spec_layout(out, "spec_passthrough") != tm:
+        raise ValueError("spec_passthrough: spec and out must share their layout")
+    lib = _lib.load()
+    _bind(spec.device)
+    st = torch.cuda.current_stream(spec.device).cuda_stream
+    B, F, T = spec.shape
+    _lib.check(lib.gsn_spec_passthrough(spec.data_ptr(), out.data_ptr(), T, B, out.shape[1], int(f_lo), F, out.shape[2],
+                                        tm, st))
+    LAUNCHES[0] += 1
+
+
+def overlap_add(frames, window, hop, length):
+    """Synthesis half of torch.istft(center=True): frames [B,T,n_fft] (irfft of every frame) -> y [B,length]."""
+    lib, st = _prep(frames, window)
+    B, T, n_fft = frames.shape
+    y = torch.empty((B, length), device=frames.device, dtype=torch.float32)
+    _lib.check(lib.gsn_overlap_add(_ptr(frames), _ptr(window), _ptr(y), B, T, n_fft, int(hop), int(length), st))
+    LAUNCHES[0] += 1
+    return y
 
 
 def _out(out, shape, like):

@@ -723,3 +723,68 @@ def test_exported_submodules_are_autograd_safe():
         layer(xin, (torch.ones(5, 40, device=DEV), torch.zeros(5, 40, device=DEV)))
     h1, _ = layer.cell(xin[0], (torch.zeros(5, 40, device=DEV), torch.zeros(5, 40, device=DEV)))
     assert h1.grad_fn is not None and h1.shape == (5, 40)
+
+
+@pytest.mark.parametrize("B,F,T,fdrc", [(3, 257, 101, 0.5), (2, 33, 34, 0.5), (1, 257, 40, 0.3), (2, 129, 77, 1.0)])
+def test_spectral_front_end_on_the_complex_stft(B, F, T, fdrc):
+    """gsn_compress_spec: |X|^fdrc straight from the complex STFT equals torch.abs(X)**fdrc in the network's
+    time-major layout (MSF:434-436, 108), and equals gsn_compress_mag on the materialised magnitude to 1 ulp."""
+    g = torch.Generator(device="cpu").manual_seed(B + T)
+    spec = torch.complex(torch.randn(B, F, T, generator=g), torch.randn(B, F, T, generator=g)).to(DEV)
+    cm = ops.compress_mag(spec, F - 1, fdrc)
+    ref = (spec.abs() ** fdrc)[:, :-1, :].permute(2, 0, 1)
+    assert cm.shape == (T, B, F - 1)
+    assert float((cm - ref).abs().max()) <= 2e-6 * float(ref.abs().max())
+    cm2 = ops.compress_mag(spec.abs().contiguous(), F - 1, fdrc)
+    assert float((cm - cm2).abs().max()) <= 2e-7 * float(ref.abs().max())
+    spec_tm = spec.transpose(1, 2).contiguous().transpose(1, 2)  # time-major view, as torch.stft returns it
+    assert not spec_tm.is_contiguous() and torch.equal(ops.compress_mag(spec_tm, F - 1, fdrc), cm)
+
+
+@pytest.mark.parametrize("layout", [0, 1])
+@pytest.mark.parametrize("B,N,ctr,df,S,lo,F", [(2, 8, 4, 3, 1, 0, 257), (3, 3, 32, 1, 2, 32, 257), (2, 1, 33, 3, 2, 0, 33)])
+def test_deepfilter_spec_matches_the_reference_formula(B, N, ctr, df, S, lo, F, layout):
+    """gsn_deepfilter_spec (complex in / complex out) against the reference's deep filter evaluated with torch in
+    float64 (MSF:315-346: pad df-1 frames on the left, sum_d spec[t - (df-1) + d] * coef[d]) for both proj feature
+    orders, plus the Nyquist pass-through."""
+    g = torch.Generator(device="cpu").manual_seed(ctr + df)
+    T = 29
+    spec = torch.complex(torch.randn(B, F, T, generator=g), torch.randn(B, F, T, generator=g)).to(DEV)
+    P = 2 * ctr * df * S
+    proj = torch.randn(T, B * N, P, generator=g).to(DEV)
+    out = torch.zeros(B, S, F, T, dtype=torch.complex64, device=DEV)
+    ops.deepfilter_spec(proj, spec, out, N, ctr, df, S, lo, layout=layout)
+    ops.spec_passthrough(spec, out, lo + N * ctr)
+    v = proj.double().reshape(T, B, N, *((2, ctr, df, S) if layout == 0 else (2, df, S, ctr)))
+    v = v.permute(1, 2, 3, 4, 5, 6, 0) if layout == 0 else v.permute(1, 2, 3, 6, 4, 5, 0)   # [B,N,c,fc,df,S,T]
+    coef = torch.complex(v[:, :, 0], v[:, :, 1])                                           # [B,N,fc,df,S,T]
+    band = spec[:, lo:lo + N * ctr].to(torch.complex128).reshape(B, N, ctr, T)
+    pad = torch.nn.functional.pad(band, (df - 1, 0))
+    ref = sum(pad[:, :, :, None, d:d + T] * coef[:, :, :, d] for d in range(df))           # [B,N,fc,S,T]
+    ref = ref.permute(0, 3, 1, 2, 4).reshape(B, S, N * ctr, T)
+    got = out[:, :, lo:lo + N * ctr].to(torch.complex128)
+    assert float((got - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+    assert torch.equal(out[:, :, lo + N * ctr:], spec[:, None, lo + N * ctr:].expand(-1, S, -1, -1))
+    # time-major spectra (transposed views of [B,T,F] / [B,S,T,F]): same values
+    spec_tm = spec.transpose(1, 2).contiguous().transpose(1, 2)
+    out_tm = torch.zeros(B, S, T, F, dtype=torch.complex64, device=DEV).transpose(2, 3)
+    ops.deepfilter_spec(proj, spec_tm, out_tm, N, ctr, df, S, lo, layout=layout)
+    ops.spec_passthrough(spec_tm, out_tm, lo + N * ctr)
+    assert torch.equal(out_tm[:, :, lo:], out[:, :, lo:])
+
+
+@pytest.mark.parametrize("B,n_fft,hop,L", [(3, 512, 128, 16000), (2, 64, 16, 528), (1, 512, 128, 64000), (2, 512, 128, 1000)])
+def test_fused_istft_matches_torch_istft(B, n_fft, hop, L):
+    """cuFFT inverse real FFT + gsn_overlap_add against torch.istft (audio_feature.py:297-347)."""
+    from spiking_fullsubnet_b200.modeling import _istft_fused
+    g = torch.Generator(device="cpu").manual_seed(L)
+    wave = torch.randn(B, L, generator=g).to(DEV)
+    window = torch.hann_window(n_fft, device=DEV)
+    spec = torch.stft(wave, n_fft, hop, n_fft, window=window, return_complex=True, pad_mode="constant")
+    spec = spec * torch.complex(torch.rand_like(spec.real) + 0.5, torch.rand_like(spec.real) - 0.5)  # not a valid STFT
+    ref = torch.istft(spec, n_fft, hop, n_fft, window=window, length=L)
+    got = _istft_fused(spec.contiguous(), n_fft, hop, n_fft, L)
+    assert got.shape == ref.shape
+    assert float((got - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
+    assert not spec.is_contiguous()  # torch.stft hands out the time-major view: no transpose copy on that path
+    assert torch.equal(_istft_fused(spec, n_fft, hop, n_fft, L), got)
