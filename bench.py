@@ -230,9 +230,8 @@ def main():
     launches_per_step = ops.LAUNCHES[0]
     model.enable_cuda_graph(not args.no_graph, frame_chunks=args.chunks)
     if not args.no_graph:
-        ops.LAUNCHES[0] = 0
-        step()  # eager warm-up (launches_per_step kernels) + capture of the replayed schedule
-        launches_per_step = ops.LAUNCHES[0] - launches_per_step  # kernels inside the captured graph
+        step()  # warm-up + capture of the replayed schedule
+        launches_per_step = model.graph_launches  # kernels of this library inside one replay of the graph
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()

@@ -636,8 +636,10 @@ class _GraphedNetwork:
                 self._network(static_in)  # warm-up outside the capture (lazy CUDA initialisation)
                 torch.cuda.synchronize(mag.device)
                 graph = torch.cuda.CUDAGraph()
+                n0 = ops.LAUNCHES[0]
                 with torch.cuda.graph(graph):
                     static_out = self._network_sched(static_in)
+                self.graph_launches = ops.LAUNCHES[0] - n0  # kernels of this library inside one replay
             entry = graphs[key] = (graph, static_in, static_out)
         graph, static_in, static_out = entry
         self.refresh_folded_bn()
