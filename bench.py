@@ -38,6 +38,10 @@ def parse():
     ap.add_argument("--chunks", type=int, default=12, help="frame chunks of the wavefront schedule (graph mode)")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of "
                     "replaying the captured CUDA graph")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="infer: BASELINE configs[1] (default).  train: configs[3], one training step (forward + BPTT "
+                         "through the surrogate gradient + AdamW) per GPU, gradients all-reduced by NCCL (DDP); use with "
+                         "--size L --batch 32 --seconds 6")
     ap.add_argument("--schedule", default="auto", choices=["auto", "stream", "wavefront"],
                     help="auto/stream: frame-granular streaming pipeline of persistent kernels where it is co-resident "
                          "(else the frame-chunked wavefront); wavefront: round-1 schedule")
@@ -161,6 +165,107 @@ def cpu_leg(synth, cfg, B, T, steps, warmup):
                                                   f"{len(port_times)}"}
 
 
+def flops_per_frame(cfg):
+    """Dense 2*MAC count of the forward path per frame per utterance: input-to-hidden, hidden-to-hidden
+    and proj products of the full-band model and of every sub-band unit."""
+    g = 1 if cfg.get("shared_weights", False) else 2
+    S = cfg.get("num_spks", 1)
+    shapes = [(1, cfg["fb_input_size"], cfg["fb_hidden_size"], cfg["fb_proj_size"], cfg["fb_num_layers"])]
+    for i, (ctr, nbr, df) in enumerate(zip(cfg["center_freq_sizes"], cfg["neighbor_freq_sizes"], cfg["df_orders"])):
+        n = (cfg["freq_cutoffs"][i + 1] - cfg["freq_cutoffs"][i]) // ctr
+        shapes.append((n, 2 * ctr + 2 * nbr, cfg["sb_hidden_size"], 2 * ctr * df * S, cfg["sb_num_layers"]))
+    return sum(r * (g * 2 * H * K + (L - 1) * g * 2 * H * H + L * g * 2 * H * H + 2 * H * P) for r, K, H, P, L in shapes)
+
+
+def train_mode(args, synth, cfg, L, T, rank, world, local, dev):
+    """BASELINE configs[3]: one training step per GPU on its own shard of the utterance batch -- forward (train-mode
+    BatchNorm) + BPTT through the Triangle surrogate + the recipe's loss (recipes/.../trainer.py:33-37) + AdamW, the
+    gradients all-reduced by NCCL through DDP exactly as `accelerator.prepare(model)` sets it up in the reference
+    (recipes/intel_ndns/spiking_fullsubnet/run.py:39).  Weak scaling: `--batch` clips per GPU."""
+    import torch.distributed as dist
+    from spiking_fullsubnet_b200 import SpikingFullSubNet, losses, ops
+    B = args.batch
+    model = SpikingFullSubNet(**cfg)
+    model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in synth.make_params(cfg, 5).items()})
+    model = model.to(dev).train()
+    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
+    wave_host = torch.from_numpy(synth.make_wave(B, L, 31 + rank)).pin_memory()
+    clean = torch.from_numpy(synth.make_wave(B, L, 41 + rank)).to(dev)
+    wave = wave_host.to(dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)
+
+    def step(x):
+        opt.zero_grad(set_to_none=True)
+        enh_y = net(x)[0]
+        loss = losses.ndns_training_loss(enh_y, clean)["loss"]
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(wave)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ops.LAUNCHES[0] = 0
+    evs = []
+    for _ in range(args.steps):
+        flush.fill_(1.0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step(wave)
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    launches = ops.LAUNCHES[0]
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    # end to end: the step's waveforms come from pinned host memory and the loss value goes back to the host
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        x = wave_host.to(dev, non_blocking=True)
+        loss_host = float(step(x).detach())
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    sampler.stop_flag = True
+    sampler.join()
+    t = torch.tensor([dev_ms, e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_s = float(t[0]), float(t[1])
+    if rank == 0:
+        tf_peak, _, peak_src = peaks()
+        flops = 3.0 * flops_per_frame(cfg) * B * T  # forward + two backward contractions per product
+        ms = dev_ms / args.steps
+        line = {"metric": "training frames/sec", "value": world * B * T * args.steps / (dev_ms * 1e-3), "unit": "frames/s",
+                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32 (training forward on tcgen05 bf16x3 planes; BPTT on fp32 CUDA cores)", "data": "synthetic",
+                "config": {"workload": f"intel_ndns spiking_fullsubnet-{args.size} training step (forward + BPTT through the "
+                                       f"surrogate gradient + recipe loss + AdamW), batch {B} x {args.seconds:g} s per GPU "
+                                       f"(T={T}), DDP / NCCL gradient all-reduce", "size": args.size, "batch_per_gpu": B,
+                           "global_batch": world * B, "frames_per_clip": T, "sharding": f"utterance batch x{world}",
+                           "l2": "flushed between timed iterations (256 MiB write)",
+                           "grad_bytes_allreduced": int(sum(p.numel() for p in model.parameters()) * 4) if world > 1 else 0},
+                "clocks": sampler.summary(),
+                "e2e": {"value": world * B * T * args.steps / e2e_s, "unit": "frames/s",
+                        "h2d_bytes_per_step": int(wave_host.numel() * 4), "d2h_bytes_per_step": 4,
+                        "what": "pinned host waveform -> H2D -> training step -> loss value back on the host, every step",
+                        "last_loss": loss_host},
+                "gpu_launches": launches,
+                "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
+                             "frac": flops / (ms * 1e-3) / 1e12 / tf_peak if tf_peak else None, "traffic": None,
+                             "kernel": "whole training step (3 x the forward's algorithmic FLOPs)", "peak_source": peak_src}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", 0))
@@ -198,6 +303,8 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     from spiking_fullsubnet_b200 import SpikingFullSubNet, ops
+    if args.mode == "train":
+        return train_mode(args, synth, cfg, L, T, rank, world, local, dev)
 
     params = synth.make_params(cfg, 5)
     model = SpikingFullSubNet(**cfg)

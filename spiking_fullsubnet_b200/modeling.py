@@ -299,8 +299,12 @@ class LazyOutputs(list):
     consumer, audiozen/metric.py:303-327) are produced on first access from what the kernels actually wrote
     (bit-packed spike traces; the gather is re-run for x_norm)."""
 
-    def __init__(self, thunks):
+    def __init__(self, thunks, widths=None, spike_counts=None, trace_numel=None):
         super().__init__(thunks)
+        # for the SynOps / NeuronOps accounting (metrics.py) without materialising anything: last-dim width of every
+        # entry, the number of spikes each recurrence emitted (int64 device tensor, counted inside the kernels), and
+        # the number of elements of every spike trace
+        self.widths, self.spike_counts, self.trace_numel = widths, spike_counts, trace_numel
 
     def _resolve(self, i):
         v = list.__getitem__(self, i)
@@ -945,6 +949,9 @@ class SpikingFullSubNet(_GraphedNetwork, nn.Module):
         ncnt = sum(2 + 2 * len(d["layers"]) for d in models)
         counters = ops.frame_counters(T, dev, ncnt)
         nxt = iter(range(ncnt))
+        nrec = sum(len(d["layers"]) for d in models)
+        spike_counts = torch.zeros(nrec, device=dev, dtype=torch.int64)  # spikes emitted per (model, layer) launch
+        rec_idx = 0
         streams = _band_streams(dev, ncnt, priority=0, tag="stream_pipeline")
         st_it = iter(streams)
         # operand-image buffers of the fused layer-0 path: zero-filled ONCE (padding rows), on the main stream and
@@ -1032,7 +1039,8 @@ class SpikingFullSubNet(_GraphedNetwork, nn.Module):
                 bits = ops.spike_bits_buffer((T, R), H, dev)
                 h_out = torch.empty((T, R, H), **f32) if strict else None
                 c_out = c_l0 if l == 0 else counters[next(nxt)]
-                kw = dict(out_bits=bits, out_h=h_out, out_cnt=c_out, sm_budget=budget, in_cnt=in_cnt, in_target=in_target)
+                kw = dict(out_bits=bits, out_h=h_out, out_cnt=c_out, sm_budget=budget, in_cnt=in_cnt, in_target=in_target,
+                          spike_count=spike_counts[rec_idx + l:rec_idx + l + 1])
                 w_hh, bias = cell.weight_hh.detach(), cell.bias_ih.detach()
                 fused = ly["fused"] or (l == 0 and d["fused0"])
                 if record is not None:
@@ -1094,14 +1102,18 @@ class SpikingFullSubNet(_GraphedNetwork, nn.Module):
             for bits, h_out in zip(bits_all, h_all):
                 entries.append(h_out if strict else (lambda bits=bits, H=H: ops.unpack_spikes(bits, H)))
             entries.append(proj)
-            results.append((proj, LazyOutputs(entries), bits_all))
+            nl = len(cells)
+            results.append((proj, LazyOutputs(entries, widths=[K] + [H] * nl + [P],
+                                              spike_counts=spike_counts[rec_idx:rec_idx + nl], trace_numel=T * R * H),
+                            bits_all))
+            rec_idx += nl
         for stq in used:
             done = torch.cuda.Event()
             done.record(stq)
             main.wait_event(done)
         if record is not None:
             self.stream_launches = record
-        self._keepalive = (cm, counters, results, hold)
+        self._keepalive = (cm, counters, results, hold, spike_counts)
         self.last_spike_bits = [r[2] for r in results]
         return [r[0] for r in results[1:]], results[0][1], [r[1] for r in results[1:]]
 

@@ -309,3 +309,31 @@ def test_recurrence_stream_chain_bit_identical_to_chunk_kernel(T, R, K, H):
     if fused:
         assert torch.equal(ob1, bits1)
         assert bool((cnt[1] == ops.stream_ctas(R, H, H, True)).all())
+
+
+def test_synops_accounting_from_in_kernel_spike_counts():
+    """Row f4 on the streaming schedule: compute_synops / compute_neuronops (audiozen/metric.py:303-340) come out of the
+    spike counts the recurrence kernels accumulate while they run (popcount of their ballot words) -- equal to the
+    reference formula evaluated on fully materialised fp32 traces, without materialising any trace."""
+    from spiking_fullsubnet_b200 import metrics
+    g = load_golden("tiny_shared_bn")
+    cfg = g["cfg"]
+    m = _model(cfg, golden_params(g))
+    mag = _t(g["mag"])
+    with torch.no_grad():
+        _, fbe, sbe = m.network(mag)                      # eager schedule: fp32 traces
+        want_syn = metrics.compute_synops(fbe, sbe, shared_weights=True)
+        want_neu = metrics.compute_neuronops(fbe, sbe)
+        _streaming(m, mag.shape[0], graph=True)
+        for _ in range(2):
+            _, fbs, sbs = m.network(mag)
+        got_syn = metrics.compute_synops(fbs, sbs, shared_weights=True)
+        got_neu = metrics.compute_neuronops(fbs, sbs)
+    assert got_neu == want_neu
+    assert abs(got_syn - want_syn) <= 1e-6 * abs(want_syn)
+    for tr in [fbs] + list(sbs):  # nothing was materialised for the accounting
+        assert all(callable(list.__getitem__(tr, i)) for i in range(1, len(tr) - 1))
+    for tr, bits in zip([fbs] + list(sbs), m.last_spike_bits):
+        H = tr.widths[1]
+        counted = [int(ops.unpack_spikes(b, H).sum()) for b in bits]
+        assert counted == [int(c) for c in tr.spike_counts.tolist()]
