@@ -1232,7 +1232,7 @@ class CirmGSN(_GraphedNetwork, nn.Module):
         ops.deepfilter_spec(act.contiguous(), cmp, enh, 1, F, self.df_order, S, 0, layout=1)  # CGN:128, 233
         if S > 1:
             y = _istft_fused(_merge_speakers(enh), self.n_fft, self.hop_length, self.win_length, L)
-            return y.reshape(B, S, L), all_out
+            return y.reshape(B, S, L), [all_out]  # the reference returns `*_` of fb_model(...): [all_layer_outputs]
         enh = enh[:, 0]
         return _istft_fused(enh, self.n_fft, self.hop_length, self.win_length, L), enh.abs()
 
@@ -1341,21 +1341,54 @@ class _FreezeSubbandModel(nn.Module):
         cuts = [0] + list(self.freq_cutoffs) + [num_freqs]
         return [(cuts[i], cuts[i + 1]) for i in range(len(self.sb_models))]
 
+    concurrent_bands = True
+
     def run_time_major(self, cm, fb):
         T, B, F = cm.shape
-        projs, traces = [], []
-        for i, (m, (lo, hi)) in enumerate(zip(self.sb_models, self.band_edges(F))):
-            ctr, nbr = self.sb_num_center_freqs[i], self.sb_num_neighbor_freqs[i]
+        edges = self.band_edges(F)
+        for i, (lo, hi) in enumerate(edges):
+            ctr = self.sb_num_center_freqs[i]
             if (hi - lo) % ctr != 0:
                 raise ValueError(f"The number of center frequencies should be divisible by the subband freqency "
                                  f"interval. Got num_center_freqs={ctr}, upper_cutoff_freq={hi}, and "
                                  f"lower_cutoff_freq={lo}.")
+
+        def run_band(i):
+            m, (lo, hi) = self.sb_models[i], edges[i]
+            ctr, nbr = self.sb_num_center_freqs[i], self.sb_num_neighbor_freqs[i]
             x = ops.subband_features(cm, fb, (hi - lo) // ctr, lo, ctr, nbr)
             x = _utterance_norm(x, B, self.norm_type).contiguous()
             proj, act, trace = m.run_time_major(x)
-            projs.append(act)
-            traces.append(trace)
-        return projs, traces
+            return act, trace
+
+        n = len(self.sb_models)
+        # the sub-band models are independent latency-bound recurrences: one stream each, the SMs split between them in
+        # proportion to their rows (as SubbandModel.run_time_major does for surface A)
+        demands = [_cluster_ctas(B * ((hi - lo) // self.sb_num_center_freqs[i]), m.hidden_size,
+                                 m.sequence_model.layers[0].cell.shared_weights)
+                   for i, (m, (lo, hi)) in enumerate(zip(self.sb_models, edges))]
+        budgets = _sm_budgets(demands) if self.concurrent_bands and n > 1 else [0] * n
+        for m, b in zip(self.sb_models, budgets):
+            m.sequence_model.sm_budget = b
+        if not self.concurrent_bands or n == 1:
+            res = [run_band(i) for i in range(n)]
+        else:
+            main = torch.cuda.current_stream(cm.device)
+            streams = _band_streams(cm.device, n, tag="surface_b")
+            fork = torch.cuda.Event()
+            fork.record(main)
+            res = []
+            for i in range(n):
+                streams[i].wait_event(fork)
+                with torch.cuda.stream(streams[i]):
+                    res.append(run_band(i))
+                    done = torch.cuda.Event()
+                    done.record(streams[i])
+                main.wait_event(done)
+                if not torch.cuda.is_current_stream_capturing():
+                    for t in [res[-1][0]] + list(res[-1][1]):
+                        t.record_stream(main)
+        return [r[0] for r in res], [r[1] for r in res]
 
 
 class Separator(_GraphedNetwork, nn.Module):

@@ -788,3 +788,27 @@ def test_fused_istft_matches_torch_istft(B, n_fft, hop, L):
     assert float((got - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
     assert not spec.is_contiguous()  # torch.stft hands out the time-major view: no transpose copy on that path
     assert torch.equal(_istft_fused(spec, n_fft, hop, n_fft, L), got)
+
+
+def test_loss_terms_on_the_gpu_match_reference_values_and_gradient():
+    """Row f3 on the device the training step runs on: freq_MAE / mag_MAE / SISNRLoss and the recipe's combined loss
+    (audiozen/loss.py:138-190, 11-40; recipes/.../trainer.py:33-37) against values and the waveform gradient the
+    reference produced (tests/golden/loss_ref.npz); cuFFT vs the CPU FFT: 1e-5 relative."""
+    import os
+    from spiking_fullsubnet_b200 import losses
+    from tests.helpers import loss_waveforms
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "loss_ref.npz"))
+    est, clean = (_t(a) for a in loss_waveforms())
+
+    def close(a, b, rel=1e-5):
+        return abs(float(a) - float(b)) <= rel * max(1.0, abs(float(b)))
+
+    assert close(losses.freq_MAE(est, clean), G["loss_freq_mae"])
+    assert close(losses.mag_MAE(est, clean), G["loss_mag_mae"])
+    assert close(losses.SISNRLoss()(est, clean), G["loss_sdr"], 1e-4)
+    est.requires_grad_(True)
+    out = losses.ndns_training_loss(est, clean)
+    assert close(out["loss"], G["loss"])
+    out["loss"].backward()
+    ref = G["grad"]
+    assert np.abs(est.grad.cpu().numpy() - ref).max() <= 1e-4 * np.abs(ref).max()
