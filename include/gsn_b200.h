@@ -202,9 +202,13 @@ GSN_API int gsn_linear_spike_bits_stream(const uint32_t* a_bits, const float* w,
 GSN_API size_t gsn_xplanes_bytes(int T, int R, int K, int nt);
 /* ring: frames the buffer holds (gsn_xplanes_bytes(ring, ...) bytes; <= 0 or >= T: T).  With a ring shorter than T the
  * images stay L2-resident instead of making a DRAM round trip; frame t then waits for bp_cnt[t - ring] >= bp_target
- * (bp_cnt = the out_cnt of the consuming gsn_recurrence_stream, bp_target = its CTA count). */
+ * (bp_cnt = the out_cnt of the consuming gsn_recurrence_stream, bp_target = its CTA count).
+ * row_div (may be NULL): every feature of a row is DIVIDED by row_div[b] (div_mode 1, b = utterance: surface B's
+ * offline_laplace_norm, model_low_freq.py:146-171, with mu + eps precomputed) or by row_div[t * R + r] (div_mode 2: the
+ * cumulative norm of model_low_freq_count_time.py:173-204) after the optional LayerNorm. */
 GSN_API int gsn_xplanes_stream(const float* cm, int f_cm, const float* fb, int f_fb, const float* ln_weight,
-                               const float* ln_bias, float ln_eps, float* x_out, void* xop, int ring,
+                               const float* ln_bias, float ln_eps, const float* row_div, int div_mode, float* x_out,
+                               void* xop, int ring,
                                const unsigned int* in_cnt, unsigned int in_target, unsigned int* out_cnt,
                                const unsigned int* bp_cnt, unsigned int bp_target, int T, int B, int N, int lo,
                                int ctr, int nbr, int nt, int ctas, gsn_stream_t stream);

@@ -41,7 +41,7 @@ SIGNATURES = {
     "gsn_overlap_add": (_i, [_p, _p, _p] + [_i] * 5 + [_p]),
     "gsn_stream_preload": (_i, []),
     "gsn_xplanes_bytes": (_sz, [_i] * 4),
-    "gsn_xplanes_stream": (_i, [_p, _i, _p, _i, _p, _p, _f, _p, _p, _i, _p, C.c_uint, _p, _p, C.c_uint] + [_i] * 8 + [_p]),
+    "gsn_xplanes_stream": (_i, [_p, _i, _p, _i, _p, _p, _f, _p, _i, _p, _p, _i, _p, C.c_uint, _p, _p, C.c_uint] + [_i] * 8 + [_p]),
     "gsn_linear_spike_bits_stream": (_i, [_p] * 5 + [_i] * 6 + [_p, C.c_uint, _p, _p]),
     "gsn_pre_stream_supported": (_i, [_i, _i]),
     "gsn_pre_stream": (_i, [_p, _i, _p, _i, _p, _p, _f, _p, _p, _p, _p, C.c_uint, _p] + [_i] * 8 + [_p]),

@@ -30,6 +30,8 @@ struct XpParams {
   const float* fb;      // [T, B, f_fb] full-band output or null
   const float* ln_w;    // [K] or null
   const float* ln_b;
+  const float* row_div; // or null: divisor of every feature of a row (surface B's laplace norms, model_low_freq.py:146-204)
+  int div_mode;         // 1: row_div[b] per utterance (offline norm);  2: row_div[t * R + r] (cumulative norm)
   float* x_out;         // [T, R, K] normalised input (all_layer_outputs[0]) or null
   uint8_t* xop;         // operand images, see above
   const unsigned int* in_cnt;  // [T] or null
@@ -250,6 +252,13 @@ __global__ void __launch_bounds__(kXpThreads, 1) k_xplanes_stream(const XpParams
             }
           }
         }
+        if (p.row_div != nullptr) {  // x / (mu + eps), the division the reference performs (not a reciprocal multiply)
+          const float dv = rv ? (p.div_mode == 1 ? p.row_div[r / p.N] : p.row_div[(size_t)t * R + r]) : 1.f;
+#pragma unroll
+          for (int jc = 0; jc < J; ++jc)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[jc][e] = __fdiv_rn(v[jc][e], dv);
+        }
         float* xo = (p.x_out != nullptr && rv) ? p.x_out + ((size_t)t * R + r) * K : nullptr;
         const int tile = r / NT, n = r - tile * NT;  // row tile of the recurrence and the row inside it
         uint8_t* blk = p.xop + ((size_t)(t % p.ring) * ntiles + tile) * 3 * plane_bytes + (size_t)(n >> 3) * SBO + (n & 7) * 16;
@@ -339,7 +348,8 @@ extern "C" size_t gsn_xplanes_bytes(int T, int R, int K, int nt) {
 }
 
 extern "C" int gsn_xplanes_stream(const float* cm, int f_cm, const float* fb, int f_fb, const float* ln_weight,
-                                  const float* ln_bias, float ln_eps, float* x_out, void* xop, int ring,
+                                  const float* ln_bias, float ln_eps, const float* row_div, int div_mode, float* x_out,
+                                  void* xop, int ring,
                                   const unsigned int* in_cnt, unsigned int in_target, unsigned int* out_cnt,
                                   const unsigned int* bp_cnt, unsigned int bp_target, int T, int B, int N, int lo,
                                   int ctr, int nbr, int nt, int ctas, gsn_stream_t stream) {
@@ -356,10 +366,12 @@ extern "C" int gsn_xplanes_stream(const float* cm, int f_cm, const float* fb, in
   GSN_REQUIRE(!fb || (f_fb > 0 && ctr <= f_fb), "gsn_xplanes_stream: f_fb=%d must be >= ctr=%d", f_fb, ctr);
   GSN_REQUIRE((long long)T * B * (f_cm > f_fb ? f_cm : f_fb) < (1ll << 31), "gsn_xplanes_stream: inputs too large");
   GSN_REQUIRE((ln_weight == nullptr) == (ln_bias == nullptr), "gsn_xplanes_stream: ln params");
+  GSN_REQUIRE(row_div == nullptr || div_mode == 1 || div_mode == 2, "gsn_xplanes_stream: div_mode %d", div_mode);
   if (ring <= 0 || ring > T) ring = T;
   GSN_REQUIRE(ring == T || bp_cnt != nullptr, "gsn_xplanes_stream: a ring shorter than T needs the consumer's counters");
   XpParams p{};
   p.cm = cm; p.fb = fb; p.ln_w = ln_weight; p.ln_b = ln_bias; p.x_out = x_out; p.xop = static_cast<uint8_t*>(xop);
+  p.row_div = row_div; p.div_mode = div_mode;
   p.in_cnt = in_cnt; p.in_target = in_target; p.out_cnt = out_cnt;
   p.bp_cnt = ring < T ? bp_cnt : nullptr; p.bp_target = bp_target; p.ring = ring;
   p.T = T; p.B = B; p.N = N; p.lo = lo; p.ctr = ctr; p.nbr = nbr; p.f_cm = f_cm; p.f_fb = f_fb;

@@ -652,7 +652,302 @@ class _GraphedNetwork:
         return static_out
 
 
-class SpikingFullSubNet(_GraphedNetwork, nn.Module):
+class _StreamingPipeline:
+    """The streaming schedule shared by surface A and surface B: plan + launch of the persistent stages."""
+
+    # ---- streaming schedule: every stage of every sequence model is ONE persistent kernel for all T frames, chained
+    #      to its producers through per-frame counters (gsn_recurrence_stream / gsn_pre_stream /
+    #      gsn_linear_spike_bits_stream); ~20 launches per step, no xproj of layers >= 1, bit-packed traces only.
+    streaming = False
+    strict_outputs = False
+
+    def enable_streaming(self, flag=True, strict_outputs=False):
+        """Run the hot path as the frame-granular streaming pipeline where it fits on the device (else the previous
+        schedules).  strict_outputs=True also materialises the reference-shaped fp32 traces inside the kernels."""
+        self.streaming = bool(flag)
+        self.strict_outputs = bool(strict_outputs)
+        self._graphs = {}
+        return self
+
+    def _stream_models(self, B):
+        sb = self.sb_model
+        out = [dict(m=self.fb_model, R=B, N=1, lo=0, ctr=self.fb_input_size, nbr=0, fb=False)]
+        for i, m in enumerate(sb.sb_models):
+            lo, hi, ctr = sb.freq_cutoffs[i], sb.freq_cutoffs[i + 1], sb.center_freq_sizes[i]
+            if (hi - lo) % ctr != 0:
+                raise ValueError(f"Number of frequency bins must be divisible by the center frequency."
+                                 f"GOT: ctr_freq={ctr}, upper_cutoff_freq={hi}, lower_cutoff_freq={lo}")
+            N = (hi - lo) // ctr
+            out.append(dict(m=m, R=B * N, N=N, lo=lo, ctr=ctr, nbr=sb.neighbor_freq_sizes[i], fb=True))
+        return out
+
+    # cost model of the helper stages (measured on B200, tools/stream_stage_timing.py / stream_fused0_check.py):
+    #   gsn_xplanes_stream: (0.009 + 0.00028 Kmma) us per row per CTA;
+    #   tcgen05 stages: ~75 cycles per MMA at 64-row tiles (3 planes for spike inputs, 8 plane pairs for real inputs)
+    _STREAM_TARGET_US = 1.0   # helper stages must be faster than the recurrences' frame time (1.2 - 1.3 us)
+    _XOP_RING = 64            # frames of layer-0 operand images kept (ring; S: 64 x 202 KB = 13 MB, L2-resident)
+
+    @staticmethod
+    def _xplanes_ctas(R, K, target):
+        kmma = (K + 15) // 16 * 16
+        return max(1, int(math.ceil(R * (0.009 + 0.00028 * kmma) / target)))
+
+    @staticmethod
+    def _stage_ctas(R, K, passes, target):
+        kmma = (K + 15) // 16 * 16
+        us = (R / 64.0) * passes * (kmma // 16) * 75.0 / 1965.0
+        return max(1, int(math.ceil(us / target)))
+
+    def _stream_plan(self, B, sm_total=None):
+        """Plan of the whole network at batch B (None: not co-resident)."""
+        return self._stream_plan_for(self._stream_models(B), sm_total)
+
+    def _stream_plan_for(self, models, sm_total=None):
+        """Stage list with CTA counts, or None when the pipeline cannot be co-resident (all kernels spin on each
+        other's counters, so every CTA of every stage must be resident at once: one CTA per SM)."""
+        if sm_total is None:
+            sm_total = int(os.environ.get("GSN_STREAM_SMS", "146"))
+        target = float(os.environ.get("GSN_STREAM_TARGET_US", self._STREAM_TARGET_US))
+        helpers = 0
+        for d in models:
+            m = d["m"]
+            cells = [l.cell for l in m.sequence_model.layers]
+            if any(not c.shared_weights for c in cells) or any(c.use_bn and c.batchnorm.training for c in cells):
+                return None
+            H, K, R = m.hidden_size, m.input_size, d["R"]
+            if not isinstance(m.proj, nn.Linear) or m.proj_size > 2048 or H > 320 or K > 256:
+                return None
+            C = (H + 127) // 128
+            d["C"] = C
+            d["fused0"] = ops.stream_ctas(R, H, K, True) > 0
+            d["layers"] = [dict(fused=(l > 0 and ops.stream_ctas(R, H, H, True) > 0)) for l in range(len(cells))]
+            if d["fused0"]:
+                d["pre_p"] = self._xplanes_ctas(R, K, target)
+                helpers += d["pre_p"]
+            else:
+                if not _lib_supported_pre(K, H) or d.get("needs_div"):
+                    return None  # (the separate front end has no row divisor: surface B needs the fused layer 0)
+                d["pre_p"] = self._stage_ctas(R, K, 8, target)
+                helpers += C * d["pre_p"]
+            d["lin_p"] = self._stage_ctas(R, H, 3, target)
+            d["proj_p"] = self._stage_ctas(R, H, 3, target)
+            helpers += sum(0 if (ly["fused"] or i == 0) else C * d["lin_p"] for i, ly in enumerate(d["layers"]))
+            helpers += ((m.proj_size + 127) // 128) * d["proj_p"]
+        # only with the finest row tile: 32- and 64-row frames cost 2.9 / 5.1 us, the chunked wavefront is faster there
+        nt = 16
+        rec = sum(((d["R"] + nt - 1) // nt) * d["C"] * len(d["layers"]) for d in models)
+        if rec + helpers > sm_total:
+            return None
+        for d in models:
+            d["nt"] = nt
+        return models
+
+    def _network_stream(self, mag):
+        dev = mag.device
+        B, F, T = mag.shape
+        models = self._stream_plan(B)
+        if models is None:
+            return None
+        fbm = self.fb_model
+        rep = (self.n_fft // 2 + 1) // self.fb_input_size
+        if rep * fbm.proj_size < F - 1:
+            raise ValueError(f"full-band output ({fbm.proj_size} bins x {rep}) does not cover {F - 1} bins")
+        ops.stream_preload(dev)
+        cm = ops.compress_mag(mag if mag.is_complex() else mag.contiguous(), F - 1, self.fdrc)
+        results = self._stream_run(models, cm, tag="a")
+        return [r[0] for r in results[1:]], results[0][1], [r[1] for r in results[1:]]
+
+    def _stream_run(self, models, cm, fb_act=None, tag=""):
+        """Launch the streaming pipeline of `models` (a plan of _stream_plan_for) on the compressed magnitude cm
+        [T,B,F]: every stage on its own stream, forked from and joined to the current one.  A model with d["fb"] reads
+        the full-band output: of the plan's own full-band model (frame by frame, through its proj stage's counters) or
+        `fb_act` [T,B,f_fb] when that is already complete.  d["div"]: per-row divisor of the layer-0 input (surface
+        B's norms).  Returns [(proj, all_layer_outputs, bits)] per model."""
+        dev = cm.device
+        T, B, _ = cm.shape
+        strict = self.strict_outputs
+        main = torch.cuda.current_stream(dev)
+        f32 = dict(device=dev, dtype=torch.float32)
+        ncnt = sum(2 + 2 * len(d["layers"]) for d in models)
+        counters = ops.frame_counters(T, dev, ncnt)
+        nxt = iter(range(ncnt))
+        nrec = sum(len(d["layers"]) for d in models)
+        spike_counts = torch.zeros(nrec, device=dev, dtype=torch.int64)  # spikes emitted per (model, layer) launch
+        rec_idx = 0
+        streams = _band_streams(dev, ncnt, priority=0, tag=("stream_pipeline", tag))
+        st_it = iter(streams)
+        # operand-image buffers of the fused layer-0 path: zero-filled ONCE (padding rows), on the main stream and
+        # before the fork, then reused by every call of this shape
+        keep = self.__dict__.setdefault("_xop_cache", {})
+        for mi, d in enumerate(models):
+            if d["fused0"]:
+                m = d["m"]
+                budget = ((d["R"] + d["nt"] - 1) // d["nt"]) * d["C"]
+                nt0 = ops.stream_tile(d["R"], m.hidden_size, m.input_size, True, budget)
+                # a RING of frames (the layer-0 recurrence's out counters are the producer's back-pressure): the images
+                # are consumed microseconds after they are written and never need to reach DRAM
+                ring = min(T, int(os.environ.get("GSN_XOP_RING", self._XOP_RING)))
+                key = (tag, mi, ring, d["R"], m.input_size, nt0, dev.index)
+                if key not in keep:
+                    keep[key] = ops.xplanes_buffer(ring, d["R"], m.input_size, nt0, dev)
+                d["xop"], d["nt0"], d["ring"] = keep[key], nt0, ring
+        # folded BatchNorm affines are (re)computed by torch kernels on the main stream while a graph is captured: they
+        # must precede the fork too.  `hold` keeps every buffer of this call alive until the next one, so that the
+        # caching allocator cannot hand a block to a later allocation while a concurrently running stage still uses it
+        hold = []
+        for d in models:
+            d["bn"] = [l.cell.folded_bn() for l in d["m"].sequence_model.layers]
+            hold.append(d["bn"])
+        fork = torch.cuda.Event()
+        fork.record(main)
+        used = []
+
+        def on_stream(fn):
+            stq = next(st_it)
+            stq.wait_event(fork)
+            with torch.cuda.stream(stq):
+                fn()
+            used.append(stq)
+
+        def ln(m):
+            if not m.use_pre_layer_norm:
+                return None, None, 1e-5
+            return m.pre_layer_norm.weight.detach(), m.pre_layer_norm.bias.detach(), m.pre_layer_norm.eps
+
+        fb_cnt = None
+        fb_target = 0
+        results = []
+        record = [] if self.__dict__.get("record_stream_launches") else None
+        # The recurrences (thread-block clusters) are enqueued before the helper stages of their model so that cluster
+        # placement is not fragmented by single-CTA kernels; consumers spin on their producers' frame counters.
+        for mi, d in enumerate(models):
+            m, R = d["m"], d["R"]
+            H, K, C = m.hidden_size, m.input_size, d["C"]
+            cells = [l.cell for l in m.sequence_model.layers]
+            nt = d["nt"]
+            budget = ((R + nt - 1) // nt) * C  # makes the tile picker choose nt
+            w_ln, b_ln, e_ln = ln(m)
+            x_out = torch.empty((T, R, K), **f32) if strict else None
+            geo = (d["N"], d["lo"], d["ctr"], d["nbr"])
+            fbt = fb_act if d["fb"] else None
+            c_pre = counters[next(nxt)]
+            c_l0 = counters[next(nxt)]  # out counters of the layer-0 recurrence
+            pre_in = dict(in_cnt=fb_cnt if d["fb"] else None, in_target=fb_target)
+            w_ih0 = cells[0].weight_ih.detach()
+            if d["fused0"]:
+                xop, nt0 = d["xop"], d["nt0"]
+                xproj = None
+                bp = dict(ring=d["ring"], bp_cnt=c_l0, bp_target=ops.stream_ctas(R, H, K, True, budget),
+                          row_div=d.get("div"))
+                pre = (lambda geo=geo, fbt=fbt, nt0=nt0, xop=xop, w_ln=w_ln, b_ln=b_ln, e_ln=e_ln, x_out=x_out, c_pre=c_pre,
+                       pre_in=pre_in, d=d, bp=bp: ops.xplanes_stream(cm, fbt, *geo, nt0, xop, w_ln, b_ln, e_ln, out_x=x_out,
+                                                                      out_cnt=c_pre, ctas=d["pre_p"], **pre_in, **bp))
+                pre_target = R
+            else:
+                xop = None
+                xproj = torch.empty((T, R, H), **f32)
+                hold.append(xproj)
+                pre = (lambda geo=geo, fbt=fbt, w_ih0=w_ih0, xproj=xproj, w_ln=w_ln, b_ln=b_ln, e_ln=e_ln, x_out=x_out,
+                       c_pre=c_pre, pre_in=pre_in, d=d: ops.pre_stream(cm, fbt, *geo, w_ih0, w_ln, b_ln, e_ln, out_x=x_out,
+                                                                       out_xproj=xproj, out_cnt=c_pre,
+                                                                       ctas_per_slice=d["pre_p"], **pre_in))
+                pre_target = R * C
+            in_cnt, in_target = c_pre, pre_target
+            bits_prev = None
+            bits_all, h_all = [], []
+            helpers = [pre]
+            for l, (cell, ly) in enumerate(zip(cells, d["layers"])):
+                a, b = d["bn"][l]
+                bits = ops.spike_bits_buffer((T, R), H, dev)
+                h_out = torch.empty((T, R, H), **f32) if strict else None
+                c_out = c_l0 if l == 0 else counters[next(nxt)]
+                kw = dict(out_bits=bits, out_h=h_out, out_cnt=c_out, sm_budget=budget, in_cnt=in_cnt, in_target=in_target,
+                          spike_count=spike_counts[rec_idx + l:rec_idx + l + 1])
+                w_hh, bias = cell.weight_hh.detach(), cell.bias_ih.detach()
+                fused = ly["fused"] or (l == 0 and d["fused0"])
+                if record is not None:
+                    # the same launch without counters (its inputs are complete once this step has run): timed alone
+                    kin = (K if l == 0 else H) if fused else 0
+                    ins = (dict(in_planes=xop, w_ih=w_ih0, frames_rows=(T, R), planes_ring=d["ring"]) if (l == 0 and d["fused0"]) else
+                           dict(in_bits=bits_prev, w_ih=cell.weight_ih.detach()) if ly["fused"] else None)
+                    record.append(dict(model=mi, layer=l, T=T, R=R, H=H, K_in=kin, fused=fused,
+                                       flops=2.0 * T * R * H * (H + kin), w_hh=w_hh, bias=bias, a=a, b=b, ins=ins,
+                                       out_bits=bits, budget=budget, out_cnt=c_out))
+                if l == 0 and d["fused0"]:
+                    on_stream(lambda w_hh=w_hh, bias=bias, a=a, b=b, kw=kw, xop=xop, w_ih0=w_ih0, R=R, ring=d["ring"]:
+                              ops.recurrence_stream(w_hh, bias, a, b, in_planes=xop, w_ih=w_ih0, frames_rows=(T, R),
+                                                    planes_ring=ring, **kw))
+                elif l == 0:
+                    if record is not None:
+                        record[-1]["ins"] = dict(xproj=xproj)
+                    on_stream(lambda w_hh=w_hh, bias=bias, a=a, b=b, kw=kw, xp=xproj:
+                              ops.recurrence_stream(w_hh, bias, a, b, xproj=xp, **kw))
+                elif ly["fused"]:
+                    on_stream(lambda w_hh=w_hh, bias=bias, a=a, b=b, kw=kw, bp=bits_prev, w=cell.weight_ih.detach():
+                              ops.recurrence_stream(w_hh, bias, a, b, in_bits=bp, w_ih=w, **kw))
+                else:
+                    xp = torch.empty((T, R, H), **f32)
+                    hold.append(xp)
+                    c_lin = counters[next(nxt)]
+                    helpers.append(lambda w=cell.weight_ih.detach(), bp=bits_prev, xp=xp, ic=in_cnt, it=in_target,
+                                   c_lin=c_lin, d=d: ops.linear_bits_stream(bp, w, out=xp, ctas=C * d["lin_p"], in_cnt=ic,
+                                                                            in_target=it, out_cnt=c_lin))
+                    kw.update(in_cnt=c_lin, in_target=R * C)
+                    if record is not None:
+                        record[-1]["ins"] = dict(xproj=xp)
+                    on_stream(lambda w_hh=w_hh, bias=bias, a=a, b=b, kw=kw, xp=xp:
+                              ops.recurrence_stream(w_hh, bias, a, b, xproj=xp, **kw))
+                in_cnt, in_target = c_out, ops.stream_ctas(R, H, (K if l == 0 else H) if fused else 0, fused, budget)
+                bits_prev = bits
+                bits_all.append(bits)
+                h_all.append(h_out)
+            P = m.proj_size
+            proj = torch.empty((T, R, P), **f32)
+            act = torch.empty_like(proj) if m._act else proj
+            hold.append(act)
+            c_proj = counters[next(nxt)]
+            pslices = (P + 127) // 128
+            helpers.append(lambda m=m, bp=bits_prev, proj=proj, act=act, ic=in_cnt, it=in_target, c_proj=c_proj, d=d:
+                           ops.linear_bits_stream(bp, m.proj.weight.detach(), m.proj.bias.detach(), act=m._act, out=proj,
+                                                  out_act=act if m._act else None, ctas=pslices * d["proj_p"], in_cnt=ic,
+                                                  in_target=it, out_cnt=c_proj))
+            for fn in helpers:
+                on_stream(fn)
+            if not d["fb"]:
+                fb_cnt, fb_target, fb_act = c_proj, R * pslices, act
+
+            # all_layer_outputs in the reference's positions; fp32 traces on demand unless strict
+            def lazy_x(geo=geo, fbt=fbt, w_ln=w_ln, b_ln=b_ln, e_ln=e_ln, div=d.get("div")):
+                x = ops.subband_features(cm, fbt, geo[0], geo[1], geo[2], geo[3], w_ln, b_ln, e_ln)
+                if div is None:
+                    return x
+                if div.dim() == 1:  # per utterance
+                    return (x.view(T, B, -1) / div.view(1, B, 1)).view_as(x)
+                return x / div.unsqueeze(-1)
+
+            entries = [x_out if strict else lazy_x]
+            for bits, h_out in zip(bits_all, h_all):
+                entries.append(h_out if strict else (lambda bits=bits, H=H: ops.unpack_spikes(bits, H)))
+            entries.append(proj)
+            nl = len(cells)
+            results.append((proj, LazyOutputs(entries, widths=[K] + [H] * nl + [P],
+                                              spike_counts=spike_counts[rec_idx:rec_idx + nl], trace_numel=T * R * H),
+                            bits_all, act))
+            rec_idx += nl
+        for stq in used:
+            done = torch.cuda.Event()
+            done.record(stq)
+            main.wait_event(done)
+        if record is not None:
+            self.stream_launches = record
+        self.__dict__.setdefault("_stream_keepalive", {})[tag] = (cm, counters, results, hold, spike_counts, fb_act)
+        bits = [r[2] for r in results]
+        # spike bits of the whole network in model order; a two-phase caller (surface B) runs "b1" (full band) then "b2"
+        self.last_spike_bits = self.__dict__.get("last_spike_bits", []) + bits if tag == "b2" else bits
+        return results
+
+
+class SpikingFullSubNet(_StreamingPipeline, _GraphedNetwork, nn.Module):
     """Surface A (MSF:349-474).  forward(wave [B,L]) ->
     (enh_y [B,L], enh_mag [B,F,T], fb_all_layer_outputs, sb_all_layer_outputs), or for num_spks > 1
     (enh_y [B,S,L], fb_all_layer_outputs, sb_all_layer_outputs)."""
@@ -847,276 +1142,6 @@ class SpikingFullSubNet(_GraphedNetwork, nn.Module):
                           ops.subband_features(cm[t0:t1], fbp.act[t0:t1], N, lo, ctr, nbr, w_sb, b_sb, e_sb,
                                                out=p.x[t0:t1]), ev_fb)
 
-    # ---- streaming schedule: every stage of every sequence model is ONE persistent kernel for all T frames, chained
-    #      to its producers through per-frame counters (gsn_recurrence_stream / gsn_pre_stream /
-    #      gsn_linear_spike_bits_stream); ~20 launches per step, no xproj of layers >= 1, bit-packed traces only.
-    streaming = False
-    strict_outputs = False
-
-    def enable_streaming(self, flag=True, strict_outputs=False):
-        """Run the hot path as the frame-granular streaming pipeline where it fits on the device (else the previous
-        schedules).  strict_outputs=True also materialises the reference-shaped fp32 traces inside the kernels."""
-        self.streaming = bool(flag)
-        self.strict_outputs = bool(strict_outputs)
-        self._graphs = {}
-        return self
-
-    def _stream_models(self, B):
-        sb = self.sb_model
-        out = [dict(m=self.fb_model, R=B, N=1, lo=0, ctr=self.fb_input_size, nbr=0, fb=False)]
-        for i, m in enumerate(sb.sb_models):
-            lo, hi, ctr = sb.freq_cutoffs[i], sb.freq_cutoffs[i + 1], sb.center_freq_sizes[i]
-            if (hi - lo) % ctr != 0:
-                raise ValueError(f"Number of frequency bins must be divisible by the center frequency."
-                                 f"GOT: ctr_freq={ctr}, upper_cutoff_freq={hi}, lower_cutoff_freq={lo}")
-            N = (hi - lo) // ctr
-            out.append(dict(m=m, R=B * N, N=N, lo=lo, ctr=ctr, nbr=sb.neighbor_freq_sizes[i], fb=True))
-        return out
-
-    # cost model of the helper stages (measured on B200, tools/stream_stage_timing.py / stream_fused0_check.py):
-    #   gsn_xplanes_stream: (0.009 + 0.00028 Kmma) us per row per CTA;
-    #   tcgen05 stages: ~75 cycles per MMA at 64-row tiles (3 planes for spike inputs, 8 plane pairs for real inputs)
-    _STREAM_TARGET_US = 1.0   # helper stages must be faster than the recurrences' frame time (1.2 - 1.3 us)
-    _XOP_RING = 64            # frames of layer-0 operand images kept (ring; S: 64 x 202 KB = 13 MB, L2-resident)
-
-    @staticmethod
-    def _xplanes_ctas(R, K, target):
-        kmma = (K + 15) // 16 * 16
-        return max(1, int(math.ceil(R * (0.009 + 0.00028 * kmma) / target)))
-
-    @staticmethod
-    def _stage_ctas(R, K, passes, target):
-        kmma = (K + 15) // 16 * 16
-        us = (R / 64.0) * passes * (kmma // 16) * 75.0 / 1965.0
-        return max(1, int(math.ceil(us / target)))
-
-    def _stream_plan(self, B, sm_total=None):
-        """Stage list with CTA counts, or None when the pipeline cannot be co-resident (all kernels spin on each
-        other's counters, so every CTA of every stage must be resident at once: one CTA per SM)."""
-        if sm_total is None:
-            sm_total = int(os.environ.get("GSN_STREAM_SMS", "146"))
-        target = float(os.environ.get("GSN_STREAM_TARGET_US", self._STREAM_TARGET_US))
-        models = self._stream_models(B)
-        helpers = 0
-        for d in models:
-            m = d["m"]
-            cells = [l.cell for l in m.sequence_model.layers]
-            if any(not c.shared_weights for c in cells) or any(c.use_bn and c.batchnorm.training for c in cells):
-                return None
-            H, K, R = m.hidden_size, m.input_size, d["R"]
-            if not isinstance(m.proj, nn.Linear) or m.proj_size > 2048 or H > 320 or K > 256:
-                return None
-            C = (H + 127) // 128
-            d["C"] = C
-            d["fused0"] = ops.stream_ctas(R, H, K, True) > 0
-            d["layers"] = [dict(fused=(l > 0 and ops.stream_ctas(R, H, H, True) > 0)) for l in range(len(cells))]
-            if d["fused0"]:
-                d["pre_p"] = self._xplanes_ctas(R, K, target)
-                helpers += d["pre_p"]
-            else:
-                if not _lib_supported_pre(K, H):
-                    return None
-                d["pre_p"] = self._stage_ctas(R, K, 8, target)
-                helpers += C * d["pre_p"]
-            d["lin_p"] = self._stage_ctas(R, H, 3, target)
-            d["proj_p"] = self._stage_ctas(R, H, 3, target)
-            helpers += sum(0 if (ly["fused"] or i == 0) else C * d["lin_p"] for i, ly in enumerate(d["layers"]))
-            helpers += ((m.proj_size + 127) // 128) * d["proj_p"]
-        # only with the finest row tile: 32- and 64-row frames cost 2.9 / 5.1 us, the chunked wavefront is faster there
-        nt = 16
-        rec = sum(((d["R"] + nt - 1) // nt) * d["C"] * len(d["layers"]) for d in models)
-        if rec + helpers > sm_total:
-            return None
-        for d in models:
-            d["nt"] = nt
-        return models
-
-    def _network_stream(self, mag):
-        dev = mag.device
-        B, F, T = mag.shape
-        models = self._stream_plan(B)
-        if models is None:
-            return None
-        fbm = self.fb_model
-        rep = (self.n_fft // 2 + 1) // self.fb_input_size
-        if rep * fbm.proj_size < F - 1:
-            raise ValueError(f"full-band output ({fbm.proj_size} bins x {rep}) does not cover {F - 1} bins")
-        strict = self.strict_outputs
-        ops.stream_preload(dev)
-        main = torch.cuda.current_stream(dev)
-        cm = ops.compress_mag(mag if mag.is_complex() else mag.contiguous(), F - 1, self.fdrc)
-        f32 = dict(device=dev, dtype=torch.float32)
-        ncnt = sum(2 + 2 * len(d["layers"]) for d in models)
-        counters = ops.frame_counters(T, dev, ncnt)
-        nxt = iter(range(ncnt))
-        nrec = sum(len(d["layers"]) for d in models)
-        spike_counts = torch.zeros(nrec, device=dev, dtype=torch.int64)  # spikes emitted per (model, layer) launch
-        rec_idx = 0
-        streams = _band_streams(dev, ncnt, priority=0, tag="stream_pipeline")
-        st_it = iter(streams)
-        # operand-image buffers of the fused layer-0 path: zero-filled ONCE (padding rows), on the main stream and
-        # before the fork, then reused by every call of this shape
-        keep = self.__dict__.setdefault("_xop_cache", {})
-        for mi, d in enumerate(models):
-            if d["fused0"]:
-                m = d["m"]
-                budget = ((d["R"] + d["nt"] - 1) // d["nt"]) * d["C"]
-                nt0 = ops.stream_tile(d["R"], m.hidden_size, m.input_size, True, budget)
-                # a RING of frames (the layer-0 recurrence's out counters are the producer's back-pressure): the images
-                # are consumed microseconds after they are written and never need to reach DRAM
-                ring = min(T, int(os.environ.get("GSN_XOP_RING", self._XOP_RING)))
-                key = (mi, ring, d["R"], m.input_size, nt0, dev.index)
-                if key not in keep:
-                    keep[key] = ops.xplanes_buffer(ring, d["R"], m.input_size, nt0, dev)
-                d["xop"], d["nt0"], d["ring"] = keep[key], nt0, ring
-        # folded BatchNorm affines are (re)computed by torch kernels on the main stream while a graph is captured: they
-        # must precede the fork too.  `hold` keeps every buffer of this call alive until the next one, so that the
-        # caching allocator cannot hand a block to a later allocation while a concurrently running stage still uses it
-        hold = []
-        for d in models:
-            d["bn"] = [l.cell.folded_bn() for l in d["m"].sequence_model.layers]
-            hold.append(d["bn"])
-        fork = torch.cuda.Event()
-        fork.record(main)
-        used = []
-
-        def on_stream(fn):
-            stq = next(st_it)
-            stq.wait_event(fork)
-            with torch.cuda.stream(stq):
-                fn()
-            used.append(stq)
-
-        def ln(m):
-            if not m.use_pre_layer_norm:
-                return None, None, 1e-5
-            return m.pre_layer_norm.weight.detach(), m.pre_layer_norm.bias.detach(), m.pre_layer_norm.eps
-
-        fb_cnt = None
-        fb_target = 0
-        fb_act = None
-        results = []
-        record = [] if self.__dict__.get("record_stream_launches") else None
-        # The recurrences (thread-block clusters) are enqueued before the helper stages of their model so that cluster
-        # placement is not fragmented by single-CTA kernels; consumers spin on their producers' frame counters.
-        for mi, d in enumerate(models):
-            m, R = d["m"], d["R"]
-            H, K, C = m.hidden_size, m.input_size, d["C"]
-            cells = [l.cell for l in m.sequence_model.layers]
-            nt = d["nt"]
-            budget = ((R + nt - 1) // nt) * C  # makes the tile picker choose nt
-            w_ln, b_ln, e_ln = ln(m)
-            x_out = torch.empty((T, R, K), **f32) if strict else None
-            geo = (d["N"], d["lo"], d["ctr"], d["nbr"])
-            fbt = fb_act if d["fb"] else None
-            c_pre = counters[next(nxt)]
-            c_l0 = counters[next(nxt)]  # out counters of the layer-0 recurrence
-            pre_in = dict(in_cnt=fb_cnt if d["fb"] else None, in_target=fb_target)
-            w_ih0 = cells[0].weight_ih.detach()
-            if d["fused0"]:
-                xop, nt0 = d["xop"], d["nt0"]
-                xproj = None
-                bp = dict(ring=d["ring"], bp_cnt=c_l0, bp_target=ops.stream_ctas(R, H, K, True, budget))
-                pre = (lambda geo=geo, fbt=fbt, nt0=nt0, xop=xop, w_ln=w_ln, b_ln=b_ln, e_ln=e_ln, x_out=x_out, c_pre=c_pre,
-                       pre_in=pre_in, d=d, bp=bp: ops.xplanes_stream(cm, fbt, *geo, nt0, xop, w_ln, b_ln, e_ln, out_x=x_out,
-                                                                      out_cnt=c_pre, ctas=d["pre_p"], **pre_in, **bp))
-                pre_target = R
-            else:
-                xop = None
-                xproj = torch.empty((T, R, H), **f32)
-                hold.append(xproj)
-                pre = (lambda geo=geo, fbt=fbt, w_ih0=w_ih0, xproj=xproj, w_ln=w_ln, b_ln=b_ln, e_ln=e_ln, x_out=x_out,
-                       c_pre=c_pre, pre_in=pre_in, d=d: ops.pre_stream(cm, fbt, *geo, w_ih0, w_ln, b_ln, e_ln, out_x=x_out,
-                                                                       out_xproj=xproj, out_cnt=c_pre,
-                                                                       ctas_per_slice=d["pre_p"], **pre_in))
-                pre_target = R * C
-            in_cnt, in_target = c_pre, pre_target
-            bits_prev = None
-            bits_all, h_all = [], []
-            helpers = [pre]
-            for l, (cell, ly) in enumerate(zip(cells, d["layers"])):
-                a, b = d["bn"][l]
-                bits = ops.spike_bits_buffer((T, R), H, dev)
-                h_out = torch.empty((T, R, H), **f32) if strict else None
-                c_out = c_l0 if l == 0 else counters[next(nxt)]
-                kw = dict(out_bits=bits, out_h=h_out, out_cnt=c_out, sm_budget=budget, in_cnt=in_cnt, in_target=in_target,
-                          spike_count=spike_counts[rec_idx + l:rec_idx + l + 1])
-                w_hh, bias = cell.weight_hh.detach(), cell.bias_ih.detach()
-                fused = ly["fused"] or (l == 0 and d["fused0"])
-                if record is not None:
-                    # the same launch without counters (its inputs are complete once this step has run): timed alone
-                    kin = (K if l == 0 else H) if fused else 0
-                    ins = (dict(in_planes=xop, w_ih=w_ih0, frames_rows=(T, R), planes_ring=d["ring"]) if (l == 0 and d["fused0"]) else
-                           dict(in_bits=bits_prev, w_ih=cell.weight_ih.detach()) if ly["fused"] else None)
-                    record.append(dict(model=mi, layer=l, T=T, R=R, H=H, K_in=kin, fused=fused,
-                                       flops=2.0 * T * R * H * (H + kin), w_hh=w_hh, bias=bias, a=a, b=b, ins=ins,
-                                       out_bits=bits, budget=budget, out_cnt=c_out))
-                if l == 0 and d["fused0"]:
-                    on_stream(lambda w_hh=w_hh, bias=bias, a=a, b=b, kw=kw, xop=xop, w_ih0=w_ih0, R=R, ring=d["ring"]:
-                              ops.recurrence_stream(w_hh, bias, a, b, in_planes=xop, w_ih=w_ih0, frames_rows=(T, R),
-                                                    planes_ring=ring, **kw))
-                elif l == 0:
-                    if record is not None:
-                        record[-1]["ins"] = dict(xproj=xproj)
-                    on_stream(lambda w_hh=w_hh, bias=bias, a=a, b=b, kw=kw, xp=xproj:
-                              ops.recurrence_stream(w_hh, bias, a, b, xproj=xp, **kw))
-                elif ly["fused"]:
-                    on_stream(lambda w_hh=w_hh, bias=bias, a=a, b=b, kw=kw, bp=bits_prev, w=cell.weight_ih.detach():
-                              ops.recurrence_stream(w_hh, bias, a, b, in_bits=bp, w_ih=w, **kw))
-                else:
-                    xp = torch.empty((T, R, H), **f32)
-                    hold.append(xp)
-                    c_lin = counters[next(nxt)]
-                    helpers.append(lambda w=cell.weight_ih.detach(), bp=bits_prev, xp=xp, ic=in_cnt, it=in_target,
-                                   c_lin=c_lin, d=d: ops.linear_bits_stream(bp, w, out=xp, ctas=C * d["lin_p"], in_cnt=ic,
-                                                                            in_target=it, out_cnt=c_lin))
-                    kw.update(in_cnt=c_lin, in_target=R * C)
-                    if record is not None:
-                        record[-1]["ins"] = dict(xproj=xp)
-                    on_stream(lambda w_hh=w_hh, bias=bias, a=a, b=b, kw=kw, xp=xp:
-                              ops.recurrence_stream(w_hh, bias, a, b, xproj=xp, **kw))
-                in_cnt, in_target = c_out, ops.stream_ctas(R, H, (K if l == 0 else H) if fused else 0, fused, budget)
-                bits_prev = bits
-                bits_all.append(bits)
-                h_all.append(h_out)
-            P = m.proj_size
-            proj = torch.empty((T, R, P), **f32)
-            act = torch.empty_like(proj) if m._act else proj
-            hold.append(act)
-            c_proj = counters[next(nxt)]
-            pslices = (P + 127) // 128
-            helpers.append(lambda m=m, bp=bits_prev, proj=proj, act=act, ic=in_cnt, it=in_target, c_proj=c_proj, d=d:
-                           ops.linear_bits_stream(bp, m.proj.weight.detach(), m.proj.bias.detach(), act=m._act, out=proj,
-                                                  out_act=act if m._act else None, ctas=pslices * d["proj_p"], in_cnt=ic,
-                                                  in_target=it, out_cnt=c_proj))
-            for fn in helpers:
-                on_stream(fn)
-            if not d["fb"]:
-                fb_cnt, fb_target, fb_act = c_proj, R * pslices, act
-
-            # all_layer_outputs in the reference's positions; fp32 traces on demand unless strict
-            def lazy_x(geo=geo, fbt=fbt, w_ln=w_ln, b_ln=b_ln, e_ln=e_ln):
-                return ops.subband_features(cm, fbt, geo[0], geo[1], geo[2], geo[3], w_ln, b_ln, e_ln)
-
-            entries = [x_out if strict else lazy_x]
-            for bits, h_out in zip(bits_all, h_all):
-                entries.append(h_out if strict else (lambda bits=bits, H=H: ops.unpack_spikes(bits, H)))
-            entries.append(proj)
-            nl = len(cells)
-            results.append((proj, LazyOutputs(entries, widths=[K] + [H] * nl + [P],
-                                              spike_counts=spike_counts[rec_idx:rec_idx + nl], trace_numel=T * R * H),
-                            bits_all))
-            rec_idx += nl
-        for stq in used:
-            done = torch.cuda.Event()
-            done.record(stq)
-            main.wait_event(done)
-        if record is not None:
-            self.stream_launches = record
-        self._keepalive = (cm, counters, results, hold, spike_counts)
-        self.last_spike_bits = [r[2] for r in results]
-        return [r[0] for r in results[1:]], results[0][1], [r[1] for r in results[1:]]
-
     def coefficients(self, mag):
         """Deep-filter coefficient tensors [B, df_i, S, F_i, T, 2] in the reference layout."""
         projs, fb_all, sb_all = self.network(mag)
@@ -1267,6 +1292,21 @@ class _FreezeSequenceModel(nn.Module):
         self.output_size, self.input_size, self.hidden_size, self.num_layers = output_size, input_size, hidden_size, num_layers
         self.sequence_model_name = sequence_model
 
+    # the interface the streaming plan reads (same names as SequenceModel)
+    use_pre_layer_norm = False
+
+    @property
+    def proj(self):
+        return self.fc_output_layer if int(self.output_size) else None
+
+    @property
+    def proj_size(self):
+        return int(self.output_size)
+
+    @property
+    def _act(self):
+        return {"Tanh": "tanh", "ReLU": "relu"}.get(self.output_activate_function_name or None)
+
     def run_time_major(self, x):
         """x [T,R,K] (already normalised) -> (fc_out [T,R,P], activated, all_layer_outputs)."""
         out, _, trace = self.sequence_model(x, None)
@@ -1314,6 +1354,21 @@ def _utterance_norm(x, B, norm_type):
         return x / ((cum / count).unsqueeze(-1) + EPSILON)
     raise NotImplementedError("You must set up a type of Norm. e.g. offline_laplace_norm, "
                               "cumulative_laplace_norm, forgetting_norm, etc.")
+
+
+def _utterance_divisor(x, B, norm_type):
+    """The divisor `_utterance_norm` applies, for the streaming front end (gsn_xplanes_stream row_div): [B] per
+    utterance for offline_laplace_norm, [T, B*N] per row and frame for cumulative_laplace_norm; None when the norm is
+    not a pure division (offline_gaussian_norm).  Same torch reductions as `_utterance_norm`: identical values."""
+    T = x.shape[0]
+    if norm_type == "offline_laplace_norm":
+        return (x.view(T, B, -1).mean(dim=(0, 2)) + EPSILON).contiguous()
+    if norm_type == "cumulative_laplace_norm":
+        K = x.shape[2]
+        cum = torch.cumsum(x.sum(dim=2), dim=0)
+        count = torch.arange(K, K * T + 1, K, dtype=x.dtype, device=x.device).view(T, 1)
+        return (cum / count + EPSILON).contiguous()
+    return None
 
 
 class _FreezeSubbandModel(nn.Module):
@@ -1391,7 +1446,7 @@ class _FreezeSubbandModel(nn.Module):
         return [r[0] for r in res], [r[1] for r in res]
 
 
-class Separator(_GraphedNetwork, nn.Module):
+class Separator(_StreamingPipeline, _GraphedNetwork, nn.Module):
     """Surface B `model_low_freq.Separator` (:485-618): same network as SpikingFullSubNet with utterance-level
     laplace normalisation instead of LayerNorm; the class the model-zoo checkpoints were trained with.
     forward(wave [B,L] or [B,1,L]) -> (enhanced_y, enhanced_mag, fb_all_layer_outputs, sb_all_layer_outputs)."""
@@ -1403,7 +1458,7 @@ class Separator(_GraphedNetwork, nn.Module):
         super().__init__()
         self.n_fft, self.hop_length, self.win_length, self.fdrc = n_fft, hop_length, win_length, fdrc
         self.freq_cutoffs, self.sb_df_orders = freq_cutoffs, sb_df_orders
-        self.num_repeats, self.fb_freqs = num_freqs // fb_freqs, fb_freqs
+        self.num_repeats, self.fb_freqs, self.num_freqs = num_freqs // fb_freqs, fb_freqs, num_freqs
         self.norm_type = norm_type
         _utterance_norm(torch.zeros(1, 1, 1), 1, norm_type)  # unknown / unsupported norm types fail here
         self.fb_model = _FreezeSequenceModel(input_size=fb_freqs, output_size=fb_freqs, hidden_size=fb_hidden_size,
@@ -1436,6 +1491,63 @@ class Separator(_GraphedNetwork, nn.Module):
             raise ValueError("full-band output does not cover the spectrum")
         projs, sb_all = self.sb_model.run_time_major(cm, fb_act.contiguous())
         return projs, fb_all, sb_all
+
+    def _network_sched(self, mag):
+        if self.streaming:
+            res = self._network_stream(mag)
+            if res is not None:
+                return res
+        return self._network(mag)
+
+    def _stream_models(self, B):
+        """(full-band plan entry, sub-band plan entries): surface B runs them as TWO pipelines, because its norms
+        divide the sub-band input by statistics of the full-band output over all frames."""
+        sbm = self.sb_model
+        fb = dict(m=self.fb_model, R=B, N=1, lo=0, ctr=self.fb_freqs, nbr=0, fb=False, needs_div=True)
+        sbs = []
+        for i, (m, (lo, hi)) in enumerate(zip(sbm.sb_models, sbm.band_edges(self.num_freqs))):
+            ctr, nbr = sbm.sb_num_center_freqs[i], sbm.sb_num_neighbor_freqs[i]
+            if (hi - lo) % ctr != 0:
+                raise ValueError(f"The number of center frequencies should be divisible by the subband freqency "
+                                 f"interval. Got num_center_freqs={ctr}, upper_cutoff_freq={hi}, and "
+                                 f"lower_cutoff_freq={lo}.")
+            N = (hi - lo) // ctr
+            sbs.append(dict(m=m, R=B * N, N=N, lo=lo, ctr=ctr, nbr=nbr, fb=True, needs_div=True))
+        return fb, sbs
+
+    def _stream_plan(self, B, sm_total=None):
+        if self.norm_type not in ("offline_laplace_norm", "cumulative_laplace_norm"):
+            return None
+        fb, sbs = self._stream_models(B)
+        for d in [fb] + sbs:
+            if d["m"].proj is None or (d["m"].output_activate_function_name and d["m"]._act is None):
+                return None
+        p1, p2 = self._stream_plan_for([fb], sm_total), self._stream_plan_for(sbs, sm_total)
+        return None if p1 is None or p2 is None else (p1, p2)
+
+    def _network_stream(self, mag):
+        """The streaming schedule for surface B: pipeline 1 = the full-band model, pipeline 2 = all sub-band models (their
+        input is divided by utterance-level statistics of the COMPLETE full-band output, model_low_freq.py:146-171,
+        475).  The statistics come from the same gather + torch reductions as the eager path (identical divisors); the
+        division itself happens in gsn_xplanes_stream."""
+        B, F, T = mag.shape
+        plan = self._stream_plan(B)
+        if plan is None or F - 1 != self.num_freqs:
+            return None
+        p1, p2 = plan
+        dev = mag.device
+        ops.stream_preload(dev)
+        cm = ops.compress_mag(mag if mag.is_complex() else mag.contiguous(), F - 1, self.fdrc)
+        p1[0]["div"] = _utterance_divisor(ops.subband_features(cm, None, 1, 0, self.fb_freqs, 0), B, self.norm_type)
+        r1 = self._stream_run(p1, cm, tag="b1")
+        fb_act = r1[0][3]
+        if self.num_repeats * fb_act.shape[2] < F - 1:
+            raise ValueError("full-band output does not cover the spectrum")
+        for d in p2:
+            d["div"] = _utterance_divisor(ops.subband_features(cm, fb_act, d["N"], d["lo"], d["ctr"], d["nbr"]), B,
+                                          self.norm_type)
+        r2 = self._stream_run(p2, cm, fb_act=fb_act, tag="b2")
+        return [r[3] for r in r2], r1[0][1], [r[1] for r in r2]
 
     def coefficients(self, mag):
         """[B, df, F_i, T, 2] per band: '(b n) (c fc df) t -> b df (n fc) t c' (model_low_freq.py:257-263)."""

@@ -347,19 +347,25 @@ def xplanes_buffer(T, R, K, nt, device):
 
 
 def xplanes_stream(cm, fb, N, lo, ctr, nbr, nt, xop, ln_weight=None, ln_bias=None, eps=1e-5, out_x=None, in_cnt=None,
-                   in_target=0, out_cnt=None, ctas=1, ring=0, bp_cnt=None, bp_target=0):
+                   in_target=0, out_cnt=None, ctas=1, ring=0, bp_cnt=None, bp_target=0, row_div=None):
     """Streaming gather + LayerNorm + bf16x3 split of a sequence model's layer-0 input into the B-operand images the
     fused layer-0 recurrence reads (gsn_xplanes_stream).  `xop` from `xplanes_buffer` (same nt)."""
-    lib, st = _prep(cm, fb, ln_weight, ln_bias, out_x)
+    lib, st = _prep(cm, fb, ln_weight, ln_bias, out_x, row_div)
     T, B, f_cm = cm.shape
     K = ctr + 2 * nbr + (ctr if fb is not None else 0)
+    div_mode = 0
+    if row_div is not None:  # [B]: per utterance (offline laplace norm); [T, B*N]: per row and frame (cumulative)
+        div_mode = 1 if row_div.numel() == B and row_div.dim() == 1 else 2
+        if div_mode == 2 and tuple(row_div.shape) != (T, B * N):
+            raise ValueError("xplanes_stream: row_div must be [B] or [T, B*N]")
     frames = T if (ring <= 0 or ring > T) else int(ring)
     if xop.dtype != torch.uint8 or xop.numel() < lib.gsn_xplanes_bytes(frames, B * N, K, nt) or xop.device != cm.device:
         raise ValueError("xplanes_stream: xop buffer")
     if out_x is not None and tuple(out_x.shape) != (T, B * N, K):
         raise ValueError("xplanes_stream: out_x shape")
     _lib.check(lib.gsn_xplanes_stream(_ptr(cm), f_cm, _ptr(fb), fb.shape[2] if fb is not None else 0, _ptr(ln_weight),
-                                      _ptr(ln_bias), float(eps), _ptr(out_x), xop.data_ptr(), int(ring), _ptr(in_cnt),
+                                      _ptr(ln_bias), float(eps), _ptr(row_div), div_mode, _ptr(out_x), xop.data_ptr(),
+                                      int(ring), _ptr(in_cnt),
                                       int(in_target), _ptr(out_cnt), _ptr(bp_cnt), int(bp_target), T, B, N, lo, ctr,
                                       nbr, int(nt), int(ctas), st))
     LAUNCHES[0] += 1

@@ -337,3 +337,51 @@ def test_synops_accounting_from_in_kernel_spike_counts():
         H = tr.widths[1]
         counted = [int(ops.unpack_spikes(b, H).sum()) for b in bits]
         assert counted == [int(c) for c in tr.spike_counts.tolist()]
+
+
+@pytest.mark.parametrize("graph", [False, True])
+@pytest.mark.parametrize("name", ["tiny_surface_b", "tiny_surface_b_cumnorm", "zoo_s_1s"])
+def test_streaming_surface_b_vs_golden(name, graph):
+    """Surface B `Separator` on the streaming schedule (two pipelines: full band, then all sub-bands; the laplace norm's
+    division inside gsn_xplanes_stream) against the reference's fixtures, including the TRAINED zoo-S checkpoint and
+    the cumulative norm the recipe TOMLs select: spike flips within the reference's own noise floor (3.5e-4; zero on the
+    synthetic fixtures), waveform and coefficients within 1e-3 when nothing flipped."""
+    from spiking_fullsubnet_b200 import Separator
+    from tests.helpers import load_golden_weights
+    g = load_golden(name)
+    cfg = g["cfg"]
+    params = load_golden_weights(name) if name.startswith("zoo") else synth.make_params_b(cfg, g["seed"])
+    m = Separator(**cfg)
+    m.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in params.items()}, strict=True)
+    m = m.eval().to(DEV)
+    m.enable_streaming(True)
+    if m._stream_plan(g["mag"].shape[0]) is None:
+        pytest.skip("not co-resident on this device")
+    if graph:
+        m.enable_cuda_graph(True)
+    with torch.no_grad():
+        for _ in range(2):
+            coefs, fb_all, sb_all = m.coefficients(_t(g["mag"]))
+        enh_y, enh_mag, _, _ = m(_t(g["wave"]))
+    assert _rel(fb_all[0].cpu().numpy(), g["fb_x"]) < 1e-4
+    flips = total = 0
+    for l in range(2):
+        ref = unpack(g[f"fb_h{l}"], cfg["fb_hidden_size"])
+        flips += (fb_all[1 + l].cpu().numpy() != ref).sum()
+        total += ref.size
+    for i in range(3):
+        assert _rel(sb_all[i][0].cpu().numpy(), g[f"sb{i}_x"]) < 1e-4
+        for l in range(2):
+            ref = unpack(g[f"sb{i}_h{l}"], cfg["sb_hidden_size"])
+            flips += (sb_all[i][1 + l].cpu().numpy() != ref).sum()
+            total += ref.size
+    record_parity(f"streaming_surface_b/{name}/{'graph' if graph else 'eager'}", {"flips": int(flips), "total": int(total)})
+    assert flips / total <= 3.5e-4
+    if not name.startswith("zoo"):
+        assert flips == 0
+    if flips == 0:
+        for i in range(3):
+            assert coefs[i].shape == g[f"coef{i}"].shape
+            assert _rel(coefs[i].cpu().numpy(), g[f"coef{i}"]) < 1e-3
+        assert _rel(enh_y.cpu().numpy(), g["enh_y"]) < 1e-3
+        assert _rel(enh_mag.cpu().numpy(), g["enh_mag"]) < 1e-3

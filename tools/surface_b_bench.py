@@ -58,3 +58,13 @@ with torch.no_grad():
     m.enable_cuda_graph(False)
     f = timed(lambda: m(wave))
     print(f"   forward() eager {f:.3f} ms -> {B * T / f / 1e3:.2f} M frames/s")
+    m.enable_streaming(True)
+    if m._stream_plan(B) is None:
+        print("   streaming: not co-resident")
+    else:
+        e = timed(lambda: m.network(mag))
+        m.enable_cuda_graph(True)
+        g = timed(lambda: m.network(mag))
+        f = timed(lambda: m(wave))
+        print(f"   STREAMING (two pipelines): network eager {e:.3f} ms, graph {g:.3f} ms -> {B * T / g / 1e3:.2f} M frames/s; "
+              f"forward() {f:.3f} ms -> {B * T / f / 1e3:.2f} M frames/s")
