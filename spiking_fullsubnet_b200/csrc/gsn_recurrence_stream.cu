@@ -21,6 +21,8 @@
 //     adds 1 to out_cnt[t] (release) once every epilogue warp's stores of frame t are done.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "gsn_common.cuh"
 #include "gsn_tc.cuh"
 
@@ -45,6 +47,7 @@ struct RecStreamParams {
   unsigned int in_target;
   unsigned int poll_ns;         // back-off between two polls of in_cnt
   int pub_nofence;              // TIMING EXPERIMENT ONLY (GSN_PUB_NOFENCE=1): publish without the release fence
+  int dbg;                      // PROF builds only (GSN_TC_DBG): timing experiments, wrong results possible
   int direct;                   // epilogue warps write the bf16 hh operand of the next frame straight into every CTA
   unsigned int* out_cnt;        // [T] or null: += 1 per CTA when its part of frame t is globally visible
   unsigned long long* spike_count;  // or null: += number of spikes emitted by this launch (SynOps accounting)
@@ -79,7 +82,7 @@ __host__ __device__ inline int st_kw_padded(int C) { return 4 * C + 1; }
 
 // shared-memory carve-up (bytes); everything is a function of (NT, Kmma, Kin_mma, C, FUSED)
 struct StLayout {
-  size_t sB, bits, ring, bars, stage, total;
+  size_t sB, bits, ring, bars, lut, stage, total;
 };
 enum { kInXproj = 0, kInBits = 1, kInPlanes = 2 };
 template <int NT, int IN>
@@ -96,6 +99,8 @@ __host__ __device__ inline StLayout st_layout(int Kmma, int Kin_mma, int C, int 
   else off += (size_t)StCfg<NT>::RX * NT * 128 * 4;
   L.bars = off;
   off += 256;
+  L.lut = off;  // 256 x 16 bytes: 8 spike bits -> 8 bf16 {0, 1} (one operand chunk)
+  off += 4096;
   L.stage = off;  // weight staging (prologue only)
   off += (size_t)128 * wpitch_max * 4;
   L.total = (off + 127) / 128 * 128;
@@ -247,7 +252,14 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
   volatile int* pub_done = reinterpret_cast<volatile int*>(bars + 21);
   float* wst = reinterpret_cast<float*>(smem + L.stage);
-  constexpr int RING_IN = FUSED ? kRI : RX;
+  const uint4* lut = reinterpret_cast<const uint4*>(smem + L.lut);
+  if (tid < 256) {  // spike byte -> operand chunk (replaces ~20 shift / mask instructions per chunk in the frame loop)
+    uint32_t v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      v[e] = ((tid >> (2 * e)) & 1 ? kOneBf : 0u) | ((tid >> (2 * e + 1)) & 1 ? (kOneBf << 16) : 0u);
+    reinterpret_cast<uint4*>(smem + L.lut)[tid] = make_uint4(v[0], v[1], v[2], v[3]);
+  }
 
   if (tid == 0) {
     tc::mbar_init(bar_w, 1);
@@ -354,51 +366,103 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
     const uint32_t op_bytes = (uint32_t)NT * 16u * (uint32_t)(Kmma / 8 - (own_k8 > 0 ? own_k8 : 0));
     const uint32_t ih_slot_bytes = (uint32_t)((IN == kInPlanes ? 3 : 1) * (((size_t)NT * p.Kin_mma * 2 + 127) / 128 * 128));
     const int ksteps_in = FUSED ? p.Kin_mma / 16 : 0;
-    auto issue_ih = [&](int tt) {  // input-to-hidden product of frame tt -> D_ih
+    auto issue_ih = [&](int tt, auto ksi_tag) {  // input-to-hidden product of frame tt -> D_ih
+      constexpr int KSI = decltype(ksi_tag)::value;  // k steps of the input product; 0 = runtime count
       const int slot = tt % kRI;
       if (!tc::mbar_wait_cta(&bar_in_full[slot], (uint32_t)((tt / kRI) & 1))) __trap();
       if (tt > 0 && !tc::mbar_wait_cta(bar_dih_free, (uint32_t)((tt - 1) & 1))) __trap();
       tc::tc_fence_after();
       const uint64_t db = tc::make_smem_desc(tc::smem_u32(ring + (size_t)slot * ih_slot_bytes), 128, 16u * p.Kin_mma);
       if (leader) {
-        if (IN == kInPlanes) {  // real-valued input: 8 plane pairs; 6 for wide inputs (see kWidePairsKsteps)
-          if (ksteps_in >= kWidePairsKsteps) tc::mma_pairs<NT, 6>(ksteps_in, tmem_dih, tmem_aih, db, idesc);
+        if constexpr (IN == kInPlanes) {  // real-valued input: 8 plane pairs; 6 for wide inputs (see kWidePairsKsteps)
+          if constexpr (KSI >= kWidePairsKsteps) tc::mma_pairs_unrolled<KSI, NT * KSI * 2, 6>(tmem_dih, tmem_aih, db, idesc);
+          else if constexpr (KSI > 0) tc::mma_pairs_unrolled<KSI, NT * KSI * 2, 8>(tmem_dih, tmem_aih, db, idesc);
+          else if (ksteps_in >= kWidePairsKsteps) tc::mma_pairs<NT, 6>(ksteps_in, tmem_dih, tmem_aih, db, idesc);
           else tc::mma_pairs<NT, 8>(ksteps_in, tmem_dih, tmem_aih, db, idesc);
+        } else if constexpr (KSI > 0) {
+          tc::mma_planes_unrolled<KSI, kStPlanes>(tmem_dih, tmem_aih, db, idesc);
+        } else {
+          tc::mma_planes<kStPlanes>(ksteps_in, tmem_dih, tmem_aih, db, idesc);
         }
-        else tc::mma_planes<kStPlanes>(ksteps_in, tmem_dih, tmem_aih, db, idesc);
         tc::mma_commit(&bar_in_free[slot]);
         tc::mma_commit(bar_dih_full);
       }
       __syncwarp();
     };
-    if (FUSED) issue_ih(0);
     long long ic[3] = {0, 0, 0};
-    for (int t = 0; t < T; ++t) {
-      const long long i0 = PROF ? clock64() : 0;
-      if (direct) {
-        // operand of frame t (buffer t&1) = st.async stores of every epilogue warp of the cluster, counted in bytes
-        if (t > 0 && !tc::mbar_wait_cta(&bar_bits[t & 1], (uint32_t)(((t - 1) >> 1) & 1))) __trap();
-        tc::fence_proxy_async_smem();
-      } else if (!tc::mbar_wait_cta(bar_B, (uint32_t)(t & 1))) {
-        __trap();
-      }
-      tc::tc_fence_after();
-      const long long i1 = PROF ? clock64() : 0;
-      if (leader) {
+    // The frame loop is instantiated per number of k steps (KS = 0: runtime count, switch per frame): with the
+    // straight-line MMA list selected OUTSIDE the loop its descriptors / tensor-memory addresses are loop invariants
+    // (one list per operand buffer), and the per-frame jump table + ~40 descriptor instructions in front of the
+    // first MMA (about 270 cycles of every frame) are gone.
+    auto issue_loop = [&](auto ks_tag, auto ksi_tag) {
+      constexpr int KS = decltype(ks_tag)::value;
+      if (FUSED) issue_ih(0, ksi_tag);
+      for (int t = 0; t < T; ++t) {
+        const long long i0 = PROF ? clock64() : 0;
         if (direct) {
-          if (t + 1 < T) tc::mbar_arrive_expect_tx(&bar_bits[(t + 1) & 1], op_bytes);  // arm the next frame's operand
-          tc::mma_planes<kStPlanes>(ksteps, tmem_dhh, tmem_ahh, (t & 1) ? desc_b1 : desc_b0, idesc);
-        } else {
-          tc::mbar_arrive_expect_tx(&bar_bits[t & 1], bits_bytes);  // arm this frame's spike-bit exchange
-          tc::mma_planes<kStPlanes>(ksteps, tmem_dhh, tmem_ahh, desc_b0, idesc);
+          // operand of frame t (buffer t&1) = st.async stores of every epilogue warp of the cluster, counted in bytes
+          if (t > 0 && !tc::mbar_wait_cta(&bar_bits[t & 1], (uint32_t)(((t - 1) >> 1) & 1))) __trap();
+          if (!(PROF && (p.dbg & 1))) tc::fence_proxy_async_smem();
+        } else if (!tc::mbar_wait_cta(bar_B, (uint32_t)(t & 1))) {
+          __trap();
         }
-        tc::mma_commit(bar_mma);
+        tc::tc_fence_after();
+        const long long i1 = PROF ? clock64() : 0;
+        if (leader) {
+          if (direct) {
+            if constexpr (KS > 0) {
+              if (t & 1) tc::mma_planes_unrolled<KS, kStPlanes>(tmem_dhh, tmem_ahh, desc_b1, idesc);
+              else tc::mma_planes_unrolled<KS, kStPlanes>(tmem_dhh, tmem_ahh, desc_b0, idesc);
+            } else {
+              tc::mma_planes<kStPlanes>(ksteps, tmem_dhh, tmem_ahh, (t & 1) ? desc_b1 : desc_b0, idesc);
+            }
+            tc::mma_commit(bar_mma);
+            // arm the next frame's operand barrier (its phase cannot complete before this arrival, so peers' bytes
+            // that land earlier are only counted early)
+            if (t + 1 < T) tc::mbar_arrive_expect_tx(&bar_bits[(t + 1) & 1], (PROF && (p.dbg & 4)) ? 0u : op_bytes);
+          } else {
+            tc::mbar_arrive_expect_tx(&bar_bits[t & 1], bits_bytes);  // arm this frame's spike-bit exchange
+            if constexpr (KS > 0) tc::mma_planes_unrolled<KS, kStPlanes>(tmem_dhh, tmem_ahh, desc_b0, idesc);
+            else tc::mma_planes<kStPlanes>(ksteps, tmem_dhh, tmem_ahh, desc_b0, idesc);
+            tc::mma_commit(bar_mma);
+          }
+        }
+        __syncwarp();
+        const long long i2 = PROF ? clock64() : 0;
+        if (FUSED && t + 1 < T) issue_ih(t + 1, ksi_tag);
+        if (PROF) { ic[0] += i1 - i0; ic[1] += i2 - i1; ic[2] += clock64() - i2; }
       }
-      __syncwarp();
-      const long long i2 = PROF ? clock64() : 0;
-      if (FUSED && t + 1 < T) issue_ih(t + 1);
-      if (PROF) { ic[0] += i1 - i0; ic[1] += i2 - i1; ic[2] += clock64() - i2; }
+    };
+    // instantiated for the (hidden, input) sizes of the S / M / L recipes and cirm_gsn that take this input mode;
+    // everything else runs the runtime lists
+#define GSN_LOOP(a, b) issue_loop(std::integral_constant<int, a>{}, std::integral_constant<int, b>{})
+    if constexpr (IN == kInXproj) {
+      switch (ksteps) {
+        case 10: GSN_LOOP(10, 0); break;
+        case 14: GSN_LOOP(14, 0); break;
+        case 15: GSN_LOOP(15, 0); break;
+        case 16: GSN_LOOP(16, 0); break;
+        case 17: GSN_LOOP(17, 0); break;
+        case 20: GSN_LOOP(20, 0); break;
+        default: GSN_LOOP(0, 0); break;
+      }
+    } else if constexpr (IN == kInBits) {
+      if (ksteps == 10 && ksteps_in == 10) GSN_LOOP(10, 10);
+      else GSN_LOOP(0, 0);
+    } else {
+      const int combo = ksteps * 100 + ksteps_in;
+      switch (combo) {
+        case 1003: GSN_LOOP(10, 3); break;
+        case 1006: GSN_LOOP(10, 6); break;
+        case 1010: GSN_LOOP(10, 10); break;
+        case 1504: GSN_LOOP(15, 4); break;
+        case 1403: GSN_LOOP(14, 3); break;
+        case 1406: GSN_LOOP(14, 6); break;
+        case 1603: GSN_LOOP(16, 3); break;
+        default: GSN_LOOP(0, 0); break;
+      }
     }
+#undef GSN_LOOP
     if (PROF && p.prof && blockIdx.x == 0 && leader)
       for (int i = 0; i < 3; ++i) p.prof[8 + i] = (unsigned long long)ic[i];
   } else if (warp == kLoadWarp) {
@@ -456,11 +520,7 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
             const int k8 = 4 * wi + e4;
             if (k8 >= k8i) break;
             const uint32_t b8 = (wd[it] >> (8 * e4)) & 0xFFu;
-            uint32_t v[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              v[e] = ((b8 >> (2 * e)) & 1u ? kOneBf : 0u) | ((b8 >> (2 * e + 1)) & 1u ? (kOneBf << 16) : 0u);
-            *reinterpret_cast<uint4*>(dst + (uint32_t)(nhi * SBOi + k8 * 128 + nlo * 16)) = make_uint4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<uint4*>(dst + (uint32_t)(nhi * SBOi + k8 * 128 + nlo * 16)) = lut[b8];
           }
         }
         tc::fence_proxy_async_smem();
@@ -598,11 +658,8 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
         if (t + 1 < T) {
           // my warp's 32 neurons x 4 rows as sixteen 16-byte operand chunks, to every CTA of the cluster
           const uint32_t wrow = __shfl_sync(0xffffffffu, myw, dir_i);
-          const uint32_t b8 = (wrow >> (8 * dir_sub)) & 0xFFu;
-          uint32_t v[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            v[e] = ((b8 >> (2 * e)) & 1u ? kOneBf : 0u) | ((b8 >> (2 * e + 1)) & 1u ? (kOneBf << 16) : 0u);
+          const uint4 v4 = lut[(wrow >> (8 * dir_sub)) & 0xFFu];
+          const uint32_t v[4] = {v4.x, v4.y, v4.z, v4.w};
           const uint32_t local = tc::smem_u32(sB + (par ? 0u : sB_bytes)) + dir_off;  // buffer (t+1)&1
           const uint32_t lbar = tc::smem_u32(&bar_bits[par ^ 1]);
           // The chunk for this CTA is a plain store (the st.async path takes ~1.4 cycles per 16-byte packet: 512
@@ -610,15 +667,21 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
           // proxy and announced with one arrival per warp; the remote chunks follow as st.async, counted in bytes on
           // the peer's barrier (issued after the proxy fence, which would otherwise wait for them)
           if (dir_ok && (slice & 1u) == (uint32_t)(lane >> 4))
-            *reinterpret_cast<uint4*>(sB + (par ? 0u : sB_bytes) + dir_off) = make_uint4(v[0], v[1], v[2], v[3]);
-          tc::fence_proxy_async_smem();
+            *reinterpret_cast<uint4*>(sB + (par ? 0u : sB_bytes) + dir_off) = v4;
+          if (!(PROF && (p.dbg & 2))) tc::fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(&bar_bits[par ^ 1]);
           if (PROF) pc[6] += clock64() - q3;
-          for (uint32_t r0 = 0; r0 < C; r0 += 2) {
-            const uint32_t r = r0 + (lane >> 4);
-            if (dir_ok && r < C && r != slice)
+          if (C <= 2) {  // one peer at most: lanes 16-31 of CTA 0 / lanes 0-15 of CTA 1 send
+            const uint32_t r = (uint32_t)(lane >> 4);
+            if (dir_ok && r < C && r != slice && !(PROF && (p.dbg & 4)))
               tc::st_async_v4(tc::map_shared_rank(local, r), v, tc::map_shared_rank(lbar, r));
+          } else {
+            for (uint32_t r0 = 0; r0 < C; r0 += 2) {
+              const uint32_t r = r0 + (lane >> 4);
+              if (dir_ok && r < C && r != slice && !(PROF && (p.dbg & 4)))
+                tc::st_async_v4(tc::map_shared_rank(local, r), v, tc::map_shared_rank(lbar, r));
+            }
           }
           if (PROF) pc[7] += clock64() - q3;
         }
@@ -664,11 +727,7 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
         for (int it = 0; it < MAXT; ++it) {
           if (task_dst[it] == 0xFFFFFFFFu) continue;
           const uint32_t b8 = (src[task_src[it] & 0xFFFFFFu] >> (task_src[it] >> 24)) & 0xFFu;
-          uint32_t v[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            v[e] = ((b8 >> (2 * e)) & 1u ? kOneBf : 0u) | ((b8 >> (2 * e + 1)) & 1u ? (kOneBf << 16) : 0u);
-          *reinterpret_cast<uint4*>(sB + task_dst[it]) = make_uint4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<uint4*>(sB + task_dst[it]) = lut[b8];
         }
         tc::fence_proxy_async_smem();
         __syncwarp();
@@ -823,6 +882,8 @@ extern "C" int gsn_recurrence_stream(const float* xproj, const uint32_t* in_bits
   p.direct = (direct != 0 && nt == 16) ? 1 : 0;
   static const int nofence = getenv("GSN_PUB_NOFENCE") ? atoi(getenv("GSN_PUB_NOFENCE")) : 0;
   p.pub_nofence = nofence;
+  static const int dbg = getenv("GSN_TC_DBG") ? atoi(getenv("GSN_TC_DBG")) : 0;
+  p.dbg = dbg;
   p.prof = reinterpret_cast<unsigned long long*>(workspace);
   p.T = T; p.R = R; p.H = H; p.Kmma = (H + 15) / 16 * 16;
   p.K_in = fused ? K_in : 0; p.Kin_mma = fused ? (K_in + 15) / 16 * 16 : 0;
