@@ -428,8 +428,11 @@ def main():
         for r in recs:
             def one(r=r):
                 # (out_cnt: the ring-buffered operand images of a fused layer 0 require the back-pressure counters)
-                ops.recurrence_stream(r["w_hh"], r["bias"], r["a"], r["b"], out_bits=r["out_bits"],
-                                      sm_budget=r["budget"], out_cnt=r["out_cnt"], **r["ins"])
+                # (a layer fed by the ring of spike operand images finds only the last frames there when it runs alone:
+                # same work, but its output goes to a scratch trace)
+                ops.recurrence_stream(r["w_hh"], r["bias"], r["a"], r["b"],
+                                      out_bits=torch.empty_like(r["out_bits"]) if r.get("scratch_out") else r["out_bits"],
+                                      sm_budget=r["budget"], out_cnt=r["out_cnt"], **r["ins"], **r.get("img", {}))
             one()
             torch.cuda.synchronize()
             ts = []

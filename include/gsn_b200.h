@@ -160,7 +160,15 @@ GSN_API int gsn_overlap_add(const float* frames, const float* window, float* y, 
  *                                   fp32-faithful), one bulk copy per frame; same tensor-memory condition, K_in <= 256;
  *                                   planes_ring = frames the image buffer holds (frame t in slot t % planes_ring;
  *                                   <= 0 or >= T: one slot per frame; a shorter ring needs out_cnt, which the
- *                                   producer reads as back-pressure);
+ *                                   producer reads as back-pressure), or
+ *       in_image                    the spikes of the layer below as the bf16 operand image that layer wrote through
+ *                                   its img_out (same rows, 16-row tiles, K_in = its H; ring = planes_ring) + w_ih:
+ *                                   like in_bits, but the input arrives with one bulk copy per frame instead of
+ *                                   being expanded from bits by the loader warp (0.15 us per frame at H = 160);
+ *   - img_out (may be NULL; 16-row tiles only): this layer's spikes of frame t as the operand image of the layer
+ *     above, [img_ring][ceil(R/16)][16 x ceil16(H) bf16] = gsn_spike_image_bytes(img_ring, R, H) bytes, slot
+ *     t % img_ring; with a ring shorter than T the input of frame t waits for bp_cnt[t - img_ring] >= bp_target
+ *     (bp_cnt = the out_cnt of the consuming launch, bp_target = its CTA count), so the ring stays L2-resident;
  *   - in_cnt [T] (may be NULL): frame t of the input may be read once in_cnt[t] >= in_target (acquire);
  *   - h_bits [T,R,ceil(H/32)]: the spike trace, bit-packed (always); h_out / c_out [T,R,H] fp32 optional (NULL);
  *     hT / cT [R,H] optional;
@@ -174,7 +182,10 @@ GSN_API int gsn_recurrence_stream(const float* xproj, const uint32_t* in_bits, c
                                   const float* bn_scale, const float* bn_shift, uint32_t* h_bits, float* h_out,
                                   float* c_out, float* hT, float* cT, const unsigned int* in_cnt,
                                   unsigned int in_target, unsigned int* out_cnt, unsigned long long* spike_count,
-                                  int T, int R, int H, int sm_budget, void* workspace, gsn_stream_t stream);
+                                  const void* in_image, void* img_out, int img_ring, const unsigned int* bp_cnt,
+                                  unsigned int bp_target, int T, int R, int H, int sm_budget, void* workspace,
+                                  gsn_stream_t stream);
+GSN_API size_t gsn_spike_image_bytes(int frames, int R, int H);
 /* Loads every kernel of the streaming pipeline into the context.  The pipeline's kernels spin on counters their
  * producers advance, and with lazy module loading the first launch of a kernel synchronises with running kernels:
  * call once per process and device BEFORE the first pipeline launch (a spinning consumer would otherwise wait for a

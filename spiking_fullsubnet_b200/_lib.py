@@ -34,7 +34,9 @@ SIGNATURES = {
     "gsn_layer_recurrence": (_i, [_p] * 11 + [_i] * 6 + [_p, _p]),
     "gsn_layer_recurrence_bits": (_i, [_p] * 12 + [_i] * 6 + [_p, _p]),
     "gsn_pack_spikes": (_i, [_p, _p, _i64, _i, _p]),
-    "gsn_recurrence_stream": (_i, [_p, _p, _p, _i, _p, _i] + [_p] * 9 + [_p, C.c_uint, _p, _p] + [_i] * 4 + [_p, _p]),
+    "gsn_recurrence_stream": (_i, [_p, _p, _p, _i, _p, _i] + [_p] * 9 + [_p, C.c_uint, _p, _p]
+                              + [_p, _p, _i, _p, C.c_uint] + [_i] * 4 + [_p, _p]),
+    "gsn_spike_image_bytes": (_sz, [_i] * 3),
     "gsn_compress_spec": (_i, [_p, _p, _i, _i, _i, _i, _f, _i, _p]),
     "gsn_deepfilter_spec": (_i, [_p, _p, _p] + [_i] * 11 + [_p]),
     "gsn_spec_passthrough": (_i, [_p, _p] + [_i] * 7 + [_p]),

@@ -33,6 +33,10 @@ struct RecStreamParams {
   const uint32_t* in_bits;   // IN_BITS: [T, R, Wi] bit-packed spikes of the layer below, Wi = ceil(K_in / 32)
   const uint8_t* in_planes;  // IN_PLANES: operand images of gsn_xplanes_stream, [ring][tiles][3][NT x Kin_mma] bf16
   int planes_ring;           // frames the image buffer holds (frame t in slot t % planes_ring)
+  uint8_t* img_out;          // or null: bf16 operand image of this layer's spikes, [img_ring][tiles][NT x Kmma] (16-row tiles)
+  int img_ring;              // frames img_out holds
+  const unsigned int* bp_cnt;  // or null: frame t may overwrite slot t % img_ring once bp_cnt[t - img_ring] >= bp_target
+  unsigned int bp_target;
   const float* w_ih;         // FUSED: [H, K_in]
   const float* w_hh;         // [H, H]
   const float* bias;         // [2H]
@@ -84,7 +88,7 @@ __host__ __device__ inline int st_kw_padded(int C) { return 4 * C + 1; }
 struct StLayout {
   size_t sB, bits, ring, bars, lut, stage, total;
 };
-enum { kInXproj = 0, kInBits = 1, kInPlanes = 2 };
+enum { kInXproj = 0, kInBits = 1, kInPlanes = 2, kInImage = 3 };
 template <int NT, int IN>
 __host__ __device__ inline StLayout st_layout(int Kmma, int Kin_mma, int C, int wpitch_max, bool direct) {
   constexpr bool FUSED = IN != kInXproj;
@@ -115,6 +119,20 @@ __device__ __forceinline__ void st_split3(float w, uint32_t& hi, uint32_t& mid, 
   mid = r1b >> 16;
   const float r2 = r1 - __uint_as_float(r1b & 0xFFFF0000u);
   lo = __float_as_uint(r2) >> 16;
+}
+
+// 8 spike bits -> 8 bf16 {0, 1} (one 16-byte operand chunk) without a table: x * 0x10204080 moves bit i of a nibble to
+// bit 8i + 7 (the 16 partial products land on distinct bits, so nothing carries), PRMT replicates those byte sign bits
+// over half-words, and the mask leaves 0x3F80 = bf16 1.0 where the bit was set.
+__device__ __forceinline__ uint4 spike_byte_to_bf16x8(uint32_t b8) {
+  const uint32_t r0 = (b8 & 0xFu) * 0x10204080u, r1 = ((b8 >> 4) & 0xFu) * 0x10204080u;
+  uint4 v;  // (prmt.b32 directly: __byte_perm drops the sign-replication bit of the selector nibbles)
+  asm("prmt.b32 %0, %1, 0, 0x9988;" : "=r"(v.x) : "r"(r0));
+  asm("prmt.b32 %0, %1, 0, 0xBBAA;" : "=r"(v.y) : "r"(r0));
+  asm("prmt.b32 %0, %1, 0, 0x9988;" : "=r"(v.z) : "r"(r1));
+  asm("prmt.b32 %0, %1, 0, 0xBBAA;" : "=r"(v.w) : "r"(r1));
+  v.x &= 0x3F803F80u; v.y &= 0x3F803F80u; v.z &= 0x3F803F80u; v.w &= 0x3F803F80u;
+  return v;
 }
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
@@ -446,7 +464,7 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
         case 20: GSN_LOOP(20, 0); break;
         default: GSN_LOOP(0, 0); break;
       }
-    } else if constexpr (IN == kInBits) {
+    } else if constexpr (IN == kInBits || IN == kInImage) {
       if (ksteps == 10 && ksteps_in == 10) GSN_LOOP(10, 10);
       else GSN_LOOP(0, 0);
     } else {
@@ -468,13 +486,22 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
   } else if (warp == kLoadWarp) {
     // =============================== loader warp ===============================
     int ready = 0;  // frames [0, ready) of the input are known complete
-    if (IN == kInPlanes) {
-      // one bulk copy per frame: the three operand planes of this row tile, already in the B-operand layout
-      const uint32_t blk_bytes = 3u * (uint32_t)NT * (uint32_t)p.Kin_mma * 2u;
+    int ready_bp = 0;  // frames [0, ready_bp) of this layer's operand images have been consumed downstream
+    // ring reuse of img_out: the epilogue runs at most a ring of input slots behind this warp, so gating the INPUT of
+    // frame tt on the consumer having finished frame tt - img_ring keeps slot tt % img_ring free for the epilogue
+    auto bp_wait = [&](int tt) -> bool {
+      if (p.bp_cnt == nullptr || tt < p.img_ring || ready_bp > tt - p.img_ring) return true;
+      return poll_frames(p.bp_cnt, p.bp_target, T, ready_bp, tt - p.img_ring, true, p.poll_ns, lane);
+    };
+    if (IN == kInPlanes || IN == kInImage) {
+      // one bulk copy per frame: the operand planes of this row tile (three for a real-valued input, one for the spike
+      // image the layer below wrote), already in the B-operand layout
+      const uint32_t blk_bytes = (IN == kInPlanes ? 3u : 1u) * (uint32_t)NT * (uint32_t)p.Kin_mma * 2u;
       const int ntiles = (R + NT - 1) / NT, tile = blockIdx.x / C;
       for (int tt = 0; tt < T; ++tt) {
         const int slot = tt % kRI;
         if (tt >= kRI && !tc::mbar_wait_cta(&bar_in_free[slot], (uint32_t)(((tt / kRI) - 1) & 1))) { alive = false; break; }
+        if (!bp_wait(tt)) { alive = false; break; }
         if (p.in_cnt && ready <= tt) {
           if (!poll_frames(p.in_cnt, p.in_target, T, ready, tt, true, p.poll_ns, lane)) { alive = false; break; }
           asm volatile("fence.proxy.async;" ::: "memory");  // the bulk copy below reads what the producer wrote
@@ -495,6 +522,7 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
       for (int tt = 0; tt < T; ++tt) {
         const int slot = tt % kRI;
         if (tt >= kRI && !tc::mbar_wait_cta(&bar_in_free[slot], (uint32_t)(((tt / kRI) - 1) & 1))) { alive = false; break; }
+        if (!bp_wait(tt)) { alive = false; break; }
         if (p.in_cnt && ready <= tt && !poll_frames(p.in_cnt, p.in_target, T, ready, tt, true, p.poll_ns, lane)) {
           alive = false;
           break;
@@ -506,14 +534,14 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
           const int i = lane + 32 * it;
           const int nlo = i & 7, wi = (i >> 3) % nw, nhi = (i >> 3) / nw;
           const int row = row0 + nhi * 8 + nlo;
-          wd[it] = (i < NT * nw && row < R && wi < Wi) ? ld_cg_u32(p.in_bits + ((size_t)tt * R + row) * Wi + wi) : 0u;
+          wd[it] = (i < NT * nw && row < R && wi < Wi && !(p.dbg & 16)) ? ld_cg_u32(p.in_bits + ((size_t)tt * R + row) * Wi + wi) : 0u;
         }
         // poll ahead while the words of frame tt are in flight
         if (p.in_cnt && ready <= tt + 1 && tt + 1 < T) poll_frames(p.in_cnt, p.in_target, T, ready, tt + 1, false, 0, lane);
 #pragma unroll
         for (int it = 0; it < MAXW; ++it) {
           const int i = lane + 32 * it;
-          if (i >= NT * nw) break;
+          if (i >= NT * nw || ((p.dbg & 8) && tt >= kRI)) break;
           const int nlo = i & 7, wi = (i >> 3) % nw, nhi = (i >> 3) / nw;
 #pragma unroll
           for (int e4 = 0; e4 < 4; ++e4) {
@@ -536,6 +564,7 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
       for (int tt = 0; tt < T; ++tt) {
         const int slot = tt % RX;
         if (tt >= RX && !tc::mbar_wait_cta(&bar_in_free[slot], (uint32_t)(((tt / RX) - 1) & 1))) { alive = false; break; }
+        if (!bp_wait(tt)) { alive = false; break; }
         if (p.in_cnt && ready <= tt) {
           if (!poll_frames(p.in_cnt, p.in_target, T, ready, tt, true, p.poll_ns, lane)) { alive = false; break; }
           asm volatile("fence.proxy.async;" ::: "memory");  // the bulk copies below read what the producer wrote
@@ -586,6 +615,13 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
     uint32_t* hb_ptr = p.h_bits + (size_t)(hb_ok ? hb_row : 0) * Wb + (hb_ok ? slice * 4 + q : 0);
     const size_t hb_step = (size_t)R * Wb;
     const bool do_h = p.h_out != nullptr, do_c = p.c_out != nullptr, do_pub = p.out_cnt != nullptr;
+    // operand image of my spikes for the layer above: [img_ring][tiles][NT x Kmma bf16] in this kernel's own operand layout
+    const bool do_img = direct && p.img_out != nullptr;
+    const bool dir_mine = dir_ok && (slice & 1u) == (uint32_t)(lane >> 4);
+    const size_t img_step = (size_t)((R + NT - 1) / NT) * sB_bytes;
+    uint8_t* const img_base = p.img_out + (size_t)(blockIdx.x / C) * sB_bytes;
+    uint8_t* img_ptr = img_base;
+    int img_slot = 0;
     char* h_ptr = reinterpret_cast<char*>(p.h_out) + boff0;
     char* c_ptr = reinterpret_cast<char*>(p.c_out) + boff0;
     // frame-0 operand is in place (zeros)
@@ -655,35 +691,44 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
       const long long q3 = PROF ? clock64() : 0;
       // ---- exchange first (critical path), then the trace (running pointers: no per-frame address arithmetic) ----
       if (direct) {
-        if (t + 1 < T) {
+        const bool more = t + 1 < T;
+        if (more || do_img) {
           // my warp's 32 neurons x 4 rows as sixteen 16-byte operand chunks, to every CTA of the cluster
           const uint32_t wrow = __shfl_sync(0xffffffffu, myw, dir_i);
-          const uint4 v4 = lut[(wrow >> (8 * dir_sub)) & 0xFFu];
+          const uint4 v4 = spike_byte_to_bf16x8(wrow >> (8 * dir_sub));
           const uint32_t v[4] = {v4.x, v4.y, v4.z, v4.w};
-          const uint32_t local = tc::smem_u32(sB + (par ? 0u : sB_bytes)) + dir_off;  // buffer (t+1)&1
-          const uint32_t lbar = tc::smem_u32(&bar_bits[par ^ 1]);
-          // The chunk for this CTA is a plain store (the st.async path takes ~1.4 cycles per 16-byte packet: 512
-          // packets per frame would cost more than the bit exchange it replaces), made visible to the tensor core's
-          // proxy and announced with one arrival per warp; the remote chunks follow as st.async, counted in bytes on
-          // the peer's barrier (issued after the proxy fence, which would otherwise wait for them)
-          if (dir_ok && (slice & 1u) == (uint32_t)(lane >> 4))
-            *reinterpret_cast<uint4*>(sB + (par ? 0u : sB_bytes) + dir_off) = v4;
-          if (!(PROF && (p.dbg & 2))) tc::fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) tc::mbar_arrive(&bar_bits[par ^ 1]);
-          if (PROF) pc[6] += clock64() - q3;
-          if (C <= 2) {  // one peer at most: lanes 16-31 of CTA 0 / lanes 0-15 of CTA 1 send
-            const uint32_t r = (uint32_t)(lane >> 4);
-            if (dir_ok && r < C && r != slice && !(PROF && (p.dbg & 4)))
-              tc::st_async_v4(tc::map_shared_rank(local, r), v, tc::map_shared_rank(lbar, r));
-          } else {
-            for (uint32_t r0 = 0; r0 < C; r0 += 2) {
-              const uint32_t r = r0 + (lane >> 4);
+          if (more) {
+            const uint32_t local = tc::smem_u32(sB + (par ? 0u : sB_bytes)) + dir_off;  // buffer (t+1)&1
+            const uint32_t lbar = tc::smem_u32(&bar_bits[par ^ 1]);
+            // The chunk for this CTA is a plain store (the st.async path takes ~1.4 cycles per 16-byte packet: 512
+            // packets per frame would cost more than the bit exchange it replaces), made visible to the tensor core's
+            // proxy and announced with one arrival per warp; the remote chunks follow as st.async, counted in bytes on
+            // the peer's barrier (issued after the proxy fence, which would otherwise wait for them)
+            if (dir_mine) *reinterpret_cast<uint4*>(sB + (par ? 0u : sB_bytes) + dir_off) = v4;
+            if (!(PROF && (p.dbg & 2))) tc::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&bar_bits[par ^ 1]);
+            if (PROF) pc[6] += clock64() - q3;
+            if (C <= 2) {  // one peer at most: lanes 16-31 of CTA 0 / lanes 0-15 of CTA 1 send
+              const uint32_t r = (uint32_t)(lane >> 4);
               if (dir_ok && r < C && r != slice && !(PROF && (p.dbg & 4)))
                 tc::st_async_v4(tc::map_shared_rank(local, r), v, tc::map_shared_rank(lbar, r));
+            } else {
+              for (uint32_t r0 = 0; r0 < C; r0 += 2) {
+                const uint32_t r = r0 + (lane >> 4);
+                if (dir_ok && r < C && r != slice && !(PROF && (p.dbg & 4)))
+                  tc::st_async_v4(tc::map_shared_rank(local, r), v, tc::map_shared_rank(lbar, r));
+              }
             }
+            if (PROF) pc[7] += clock64() - q3;
           }
-          if (PROF) pc[7] += clock64() - q3;
+          // the same chunks as this frame's operand image for the layer above (it fetches its input with one bulk
+          // copy per frame instead of expanding spike bits): off the critical path, before the frame is published
+          if (do_img) {
+            if (dir_mine) *reinterpret_cast<uint4*>(img_ptr + dir_off) = v4;
+            img_ptr += img_step;
+            if (++img_slot == p.img_ring) { img_slot = 0; img_ptr = img_base; }
+          }
         }
       } else if (sender) {
         tc::st_async_u32(par ? snd_cell1 : snd_cell0, myw, par ? snd_bar1 : snd_bar0);
@@ -829,6 +874,7 @@ int preload_recurrence_stream() {
   GSN_PRE(16, kInXproj) GSN_PRE(32, kInXproj) GSN_PRE(64, kInXproj)
   GSN_PRE(16, kInBits) GSN_PRE(32, kInBits) GSN_PRE(64, kInBits)
   GSN_PRE(16, kInPlanes) GSN_PRE(32, kInPlanes) GSN_PRE(64, kInPlanes)
+  GSN_PRE(16, kInImage)
 #undef GSN_PRE
   return GSN_OK;
 }
@@ -842,6 +888,11 @@ extern "C" int gsn_recurrence_stream_tile(int R, int H, int K_in, int fused, int
   return gsn::recurrence_stream_tile(R, H, K_in, fused, sms);
 }
 
+extern "C" size_t gsn_spike_image_bytes(int frames, int R, int H) {
+  if (frames <= 0 || R <= 0 || H <= 0) return 0;
+  return (size_t)frames * (size_t)((R + 15) / 16) * 16u * (size_t)((H + 15) / 16 * 16) * 2u;
+}
+
 extern "C" int gsn_recurrence_stream_ctas(int R, int H, int K_in, int fused, int sm_budget) {
   const int nt = gsn_recurrence_stream_tile(R, H, K_in, fused, sm_budget);
   return nt ? ((R + nt - 1) / nt) * ((H + 127) / 128) : 0;
@@ -852,13 +903,19 @@ extern "C" int gsn_recurrence_stream(const float* xproj, const uint32_t* in_bits
                                      const float* bn_scale, const float* bn_shift, uint32_t* h_bits, float* h_out,
                                      float* c_out, float* hT, float* cT, const unsigned int* in_cnt,
                                      unsigned int in_target, unsigned int* out_cnt, unsigned long long* spike_count,
-                                     int T, int R, int H, int sm_budget, void* workspace, gsn_stream_t stream) {
+                                     const void* in_image, void* img_out, int img_ring, const unsigned int* bp_cnt,
+                                     unsigned int bp_target, int T, int R, int H, int sm_budget, void* workspace,
+                                     gsn_stream_t stream) {
   using namespace gsn;
-  const int in_mode = in_bits != nullptr ? kInBits : (in_planes != nullptr ? kInPlanes : kInXproj);
+  const int in_mode = in_bits != nullptr ? kInBits : (in_planes != nullptr ? kInPlanes : (in_image != nullptr ? kInImage : kInXproj));
   const bool fused = in_mode != kInXproj;
   GSN_REQUIRE(w_hh && bias && h_bits, "gsn_recurrence_stream: null pointer");
-  GSN_REQUIRE((xproj != nullptr) + (in_bits != nullptr) + (in_planes != nullptr) == 1,
-              "gsn_recurrence_stream: pass exactly one of xproj, (in_bits, w_ih), (in_planes, w_ih)");
+  GSN_REQUIRE((xproj != nullptr) + (in_bits != nullptr) + (in_planes != nullptr) + (in_image != nullptr) == 1,
+              "gsn_recurrence_stream: pass exactly one of xproj, (in_bits, w_ih), (in_planes, w_ih), (in_image, w_ih)");
+  GSN_REQUIRE(in_mode != kInImage || (reinterpret_cast<uintptr_t>(in_image) & 15) == 0,
+              "gsn_recurrence_stream: in_image needs 16-byte alignment");
+  GSN_REQUIRE(img_out == nullptr || (reinterpret_cast<uintptr_t>(img_out) & 15) == 0,
+              "gsn_recurrence_stream: img_out needs 16-byte alignment");
   GSN_REQUIRE(!fused || (w_ih && K_in > 0), "gsn_recurrence_stream: fused input needs w_ih and K_in");
   GSN_REQUIRE(in_mode != kInPlanes || (K_in <= 256 && (reinterpret_cast<uintptr_t>(in_planes) & 15) == 0),
               "gsn_recurrence_stream: in_planes needs K_in <= 256 and 16-byte alignment");
@@ -869,10 +926,19 @@ extern "C" int gsn_recurrence_stream(const float* xproj, const uint32_t* in_bits
     return fail(GSN_ENOSUP, "gsn_recurrence_stream: H=%d K_in=%d fused=%d does not fit tensor memory", H, K_in,
                 (int)fused);
   RecStreamParams p{};
-  p.xproj = xproj; p.in_bits = in_bits; p.in_planes = static_cast<const uint8_t*>(in_planes); p.w_ih = w_ih;
+  p.xproj = xproj; p.in_bits = in_bits; p.w_ih = w_ih;
+  p.in_planes = static_cast<const uint8_t*>(in_mode == kInImage ? in_image : in_planes);
   p.planes_ring = (planes_ring <= 0 || planes_ring > T) ? T : planes_ring;
-  GSN_REQUIRE(in_mode != kInPlanes || p.planes_ring == T || out_cnt != nullptr,
+  GSN_REQUIRE((in_mode != kInPlanes && in_mode != kInImage) || p.planes_ring == T || out_cnt != nullptr,
               "gsn_recurrence_stream: a ring shorter than T needs out_cnt (the producer's back-pressure)");
+  GSN_REQUIRE(in_mode != kInImage || nt == 16, "gsn_recurrence_stream: in_image needs the 16-row tile (R=%d H=%d)", R, H);
+  GSN_REQUIRE(img_out == nullptr || nt == 16, "gsn_recurrence_stream: img_out needs the 16-row tile (R=%d H=%d)", R, H);
+  p.img_out = static_cast<uint8_t*>(img_out);
+  p.img_ring = (img_ring <= 0 || img_ring > T) ? T : img_ring;
+  GSN_REQUIRE(img_out == nullptr || p.img_ring == T || bp_cnt != nullptr,
+              "gsn_recurrence_stream: an image ring shorter than T needs bp_cnt (the consumer's out_cnt)");
+  p.bp_cnt = img_out != nullptr && p.img_ring < T ? bp_cnt : nullptr;
+  p.bp_target = bp_target;
   p.w_hh = w_hh; p.bias = bias; p.bn_scale = bn_scale;
   p.bn_shift = bn_shift; p.h_bits = h_bits; p.h_out = h_out; p.c_out = c_out; p.hT = hT; p.cT = cT;
   p.in_cnt = in_cnt; p.in_target = in_target; p.out_cnt = out_cnt; p.spike_count = spike_count;
@@ -896,6 +962,7 @@ extern "C" int gsn_recurrence_stream(const float* xproj, const uint32_t* in_bits
     case 32: return launch_stream<32, MODE>(p, C, st);          \
     default: return launch_stream<64, MODE>(p, C, st);          \
   }
+  if (in_mode == kInImage) return launch_stream<16, kInImage>(p, C, st);
   if (in_mode == kInBits) { GSN_ST_DISPATCH(kInBits) }
   if (in_mode == kInPlanes) { GSN_ST_DISPATCH(kInPlanes) }
   GSN_ST_DISPATCH(kInXproj)

@@ -821,6 +821,17 @@ class _StreamingPipeline:
                 if key not in keep:
                     keep[key] = ops.xplanes_buffer(ring, d["R"], m.input_size, nt0, dev)
                 d["xop"], d["nt0"], d["ring"] = keep[key], nt0, ring
+            # spike operand images between fused layers (layer l-1 writes, layer l fetches with one bulk copy per frame
+            # instead of expanding bits in its loader warp): rings like the layer-0 images, L2-resident
+            d["img"] = {}
+            if d["nt"] == 16 and os.environ.get("GSN_STREAM_IMAGES", "1") != "0":
+                iring = min(T, int(os.environ.get("GSN_XOP_RING", self._XOP_RING)))
+                for l, ly in enumerate(d["layers"]):
+                    if l > 0 and ly["fused"]:
+                        key = (tag, mi, "img", l, iring, d["R"], d["m"].hidden_size, dev.index)
+                        if key not in keep:
+                            keep[key] = ops.spike_image_buffer(iring, d["R"], d["m"].hidden_size, dev)
+                        d["img"][l] = (keep[key], iring)
         # folded BatchNorm affines are (re)computed by torch kernels on the main stream while a graph is captured: they
         # must precede the fork too.  `hold` keeps every buffer of this call alive until the next one, so that the
         # caching allocator cannot hand a block to a later allocation while a concurrently running stage still uses it
@@ -884,15 +895,22 @@ class _StreamingPipeline:
                 pre_target = R * C
             in_cnt, in_target = c_pre, pre_target
             bits_prev = None
+            c_pending = None  # out counters of the next layer when the current one already needs them (back-pressure)
             bits_all, h_all = [], []
             helpers = [pre]
             for l, (cell, ly) in enumerate(zip(cells, d["layers"])):
                 a, b = d["bn"][l]
                 bits = ops.spike_bits_buffer((T, R), H, dev)
                 h_out = torch.empty((T, R, H), **f32) if strict else None
-                c_out = c_l0 if l == 0 else counters[next(nxt)]
+                c_out = c_l0 if l == 0 else (c_pending if c_pending is not None else counters[next(nxt)])
                 kw = dict(out_bits=bits, out_h=h_out, out_cnt=c_out, sm_budget=budget, in_cnt=in_cnt, in_target=in_target,
                           spike_count=spike_counts[rec_idx + l:rec_idx + l + 1])
+                if l + 1 in d["img"]:  # my spikes also leave as the operand image of layer l + 1 (its counters = my back-pressure)
+                    c_next = counters[next(nxt)]
+                    kw.update(img_out=d["img"][l + 1][0], img_ring=d["img"][l + 1][1], bp_cnt=c_next,
+                              bp_target=ops.stream_ctas(R, H, H, True, budget))
+                else:
+                    c_next = None
                 w_hh, bias = cell.weight_hh.detach(), cell.bias_ih.detach()
                 fused = ly["fused"] or (l == 0 and d["fused0"])
                 if record is not None:
@@ -902,7 +920,8 @@ class _StreamingPipeline:
                            dict(in_bits=bits_prev, w_ih=cell.weight_ih.detach()) if ly["fused"] else None)
                     record.append(dict(model=mi, layer=l, T=T, R=R, H=H, K_in=kin, fused=fused,
                                        flops=2.0 * T * R * H * (H + kin), w_hh=w_hh, bias=bias, a=a, b=b, ins=ins,
-                                       out_bits=bits, budget=budget, out_cnt=c_out))
+                                       out_bits=bits, budget=budget, out_cnt=c_out,
+                                       img={k: kw[k] for k in ("img_out", "img_ring", "bp_cnt", "bp_target") if k in kw}))
                 if l == 0 and d["fused0"]:
                     on_stream(lambda w_hh=w_hh, bias=bias, a=a, b=b, kw=kw, xop=xop, w_ih0=w_ih0, R=R, ring=d["ring"]:
                               ops.recurrence_stream(w_hh, bias, a, b, in_planes=xop, w_ih=w_ih0, frames_rows=(T, R),
@@ -912,6 +931,14 @@ class _StreamingPipeline:
                         record[-1]["ins"] = dict(xproj=xproj)
                     on_stream(lambda w_hh=w_hh, bias=bias, a=a, b=b, kw=kw, xp=xproj:
                               ops.recurrence_stream(w_hh, bias, a, b, xproj=xp, **kw))
+                elif ly["fused"] and l in d["img"]:
+                    if record is not None:
+                        record[-1]["ins"] = dict(in_image=d["img"][l][0], planes_ring=d["img"][l][1], frames_rows=(T, R),
+                                                 w_ih=cell.weight_ih.detach())
+                        record[-1]["scratch_out"] = True  # relaunched alone the ring holds the last frames only
+                    on_stream(lambda w_hh=w_hh, bias=bias, a=a, b=b, kw=kw, im=d["img"][l], w=cell.weight_ih.detach():
+                              ops.recurrence_stream(w_hh, bias, a, b, in_image=im[0], planes_ring=im[1],
+                                                    frames_rows=(T, R), w_ih=w, **kw))
                 elif ly["fused"]:
                     on_stream(lambda w_hh=w_hh, bias=bias, a=a, b=b, kw=kw, bp=bits_prev, w=cell.weight_ih.detach():
                               ops.recurrence_stream(w_hh, bias, a, b, in_bits=bp, w_ih=w, **kw))
@@ -929,6 +956,7 @@ class _StreamingPipeline:
                               ops.recurrence_stream(w_hh, bias, a, b, xproj=xp, **kw))
                 in_cnt, in_target = c_out, ops.stream_ctas(R, H, (K if l == 0 else H) if fused else 0, fused, budget)
                 bits_prev = bits
+                c_pending = c_next
                 bits_all.append(bits)
                 h_all.append(h_out)
             P = m.proj_size

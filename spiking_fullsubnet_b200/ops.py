@@ -293,17 +293,23 @@ def stream_ctas(R, H, K_in=0, fused=False, sm_budget=0):
 
 def recurrence_stream(w_hh, bias, bn_scale=None, bn_shift=None, xproj=None, in_bits=None, w_ih=None, out_bits=None,
                       out_h=None, out_c=None, out_hT=None, out_cT=None, in_cnt=None, in_target=0, out_cnt=None,
-                      spike_count=None, sm_budget=0, workspace=None, in_planes=None, frames_rows=None, planes_ring=0):
+                      spike_count=None, sm_budget=0, workspace=None, in_planes=None, frames_rows=None, planes_ring=0,
+                      in_image=None, img_out=None, img_ring=0, bp_cnt=None, bp_target=0):
     """One GSULayer over all frames as a persistent streaming launch (gsn_recurrence_stream): zero initial state,
     shared gate weights.  Input: xproj [T,R,H], OR (in_bits [T,R,ceil(K/32)] int32, w_ih [H,K]) for the fused
     spike-input product, OR (in_planes = the operand images of `xplanes_stream`, w_ih [H,K], frames_rows = (T, R)) for
-    the fused real-input product of layer 0.  Returns the bit-packed spike trace int32 [T,R,ceil(H/32)]."""
+    the fused real-input product of layer 0, OR (in_image = the `img_out` buffer of the layer below (ring =
+    planes_ring), w_ih [H,K], frames_rows) -- the spike-input product again, fetched with one bulk copy per frame.
+    img_out (from `spike_image_buffer`, ring of img_ring frames, back-pressure bp_cnt / bp_target = the consumer's
+    out_cnt / CTA count): also write this layer's spikes as the operand image of the layer above.
+    Returns the bit-packed spike trace int32 [T,R,ceil(H/32)]."""
     lib, st = _prep(w_hh, bias, bn_scale, bn_shift, xproj, w_ih, out_h, out_c, out_hT, out_cT)
     H = w_hh.shape[1]
     if w_hh.shape[0] != H or bias.numel() != 2 * H:
         raise ValueError("recurrence_stream: shared gate weights only (w_hh [H,H], bias [2H])")
-    if (xproj is not None) + (in_bits is not None) + (in_planes is not None) != 1:
-        raise ValueError("recurrence_stream: pass exactly one of xproj, (in_bits, w_ih), (in_planes, w_ih)")
+    if (xproj is not None) + (in_bits is not None) + (in_planes is not None) + (in_image is not None) != 1:
+        raise ValueError("recurrence_stream: pass exactly one of xproj, (in_bits, w_ih), (in_planes, w_ih), "
+                         "(in_image, w_ih)")
     if xproj is not None:
         T, R, _ = xproj.shape
         K_in = 0
@@ -312,6 +318,12 @@ def recurrence_stream(w_hh, bias, bn_scale=None, bn_shift=None, xproj=None, in_b
         K_in = w_ih.shape[1]
         if in_bits.dtype != torch.int32 or not in_bits.is_contiguous() or Wi != (K_in + 31) // 32 or w_ih.shape[0] != H:
             raise ValueError("recurrence_stream: in_bits / w_ih shapes")
+    elif in_image is not None:
+        T, R = frames_rows
+        K_in = w_ih.shape[1]
+        ring = T if (planes_ring <= 0 or planes_ring > T) else int(planes_ring)
+        if w_ih.shape[0] != H or in_image.numel() * in_image.element_size() < lib.gsn_spike_image_bytes(ring, R, K_in):
+            raise ValueError("recurrence_stream: in_image / w_ih shapes")
     else:
         T, R = frames_rows
         K_in = w_ih.shape[1]
@@ -325,16 +337,29 @@ def recurrence_stream(w_hh, bias, bn_scale=None, bn_shift=None, xproj=None, in_b
         out_bits = torch.empty((T, R, Wb), device=w_hh.device, dtype=torch.int32)
     elif out_bits.dtype != torch.int32 or not out_bits.is_contiguous() or tuple(out_bits.shape) != (T, R, Wb):
         raise ValueError("recurrence_stream: out_bits")
-    for cnt in (in_cnt, out_cnt):
+    for cnt in (in_cnt, out_cnt, bp_cnt):
         if cnt is not None and (cnt.dtype != torch.int32 or cnt.numel() != T or not cnt.is_contiguous()):
             raise ValueError("recurrence_stream: counters must be contiguous int32 [T]")
+    if img_out is not None:
+        ring_o = T if (img_ring <= 0 or img_ring > T) else int(img_ring)
+        if img_out.numel() * img_out.element_size() < lib.gsn_spike_image_bytes(ring_o, R, H):
+            raise ValueError("recurrence_stream: img_out too small")
     _lib.check(lib.gsn_recurrence_stream(
         _ptr(xproj), _ptr(in_bits), _ptr(in_planes), int(planes_ring), _ptr(w_ih), int(K_in), _ptr(w_hh), _ptr(bias),
         _ptr(bn_scale),
         _ptr(bn_shift), out_bits.data_ptr(), _ptr(out_h), _ptr(out_c), _ptr(out_hT), _ptr(out_cT), _ptr(in_cnt),
-        int(in_target), _ptr(out_cnt), _ptr(spike_count), T, R, H, int(sm_budget), _ptr(workspace), st))
+        int(in_target), _ptr(out_cnt), _ptr(spike_count), _ptr(in_image), _ptr(img_out), int(img_ring), _ptr(bp_cnt),
+        int(bp_target), T, R, H, int(sm_budget), _ptr(workspace), st))
     LAUNCHES[0] += 1
     return out_bits
+
+
+def spike_image_buffer(frames, R, H, device):
+    """Operand-image buffer (ring of `frames` frames) a streaming recurrence fills through img_out for the layer above."""
+    n = _lib.load().gsn_spike_image_bytes(int(frames), int(R), int(H))
+    if n == 0:
+        raise ValueError(f"spike_image_buffer: bad shape frames={frames} R={R} H={H}")
+    return torch.zeros(n, device=device, dtype=torch.uint8)
 
 
 def xplanes_buffer(T, R, K, nt, device):

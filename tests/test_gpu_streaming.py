@@ -311,6 +311,43 @@ def test_recurrence_stream_chain_bit_identical_to_chunk_kernel(T, R, K, H):
         assert bool((cnt[1] == ops.stream_ctas(R, H, H, True)).all())
 
 
+@pytest.mark.parametrize("T,R,H,ring", [(200, 70, 160, 16), (90, 32, 128, 0), (150, 250, 160, 8), (64, 37, 100, 4)])
+def test_recurrence_stream_spike_images_bit_identical_to_bit_input(T, R, H, ring):
+    """Layer hand-over through bf16 operand images: layer 0 writes its spikes of every frame as the B-operand image of
+    the layer above (img_out, a ring of `ring` frames reused under back-pressure from the consumer's counters; 0 = one
+    slot per frame), layer 1 fetches it with one bulk copy per frame (in_image).  Traces and counters must equal the
+    bit-input form of the same two launches; the consumer is launched first, on zeroed buffers."""
+    rs = np.random.RandomState(R * 7 + H)
+    s = 1 / np.sqrt(H)
+    xproj = _t(rs.uniform(-1, 1, (T, R, H)).astype(np.float32))
+    W = [(_t(rs.uniform(-s, s, (H, H)).astype(np.float32)), _t(rs.uniform(-s, s, 2 * H).astype(np.float32)),
+          _t(rs.uniform(0.6, 1.2, H).astype(np.float32)), _t(rs.normal(0, 0.1, H).astype(np.float32))) for _ in range(2)]
+    w_ih1 = _t(rs.uniform(-s, s, (H, H)).astype(np.float32))
+    assert ops.stream_ctas(R, H, H, True) > 0
+    ops.stream_preload(DEV)
+    want0 = ops.recurrence_stream(W[0][0], W[0][1], W[0][2], W[0][3], xproj=xproj)
+    want1 = ops.recurrence_stream(W[1][0], W[1][1], W[1][2], W[1][3], in_bits=want0, w_ih=w_ih1)
+    torch.cuda.synchronize()
+    assert int(want1.ne(0).sum()) > 0
+    cnt = ops.frame_counters(T, DEV, 2)
+    img = ops.spike_image_buffer(ring if ring else T, R, H, DEV)
+    img.fill_(0x7F)  # poison: every byte the consumer reads must have been written by the producer
+    ob0, ob1 = torch.zeros_like(want0), torch.zeros_like(want1)
+    s0, s1 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    n1 = ops.stream_ctas(R, H, H, True)
+    with torch.cuda.stream(s1):
+        ops.recurrence_stream(W[1][0], W[1][1], W[1][2], W[1][3], in_image=img, planes_ring=ring, frames_rows=(T, R),
+                              w_ih=w_ih1, out_bits=ob1, in_cnt=cnt[0], in_target=ops.stream_ctas(R, H), out_cnt=cnt[1])
+    with torch.cuda.stream(s0):
+        ops.recurrence_stream(W[0][0], W[0][1], W[0][2], W[0][3], xproj=xproj, out_bits=ob0, out_cnt=cnt[0],
+                              img_out=img, img_ring=ring, bp_cnt=cnt[1], bp_target=n1)
+    torch.cuda.synchronize()
+    assert torch.equal(ob0, want0)
+    assert torch.equal(ob1, want1)
+    assert bool((cnt[1] == n1).all())
+
+
 def test_synops_accounting_from_in_kernel_spike_counts():
     """Row f4 on the streaming schedule: compute_synops / compute_neuronops (audiozen/metric.py:303-340) come out of the
     spike counts the recurrence kernels accumulate while they run (popcount of their ballot words) -- equal to the
