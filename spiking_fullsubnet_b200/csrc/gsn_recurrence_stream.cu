@@ -605,9 +605,15 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
     __syncwarp();
   } else {
     // =============================== epilogue warps ===============================
-    float c[CPT], hval[CPT];
+    float c[CPT];
 #pragma unroll
-    for (int i = 0; i < CPT; ++i) { c[i] = 0.f; hval[i] = 0.f; }
+    for (int i = 0; i < CPT; ++i) c[i] = 0.f;
+    // Rows are independent columns of the MMA, so rows past R (and neurons past H: their lanes never spike, bs_ = 0 and
+    // bt_ = -1 below) need no per-element predicate: their ballot words are masked once, here
+    const int rows_w = R - rfirst < CPT ? (R - rfirst > 0 ? R - rfirst : 0) : CPT;  // valid rows of this warp
+    const uint32_t row_mask = (lane % CPT) < rows_w ? 0xFFFFFFFFu : 0u;
+    const float bs_ = comp ? bs : 0.f, bt_ = comp ? bt : -1.f;
+    uint32_t lastw[CPT];  // ballot words of the last frame (hT)
     unsigned int nspk = 0;
     // running output pointers of this thread
     const int hb_row = row0 + g * CPT + lane;
@@ -652,7 +658,7 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
         if (!tc::mbar_wait_cta(&bar_in_full[slot], (uint32_t)((t / RX) & 1))) { alive = false; break; }
         const float* xs = reinterpret_cast<const float*>(ring) + (size_t)slot * NT * 128 + (size_t)(g * CPT) * 128 + tl;
 #pragma unroll
-        for (int i = 0; i < CPT; ++i) xn[i] = i < nv ? xs[i * 128] : 0.f;
+        for (int i = 0; i < CPT; ++i) xn[i] = xs[i * 128];  // (rows past R: stale ring contents, masked below)
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&bar_in_free[slot]);
       }
@@ -675,18 +681,19 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
         tc::tmem_wait_ld();
 #pragma unroll
         for (int u = 0; u < CH; ++u) {
+          // (scalar on purpose: the packed FADD2 / FMUL2 / FFMA2 forms of this block measured 2 % SLOWER per frame)
           const float z = __uint_as_float(zr[u]);
           const float sg = sigmoid_f32(__fadd_rn(xf_[i0 + u], z));
           const float gh = __fadd_rn(xg_[i0 + u], z);
           const float ctil = __fadd_rn(__fmul_rn(sg, c[i0 + u]), __fmul_rn(__fsub_rn(1.0f, sg), gh));
-          const float cn = __fadd_rn(__fmul_rn(ctil, bs), bt);
+          const float cn = __fadd_rn(__fmul_rn(ctil, bs_), bt_);
           c[i0 + u] = cn;
-          const bool spike = (i0 + u < nv) && cn >= 0.f;
-          hval[i0 + u] = spike ? 1.0f : 0.0f;
-          const uint32_t w = __ballot_sync(0xffffffffu, spike);
+          const uint32_t w = __ballot_sync(0xffffffffu, cn >= 0.f);
+          lastw[i0 + u] = w;
           myw = (lane % CPT) == (i0 + u) ? w : myw;
         }
       }
+      myw &= row_mask;
       tc::tc_fence_before();
       const long long q3 = PROF ? clock64() : 0;
       // ---- exchange first (critical path), then the trace (running pointers: no per-frame address arithmetic) ----
@@ -741,7 +748,7 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
       if (do_h) {
 #pragma unroll
         for (int i = 0; i < CPT; ++i)
-          if (i < nv) *reinterpret_cast<float*>(h_ptr + i * hstride) = hval[i];
+          if (i < nv) *reinterpret_cast<float*>(h_ptr + i * hstride) = (lastw[i] >> lane) & 1u ? 1.0f : 0.0f;
         h_ptr += frame_bytes;
       }
       if (do_c) {
@@ -753,7 +760,9 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
       if (do_pub) {
         __syncwarp();
         if (lane == 0) {
-          if (t >= kPubRing) {  // never run a whole ring ahead of the publisher (mbarrier phases would alias)
+          // never run a whole ring ahead of the publisher (mbarrier phases would alias); the phase of frame t needs
+          // every warp's arrival, so holding back ONE warp holds the phase
+          if (warp == 0 && t >= kPubRing) {
             unsigned int spins = 0;
             while (pub_done[t % kPubWarps] < t - kPubRing + 1) {
               if (++spins > (1u << 24)) __trap();
@@ -791,7 +800,7 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
     for (int i = 0; i < CPT; ++i) {
       if (i < nv) {
         if (p.cT) *reinterpret_cast<float*>(reinterpret_cast<char*>(p.cT) + boff0 + i * hstride) = c[i];
-        if (p.hT) *reinterpret_cast<float*>(reinterpret_cast<char*>(p.hT) + boff0 + i * hstride) = hval[i];
+        if (p.hT) *reinterpret_cast<float*>(reinterpret_cast<char*>(p.hT) + boff0 + i * hstride) = (lastw[i] >> lane) & 1u ? 1.0f : 0.0f;
       }
     }
     if (p.spike_count && lane < CPT && nspk) atomicAdd(p.spike_count, (unsigned long long)nspk);
