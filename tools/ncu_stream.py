@@ -58,13 +58,16 @@ with torch.no_grad():
             ops.xplanes_stream(cm, fbt, *geo, nt, xop, lnw, lnb, 1e-5, ctas=pl["pre_p"])
             a0, b0 = cells[0].folded_bn()
             flush.fill_(1.0)
+            fused1 = pl["layers"][1]["fused"]
+            # (one image slot per frame here: alone, the layers do not overlap, so there is no ring to reuse)
+            img = ops.spike_image_buffer(T, R, H, DEV) if fused1 else None
             bits0 = ops.recurrence_stream(cells[0].weight_hh.detach(), cells[0].bias_ih.detach(), a0, b0, in_planes=xop,
-                                          w_ih=cells[0].weight_ih.detach(), frames_rows=(T, R))
+                                          w_ih=cells[0].weight_ih.detach(), frames_rows=(T, R), img_out=img)
             a1, b1 = cells[1].folded_bn()
             flush.fill_(1.0)
-            if pl["layers"][1]["fused"]:
+            if fused1:
                 bits1 = ops.recurrence_stream(cells[1].weight_hh.detach(), cells[1].bias_ih.detach(), a1, b1,
-                                              in_bits=bits0, w_ih=cells[1].weight_ih.detach())
+                                              in_image=img, frames_rows=(T, R), w_ih=cells[1].weight_ih.detach())
             else:
                 xp1 = ops.linear_bits_stream(bits0, cells[1].weight_ih.detach(), ctas=pl["C"] * pl["lin_p"])
                 flush.fill_(1.0)

@@ -40,5 +40,5 @@ names = {1: "linear", 2: "recur", 3: "feat", 4: "lin_tc", 5: "rcta", 6: "pre", 7
 print(f"{n} traced launches, span {(max(rec['t1'].max(), rec['t0'].max()) - t_min) / 1e3:.1f} us")
 for r in sorted(rec, key=lambda r: r["t0"]):
     dur = (int(r["t1"]) - int(r["t0"])) / 1e3 if r["t1"] else 0
-    extra = f"  SM clock {int(r['c']) * 1.024 / dur:.0f} MHz" if (int(r['kind']) == 2 and dur > 0 and os.environ.get("GSN_TIMELINE_STREAM")) else ""
+    extra = f"  SM clock {int(r['c']) * 1024 / dur:.0f} MHz" if (int(r['kind']) == 2 and dur > 0 and os.environ.get("GSN_TIMELINE_STREAM")) else ""
     print(f"{(int(r['t0']) - int(t_min)) / 1e3:9.1f} us  +{dur:7.1f}  {names.get(int(r['kind']), '?'):6s} {int(r['a']):7d} {int(r['b']):5d} {int(r['c']):4d}{extra}")
