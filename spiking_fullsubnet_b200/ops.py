@@ -8,7 +8,6 @@ import torch
 from . import _lib
 
 _ACT = {None: 0, False: 0, "tanh": 1, "sigmoid": 2, "relu": 3}
-_bound_device = [None]
 LAUNCHES = [0]   # number of libgsn_b200 kernels enqueued so far (bench.py reports it)
 LAST_WS = [None]  # workspace of the last recurrence call (tcgen05 backend: 8 cycle counters of CTA 0)
 PROFILE = None   # bench.py sets a list: (algorithmic flops, start event, stop event, (T, R, H)) per recurrence call

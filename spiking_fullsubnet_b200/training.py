@@ -24,7 +24,17 @@ class GSNLayerFn(torch.autograd.Function):
     def forward(ctx, xproj, w_hh, bias, bn_weight, bn_bias, cell):
         bn = cell.batchnorm if cell.use_bn else None
         training = bool(bn is not None and bn.training)
-        momentum = 0.1 if bn is None or bn.momentum is None else bn.momentum
+        if training and bn.momentum is None:
+            raise NotImplementedError("BatchNorm1d(momentum=None) (cumulative moving average) is not supported by the "
+                                      "training kernels; the reference recipes use the default momentum")
+        momentum = 0.1 if bn is None else bn.momentum
+        if bn is not None and not training and (ctx.needs_input_grad[3] or ctx.needs_input_grad[4]):
+            # eval-mode BatchNorm with gradients enabled: the reference's autograd would give bn.weight / bn.bias a
+            # gradient through c; the kernels only form them from batch statistics.  Say so instead of returning
+            # silent Nones (freeze the affine with requires_grad_(False) to fine-tune with frozen statistics).
+            import warnings
+            warnings.warn("spiking_fullsubnet_b200: BatchNorm in eval mode gets no weight / bias gradient from the GSN "
+                          "training kernels (its parameters are treated as frozen)", stacklevel=2)
         eps = 1e-5 if bn is None else bn.eps
         rm = bn.running_mean if bn is not None else None
         rv = bn.running_var if bn is not None else None
