@@ -142,6 +142,11 @@ GSN_API int gsn_deepfilter_spec(const float* proj, const float* spec_ri, float* 
                                 gsn_stream_t stream);
 GSN_API int gsn_spec_passthrough(const float* spec_ri, float* out_ri, int T, int B, int S, int f_lo, int F, int F_out,
                                  int time_major, gsn_stream_t stream);
+/* gsn_frame_signal    : analysis half of torch.stft(center=True, pad_mode="constant") in front of the real FFT
+ *                       (audio_feature.py:236-294): y [B, L] -> frames [B, T, n_fft], T = 1 + L / hop, zero padding of
+ *                       n_fft/2 on both sides, framing, analysis window -- one pass instead of pad + unfold + multiply. */
+GSN_API int gsn_frame_signal(const float* y, const float* window, float* frames, int B, int L, int T, int n_fft, int hop,
+                             gsn_stream_t stream);
 GSN_API int gsn_overlap_add(const float* frames, const float* window, float* y, int B, int T, int n_fft, int hop,
                             int length, gsn_stream_t stream);
 

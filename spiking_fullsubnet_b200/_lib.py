@@ -41,6 +41,7 @@ SIGNATURES = {
     "gsn_deepfilter_spec": (_i, [_p, _p, _p] + [_i] * 11 + [_p]),
     "gsn_spec_passthrough": (_i, [_p, _p] + [_i] * 7 + [_p]),
     "gsn_overlap_add": (_i, [_p, _p, _p] + [_i] * 5 + [_p]),
+    "gsn_frame_signal": (_i, [_p, _p, _p] + [_i] * 5 + [_p]),
     "gsn_stream_preload": (_i, []),
     "gsn_xplanes_bytes": (_sz, [_i] * 4),
     "gsn_xplanes_stream": (_i, [_p, _i, _p, _i, _p, _p, _f, _p, _i, _p, _p, _i, _p, C.c_uint, _p, _p, C.c_uint] + [_i] * 8 + [_p]),

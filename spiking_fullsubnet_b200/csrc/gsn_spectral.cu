@@ -171,7 +171,50 @@ __global__ void __launch_bounds__(256) k_overlap_add(const float* __restrict__ f
   y[idx] = acc / env;
 }
 
+// y [B, L] -> frames [B, T, n_fft]: the analysis half of torch.stft(center=True, pad_mode="constant") in front of the
+// real FFT (audio_feature.py:236-294): zero padding of n_fft/2 samples on both sides, framing at `hop`, analysis window.
+// One float4 per thread; hop and n_fft are multiples of 4 and y is 16-byte aligned per row when L % 4 == 0, else scalar.
+__global__ void __launch_bounds__(256) k_frame_signal(const float* __restrict__ y, const float* __restrict__ window,
+                                                      float* __restrict__ frames, int B, int L, int T, int n_fft, int hop) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over B * T * n_fft / 4
+  const int q4 = n_fft / 4;
+  if (idx >= (size_t)B * T * q4) return;
+  const int k = (int)(idx % q4) * 4;
+  const size_t bt = idx / q4;
+  const int t = (int)(bt % T), b = (int)(bt / T);
+  const int s0 = t * hop + k - n_fft / 2;  // first of my four samples in the unpadded signal
+  const float* yb = y + (size_t)b * L;
+  float4 v;
+  if (s0 >= 0 && s0 + 3 < L && ((L | hop | (n_fft / 2)) & 3) == 0) {
+    v = *reinterpret_cast<const float4*>(yb + s0);
+  } else {
+    v.x = (s0 + 0 >= 0 && s0 + 0 < L) ? yb[s0 + 0] : 0.f;
+    v.y = (s0 + 1 >= 0 && s0 + 1 < L) ? yb[s0 + 1] : 0.f;
+    v.z = (s0 + 2 >= 0 && s0 + 2 < L) ? yb[s0 + 2] : 0.f;
+    v.w = (s0 + 3 >= 0 && s0 + 3 < L) ? yb[s0 + 3] : 0.f;
+  }
+  const float4 w = *reinterpret_cast<const float4*>(window + k);
+  v.x = __fmul_rn(v.x, w.x); v.y = __fmul_rn(v.y, w.y); v.z = __fmul_rn(v.z, w.z); v.w = __fmul_rn(v.w, w.w);
+  *reinterpret_cast<float4*>(frames + idx * 4) = v;
+}
+
 }  // namespace gsn
+
+extern "C" int gsn_frame_signal(const float* y, const float* window, float* frames, int B, int L, int T, int n_fft,
+                                int hop, gsn_stream_t stream) {
+  GSN_REQUIRE(y && window && frames, "gsn_frame_signal: null pointer");
+  GSN_REQUIRE(B > 0 && L > 0 && T > 0 && n_fft > 0 && n_fft % 8 == 0 && hop > 0 && hop <= n_fft,
+              "gsn_frame_signal: bad shape B=%d L=%d T=%d n_fft=%d hop=%d", B, L, T, n_fft, hop);
+  GSN_REQUIRE(T == 1 + L / hop, "gsn_frame_signal: T must be 1 + L / hop (center=True), got T=%d L=%d hop=%d", T, L, hop);
+  GSN_REQUIRE((reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(window) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(frames) & 15) == 0, "gsn_frame_signal: 16-byte alignment");
+  const unsigned long long n4 = (unsigned long long)B * T * (n_fft / 4);
+  const unsigned long long blocks = (n4 + 255) / 256;
+  GSN_REQUIRE(blocks < 2147483647ULL, "gsn_frame_signal: too large");
+  gsn::k_frame_signal<<<(unsigned)blocks, 256, 0, gsn::as_stream(stream)>>>(y, window, frames, B, L, T, n_fft, hop);
+  GSN_LAUNCH_CHECK("k_frame_signal");
+  return GSN_OK;
+}
 
 extern "C" int gsn_compress_spec(const float* spec_ri, float* cm, int B, int F, int f_keep, int T, float fdrc,
                                  int time_major, gsn_stream_t stream) {

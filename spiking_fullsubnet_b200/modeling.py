@@ -521,6 +521,19 @@ def _stft(y, n_fft, hop, win):
     return torch.stft(y, n_fft, hop, win, window=window, return_complex=True, pad_mode="constant")
 
 
+def _stft_fused(y, n_fft, hop, win):
+    """_stft for the inference path: ONE framing kernel (gsn_frame_signal: zero padding, framing, window) + cuFFT's
+    batched real FFT instead of torch.stft's pad / as_strided / multiply / FFT sequence.  Same [B,F,T] view of cuFFT's
+    [B,T,F] output.  (torch.stft stays on the training path: it is differentiable.)"""
+    if win != n_fft or n_fft % 8 != 0 or y.dim() != 2 or y.requires_grad or not y.is_contiguous() or y.data_ptr() % 16:
+        return _stft(y, n_fft, hop, win)
+    key = (n_fft, y.device.index)
+    window = _HANN.get(key)
+    if window is None:
+        window = _HANN[key] = torch.hann_window(n_fft, device=y.device)
+    return torch.fft.rfft(ops.frame_signal(y, window, hop), dim=-1).transpose(1, 2)
+
+
 def _istft(spec, n_fft, hop, win, length):
     # audiozen/acoustics/audio_feature.py:297-347
     window = torch.hann_window(n_fft, device=spec.device)
@@ -1250,7 +1263,7 @@ class SpikingFullSubNet(_StreamingPipeline, _GraphedNetwork, nn.Module):
         """STFT -> network -> deep filter, all on the complex spectrum (no |stft| / real / imag / repeat /
         torch.complex passes: gsn_compress_spec, gsn_deepfilter_spec, gsn_spec_passthrough)."""
         B, L = input.shape
-        cmp = _stft(input, self.n_fft, self.hop_length, self.win_length)  # [B,F,T] complex, time-major view
+        cmp = _stft_fused(input, self.n_fft, self.hop_length, self.win_length)  # [B,F,T] complex, time-major view
         projs, fb_all, sb_all = self.network(cmp)
         F, T = cmp.shape[1], cmp.shape[2]
         S = self.num_spks
@@ -1307,7 +1320,7 @@ class CirmGSN(_GraphedNetwork, nn.Module):
             from . import training
             return training.cirm_gsn_forward(self, input)
         B, L = input.shape
-        cmp = _stft(input, self.n_fft, self.hop_length, self.win_length)
+        cmp = _stft_fused(input, self.n_fft, self.hop_length, self.win_length)
         act, all_out = self.network(cmp)  # activated proj [T,B,P], features (c d s f) (CGN:230)
         F, T = cmp.shape[1], cmp.shape[2]
         S = self.num_spks
@@ -1626,7 +1639,7 @@ class Separator(_StreamingPipeline, _GraphedNetwork, nn.Module):
             from . import training
             return training.separator_forward(self, noisy_y)
         B, L = noisy_y.shape
-        cmp = _stft(noisy_y, self.n_fft, self.hop_length, self.win_length)
+        cmp = _stft_fused(noisy_y, self.n_fft, self.hop_length, self.win_length)
         projs, fb_all, sb_all = self.network(cmp)
         F, T = cmp.shape[1], cmp.shape[2]
         enh = _empty_spec_like(cmp, 1)

@@ -116,6 +116,18 @@ def spec_passthrough(spec, out, f_lo):
     LAUNCHES[0] += 1
 
 
+def frame_signal(y, window, hop):
+    """Analysis half of torch.stft(center=True, pad_mode="constant"): y [B,L] -> windowed frames [B,T,n_fft]."""
+    lib, st = _prep(y, window)
+    B, L = y.shape
+    n_fft = window.numel()
+    T = 1 + L // int(hop)
+    frames = torch.empty((B, T, n_fft), device=y.device, dtype=torch.float32)
+    _lib.check(lib.gsn_frame_signal(_ptr(y), _ptr(window), _ptr(frames), B, L, T, n_fft, int(hop), st))
+    LAUNCHES[0] += 1
+    return frames
+
+
 def overlap_add(frames, window, hop, length):
     """Synthesis half of torch.istft(center=True): frames [B,T,n_fft] (irfft of every frame) -> y [B,length]."""
     lib, st = _prep(frames, window)

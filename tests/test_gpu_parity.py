@@ -790,6 +790,28 @@ def test_fused_istft_matches_torch_istft(B, n_fft, hop, L):
     assert torch.equal(_istft_fused(spec, n_fft, hop, n_fft, L), got)
 
 
+@pytest.mark.parametrize("B,n_fft,hop,L", [(3, 512, 128, 16000), (2, 64, 16, 801), (1, 512, 128, 64000), (2, 128, 32, 1000),
+                                           (2, 512, 128, 300)])
+def test_fused_stft_matches_torch_stft(B, n_fft, hop, L):
+    """Row f2, analysis side: gsn_frame_signal (zero padding + framing + window in one pass) + cuFFT's batched real FFT
+    against torch.stft(center=True, pad_mode="constant", hann window) (audio_feature.py:236-294): same frame count, same
+    [B,F,T] time-major view, values within fp32 FFT rounding."""
+    from spiking_fullsubnet_b200.modeling import _stft, _stft_fused
+    rs = np.random.RandomState(L + n_fft)
+    y = _t(rs.standard_normal((B, L)).astype(np.float32))
+    want = _stft(y, n_fft, hop, n_fft)
+    launches = ops.LAUNCHES[0]
+    got = _stft_fused(y, n_fft, hop, n_fft)
+    assert ops.LAUNCHES[0] == launches + 1, "the framing kernel did not run"
+    assert got.shape == want.shape and got.stride() == want.stride()
+    err = (got - want).abs().max().item()
+    assert err <= 2e-6 * want.abs().max().item(), err
+    frames = ops.frame_signal(y, torch.hann_window(n_fft, device=DEV), hop)
+    pad = torch.nn.functional.pad(y, (n_fft // 2, n_fft // 2))
+    ref = pad.unfold(1, n_fft, hop) * torch.hann_window(n_fft, device=DEV)
+    assert torch.equal(frames, ref)
+
+
 def test_loss_terms_on_the_gpu_match_reference_values_and_gradient():
     """Row f3 on the device the training step runs on: freq_MAE / mag_MAE / SISNRLoss and the recipe's combined loss
     (audiozen/loss.py:138-190, 11-40; recipes/.../trainer.py:33-37) against values and the waveform gradient the
