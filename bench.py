@@ -313,7 +313,11 @@ def main():
     streaming = False
     if args.schedule != "wavefront" and args.backend in ("auto", "tcgen05"):
         model.enable_streaming(True)
-        streaming = model._stream_plan(B) is not None
+        # co-resident as a whole, or in waves of utterances that are (only on request or when that is the faster
+        # schedule: measured for L; S / M batches that do not fit at once are faster on the wavefront)
+        waves = model._stream_plan(B) is None
+        streaming = not waves or (model._stream_wave_size(B) is not None and
+                                  (args.schedule == "stream" or args.size in ("L", "XL")))
         if not streaming:
             if args.schedule == "stream":
                 raise SystemExit(f"--schedule stream: size {args.size} batch {B} is not co-resident on this device")
@@ -501,7 +505,10 @@ def main():
                        launch=("eager enqueue from Python" if args.no_graph else "CUDA graph replay of the step") +
                               (", streaming pipeline: every (model, layer) recurrence and helper stage is ONE persistent "
                                "kernel for all frames, chained through per-frame counters; layer-0 and layer >= 1 input "
-                               "products fused into the recurrences" if streaming else
+                               "products fused into the recurrences" +
+                               (f"; {getattr(model, 'stream_waves', (B, 1))[1]} waves of "
+                                f"{getattr(model, 'stream_waves', (B, 1))[0]} utterances, each a co-resident pipeline"
+                                if getattr(model, "stream_waves", (B, 1))[1] > 1 else "") if streaming else
                                f", frame-chunked wavefront ({args.chunks} chunks, one stream per model x layer)")),
         "clocks": sampler.summary(),
         "e2e": {"value": world * B * T * args.steps / e2e_s, "unit": "frames/s",

@@ -729,7 +729,11 @@ class _StreamingPipeline:
             sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count \
                 if torch.cuda.is_available() else 148
             sm_total = int(os.environ.get("GSN_STREAM_SMS", sms))
-        target = float(os.environ.get("GSN_STREAM_TARGET_US", self._STREAM_TARGET_US))
+        # helper stages are sized for (a bit less than) the recurrences' frame time, which grows with the hidden size:
+        # 1.15 us at H = 160, 1.36 us at H = 256 / 320 (xproj input), so wide models leave more SMs to the recurrences
+        h_max = max(d["m"].hidden_size for d in models)
+        target = float(os.environ.get("GSN_STREAM_TARGET_US",
+                                      self._STREAM_TARGET_US * (1.0 + 0.001 * max(0, h_max - 160))))
         helpers = 0
         for d in models:
             m = d["m"]
@@ -785,12 +789,64 @@ class _StreamingPipeline:
             d["nt"] = nt
         return models
 
+    def _stream_wave_size(self, B):
+        """Largest number of utterances whose whole pipeline is co-resident (None: not even one)."""
+        cache = self.__dict__.setdefault("_wave_cache", {})
+        if B not in cache:
+            cache[B] = next((b for b in range(B, 0, -1) if self._stream_plan(b) is not None), None)
+        return cache[B]
+
+    def _network_stream_waves(self, mag):
+        """Batches whose pipeline does not fit on the device at once (L at batch 64: 688 recurrence CTAs) run it in
+        WAVES of as many utterances as do fit (utterances are independent, MSF:155): the same persistent kernels, one
+        co-resident pipeline after the other, results concatenated along the rows."""
+        dev = mag.device
+        B, F, T = mag.shape
+        b = self._stream_wave_size(B)
+        if b is None or os.environ.get("GSN_STREAM_WAVES", "1") == "0":
+            return None
+        fbm = self.fb_model
+        rep = (self.n_fft // 2 + 1) // self.fb_input_size
+        if rep * fbm.proj_size < F - 1:
+            raise ValueError(f"full-band output ({fbm.proj_size} bins x {rep}) does not cover {F - 1} bins")
+        ops.stream_preload(dev)
+        cm = ops.compress_mag(mag if mag.is_complex() else mag.contiguous(), F - 1, self.fdrc)
+        waves, launches = [], []
+        for w, lo in enumerate(range(0, B, b)):
+            hi = min(B, lo + b)
+            waves.append(self._stream_run(self._stream_plan(hi - lo), cm[:, lo:hi].contiguous(), tag=f"a{w}"))
+            if self.__dict__.get("record_stream_launches"):
+                launches += self.stream_launches
+        if launches:
+            self.stream_launches = launches
+        nmod = len(waves[0])
+
+        def merged(k):  # model k over all waves: (proj, all_layer_outputs)
+            parts = [wv[k] for wv in waves]
+            proj = torch.cat([p[0] for p in parts], dim=1)
+            louts = [p[1] for p in parts]
+            n = len(louts[0])
+            thunks = [(lambda i=i: torch.cat([lo_[i] for lo_ in louts], dim=1)) for i in range(n - 1)] + [proj]
+            counts = louts[0].spike_counts
+            for lo_ in louts[1:]:
+                counts = counts + lo_.spike_counts
+            return proj, LazyOutputs(thunks, widths=louts[0].widths, spike_counts=counts,
+                                     trace_numel=sum(lo_.trace_numel for lo_ in louts))
+
+        out = [merged(k) for k in range(nmod)]
+        # bit-packed traces of the whole batch, per model and layer (rows are batch-major: waves concatenate)
+        self.last_spike_bits = [[torch.cat([wv[k][2][l] for wv in waves], dim=1) for l in range(len(waves[0][k][2]))]
+                                for k in range(nmod)]
+        self.stream_waves = (b, len(waves))
+        return [o[0] for o in out[1:]], out[0][1], [o[1] for o in out[1:]]
+
     def _network_stream(self, mag):
         dev = mag.device
         B, F, T = mag.shape
         models = self._stream_plan(B)
         if models is None:
-            return None
+            return self._network_stream_waves(mag)
+        self.stream_waves = (B, 1)
         fbm = self.fb_model
         rep = (self.n_fft // 2 + 1) // self.fb_input_size
         if rep * fbm.proj_size < F - 1:
@@ -819,6 +875,10 @@ class _StreamingPipeline:
         rec_idx = 0
         streams = _band_streams(dev, ncnt, priority=0, tag=("stream_pipeline", tag))
         st_it = iter(streams)
+        # clusters of three or more CTAs need that many free SMs inside ONE GPC: when the device is (nearly) full they must
+        # be placed before the 1- and 2-CTA kernels have scattered over the GPCs (L, H = 320: the full-band recurrences
+        # started 330 us late, after a helper stage had finished and freed its SMs) -> a higher stream priority
+        st_hi = iter(_band_streams(dev, nrec, priority=-1, tag=("stream_pipeline_hi", tag)))
         # operand-image buffers of the fused layer-0 path: zero-filled ONCE (padding rows), on the main stream and
         # before the fork, then reused by every call of this shape
         keep = self.__dict__.setdefault("_xop_cache", {})
@@ -856,8 +916,8 @@ class _StreamingPipeline:
         fork.record(main)
         used = []
 
-        def on_stream(fn):
-            stq = next(st_it)
+        def on_stream(fn, wide_cluster=False):
+            stq = next(st_hi) if wide_cluster else next(st_it)
             stq.wait_event(fork)
             with torch.cuda.stream(stq):
                 fn()
@@ -938,12 +998,12 @@ class _StreamingPipeline:
                 if l == 0 and d["fused0"]:
                     on_stream(lambda w_hh=w_hh, bias=bias, a=a, b=b, kw=kw, xop=xop, w_ih0=w_ih0, R=R, ring=d["ring"]:
                               ops.recurrence_stream(w_hh, bias, a, b, in_planes=xop, w_ih=w_ih0, frames_rows=(T, R),
-                                                    planes_ring=ring, **kw))
+                                                    planes_ring=ring, **kw), wide_cluster=C >= 3)
                 elif l == 0:
                     if record is not None:
                         record[-1]["ins"] = dict(xproj=xproj)
                     on_stream(lambda w_hh=w_hh, bias=bias, a=a, b=b, kw=kw, xp=xproj:
-                              ops.recurrence_stream(w_hh, bias, a, b, xproj=xp, **kw))
+                              ops.recurrence_stream(w_hh, bias, a, b, xproj=xp, **kw), wide_cluster=C >= 3)
                 elif ly["fused"] and l in d["img"]:
                     if record is not None:
                         record[-1]["ins"] = dict(in_image=d["img"][l][0], planes_ring=d["img"][l][1], frames_rows=(T, R),
@@ -951,10 +1011,10 @@ class _StreamingPipeline:
                         record[-1]["scratch_out"] = True  # relaunched alone the ring holds the last frames only
                     on_stream(lambda w_hh=w_hh, bias=bias, a=a, b=b, kw=kw, im=d["img"][l], w=cell.weight_ih.detach():
                               ops.recurrence_stream(w_hh, bias, a, b, in_image=im[0], planes_ring=im[1],
-                                                    frames_rows=(T, R), w_ih=w, **kw))
+                                                    frames_rows=(T, R), w_ih=w, **kw), wide_cluster=C >= 3)
                 elif ly["fused"]:
                     on_stream(lambda w_hh=w_hh, bias=bias, a=a, b=b, kw=kw, bp=bits_prev, w=cell.weight_ih.detach():
-                              ops.recurrence_stream(w_hh, bias, a, b, in_bits=bp, w_ih=w, **kw))
+                              ops.recurrence_stream(w_hh, bias, a, b, in_bits=bp, w_ih=w, **kw), wide_cluster=C >= 3)
                 else:
                     xp = torch.empty((T, R, H), **f32)
                     hold.append(xp)
@@ -966,7 +1026,7 @@ class _StreamingPipeline:
                     if record is not None:
                         record[-1]["ins"] = dict(xproj=xp)
                     on_stream(lambda w_hh=w_hh, bias=bias, a=a, b=b, kw=kw, xp=xp:
-                              ops.recurrence_stream(w_hh, bias, a, b, xproj=xp, **kw))
+                              ops.recurrence_stream(w_hh, bias, a, b, xproj=xp, **kw), wide_cluster=C >= 3)
                 in_cnt, in_target = c_out, ops.stream_ctas(R, H, (K if l == 0 else H) if fused else 0, fused, budget)
                 bits_prev = bits
                 c_pending = c_next

@@ -348,6 +348,41 @@ def test_recurrence_stream_spike_images_bit_identical_to_bit_input(T, R, H, ring
     assert bool((cnt[1] == n1).all())
 
 
+@pytest.mark.parametrize("size,B,T,graph", [("S", 40, 60, False), ("L", 12, 80, False), ("L", 12, 80, True)])
+def test_streaming_waves_equal_the_utterance_groups_run_alone(size, B, T, graph):
+    """A batch whose pipeline is not co-resident (S at batch 40: 140 recurrence CTAs + helpers; L at batch 12: clusters of
+    three CTAs at H = 320, unfused layers) runs as waves of utterances.  Utterances are independent (MSF:155), so the
+    result must be BIT-identical to each group run alone through the same pipeline, the lazily materialised traces must
+    have the whole batch's shapes, and the spike counters must add up; with graph=True the waves replay from one graph."""
+    from oracle import synth
+    from spiking_fullsubnet_b200 import metrics
+    cfg = synth.CONFIGS[size]
+    m = _model(cfg, synth.make_params(cfg, 5))
+    mag = _t(synth.make_mag(B, 257, T, 11))
+    with torch.no_grad():
+        m.enable_streaming(True)
+        assert m._stream_plan(B) is None and m._stream_wave_size(B) is not None
+        if graph:
+            m.enable_cuda_graph(True, frame_chunks=4)
+            m.network(mag)
+        projs, fb_all, sb_all = m.network(mag)
+        torch.cuda.synchronize()
+        b, nw = m.stream_waves
+        assert nw == -(-B // b) and nw > 1
+        got = [p.clone() for p in projs]
+        syn = metrics.compute_synops(fb_all, sb_all, shared_weights=True)
+        shapes = [tuple(x.shape) for x in fb_all[:]] + [tuple(x.shape) for sb in sb_all for x in sb[:]]
+        m.enable_cuda_graph(False)
+        alone = [m.network(mag[lo:lo + b].contiguous()) for lo in range(0, B, b)]
+        for k in range(len(got)):
+            assert torch.equal(got[k], torch.cat([a[0][k] for a in alone], dim=1))
+        # firing rates are spike counts over trace sizes, SynOps is linear in them: the groups weigh in by their size
+        want_syn = sum(metrics.compute_synops(a[1], a[2], shared_weights=True) * a[1][1].shape[1] for a in alone) / B
+        assert abs(syn - want_syn) <= 1e-6 * abs(want_syn)
+    H = cfg["fb_hidden_size"]
+    assert shapes[1] == (T, B, H) and shapes[0] == (T, B, cfg["fb_input_size"])
+
+
 def test_synops_accounting_from_in_kernel_spike_counts():
     """Row f4 on the streaming schedule: compute_synops / compute_neuronops (audiozen/metric.py:303-340) come out of the
     spike counts the recurrence kernels accumulate while they run (popcount of their ballot words) -- equal to the
