@@ -313,11 +313,12 @@ def main():
     streaming = False
     if args.schedule != "wavefront" and args.backend in ("auto", "tcgen05"):
         model.enable_streaming(True)
-        # co-resident as a whole, or in waves of utterances that are (only on request or when that is the faster
-        # schedule: measured for L; S / M batches that do not fit at once are faster on the wavefront)
+        # co-resident as a whole, or in waves of utterances that are (on request, or when the model's own estimate says
+        # waves beat the wavefront / band-stream schedules)
         waves = model._stream_plan(B) is None
-        streaming = not waves or (model._stream_wave_size(B) is not None and
-                                  (args.schedule == "stream" or args.size in ("L", "XL")))
+        if waves and args.schedule == "stream" and model._stream_wave_size(B) is not None:
+            os.environ.setdefault("GSN_STREAM_WAVES", "1")
+        streaming = not waves or model._waves_pay(B, T)
         if not streaming:
             if args.schedule == "stream":
                 raise SystemExit(f"--schedule stream: size {args.size} batch {B} is not co-resident on this device")

@@ -796,6 +796,23 @@ class _StreamingPipeline:
             cache[B] = next((b for b in range(B, 0, -1) if self._stream_plan(b) is not None), None)
         return cache[B]
 
+    def _waves_pay(self, B, T):
+        """Waves are latency-bound (every wave costs T frame times whatever its size), the wavefront / band-stream
+        schedules throughput-bound (measured 0.24 - 0.33 of the 6.3 row-frames per us per SM the recurrence sustains):
+        S at batch 64 = 2 waves 1.5 ms vs 4.1 ms, L at 64 x 10 s = 8 waves 15.1 vs 22.6 ms, but M at batch 32 = 3 waves
+        2.1 vs 1.7 ms.  Estimate both and take the smaller."""
+        b = self._stream_wave_size(B)
+        if b is None:
+            return False
+        mode = os.environ.get("GSN_STREAM_WAVES", "auto")
+        if mode in ("0", "1"):
+            return mode == "1"
+        models = self._stream_models(B)
+        frame_us = 1.2 if max(d["m"].hidden_size for d in models) <= 240 else 1.46
+        waves_us = -(-B // b) * (T * frame_us + 120.0)
+        row_frames = sum(d["R"] * len(d["m"].sequence_model.layers) for d in models) * T
+        return waves_us < 0.8 * row_frames / (6.3 * 148 * 0.28)  # (the estimate is only good to ~20 %: M is a tie)
+
     def _network_stream_waves(self, mag):
         """Batches whose pipeline does not fit on the device at once (L at batch 64: 688 recurrence CTAs) run it in
         WAVES of as many utterances as do fit (utterances are independent, MSF:155): the same persistent kernels, one
@@ -803,7 +820,7 @@ class _StreamingPipeline:
         dev = mag.device
         B, F, T = mag.shape
         b = self._stream_wave_size(B)
-        if b is None or os.environ.get("GSN_STREAM_WAVES", "1") == "0":
+        if not self._waves_pay(B, T):
             return None
         fbm = self.fb_model
         rep = (self.n_fft // 2 + 1) // self.fb_input_size

@@ -349,16 +349,18 @@ def test_recurrence_stream_spike_images_bit_identical_to_bit_input(T, R, H, ring
 
 
 @pytest.mark.parametrize("size,B,T,graph", [("S", 40, 60, False), ("L", 12, 80, False), ("L", 12, 80, True)])
-def test_streaming_waves_equal_the_utterance_groups_run_alone(size, B, T, graph):
+def test_streaming_waves_equal_the_utterance_groups_run_alone(size, B, T, graph, monkeypatch):
     """A batch whose pipeline is not co-resident (S at batch 40: 140 recurrence CTAs + helpers; L at batch 12: clusters of
     three CTAs at H = 320, unfused layers) runs as waves of utterances.  Utterances are independent (MSF:155), so the
     result must be BIT-identical to each group run alone through the same pipeline, the lazily materialised traces must
     have the whole batch's shapes, and the spike counters must add up; with graph=True the waves replay from one graph."""
     from oracle import synth
     from spiking_fullsubnet_b200 import metrics
+    monkeypatch.setenv("GSN_STREAM_WAVES", "1")  # (at these short clips the model's own estimate prefers the wavefront)
     cfg = synth.CONFIGS[size]
     m = _model(cfg, synth.make_params(cfg, 5))
     mag = _t(synth.make_mag(B, 257, T, 11))
+    assert m._waves_pay(64, 1251) == (size == "L") or size == "S"
     with torch.no_grad():
         m.enable_streaming(True)
         assert m._stream_plan(B) is None and m._stream_wave_size(B) is not None
