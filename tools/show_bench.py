@@ -1,6 +1,9 @@
 """Development tool: one-screen summary of a bench.py JSON line.  Usage: python tools/show_bench.py file.json"""
 import json
+import signal
 import sys
+
+signal.signal(signal.SIGPIPE, signal.SIG_DFL)  # `| head -1` is the usual way to call this
 
 d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
 print(f"value {d['value']:.4g} {d['unit']}  ms/step {d['ms_per_step']:.4f}  e2e {d['e2e']['value']:.4g}  launches {d.get('gpu_launches')}")
