@@ -316,14 +316,6 @@ GSN_API int gsn_deepfilter_band(const float* proj, const float* spec_re, const f
  * (so enable it before capturing a CUDA graph).                                                          */
 GSN_API int gsn_trace_set(void* device_buffer, size_t bytes);
 
-/* ---- self test of the tcgen05 operand encodings ------------------------------------------------
- * d[128, N] = a[128, K] @ b[N, K]^T on one CTA with the operand layouts of the recurrence kernel
- * (K-major no-swizzle shared memory; a_in_tmem != 0 keeps A resident in tensor memory).  a and b must
- * hold values exactly representable in bf16 (or fp16 if use_fp16).  status[0] = 0 ok, 1 = timeout.
- * swap_lbo_sbo is a diagnostic knob (must be 0 for a correct result).                               */
-GSN_API int gsn_tc_selftest(const float* a, const float* b, float* d, int* status, int N, int K,
-                            int a_in_tmem, int swap_lbo_sbo, int use_fp16, gsn_stream_t stream);
-
 #ifdef __cplusplus
 }
 #endif

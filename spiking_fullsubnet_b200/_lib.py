@@ -61,7 +61,6 @@ SIGNATURES = {
     "gsn_layer_recurrence_tile": (_i, [_i, _i, _i, _i, _i]),
     "gsn_deepfilter_band": (_i, [_p] * 5 + [_i] * 9 + [_p]),
     "gsn_trace_set": (_i, [_p, _sz]),
-    "gsn_tc_selftest": (_i, [_p] * 4 + [_i] * 5 + [_p]),
 }
 
 _lib = None
@@ -87,6 +86,19 @@ def load():
     if lib.gsn_abi_version() != 1:
         raise GsnError(f"ABI version mismatch: library {lib.gsn_abi_version()} != binding 1")
     _lib = lib
+    return lib
+
+
+def load_probe():
+    """The development-probe library (tools/tc_probe*.py, tools/tc_mma_timing.py): tcgen05 operand-encoding self test and
+    MMA timing kernels.  Built next to the product library, never loaded by the package itself."""
+    path = os.path.join(os.path.dirname(LIB_PATH), "libgsn_b200_probe.so")
+    if not os.path.exists(path):
+        raise GsnError(f"{path} not found: run `make -C spiking_fullsubnet_b200/csrc`")
+    lib = C.CDLL(path)
+    lib.gsn_last_error.restype = C.c_char_p
+    lib.gsn_tc_selftest.restype = _i
+    lib.gsn_tc_selftest.argtypes = [_p] * 4 + [_i] * 5 + [_p]
     return lib
 
 

@@ -289,7 +289,10 @@ extern "C" GSN_API int gsn_tc_mma_timing2(long long* out, int N, int variant, gs
   return GSN_OK;
 }
 
-extern "C" int gsn_tc_selftest(const float* a, const float* b, float* d, int* status, int N, int K,
+// d[128, N] = a[128, K] @ b[N, K]^T on one CTA with the operand layouts of the recurrence kernels (K-major no-swizzle
+// shared memory; a_in_tmem != 0 keeps A resident in tensor memory); a and b must hold values exactly representable in
+// bf16 (fp16 if use_fp16).  status[0] = 0 ok, 1 = timeout.  swap_lbo_sbo is a diagnostic knob (0 for a correct result).
+extern "C" GSN_API int gsn_tc_selftest(const float* a, const float* b, float* d, int* status, int N, int K,
                                int a_in_tmem, int swap_lbo_sbo, int use_fp16, gsn_stream_t stream) {
   GSN_REQUIRE(a && b && d && status, "gsn_tc_selftest: null pointer");
   GSN_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0, "gsn_tc_selftest: N=%d must be a multiple of 16 in [16,256]", N);

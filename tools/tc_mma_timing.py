@@ -8,7 +8,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from spiking_fullsubnet_b200 import _lib  # noqa: E402
 
-lib = _lib.load()
+lib = _lib.load_probe()
 fn = lib.gsn_tc_mma_timing
 fn.restype = C.c_int
 fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]

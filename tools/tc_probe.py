@@ -16,7 +16,7 @@ def bf16_exact(rs, shape):
 
 
 def run(N, K, a_in_tmem, swap, fp16, binary_b=False):
-    lib = _lib.load()
+    lib = _lib.load_probe()
     rs = np.random.RandomState(N * 7 + K)
     a = bf16_exact(rs, (128, K))
     b = bf16_exact(rs, (N, K))
