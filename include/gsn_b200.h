@@ -129,6 +129,7 @@ GSN_API int gsn_layer_recurrence_bits(const float* xproj, const float* w_hh, con
  * gsn_deepfilter_spec : gsn_deepfilter_band with complex in / complex out: out_ri [B, S, F_out, T, 2]; layout 0 = proj
  *                       features ordered (c fc df s) (MSF:160-167), 1 = (c df s fc) (cirm_gsn, CGN:230).
  * gsn_spec_passthrough: out[b, s, f, t] = spec[b, f, t] for f in [f_lo, F): the bins no band filters (MSF:461-468).
+ *                       mag_out (both; may be NULL): also |out| as fp32 in the same index order (enh_mag, MSF:472).
  * time_major != 0     : the spectra are [B, T, F] / [B, S, T, F_out] -- the layout cuFFT reads and writes (torch.stft
  *                       returns a transposed VIEW of it), so the whole forward() runs without a transpose copy.
  * gsn_overlap_add     : synthesis half of torch.istft(center=True) (audio_feature.py:297-347): frames [B, T, n_fft] =
@@ -137,11 +138,11 @@ GSN_API int gsn_layer_recurrence_bits(const float* xproj, const float* w_hh, con
  *                       samples past the last frame are zero.  y [B, length].                                    */
 GSN_API int gsn_compress_spec(const float* spec_ri, float* cm, int B, int F, int f_keep, int T, float fdrc,
                               int time_major, gsn_stream_t stream);
-GSN_API int gsn_deepfilter_spec(const float* proj, const float* spec_ri, float* out_ri, int T, int B, int N, int ctr,
-                                int df, int S, int lo, int F, int F_out, int layout, int time_major,
+GSN_API int gsn_deepfilter_spec(const float* proj, const float* spec_ri, float* out_ri, float* mag_out, int T, int B,
+                                int N, int ctr, int df, int S, int lo, int F, int F_out, int layout, int time_major,
                                 gsn_stream_t stream);
-GSN_API int gsn_spec_passthrough(const float* spec_ri, float* out_ri, int T, int B, int S, int f_lo, int F, int F_out,
-                                 int time_major, gsn_stream_t stream);
+GSN_API int gsn_spec_passthrough(const float* spec_ri, float* out_ri, float* mag_out, int T, int B, int S, int f_lo,
+                                 int F, int F_out, int time_major, gsn_stream_t stream);
 /* gsn_frame_signal    : analysis half of torch.stft(center=True, pad_mode="constant") in front of the real FFT
  *                       (audio_feature.py:236-294): y [B, L] -> frames [B, T, n_fft], T = 1 + L / hop, zero padding of
  *                       n_fft/2 on both sides, framing, analysis window -- one pass instead of pad + unfold + multiply. */

@@ -38,8 +38,8 @@ SIGNATURES = {
                               + [_p, _p, _i, _p, C.c_uint] + [_i] * 4 + [_p, _p]),
     "gsn_spike_image_bytes": (_sz, [_i] * 3),
     "gsn_compress_spec": (_i, [_p, _p, _i, _i, _i, _i, _f, _i, _p]),
-    "gsn_deepfilter_spec": (_i, [_p, _p, _p] + [_i] * 11 + [_p]),
-    "gsn_spec_passthrough": (_i, [_p, _p] + [_i] * 7 + [_p]),
+    "gsn_deepfilter_spec": (_i, [_p, _p, _p, _p] + [_i] * 11 + [_p]),
+    "gsn_spec_passthrough": (_i, [_p, _p, _p] + [_i] * 7 + [_p]),
     "gsn_overlap_add": (_i, [_p, _p, _p] + [_i] * 5 + [_p]),
     "gsn_frame_signal": (_i, [_p, _p, _p] + [_i] * 5 + [_p]),
     "gsn_stream_preload": (_i, []),

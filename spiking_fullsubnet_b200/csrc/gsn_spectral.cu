@@ -57,8 +57,9 @@ __global__ void __launch_bounds__(256) k_compress_spec_tf(const float2* __restri
 
 // one thread per (b, s, n, fc, t); proj [T, B*N, P] with P = (c, fc, df, s) fastest-last (MSF:160-167)
 __global__ void __launch_bounds__(256) k_deepfilter_spec(const float* __restrict__ proj, const float2* __restrict__ spec,
-                                                         float2* __restrict__ out, int T, int B, int N, int ctr, int df,
-                                                         int S, int lo, int F, int F_out, int layout) {
+                                                         float2* __restrict__ out, float* __restrict__ mag, int T, int B,
+                                                         int N, int ctr, int df, int S, int lo, int F, int F_out,
+                                                         int layout) {
   const size_t total = (size_t)B * S * N * ctr * T;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -83,13 +84,16 @@ __global__ void __launch_bounds__(256) k_deepfilter_spec(const float* __restrict
     yr += z.x * cr - z.y * ci;
     yi += z.x * ci + z.y * cr;
   }
-  out[(((size_t)b * S + s) * F_out + f) * T + t] = make_float2(yr, yi);
+  const size_t o = (((size_t)b * S + s) * F_out + f) * T + t;
+  out[o] = make_float2(yr, yi);
+  if (mag != nullptr) mag[o] = hypotf(yr, yi);  // torch.abs of a complex tensor (enh_mag, MSF:472)
 }
 
 // time-major spectra: spec [B,T,F], out [B,S,T,F_out]; one thread per (b, s, t, band bin), bins fastest
 __global__ void __launch_bounds__(256) k_deepfilter_spec_tf(const float* __restrict__ proj, const float2* __restrict__ spec,
-                                                            float2* __restrict__ out, int T, int B, int N, int ctr, int df,
-                                                            int S, int lo, int F, int F_out, int layout) {
+                                                            float2* __restrict__ out, float* __restrict__ mag, int T,
+                                                            int B, int N, int ctr, int df, int S, int lo, int F, int F_out,
+                                                            int layout) {
   const int W = N * ctr;
   const size_t total = (size_t)B * S * T * W;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -113,12 +117,15 @@ __global__ void __launch_bounds__(256) k_deepfilter_spec_tf(const float* __restr
     yr += z.x * cr - z.y * ci;
     yi += z.x * ci + z.y * cr;
   }
-  out[(((size_t)b * S + s) * T + t) * F_out + f] = make_float2(yr, yi);
+  const size_t o = (((size_t)b * S + s) * T + t) * F_out + f;
+  out[o] = make_float2(yr, yi);
+  if (mag != nullptr) mag[o] = hypotf(yr, yi);
 }
 
 // out[b, s, t, f] = spec[b, t, f] for f in [f_lo, F) (time-major spectra)
-__global__ void __launch_bounds__(256) k_copy_bins_tf(const float2* __restrict__ spec, float2* __restrict__ out, int T, int B,
-                                                      int S, int f_lo, int F, int F_out) {
+__global__ void __launch_bounds__(256) k_copy_bins_tf(const float2* __restrict__ spec, float2* __restrict__ out,
+                                                      float* __restrict__ mag, int T, int B, int S, int f_lo, int F,
+                                                      int F_out) {
   const int W = F - f_lo;
   const size_t total = (size_t)B * S * T * W;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -128,12 +135,15 @@ __global__ void __launch_bounds__(256) k_copy_bins_tf(const float2* __restrict__
   const int t = q % T; q /= T;
   const int s = q % S;
   const int b = q / S;
-  out[(((size_t)b * S + s) * T + t) * F_out + f] = spec[((size_t)b * T + t) * F + f];
+  const float2 z = spec[((size_t)b * T + t) * F + f];
+  const size_t o = (((size_t)b * S + s) * T + t) * F_out + f;
+  out[o] = z;
+  if (mag != nullptr) mag[o] = hypotf(z.x, z.y);
 }
 
 // out[b, s, f, t] = spec[b, f, t] for f in [f_lo, F)
-__global__ void __launch_bounds__(256) k_copy_bins(const float2* __restrict__ spec, float2* __restrict__ out, int T, int B,
-                                                   int S, int f_lo, int F, int F_out) {
+__global__ void __launch_bounds__(256) k_copy_bins(const float2* __restrict__ spec, float2* __restrict__ out,
+                                                   float* __restrict__ mag, int T, int B, int S, int f_lo, int F, int F_out) {
   const size_t total = (size_t)B * S * (F - f_lo) * T;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -142,7 +152,10 @@ __global__ void __launch_bounds__(256) k_copy_bins(const float2* __restrict__ sp
   const int f = f_lo + (int)(q % (F - f_lo)); q /= (F - f_lo);
   const int s = q % S;
   const int b = q / S;
-  out[(((size_t)b * S + s) * F_out + f) * T + t] = spec[((size_t)b * F + f) * T + t];
+  const float2 z = spec[((size_t)b * F + f) * T + t];
+  const size_t o = (((size_t)b * S + s) * F_out + f) * T + t;
+  out[o] = z;
+  if (mag != nullptr) mag[o] = hypotf(z.x, z.y);
 }
 
 // frames [B, T, n_fft] (inverse real FFT of every frame, unwindowed) -> y [B, length]
@@ -238,8 +251,8 @@ extern "C" int gsn_compress_spec(const float* spec_ri, float* cm, int B, int F, 
   return GSN_OK;
 }
 
-extern "C" int gsn_deepfilter_spec(const float* proj, const float* spec_ri, float* out_ri, int T, int B, int N, int ctr,
-                                   int df, int S, int lo, int F, int F_out, int layout, int time_major,
+extern "C" int gsn_deepfilter_spec(const float* proj, const float* spec_ri, float* out_ri, float* mag_out, int T, int B,
+                                   int N, int ctr, int df, int S, int lo, int F, int F_out, int layout, int time_major,
                                    gsn_stream_t stream) {
   GSN_REQUIRE(proj && spec_ri && out_ri, "gsn_deepfilter_spec: null pointer");
   GSN_REQUIRE(T > 0 && B > 0 && N > 0 && ctr > 0 && df > 0 && S > 0, "gsn_deepfilter_spec: bad shape");
@@ -252,19 +265,20 @@ extern "C" int gsn_deepfilter_spec(const float* proj, const float* spec_ri, floa
   GSN_REQUIRE(blocks < 2147483647ULL, "gsn_deepfilter_spec: too large");
   if (time_major) {
     gsn::k_deepfilter_spec_tf<<<(unsigned)blocks, 256, 0, gsn::as_stream(stream)>>>(
-        proj, reinterpret_cast<const float2*>(spec_ri), reinterpret_cast<float2*>(out_ri), T, B, N, ctr, df, S, lo, F, F_out,
-        layout);
+        proj, reinterpret_cast<const float2*>(spec_ri), reinterpret_cast<float2*>(out_ri), mag_out, T, B, N, ctr, df, S, lo,
+        F, F_out, layout);
     GSN_LAUNCH_CHECK("k_deepfilter_spec_tf");
     return GSN_OK;
   }
   gsn::k_deepfilter_spec<<<(unsigned)blocks, 256, 0, gsn::as_stream(stream)>>>(
-      proj, reinterpret_cast<const float2*>(spec_ri), reinterpret_cast<float2*>(out_ri), T, B, N, ctr, df, S, lo, F, F_out, layout);
+      proj, reinterpret_cast<const float2*>(spec_ri), reinterpret_cast<float2*>(out_ri), mag_out, T, B, N, ctr, df, S, lo, F,
+      F_out, layout);
   GSN_LAUNCH_CHECK("k_deepfilter_spec");
   return GSN_OK;
 }
 
-extern "C" int gsn_spec_passthrough(const float* spec_ri, float* out_ri, int T, int B, int S, int f_lo, int F, int F_out,
-                                    int time_major, gsn_stream_t stream) {
+extern "C" int gsn_spec_passthrough(const float* spec_ri, float* out_ri, float* mag_out, int T, int B, int S, int f_lo,
+                                    int F, int F_out, int time_major, gsn_stream_t stream) {
   GSN_REQUIRE(spec_ri && out_ri, "gsn_spec_passthrough: null pointer");
   GSN_REQUIRE(T > 0 && B > 0 && S > 0 && f_lo >= 0 && f_lo <= F && F <= F_out, "gsn_spec_passthrough: bad shape");
   if (f_lo == F) return GSN_OK;
@@ -273,12 +287,12 @@ extern "C" int gsn_spec_passthrough(const float* spec_ri, float* out_ri, int T, 
   GSN_REQUIRE(blocks < 2147483647ULL, "gsn_spec_passthrough: too large");
   if (time_major) {
     gsn::k_copy_bins_tf<<<(unsigned)blocks, 256, 0, gsn::as_stream(stream)>>>(
-        reinterpret_cast<const float2*>(spec_ri), reinterpret_cast<float2*>(out_ri), T, B, S, f_lo, F, F_out);
+        reinterpret_cast<const float2*>(spec_ri), reinterpret_cast<float2*>(out_ri), mag_out, T, B, S, f_lo, F, F_out);
     GSN_LAUNCH_CHECK("k_copy_bins_tf");
     return GSN_OK;
   }
   gsn::k_copy_bins<<<(unsigned)blocks, 256, 0, gsn::as_stream(stream)>>>(
-      reinterpret_cast<const float2*>(spec_ri), reinterpret_cast<float2*>(out_ri), T, B, S, f_lo, F, F_out);
+      reinterpret_cast<const float2*>(spec_ri), reinterpret_cast<float2*>(out_ri), mag_out, T, B, S, f_lo, F, F_out);
   GSN_LAUNCH_CHECK("k_copy_bins");
   return GSN_OK;
 }

@@ -1324,17 +1324,18 @@ class SpikingFullSubNet(_StreamingPipeline, _GraphedNetwork, nn.Module):
         return static_out
 
     def _forward_infer(self, input):
-        enh, fb_all, sb_all = self._forward_spec(input)
-        return self._finish(enh, fb_all, sb_all, input.shape[1])
+        enh, mag, fb_all, sb_all = self._forward_spec(input)
+        return self._finish(enh, fb_all, sb_all, input.shape[1], mag)
 
-    def _finish(self, enh, fb_all, sb_all, L):
+    def _finish(self, enh, fb_all, sb_all, L, mag=None):
         """enh complex [B,S,F,T] -> the reference's return tuple (iSTFT, MSF:463-474)."""
         B, S, F, T = enh.shape
         if S > 1:
             y = _istft_fused(_merge_speakers(enh), self.n_fft, self.hop_length, self.win_length, L)
             return y.reshape(B, S, L), fb_all, sb_all
-        enh = enh[:, 0]
-        return _istft_fused(enh, self.n_fft, self.hop_length, self.win_length, L), enh.abs(), fb_all, sb_all
+        enh = enh[:, 0]  # (mag: |enh| straight from the deep-filter kernels of _forward_spec)
+        return (_istft_fused(enh, self.n_fft, self.hop_length, self.win_length, L),
+                mag[:, 0] if mag is not None else enh.abs(), fb_all, sb_all)
 
     def _forward_spec(self, input):
         """STFT -> network -> deep filter, all on the complex spectrum (no |stft| / real / imag / repeat /
@@ -1345,14 +1346,16 @@ class SpikingFullSubNet(_StreamingPipeline, _GraphedNetwork, nn.Module):
         F, T = cmp.shape[1], cmp.shape[2]
         S = self.num_spks
         enh = _empty_spec_like(cmp, S)
+        # enh_mag (MSF:472) is written by the same kernels: no separate |.| pass over the enhanced spectrum
+        mag = torch.empty_strided(enh.shape, enh.stride(), dtype=torch.float32, device=enh.device) if S == 1 else None
         cuts, ctrs = self.sb_model.freq_cutoffs, self.sb_model.center_freq_sizes
         lo = 0
         for i, p in enumerate(projs):
             n = (cuts[i + 1] - cuts[i]) // ctrs[i]
-            ops.deepfilter_spec(p, cmp, enh, n, ctrs[i], self.df_orders[i], S, lo)
+            ops.deepfilter_spec(p, cmp, enh, n, ctrs[i], self.df_orders[i], S, lo, mag=mag)
             lo += n * ctrs[i]
-        ops.spec_passthrough(cmp, enh, lo)  # un-filtered bins (Nyquist) pass through (MSF:461-468)
-        return enh, fb_all, sb_all
+        ops.spec_passthrough(cmp, enh, lo, mag=mag)  # un-filtered bins (Nyquist) pass through (MSF:461-468)
+        return enh, mag, fb_all, sb_all
 
 
 class CirmGSN(_GraphedNetwork, nn.Module):

@@ -87,7 +87,16 @@ def compress_mag(mag, f_keep, fdrc):
     return cm
 
 
-def deepfilter_spec(proj, spec, out, N, ctr, df, S, lo, layout=0):
+def _mag_like(mag, out, what):
+    """mag_out of the spectral back end: fp32, same shape and (element) strides as the complex `out`."""
+    if mag is None:
+        return None
+    if mag.dtype != torch.float32 or mag.shape != out.shape or mag.stride() != out.stride() or mag.device != out.device:
+        raise ValueError(f"{what}: mag must be float32 with the shape and strides of out")
+    return mag.data_ptr()
+
+
+def deepfilter_spec(proj, spec, out, N, ctr, df, S, lo, layout=0, mag=None):
     """Deep filter of one band (MSF:315-346) from its proj output, complex in / complex out: spec [B,F,T] complex64,
     out [B,S,F_out,T] complex64 (bins [lo, lo + N*ctr) are written), both in the same layout of `_spec_layout`.
     layout 0: proj features (c fc df s), MSF:160-167; 1: (c df s fc), cirm_gsn CGN:230."""
@@ -97,12 +106,12 @@ def deepfilter_spec(proj, spec, out, N, ctr, df, S, lo, layout=0):
         raise ValueError("deepfilter_spec: spec and out must share layout and device")
     T = proj.shape[0]
     B, F, _ = spec.shape
-    _lib.check(lib.gsn_deepfilter_spec(_ptr(proj), spec.data_ptr(), out.data_ptr(), T, B, N, ctr, df, S, lo, F,
-                                       out.shape[2], int(layout), tm, st))
+    _lib.check(lib.gsn_deepfilter_spec(_ptr(proj), spec.data_ptr(), out.data_ptr(), _mag_like(mag, out, "deepfilter_spec"),
+                                       T, B, N, ctr, df, S, lo, F, out.shape[2], int(layout), tm, st))
     LAUNCHES[0] += 1
 
 
-def spec_passthrough(spec, out, f_lo):
+def spec_passthrough(spec, out, f_lo, mag=None):
     """out[b, s, f, :] = spec[b, f, :] for f >= f_lo (the bins no band filters, MSF:461-468)."""
     tm = _spec_layout(spec, "spec_passthrough")
     if _spec_layout(out, "spec_passthrough") != tm:
@@ -111,8 +120,8 @@ def spec_passthrough(spec, out, f_lo):
     _bind(spec.device)
     st = torch.cuda.current_stream(spec.device).cuda_stream
     B, F, T = spec.shape
-    _lib.check(lib.gsn_spec_passthrough(spec.data_ptr(), out.data_ptr(), T, B, out.shape[1], int(f_lo), F, out.shape[2],
-                                        tm, st))
+    _lib.check(lib.gsn_spec_passthrough(spec.data_ptr(), out.data_ptr(), _mag_like(mag, out, "spec_passthrough"), T, B,
+                                        out.shape[1], int(f_lo), F, out.shape[2], tm, st))
     LAUNCHES[0] += 1
 
 

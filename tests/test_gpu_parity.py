@@ -753,8 +753,11 @@ def test_deepfilter_spec_matches_the_reference_formula(B, N, ctr, df, S, lo, F, 
     P = 2 * ctr * df * S
     proj = torch.randn(T, B * N, P, generator=g).to(DEV)
     out = torch.zeros(B, S, F, T, dtype=torch.complex64, device=DEV)
-    ops.deepfilter_spec(proj, spec, out, N, ctr, df, S, lo, layout=layout)
-    ops.spec_passthrough(spec, out, lo + N * ctr)
+    mag = torch.full(out.shape, -1.0, device=DEV)
+    ops.deepfilter_spec(proj, spec, out, N, ctr, df, S, lo, layout=layout, mag=mag)
+    ops.spec_passthrough(spec, out, lo + N * ctr, mag=mag)
+    written = out[:, :, lo:]  # |.| of everything the two kernels wrote, as torch.abs computes it (enh_mag, MSF:472)
+    assert float((mag[:, :, lo:] - written.abs()).abs().max()) <= 2e-7 * float(written.abs().max())
     v = proj.double().reshape(T, B, N, *((2, ctr, df, S) if layout == 0 else (2, df, S, ctr)))
     v = v.permute(1, 2, 3, 4, 5, 6, 0) if layout == 0 else v.permute(1, 2, 3, 6, 4, 5, 0)   # [B,N,c,fc,df,S,T]
     coef = torch.complex(v[:, :, 0], v[:, :, 1])                                           # [B,N,fc,df,S,T]
