@@ -44,15 +44,17 @@ __global__ void __launch_bounds__(256) k_compress_spec(const float2* __restrict_
 // sides without a transpose
 __global__ void __launch_bounds__(256) k_compress_spec_tf(const float2* __restrict__ spec, float* __restrict__ cm, int B,
                                                           int F, int Fk, int T, float fdrc, int mode) {
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)T * B * Fk) return;
-  const int f = idx % Fk;
-  const size_t q = idx / Fk;
-  const int b = q % B, t = q / B;
-  const float2 z = spec[((size_t)b * T + t) * F + f];
-  float v = hypotf(z.x, z.y);
-  v = mode == 0 ? sqrtf(v) : (mode == 1 ? v : powf(v, fdrc));
-  cm[idx] = v;
+  // one block per (t, b) row of cm: the row index is decoded once per block, not per element (the per-element
+  // division / modulo cost more than the |.|^fdrc itself)
+  const int b = blockIdx.x % B, t = blockIdx.x / B;
+  const float2* src = spec + ((size_t)b * T + t) * F;
+  float* dst = cm + (size_t)blockIdx.x * Fk;
+  for (int f = threadIdx.x; f < Fk; f += blockDim.x) {
+    const float2 z = src[f];
+    float v = hypotf(z.x, z.y);
+    v = mode == 0 ? sqrtf(v) : (mode == 1 ? v : powf(v, fdrc));
+    dst[f] = v;
+  }
 }
 
 // one thread per (b, s, n, fc, t); proj [T, B*N, P] with P = (c, fc, df, s) fastest-last (MSF:160-167)
@@ -238,8 +240,9 @@ extern "C" int gsn_compress_spec(const float* spec_ri, float* cm, int B, int F, 
   GSN_REQUIRE((reinterpret_cast<uintptr_t>(spec_ri) & 7) == 0, "gsn_compress_spec: spec must be 8-byte aligned");
   const int mode = fdrc == 0.5f ? 0 : (fdrc == 1.0f ? 1 : 2);
   if (time_major) {
-    const size_t total = (size_t)T * B * f_keep;
-    gsn::k_compress_spec_tf<<<(unsigned)((total + 255) / 256), 256, 0, gsn::as_stream(stream)>>>(
+    const size_t rows = (size_t)T * B;
+    GSN_REQUIRE(rows < 2147483647ULL, "gsn_compress_spec: too many frames");
+    gsn::k_compress_spec_tf<<<(unsigned)rows, f_keep >= 256 ? 256 : (f_keep + 31) / 32 * 32, 0, gsn::as_stream(stream)>>>(
         reinterpret_cast<const float2*>(spec_ri), cm, B, F, f_keep, T, fdrc, mode);
     GSN_LAUNCH_CHECK("k_compress_spec_tf");
     return GSN_OK;
