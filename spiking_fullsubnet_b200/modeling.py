@@ -718,22 +718,29 @@ class _StreamingPipeline:
     def _stage_ctas(cls, R, K, passes, target):
         return max(1, int(math.ceil(cls._stage_us(R, K, passes) / target)))
 
-    def _stream_plan(self, B, sm_total=None):
-        """Plan of the whole network at batch B (None: not co-resident)."""
-        return self._stream_plan_for(self._stream_models(B), sm_total)
+    def _stream_plan(self, B, sm_total=None, scale=1.0):
+        """Plan of the whole network at batch B (None: not co-resident).  scale > 1 sizes the helper stages for a
+        proportionally longer frame time (fewer helper CTAs: more utterances per wave)."""
+        return self._stream_plan_for(self._stream_models(B), sm_total, scale)
 
-    def _stream_plan_for(self, models, sm_total=None):
+    def _stream_plan_for(self, models, sm_total=None, scale=1.0):
         """Stage list with CTA counts, or None when the pipeline cannot be co-resident (all kernels spin on each
         other's counters, so every CTA of every stage must be resident at once: one CTA per SM)."""
         if sm_total is None:
             sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count \
                 if torch.cuda.is_available() else 148
-            sm_total = int(os.environ.get("GSN_STREAM_SMS", sms))
+            # A thread-block cluster needs all its SMs free inside ONE GPC, the single-CTA helper stages run anywhere;
+            # when helper CTAs are placed first they can leave a GPC with an odd SM free, and a cluster still waiting
+            # would never start (every resident kernel spins on its producers).  One spare SM per GPC (8) rules that
+            # out for 2-CTA clusters whatever the launch order; wider clusters additionally run on higher-priority
+            # streams (_stream_run).  (A gate kernel that holds the helpers back until all clusters are resident was
+            # tried and dropped: with streams aliased onto few hardware queues it can block a cluster behind itself.)
+            sm_total = int(os.environ.get("GSN_STREAM_SMS", sms - 8))
         # helper stages are sized for (a bit less than) the recurrences' frame time, which grows with the hidden size:
         # 1.15 us at H = 160, 1.36 us at H = 256 / 320 (xproj input), so wide models leave more SMs to the recurrences
         h_max = max(d["m"].hidden_size for d in models)
-        target = float(os.environ.get("GSN_STREAM_TARGET_US",
-                                      self._STREAM_TARGET_US * (1.0 + 0.001 * max(0, h_max - 160))))
+        target = scale * float(os.environ.get("GSN_STREAM_TARGET_US",
+                                              self._STREAM_TARGET_US * (1.0 + 0.001 * max(0, h_max - 160))))
         helpers = 0
         for d in models:
             m = d["m"]
@@ -789,27 +796,48 @@ class _StreamingPipeline:
             d["nt"] = nt
         return models
 
-    def _stream_wave_size(self, B):
-        """Largest number of utterances whose whole pipeline is co-resident (None: not even one)."""
+    def _stream_frame_us(self, B):
+        """Frame time of the recurrences (measured): 1.2 us up to H = 240, 1.46 us for the wide models in the pipeline."""
+        return 1.2 if max(d["m"].hidden_size for d in self._stream_models(B)) <= 240 else 1.46
+
+    def _stream_wave_plan(self, B, T=501):
+        """(utterances per wave, helper scale, estimated us) of the cheapest wave schedule, or None: every wave costs T
+        frame times whatever its size, so fewer waves win even when that means slower helper stages (L: 8 waves with the
+        helpers sized for 1.5 us beat 10 waves at 1.16 us)."""
         cache = self.__dict__.setdefault("_wave_cache", {})
-        if B not in cache:
-            cache[B] = next((b for b in range(B, 0, -1) if self._stream_plan(b) is not None), None)
-        return cache[B]
+        if (B, T) not in cache:
+            best = None
+            frame_us = self._stream_frame_us(B)
+            h_max = max(d["m"].hidden_size for d in self._stream_models(B))
+            base = self._STREAM_TARGET_US * (1.0 + 0.001 * max(0, h_max - 160))
+            for scale in (1.0, 1.15, 1.3, 1.5):
+                b = next((b for b in range(B, 0, -1) if self._stream_plan(b, scale=scale) is not None), None)
+                if b is None:
+                    continue
+                us = -(-B // b) * (T * max(frame_us, base * scale) + 120.0)
+                if best is None or us < best[2] - 1e-9:
+                    best = (b, scale, us)
+            cache[(B, T)] = best
+        return cache[(B, T)]
+
+    def _stream_wave_size(self, B):
+        """Utterances per wave of the cheapest wave schedule (None: not even one utterance is co-resident)."""
+        plan = self._stream_wave_plan(B)
+        return None if plan is None else plan[0]
 
     def _waves_pay(self, B, T):
         """Waves are latency-bound (every wave costs T frame times whatever its size), the wavefront / band-stream
         schedules throughput-bound (measured 0.24 - 0.33 of the 6.3 row-frames per us per SM the recurrence sustains):
         S at batch 64 = 2 waves 1.5 ms vs 4.1 ms, L at 64 x 10 s = 8 waves 15.1 vs 22.6 ms, but M at batch 32 = 3 waves
         2.1 vs 1.7 ms.  Estimate both and take the smaller."""
-        b = self._stream_wave_size(B)
-        if b is None:
+        plan = self._stream_wave_plan(B, T)
+        if plan is None:
             return False
         mode = os.environ.get("GSN_STREAM_WAVES", "auto")
         if mode in ("0", "1"):
             return mode == "1"
         models = self._stream_models(B)
-        frame_us = 1.2 if max(d["m"].hidden_size for d in models) <= 240 else 1.46
-        waves_us = -(-B // b) * (T * frame_us + 120.0)
+        waves_us = plan[2]
         row_frames = sum(d["R"] * len(d["m"].sequence_model.layers) for d in models) * T
         return waves_us < 0.8 * row_frames / (6.3 * 148 * 0.28)  # (the estimate is only good to ~20 %: M is a tie)
 
@@ -819,9 +847,9 @@ class _StreamingPipeline:
         co-resident pipeline after the other, results concatenated along the rows."""
         dev = mag.device
         B, F, T = mag.shape
-        b = self._stream_wave_size(B)
         if not self._waves_pay(B, T):
             return None
+        b, scale, _ = self._stream_wave_plan(B, T)
         fbm = self.fb_model
         rep = (self.n_fft // 2 + 1) // self.fb_input_size
         if rep * fbm.proj_size < F - 1:
@@ -831,7 +859,7 @@ class _StreamingPipeline:
         waves, launches = [], []
         for w, lo in enumerate(range(0, B, b)):
             hi = min(B, lo + b)
-            waves.append(self._stream_run(self._stream_plan(hi - lo), cm[:, lo:hi].contiguous(), tag=f"a{w}"))
+            waves.append(self._stream_run(self._stream_plan(hi - lo, scale=scale), cm[:, lo:hi].contiguous(), tag=f"a{w}"))
             if self.__dict__.get("record_stream_launches"):
                 launches += self.stream_launches
         if launches:
@@ -947,6 +975,7 @@ class _StreamingPipeline:
 
         fb_cnt = None
         fb_target = 0
+        all_helpers = []  # enqueued after the recurrences of ALL models: clusters are placed while whole GPCs are free
         results = []
         record = [] if self.__dict__.get("record_stream_launches") else None
         # The recurrences (thread-block clusters) are enqueued before the helper stages of their model so that cluster
@@ -1059,8 +1088,7 @@ class _StreamingPipeline:
                            ops.linear_bits_stream(bp, m.proj.weight.detach(), m.proj.bias.detach(), act=m._act, out=proj,
                                                   out_act=act if m._act else None, ctas=pslices * d["proj_p"], in_cnt=ic,
                                                   in_target=it, out_cnt=c_proj))
-            for fn in helpers:
-                on_stream(fn)
+            all_helpers += helpers
             if not d["fb"]:
                 fb_cnt, fb_target, fb_act = c_proj, R * pslices, act
 
@@ -1082,6 +1110,8 @@ class _StreamingPipeline:
                                               spike_counts=spike_counts[rec_idx:rec_idx + nl], trace_numel=T * R * H),
                             bits_all, act))
             rec_idx += nl
+        for fn in all_helpers:
+            on_stream(fn)
         for stq in used:
             done = torch.cuda.Event()
             done.record(stq)
