@@ -121,20 +121,6 @@ __device__ __forceinline__ void st_split3(float w, uint32_t& hi, uint32_t& mid, 
   lo = __float_as_uint(r2) >> 16;
 }
 
-// 8 spike bits -> 8 bf16 {0, 1} (one 16-byte operand chunk) without a table: x * 0x10204080 moves bit i of a nibble to
-// bit 8i + 7 (the 16 partial products land on distinct bits, so nothing carries), PRMT replicates those byte sign bits
-// over half-words, and the mask leaves 0x3F80 = bf16 1.0 where the bit was set.
-__device__ __forceinline__ uint4 spike_byte_to_bf16x8(uint32_t b8) {
-  const uint32_t r0 = (b8 & 0xFu) * 0x10204080u, r1 = ((b8 >> 4) & 0xFu) * 0x10204080u;
-  uint4 v;  // (prmt.b32 directly: __byte_perm drops the sign-replication bit of the selector nibbles)
-  asm("prmt.b32 %0, %1, 0, 0x9988;" : "=r"(v.x) : "r"(r0));
-  asm("prmt.b32 %0, %1, 0, 0xBBAA;" : "=r"(v.y) : "r"(r0));
-  asm("prmt.b32 %0, %1, 0, 0x9988;" : "=r"(v.z) : "r"(r1));
-  asm("prmt.b32 %0, %1, 0, 0xBBAA;" : "=r"(v.w) : "r"(r1));
-  v.x &= 0x3F803F80u; v.y &= 0x3F803F80u; v.z &= 0x3F803F80u; v.w &= 0x3F803F80u;
-  return v;
-}
-
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
   unsigned int v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -702,7 +688,7 @@ __global__ void __launch_bounds__(kStThreads, 1) k_recurrence_stream(const RecSt
         if (more || do_img) {
           // my warp's 32 neurons x 4 rows as sixteen 16-byte operand chunks, to every CTA of the cluster
           const uint32_t wrow = __shfl_sync(0xffffffffu, myw, dir_i);
-          const uint4 v4 = spike_byte_to_bf16x8(wrow >> (8 * dir_sub));
+          const uint4 v4 = tc::spike_byte_to_bf16x8(wrow >> (8 * dir_sub));
           const uint32_t v[4] = {v4.x, v4.y, v4.z, v4.w};
           if (more) {
             const uint32_t local = tc::smem_u32(sB + (par ? 0u : sB_bytes)) + dir_off;  // buffer (t+1)&1

@@ -341,12 +341,7 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_stage_stream(const StageParam
           for (int e4 = 0; e4 < 4; ++e4) {
             const int k8 = 4 * wi + e4;
             if (k8 >= k8n) break;
-            const uint32_t b8 = (wd[it] >> (8 * e4)) & 0xFFu;
-            uint32_t v[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              v[e] = ((b8 >> (2 * e)) & 1u ? 0x3F80u : 0u) | ((b8 >> (2 * e + 1)) & 1u ? 0x3F800000u : 0u);
-            *reinterpret_cast<uint4*>(dst + rowoff + (uint32_t)(k8 * 128)) = make_uint4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<uint4*>(dst + rowoff + (uint32_t)(k8 * 128)) = tc::spike_byte_to_bf16x8(wd[it] >> (8 * e4));
           }
         }
       } else {

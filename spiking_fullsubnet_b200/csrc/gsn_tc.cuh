@@ -359,6 +359,20 @@ __device__ __forceinline__ bool mma_i8_planes(int ksteps, uint32_t tmem_d, uint3
   }
 }
 
+// 8 spike bits -> 8 bf16 {0, 1} (one 16-byte operand chunk) without a table: x * 0x10204080 moves bit i of a nibble to
+// bit 8i + 7 (the 16 partial products land on distinct bits, so nothing carries), PRMT replicates those byte sign bits
+// over half-words, and the mask leaves 0x3F80 = bf16 1.0 where the bit was set.
+__device__ __forceinline__ uint4 spike_byte_to_bf16x8(uint32_t b8) {
+  const uint32_t r0 = (b8 & 0xFu) * 0x10204080u, r1 = ((b8 >> 4) & 0xFu) * 0x10204080u;
+  uint4 v;  // (prmt.b32 directly: __byte_perm drops the sign-replication bit of the selector nibbles)
+  asm("prmt.b32 %0, %1, 0, 0x9988;" : "=r"(v.x) : "r"(r0));
+  asm("prmt.b32 %0, %1, 0, 0xBBAA;" : "=r"(v.y) : "r"(r0));
+  asm("prmt.b32 %0, %1, 0, 0x9988;" : "=r"(v.z) : "r"(r1));
+  asm("prmt.b32 %0, %1, 0, 0xBBAA;" : "=r"(v.w) : "r"(r1));
+  v.x &= 0x3F803F80u; v.y &= 0x3F803F80u; v.z &= 0x3F803F80u; v.w &= 0x3F803F80u;
+  return v;
+}
+
 // all previously issued MMAs of this thread arrive (once) on `bar` when complete
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
