@@ -696,7 +696,7 @@ class _StreamingPipeline:
 
     # cost model of the helper stages (measured on B200, tools/stream_stage_timing.py / stream_fused0_check.py):
     #   gsn_xplanes_stream: (0.009 + 0.00028 Kmma) us per row per CTA;
-    #   tcgen05 stages: ~75 cycles per MMA at 64-row tiles (3 planes for spike inputs, 8 plane pairs for real inputs)
+    #   tcgen05 stages: ~60 cycles per MMA at 64-row tiles (3 planes for spike inputs, 8 plane pairs for real inputs)
     _STREAM_TARGET_US = 1.0   # helper stages must be faster than the recurrences' frame time (1.2 - 1.3 us)
     _XOP_RING = 64            # frames of layer-0 operand images kept (ring; S: 64 x 202 KB = 13 MB, L2-resident)
 
@@ -707,8 +707,10 @@ class _StreamingPipeline:
 
     @staticmethod
     def _stage_us(R, K, passes):
+        # per 64-row tile: 60 cycles per 128x64x16 MMA + 0.15 us of hand-overs (tools/stage_k_timing.py: R = 96 / 256 at
+        # K = 160 1.71 / 3.90 us per frame, R = 192 / 128 at K = 256 4.4 - 5.0 / 3.3 us)
         kmma = (K + 15) // 16 * 16
-        return (R / 64.0) * passes * (kmma // 16) * 75.0 / 1965.0
+        return (R / 64.0) * (passes * (kmma // 16) * 60.0 / 1965.0 + 0.15)
 
     @classmethod
     def _xplanes_ctas(cls, R, K, target):
