@@ -150,6 +150,26 @@ GSN_API int gsn_frame_signal(const float* y, const float* window, float* frames,
                              gsn_stream_t stream);
 GSN_API int gsn_overlap_add(const float* frames, const float* window, float* y, int B, int T, int n_fft, int hop,
                             int length, gsn_stream_t stream);
+/* ---- the recipes' 512-point real FFTs fused with their neighbours (gsn_fft.cu; n_fft = win_length = 512 only) ----
+ * gsn_stft_compress   : torch.stft(center=True, pad_mode="constant", hann window; audio_feature.py:236-294) AND
+ *                       |X|^fdrc (MSF:434-436, "b f t -> t b f" MSF:108) in one pass over the waveform: y [B, L] ->
+ *                       spec_ri [B, T, 257, 2] (time-major complex spectrum, the layout of `time_major` above) and
+ *                       cm [T, B, f_keep] (may be NULL).  Replaces gsn_frame_signal + cuFFT R2C + gsn_compress_spec.
+ * gsn_irfft_frames    : spec_ri [B, T, 257, 2] -> frames [B, T, 512]: inverse real FFT of every frame with the 1/n
+ *                       normalisation of torch.fft.irfft, unwindowed -- what gsn_overlap_add reads
+ *                       (audio_feature.py:297-347).  Imaginary parts of the DC and Nyquist bins are ignored, as cuFFT does.
+ * gsn_deepfilter_irfft: the same inverse transform of the DEEP-FILTERED spectrum (MSF:315-346, 449-472; one speaker),
+ *                       computed on the fly: projs[i] [T, B*N[i], 2*ctr[i]*df[i]] are the bands' proj outputs in
+ *                       frequency order from bin 0 (feature order `layout` as gsn_deepfilter_spec), bins above the
+ *                       last band pass through (MSF:461-468).  mag_out [B, T, 257] = |enhanced| (enh_mag, MSF:472;
+ *                       may be NULL), enh_ri [B, T, 257, 2] = the enhanced spectrum itself (may be NULL: it then never
+ *                       exists in memory).  projs / N / ctr / df are HOST arrays of n_bands <= 4 entries.            */
+GSN_API int gsn_stft_compress(const float* y, const float* window, float* spec_ri, float* cm, int B, int L, int T,
+                              int n_fft, int hop, int f_keep, float fdrc, gsn_stream_t stream);
+GSN_API int gsn_irfft_frames(const float* spec_ri, float* frames, int B, int T, int n_fft, gsn_stream_t stream);
+GSN_API int gsn_deepfilter_irfft(const float* const* projs, const int* N, const int* ctr, const int* df, int n_bands,
+                                 int layout, const float* spec_ri, float* frames, float* mag_out, float* enh_ri, int B,
+                                 int T, int n_fft, gsn_stream_t stream);
 
 /* ---- streaming recurrence (gsn_recurrence_stream.cu): StackedGSU.forward ESN:50-62 as a frame-granular pipeline ---
  * One persistent, warp-specialised tcgen05 launch runs GSULayer.forward (ESN:75-81) of one layer for all T frames

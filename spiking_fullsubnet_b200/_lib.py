@@ -42,6 +42,9 @@ SIGNATURES = {
     "gsn_spec_passthrough": (_i, [_p, _p, _p] + [_i] * 7 + [_p]),
     "gsn_overlap_add": (_i, [_p, _p, _p] + [_i] * 5 + [_p]),
     "gsn_frame_signal": (_i, [_p, _p, _p] + [_i] * 5 + [_p]),
+    "gsn_stft_compress": (_i, [_p, _p, _p, _p] + [_i] * 6 + [_f, _p]),
+    "gsn_irfft_frames": (_i, [_p, _p, _i, _i, _i, _p]),
+    "gsn_deepfilter_irfft": (_i, [_p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _i, _i, _i, _p]),
     "gsn_stream_preload": (_i, []),
     "gsn_xplanes_bytes": (_sz, [_i] * 4),
     "gsn_xplanes_stream": (_i, [_p, _i, _p, _i, _p, _p, _f, _p, _i, _p, _p, _i, _p, C.c_uint, _p, _p, C.c_uint] + [_i] * 8 + [_p]),

@@ -521,17 +521,34 @@ def _stft(y, n_fft, hop, win):
     return torch.stft(y, n_fft, hop, win, window=window, return_complex=True, pad_mode="constant")
 
 
-def _stft_fused(y, n_fft, hop, win):
+def _stft_fused(y, n_fft, hop, win, f_keep=None, fdrc=None):
     """_stft for the inference path: ONE framing kernel (gsn_frame_signal: zero padding, framing, window) + cuFFT's
     batched real FFT instead of torch.stft's pad / as_strided / multiply / FFT sequence.  Same [B,F,T] view of cuFFT's
     [B,T,F] output.  (torch.stft stays on the training path: it is differentiable.)"""
     if win != n_fft or n_fft % 8 != 0 or y.dim() != 2 or y.requires_grad or not y.is_contiguous() or y.data_ptr() % 16:
         return _stft(y, n_fft, hop, win)
-    key = (n_fft, y.device.index)
+    window = _hann(n_fft, y.device)
+    if _fft_kernels(n_fft, win):
+        # the recipes' transform length: framing + window + real FFT + |X|**fdrc in ONE kernel (gsn_stft_compress); the
+        # compressed magnitude rides along on the tensor and ops.compress_mag hands it to the network as is
+        spec, cm = ops.stft_compress(y, window, hop, f_keep, 0.5 if fdrc is None else fdrc)
+        if cm is not None:
+            spec._gsn_cm = (int(f_keep), float(fdrc), cm)
+        return spec
+    return torch.fft.rfft(ops.frame_signal(y, window, hop), dim=-1).transpose(1, 2)
+
+
+def _fft_kernels(n_fft, win):
+    """True when the library's own FFT kernels apply (n_fft = win_length = 512; GSN_FFT_FUSED=0: cuFFT path)."""
+    return n_fft == ops.FFT_FUSED_N and win == n_fft and os.environ.get("GSN_FFT_FUSED", "1") != "0"
+
+
+def _hann(n_fft, device):
+    key = (n_fft, device.index)
     window = _HANN.get(key)
     if window is None:
-        window = _HANN[key] = torch.hann_window(n_fft, device=y.device)
-    return torch.fft.rfft(ops.frame_signal(y, window, hop), dim=-1).transpose(1, 2)
+        window = _HANN[key] = torch.hann_window(n_fft, device=device)
+    return window
 
 
 def _istft(spec, n_fft, hop, win, length):
@@ -597,12 +614,26 @@ def _istft_fused(spec, n_fft, hop, win, length):
     overlap-added squared window and removal of the centre padding (audio_feature.py:297-347).
     spec complex [B,F,T] -> [B,length]."""
     assert win == n_fft, "win_length != n_fft is not used by any recipe"
-    key = (n_fft, spec.device.index)
-    window = _HANN.get(key)
-    if window is None:
-        window = _HANN[key] = torch.hann_window(n_fft, device=spec.device)
-    frames = torch.fft.irfft(spec.transpose(1, 2), n=n_fft, dim=-1).contiguous()      # [B,T,n_fft]; no copy when time-major
+    window = _hann(n_fft, spec.device)
+    if _fft_kernels(n_fft, win) and spec.shape[1] == n_fft // 2 + 1 and spec.transpose(1, 2).is_contiguous():
+        frames = ops.irfft_frames(spec)  # gsn_irfft_frames: no defensive clone, no separate scaling pass
+    else:
+        frames = torch.fft.irfft(spec.transpose(1, 2), n=n_fft, dim=-1).contiguous()  # [B,T,n_fft]; no copy when time-major
     return ops.overlap_add(frames, window, hop, length)
+
+
+def _fused_back_end(projs, cmp, Ns, ctrs, dfs, layout, n_fft, hop, win, length, want_mag=True):
+    """Deep filter + pass-through + inverse FFT in one kernel (gsn_deepfilter_irfft), then the overlap-add: the back end
+    of forward() for ONE speaker at the recipes' transform length.  Returns (y [B,length], |enh| [B,F,T]) or None when
+    the fused kernel does not apply (the callers then take the per-band kernels + cuFFT)."""
+    if not _fft_kernels(n_fft, win) or len(projs) > 4 or cmp.shape[1] != n_fft // 2 + 1:
+        return None
+    if cmp.is_contiguous() or not cmp.transpose(1, 2).is_contiguous():
+        return None
+    frames, mag, _ = ops.deepfilter_irfft([p.contiguous() for p in projs], cmp, Ns, ctrs, dfs, layout=layout,
+                                          want_mag=want_mag)
+    y = ops.overlap_add(frames, _hann(n_fft, cmp.device), hop, length)
+    return y, (mag[:, 0] if mag is not None else None)
 
 
 class _GraphedNetwork:
@@ -1356,6 +1387,18 @@ class SpikingFullSubNet(_StreamingPipeline, _GraphedNetwork, nn.Module):
         return static_out
 
     def _forward_infer(self, input):
+        if self.num_spks == 1 and _fft_kernels(self.n_fft, self.win_length):
+            # wave -> (spectrum, compressed magnitude) -> network -> (deep filter + inverse FFT) -> overlap-add: the
+            # enhanced spectrum never exists in memory
+            F = self.n_fft // 2 + 1
+            cmp = _stft_fused(input, self.n_fft, self.hop_length, self.win_length, f_keep=F - 1, fdrc=self.fdrc)
+            projs, fb_all, sb_all = self.network(cmp)
+            cuts, ctrs = self.sb_model.freq_cutoffs, self.sb_model.center_freq_sizes
+            Ns = [(cuts[i + 1] - cuts[i]) // ctrs[i] for i in range(len(projs))]
+            res = _fused_back_end(projs, cmp, Ns, ctrs[:len(projs)], self.df_orders[:len(projs)], 0, self.n_fft,
+                                  self.hop_length, self.win_length, input.shape[1])
+            if res is not None:
+                return res[0], res[1], fb_all, sb_all
         enh, mag, fb_all, sb_all = self._forward_spec(input)
         return self._finish(enh, fb_all, sb_all, input.shape[1], mag)
 
@@ -1432,10 +1475,16 @@ class CirmGSN(_GraphedNetwork, nn.Module):
             from . import training
             return training.cirm_gsn_forward(self, input)
         B, L = input.shape
-        cmp = _stft_fused(input, self.n_fft, self.hop_length, self.win_length)
+        cmp = _stft_fused(input, self.n_fft, self.hop_length, self.win_length, f_keep=self.n_fft // 2 + 1,
+                          fdrc=self.fdrc)
         act, all_out = self.network(cmp)  # activated proj [T,B,P], features (c d s f) (CGN:230)
         F, T = cmp.shape[1], cmp.shape[2]
         S = self.num_spks
+        if S == 1:
+            res = _fused_back_end([act.reshape(T, B, -1)], cmp, [1], [F], [self.df_order], 1, self.n_fft,
+                                  self.hop_length, self.win_length, L)
+            if res is not None:
+                return res
         enh = _empty_spec_like(cmp, S)
         ops.deepfilter_spec(act.contiguous(), cmp, enh, 1, F, self.df_order, S, 0, layout=1)  # CGN:128, 233
         if S > 1:
@@ -1751,9 +1800,16 @@ class Separator(_StreamingPipeline, _GraphedNetwork, nn.Module):
             from . import training
             return training.separator_forward(self, noisy_y)
         B, L = noisy_y.shape
-        cmp = _stft_fused(noisy_y, self.n_fft, self.hop_length, self.win_length)
+        F = self.n_fft // 2 + 1
+        cmp = _stft_fused(noisy_y, self.n_fft, self.hop_length, self.win_length, f_keep=F - 1, fdrc=self.fdrc)
         projs, fb_all, sb_all = self.network(cmp)
         F, T = cmp.shape[1], cmp.shape[2]
+        ctrs = list(self.sb_model.sb_num_center_freqs)[:len(projs)]
+        Ns = [(b - a) // c for (a, b), c in zip(self.sb_model.band_edges(F - 1), ctrs)]
+        res = _fused_back_end(projs, cmp, Ns, ctrs, list(self.sb_df_orders)[:len(projs)], 0, self.n_fft, self.hop_length,
+                              self.win_length, L)
+        if res is not None:
+            return res[0], res[1], fb_all, sb_all
         enh = _empty_spec_like(cmp, 1)
         lo = 0
         for i, (p, (a, b)) in enumerate(zip(projs, self.sb_model.band_edges(F - 1))):

@@ -70,6 +70,9 @@ def compress_mag(mag, f_keep, fdrc):
     """mag [B,F,T] (or the complex STFT itself, in either layout of `_spec_layout`) -> cm [T,B,f_keep] = |.|**fdrc
     (MSF:434-436, time-major)."""
     if mag.is_complex():
+        pre = getattr(mag, "_gsn_cm", None)  # gsn_stft_compress already produced it (modeling._stft_fused)
+        if pre is not None and pre[0] == int(f_keep) and pre[1] == float(fdrc):
+            return pre[2]
         tm = _spec_layout(mag, "compress_mag")
         lib = _lib.load()
         _bind(mag.device)
@@ -145,6 +148,71 @@ def overlap_add(frames, window, hop, length):
     _lib.check(lib.gsn_overlap_add(_ptr(frames), _ptr(window), _ptr(y), B, T, n_fft, int(hop), int(length), st))
     LAUNCHES[0] += 1
     return y
+
+
+FFT_FUSED_N = 512  # the transform length gsn_fft.cu is built for (every recipe's n_fft)
+
+
+def stft_compress(y, window, hop, f_keep=None, fdrc=0.5):
+    """torch.stft(center=True, pad_mode="constant") of y [B,L] with the 512-sample `window` AND the network's
+    compressed magnitude in one kernel: returns (spec, cm): spec complex64 [B,F,T] as a time-major VIEW of the [B,T,F]
+    buffer the kernel writes (the layout `_spec_layout` calls 1), cm [T,B,f_keep] = |spec|**fdrc or None."""
+    import ctypes as C
+    lib, st = _prep(y, window)
+    B, L = y.shape
+    n_fft = window.numel()
+    T = 1 + L // int(hop)
+    F = n_fft // 2 + 1
+    spec = torch.empty((B, T, F), device=y.device, dtype=torch.complex64)
+    cm = torch.empty((T, B, f_keep), device=y.device, dtype=torch.float32) if f_keep else None
+    _lib.check(lib.gsn_stft_compress(_ptr(y), _ptr(window), spec.data_ptr(), _ptr(cm) if cm is not None else None, B, L, T,
+                                     n_fft, int(hop), int(f_keep or 0), float(fdrc), st))
+    LAUNCHES[0] += 1
+    return spec.transpose(1, 2), cm
+
+
+def irfft_frames(spec):
+    """spec complex64 [B,F,T] in the time-major layout -> frames [B,T,512] = torch.fft.irfft of every frame."""
+    if _spec_layout(spec, "irfft_frames") != 1:
+        raise ValueError("irfft_frames: the spectrum must be time-major ([B,T,F] in memory)")
+    lib = _lib.load()
+    _bind(spec.device)
+    st = torch.cuda.current_stream(spec.device).cuda_stream
+    B, F, T = spec.shape
+    n_fft = 2 * (F - 1)
+    frames = torch.empty((B, T, n_fft), device=spec.device, dtype=torch.float32)
+    _lib.check(lib.gsn_irfft_frames(spec.data_ptr(), _ptr(frames), B, T, n_fft, st))
+    LAUNCHES[0] += 1
+    return frames
+
+
+def deepfilter_irfft(projs, spec, Ns, ctrs, dfs, layout=0, want_mag=True, want_enh=False):
+    """Deep filter of all bands (MSF:315-346, 449-472; one speaker) + pass-through of the bins above them (MSF:461-468)
+    + inverse real FFT of every frame in ONE kernel: projs[i] [T, B*Ns[i], 2*ctrs[i]*dfs[i]] in frequency order, spec
+    complex64 [B,F,T] time-major.  Returns (frames [B,T,512], mag [B,1,F,T] view or None, enh [B,1,F,T] view or None)."""
+    import ctypes as C
+    if _spec_layout(spec, "deepfilter_irfft") != 1:
+        raise ValueError("deepfilter_irfft: the spectrum must be time-major ([B,T,F] in memory)")
+    lib, st = _prep(*projs)
+    if spec.device != projs[0].device:
+        raise ValueError("deepfilter_irfft: spec and proj on different devices")
+    B, F, T = spec.shape
+    n_fft = 2 * (F - 1)
+    nb = len(projs)
+    for p, n, c, d in zip(projs, Ns, ctrs, dfs):
+        if p.dtype != torch.float32 or not p.is_contiguous() or p.numel() != T * B * n * 2 * c * d:
+            raise ValueError(f"deepfilter_irfft: proj {tuple(p.shape)} is not [T={T}, B*N={B * n}, 2*ctr*df={2 * c * d}]")
+    frames = torch.empty((B, T, n_fft), device=spec.device, dtype=torch.float32)
+    mag = torch.empty((B, 1, T, F), device=spec.device, dtype=torch.float32) if want_mag else None
+    enh = torch.empty((B, 1, T, F), device=spec.device, dtype=torch.complex64) if want_enh else None
+    parr = (C.c_void_p * nb)(*[p.data_ptr() for p in projs])
+    iarr = [(C.c_int * nb)(*[int(v) for v in vs]) for vs in (Ns, ctrs, dfs)]
+    _lib.check(lib.gsn_deepfilter_irfft(parr, iarr[0], iarr[1], iarr[2], nb, int(layout), spec.data_ptr(), _ptr(frames),
+                                        _ptr(mag) if mag is not None else None,
+                                        enh.data_ptr() if enh is not None else None, B, T, n_fft, st))
+    LAUNCHES[0] += 1
+    return (frames, mag.transpose(2, 3) if mag is not None else None,
+            enh.transpose(2, 3) if enh is not None else None)
 
 
 def _out(out, shape, like):

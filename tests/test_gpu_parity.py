@@ -790,7 +790,10 @@ def test_fused_istft_matches_torch_istft(B, n_fft, hop, L):
     assert got.shape == ref.shape
     assert float((got - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
     assert not spec.is_contiguous()  # torch.stft hands out the time-major view: no transpose copy on that path
-    assert torch.equal(_istft_fused(spec, n_fft, hop, n_fft, L), got)
+    got_tm = _istft_fused(spec, n_fft, hop, n_fft, L)  # n_fft = 512: gsn_irfft_frames instead of cuFFT
+    assert float((got_tm - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
+    if n_fft != ops.FFT_FUSED_N:
+        assert torch.equal(got_tm, got)
 
 
 @pytest.mark.parametrize("B,n_fft,hop,L", [(3, 512, 128, 16000), (2, 64, 16, 801), (1, 512, 128, 64000), (2, 128, 32, 1000),
@@ -813,6 +816,111 @@ def test_fused_stft_matches_torch_stft(B, n_fft, hop, L):
     pad = torch.nn.functional.pad(y, (n_fft // 2, n_fft // 2))
     ref = pad.unfold(1, n_fft, hop) * torch.hann_window(n_fft, device=DEV)
     assert torch.equal(frames, ref)
+
+
+@pytest.mark.parametrize("B,hop,L,f_keep,fdrc", [(3, 128, 16000, 256, 0.5), (2, 128, 300, 257, 1.0), (1, 256, 64000, 256, 0.3),
+                                                 (2, 100, 1001, 256, 0.5), (5, 128, 40037, 64, 0.5)])
+def test_stft_compress_kernel_matches_torch_stft_and_compress(B, hop, L, f_keep, fdrc):
+    """Row f2: gsn_stft_compress (zero padding + framing + window + 512-point real FFT + |X|**fdrc, one kernel) against
+    torch.stft(center=True, pad_mode="constant", hann window) (audio_feature.py:236-294) and mag**fdrc in the network's
+    layout (MSF:434-436, MSF:108); ragged lengths, frame counts that are not a multiple of the block's four frames."""
+    rs = np.random.RandomState(L + hop)
+    y = _t(rs.standard_normal((B, L)).astype(np.float32))
+    window = torch.hann_window(512, device=DEV)
+    want = torch.stft(y, 512, hop, 512, window=window, return_complex=True, pad_mode="constant")
+    spec, cm = ops.stft_compress(y, window, hop, f_keep, fdrc)
+    assert spec.shape == want.shape and spec.stride() == want.stride() and cm.shape == (want.shape[2], B, f_keep)
+    err = (spec - want).abs().max().item()
+    assert err <= 2e-6 * want.abs().max().item(), err
+    # the compressed magnitude is that of the spectrum the kernel wrote, bit for bit (same |.| and power as
+    # gsn_compress_spec), and within FFT rounding of the reference's
+    assert torch.equal(cm, ops.compress_mag(spec, f_keep, fdrc))
+    ref_cm = (want.abs()[:, :f_keep] ** fdrc).permute(2, 0, 1)
+    assert float((cm - ref_cm).abs().max()) <= 1e-4 * float(ref_cm.abs().max())
+    spec2, none = ops.stft_compress(y, window, hop)
+    assert none is None and torch.equal(spec2, spec)
+
+
+@pytest.mark.parametrize("B,T", [(2, 126), (1, 3), (3, 501)])
+def test_irfft_frames_kernel_matches_torch_irfft(B, T):
+    """gsn_irfft_frames against torch.fft.irfft(n=512) of every frame, including the C2R convention that the imaginary
+    parts of the DC and Nyquist bins are ignored."""
+    g = torch.Generator(device="cpu").manual_seed(B * 1000 + T)
+    spec_tm = torch.complex(torch.randn(B, T, 257, generator=g), torch.randn(B, T, 257, generator=g)).to(DEV)
+    want = torch.fft.irfft(spec_tm, n=512, dim=-1)
+    got = ops.irfft_frames(spec_tm.transpose(1, 2))
+    assert got.shape == want.shape
+    assert float((got - want).abs().max()) <= 2e-6 * float(want.abs().max())
+    with pytest.raises(ValueError):
+        ops.irfft_frames(spec_tm.transpose(1, 2).contiguous())
+
+
+@pytest.mark.parametrize("layout,bands", [(0, [(4, 8, 5), (6, 16, 3), (2, 64, 1)]), (0, [(8, 32, 2)]), (1, [(1, 257, 3)]),
+                                          (0, [(2, 16, 3), (2, 16, 1), (2, 32, 2), (4, 32, 1)])])
+def test_deepfilter_irfft_kernel_matches_the_band_kernels_and_irfft(layout, bands):
+    """gsn_deepfilter_irfft (deep filter of all bands + pass-through + inverse FFT, the enhanced spectrum never in
+    memory) against gsn_deepfilter_spec / gsn_spec_passthrough + torch.fft.irfft (MSF:315-346, 449-472; CGN:230)."""
+    B, T, F = 3, 37, 257
+    g = torch.Generator(device="cpu").manual_seed(len(bands) * 7 + layout)
+    spec_tm = torch.complex(torch.randn(B, T, F, generator=g), torch.randn(B, T, F, generator=g)).to(DEV)
+    spec = spec_tm.transpose(1, 2)
+    projs = [torch.randn(T, B * n, 2 * c * d, generator=g).to(DEV) for n, c, d in bands]
+    Ns, ctrs, dfs = ([b[i] for b in bands] for i in range(3))
+    enh = torch.empty((B, 1, T, F), dtype=torch.complex64, device=DEV).transpose(2, 3)
+    mag = torch.empty((B, 1, T, F), dtype=torch.float32, device=DEV).transpose(2, 3)
+    lo = 0
+    for p, n, c, d in zip(projs, Ns, ctrs, dfs):
+        ops.deepfilter_spec(p, spec, enh, n, c, d, 1, lo, layout=layout, mag=mag)
+        lo += n * c
+    ops.spec_passthrough(spec, enh, lo, mag=mag)
+    frames, got_mag, got_enh = ops.deepfilter_irfft(projs, spec, Ns, ctrs, dfs, layout=layout, want_enh=True)
+    assert float((got_enh - enh).abs().max()) <= 1e-6 * float(enh.abs().max())
+    assert float((got_mag - mag).abs().max()) <= 1e-6 * float(mag.abs().max())
+    want = torch.fft.irfft(enh[:, 0].transpose(1, 2), n=512, dim=-1)
+    assert float((frames - want).abs().max()) <= 2e-6 * float(want.abs().max())
+    frames2, m2, e2 = ops.deepfilter_irfft(projs, spec, Ns, ctrs, dfs, layout=layout, want_mag=False)
+    assert m2 is None and e2 is None and torch.equal(frames2, frames)
+
+
+def test_forward_with_the_fused_fft_kernels_equals_its_parts():
+    """forward() at the recipes' n_fft = 512 (S, surface A): the fused front end hands the network the compressed
+    magnitude of its own spectrum, and the result is the fused back end applied to the network's coefficients; against
+    the per-band kernels + cuFFT on the SAME spectrum and coefficients the waveform agrees to FFT rounding."""
+    from spiking_fullsubnet_b200 import modeling
+    cfg = synth.CONFIGS["S"]
+    m = _model(cfg, synth.make_params(cfg, 5))
+    wave = _t(synth.make_wave(2, 16000, 3))
+    with torch.no_grad():
+        n0 = ops.LAUNCHES[0]
+        y, mag, fb_all, sb_all = m(wave)
+        fused_launches = ops.LAUNCHES[0] - n0
+        cmp = modeling._stft_fused(wave, 512, cfg["hop_length"], 512, f_keep=256, fdrc=cfg["fdrc"])
+        assert torch.equal(cmp._gsn_cm[2], ops.compress_mag(cmp.transpose(1, 2).contiguous().transpose(1, 2), 256, cfg["fdrc"]))
+        projs, _, _ = m.network(cmp)
+        # the reference composition on the same spectrum: per-band deep filter, pass-through, cuFFT, overlap-add
+        enh = modeling._empty_spec_like(cmp, 1)
+        ref_mag = torch.empty_strided(enh.shape, enh.stride(), dtype=torch.float32, device=DEV)
+        cuts, ctrs = m.sb_model.freq_cutoffs, m.sb_model.center_freq_sizes
+        lo = 0
+        for i, p in enumerate(projs):
+            n = (cuts[i + 1] - cuts[i]) // ctrs[i]
+            ops.deepfilter_spec(p, cmp, enh, n, ctrs[i], m.df_orders[i], 1, lo, mag=ref_mag)
+            lo += n * ctrs[i]
+        ops.spec_passthrough(cmp, enh, lo, mag=ref_mag)
+        window = torch.hann_window(512, device=DEV)
+        ref_y = torch.istft(enh[:, 0], 512, cfg["hop_length"], 512, window=window, length=wave.shape[1])
+    assert float((y - ref_y).abs().max()) <= 2e-5 * float(ref_y.abs().max())
+    assert float((mag - ref_mag[:, 0]).abs().max()) <= 1e-6 * float(ref_mag.abs().max())
+    os_env = __import__("os").environ
+    os_env["GSN_FFT_FUSED"] = "0"
+    try:
+        with torch.no_grad():
+            n0 = ops.LAUNCHES[0]
+            y0 = m(wave)[0]
+            assert ops.LAUNCHES[0] - n0 > fused_launches  # the cuFFT path launches more of the library's kernels
+    finally:
+        del os_env["GSN_FFT_FUSED"]
+    assert y0.shape == y.shape and torch.isfinite(y0).all()
 
 
 def test_loss_terms_on_the_gpu_match_reference_values_and_gradient():
