@@ -94,8 +94,15 @@ __device__ __forceinline__ void fft_tables(float2* tw, float2* w256) {
   for (int i = threadIdx.x; i < 256; i += blockDim.x) w256[i] = kW512[(2 * (i >> 4) * (i & 15)) & 511];
 }
 
+// |z| as torch.abs of a complex number gives it (hypotf), without hypotf's scaling on the common path: when x^2 + y^2
+// neither overflows nor loses bits to underflow, sqrt(fma(x, x, y*y)) is within one ulp of it
+__device__ __forceinline__ float cabs_fast(float2 z) {
+  const float v = fmaf(z.x, z.x, z.y * z.y);
+  if (v > 1e-30f && v < 1e30f) return sqrtf(v);
+  return hypotf(z.x, z.y);
+}
 __device__ __forceinline__ float compress_abs(float2 z, float fdrc, int mode) {
-  const float v = hypotf(z.x, z.y);  // torch.abs of a complex tensor
+  const float v = cabs_fast(z);
   return mode == 0 ? sqrtf(v) : (mode == 1 ? v : powf(v, fdrc));
 }
 
@@ -167,6 +174,7 @@ __global__ void __launch_bounds__(FFT_THREADS, 8) k_stft512(const float* __restr
 struct DfBands {
   const float* proj[4];  // [T, B*N, P], P = 2 * ctr * df (one speaker)
   int N[4], ctr[4], df[4], lo[4];
+  int shift[4];  // log2(ctr) when ctr is a power of two, else -1
   int nb;       // bands in use
   int f_pass;   // bins >= f_pass pass through unfiltered (MSF:461-468)
   int layout;   // 0 = (c fc df s), MSF:160-167;  1 = (c df s fc), CGN:230
@@ -198,37 +206,64 @@ __global__ void __launch_bounds__(FFT_THREADS, 8) k_irfft512(const float2* __res
         k_pass = bands.f_pass;
         for (int i = 0; i < bands.nb; ++i) {  // uniform over the frame's threads
           const int ctr = bands.ctr[i], df = bands.df[i], N = bands.N[i], lo = bands.lo[i], W = N * ctr;
-          const float* prow = bands.proj[i] + ((size_t)t * B + b) * (size_t)N * (size_t)(2 * ctr * df);  // the frame's N rows
+          const int shift = bands.shift[i], layout = bands.layout;
+          const float* __restrict__ prow = bands.proj[i] + ((size_t)t * B + b) * (size_t)N * (size_t)(2 * ctr * df);
+          const float2* __restrict__ xs0 = spec + ((ptrdiff_t)fr - (df - 1)) * F + lo;  // tap d reads frame t - (df-1) + d
           const int d0 = t < df - 1 ? df - 1 - t : 0;  // taps that reach in front of the first frame are skipped
-          int n = j / ctr, fc = j - n * ctr;
-          for (int q = j; q < W; q += 16) {
-            const float* pr = prow + (size_t)n * (2 * ctr * df);
-            const float2* xs = spec + ((ptrdiff_t)fr - (df - 1)) * F + lo + q;  // tap d reads frame t - (df-1) + d
-            float yr = 0.f, yi = 0.f;
-            for (int d = d0; d < df; ++d) {
-              const float cr = bands.layout == 0 ? pr[fc * df + d] : pr[d * ctr + fc];
-              const float ci = bands.layout == 0 ? pr[(ctr + fc) * df + d] : pr[(df + d) * ctr + fc];
-              const float2 z = xs[(ptrdiff_t)d * F];
-              yr += z.x * cr - z.y * ci;
-              yi += z.x * ci + z.y * cr;
+          for (int q0 = j; q0 < W; q0 += 64) {  // four bins per thread at a time: their loads are in flight together
+            float2 x[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int q = q0 + 16 * u;
+              x[u] = make_float2(0.f, 0.f);
+              if (q < W) {
+                int n, fc;
+                if (shift >= 0) { n = q >> shift; fc = q & (ctr - 1); } else { n = q / ctr; fc = q - n * ctr; }
+                const float* pr = prow + (size_t)n * (2 * ctr * df);
+                if (df == 1) {  // most bins of every recipe
+                  const float cr = pr[fc], ci = pr[ctr + fc];
+                  const float2 z = xs0[q];
+                  x[u] = make_float2(z.x * cr - z.y * ci, z.x * ci + z.y * cr);
+                } else {
+                  float yr = 0.f, yi = 0.f;
+                  for (int d = d0; d < df; ++d) {
+                    const float cr = layout == 0 ? pr[fc * df + d] : pr[d * ctr + fc];
+                    const float ci = layout == 0 ? pr[(ctr + fc) * df + d] : pr[(df + d) * ctr + fc];
+                    const float2 z = xs0[(ptrdiff_t)d * F + q];
+                    yr += z.x * cr - z.y * ci;
+                    yi += z.x * ci + z.y * cr;
+                  }
+                  x[u] = make_float2(yr, yi);
+                }
+              }
             }
-            const int k = lo + q;
-            float2 x = make_float2(yr, yi);
-            if (mrow != nullptr) mrow[k] = hypotf(yr, yi);  // enh_mag, MSF:472
-            if (erow != nullptr) erow[k] = x;
-            if (k == 0 || k == FFT_M) x.y = 0.f;  // a C2R transform ignores the imaginary parts of DC and Nyquist
-            s[k] = x;
-            fc += 16;
-            while (fc >= ctr) { fc -= ctr; ++n; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int q = q0 + 16 * u, k = lo + q;
+              if (q < W) {
+                if (mrow != nullptr) mrow[k] = cabs_fast(x[u]);  // enh_mag, MSF:472
+                if (erow != nullptr) erow[k] = x[u];
+                if (k == 0 || k == FFT_M) x[u].y = 0.f;  // a C2R transform ignores the imaginary parts of DC and Nyquist
+                s[k] = x[u];
+              }
+            }
           }
         }
       }
-      for (int k = k_pass + j; k < F; k += 16) {
-        float2 x = srow[k];
-        if (mrow != nullptr) mrow[k] = hypotf(x.x, x.y);
-        if (erow != nullptr) erow[k] = x;
-        if (k == 0 || k == FFT_M) x.y = 0.f;
-        s[k] = x;
+      for (int k0 = k_pass + j; k0 < F; k0 += 64) {
+        float2 x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) x[u] = k0 + 16 * u < F ? srow[k0 + 16 * u] : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int k = k0 + 16 * u;
+          if (k < F) {
+            if (mrow != nullptr) mrow[k] = cabs_fast(x[u]);
+            if (erow != nullptr) erow[k] = x[u];
+            if (k == 0 || k == FFT_M) x[u].y = 0.f;
+            s[k] = x[u];
+          }
+        }
       }
     }
     __syncwarp();
@@ -318,6 +353,9 @@ extern "C" int gsn_deepfilter_irfft(const float* const* projs, const int* N, con
     bands.ctr[i] = ctr[i];
     bands.df[i] = df[i];
     bands.lo[i] = lo;
+    bands.shift[i] = -1;
+    for (int sh = 0; sh < 20; ++sh)
+      if ((1 << sh) == ctr[i]) bands.shift[i] = sh;
     lo += N[i] * ctr[i];
   }
   GSN_REQUIRE(lo <= n_fft / 2 + 1, "gsn_deepfilter_irfft: the bands cover %d bins of %d", lo, n_fft / 2 + 1);

@@ -163,9 +163,9 @@ __global__ void __launch_bounds__(256) k_copy_bins(const float2* __restrict__ sp
 // frames [B, T, n_fft] (inverse real FFT of every frame, unwindowed) -> y [B, length]
 __global__ void __launch_bounds__(256) k_overlap_add(const float* __restrict__ frames, const float* __restrict__ window,
                                                      float* __restrict__ y, int B, int T, int n_fft, int hop, int length) {
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)B * length) return;
-  const int s = idx % length, b = idx / length;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;  // (no 64-bit division per sample)
+  if (s >= length) return;
+  const size_t idx = (size_t)b * length + s;
   const int j = s + n_fft / 2;  // position in the centre-padded signal
   if (j >= n_fft + hop * (T - 1)) {  // past the last frame: torch.istft pads with zeros
     y[idx] = 0.f;
@@ -304,10 +304,9 @@ extern "C" int gsn_overlap_add(const float* frames, const float* window, float* 
                                int length, gsn_stream_t stream) {
   GSN_REQUIRE(frames && window && y, "gsn_overlap_add: null pointer");
   GSN_REQUIRE(B > 0 && T > 0 && n_fft > 0 && hop > 0 && hop <= n_fft && length > 0, "gsn_overlap_add: bad shape");
-  const size_t total = (size_t)B * length;
-  const size_t blocks = (total + 255) / 256;
-  GSN_REQUIRE(blocks < 2147483647ULL, "gsn_overlap_add: too large");
-  gsn::k_overlap_add<<<(unsigned)blocks, 256, 0, gsn::as_stream(stream)>>>(frames, window, y, B, T, n_fft, hop, length);
+  GSN_REQUIRE(B <= 65535, "gsn_overlap_add: B=%d > 65535", B);
+  gsn::k_overlap_add<<<dim3((length + 255) / 256, B), 256, 0, gsn::as_stream(stream)>>>(frames, window, y, B, T, n_fft, hop,
+                                                                                     length);
   GSN_LAUNCH_CHECK("k_overlap_add");
   return GSN_OK;
 }

@@ -832,9 +832,10 @@ def test_stft_compress_kernel_matches_torch_stft_and_compress(B, hop, L, f_keep,
     assert spec.shape == want.shape and spec.stride() == want.stride() and cm.shape == (want.shape[2], B, f_keep)
     err = (spec - want).abs().max().item()
     assert err <= 2e-6 * want.abs().max().item(), err
-    # the compressed magnitude is that of the spectrum the kernel wrote, bit for bit (same |.| and power as
-    # gsn_compress_spec), and within FFT rounding of the reference's
-    assert torch.equal(cm, ops.compress_mag(spec, f_keep, fdrc))
+    # the compressed magnitude is that of the spectrum the kernel wrote (to the last ulp or two: |.| without hypotf's
+    # scaling on the common path), and within FFT rounding of the reference's
+    own = ops.compress_mag(spec, f_keep, fdrc)
+    assert float(((cm - own).abs() / own.clamp_min(1e-20)).max()) <= 4e-7
     ref_cm = (want.abs()[:, :f_keep] ** fdrc).permute(2, 0, 1)
     assert float((cm - ref_cm).abs().max()) <= 1e-4 * float(ref_cm.abs().max())
     spec2, none = ops.stft_compress(y, window, hop)
@@ -895,7 +896,8 @@ def test_forward_with_the_fused_fft_kernels_equals_its_parts():
         y, mag, fb_all, sb_all = m(wave)
         fused_launches = ops.LAUNCHES[0] - n0
         cmp = modeling._stft_fused(wave, 512, cfg["hop_length"], 512, f_keep=256, fdrc=cfg["fdrc"])
-        assert torch.equal(cmp._gsn_cm[2], ops.compress_mag(cmp.transpose(1, 2).contiguous().transpose(1, 2), 256, cfg["fdrc"]))
+        own = ops.compress_mag(cmp.transpose(1, 2).contiguous().transpose(1, 2), 256, cfg["fdrc"])
+        assert float(((cmp._gsn_cm[2] - own).abs() / own.clamp_min(1e-20)).max()) <= 4e-7
         projs, _, _ = m.network(cmp)
         # the reference composition on the same spectrum: per-band deep filter, pass-through, cuFFT, overlap-add
         enh = modeling._empty_spec_like(cmp, 1)

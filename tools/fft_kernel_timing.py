@@ -12,20 +12,23 @@ flush = torch.empty(64 << 20, device=dev)
 
 
 def timed(fn, n=10):
+    """Mean GPU duration of everything fn() launches (torch profiler: CUDA-event brackets would time the Python launch
+    overhead of these 10 - 50 us kernels), L2 flushed in front of every call."""
+    from torch.profiler import profile, ProfilerActivity
     fn(); torch.cuda.synchronize()
-    ms = []
-    for _ in range(n):
-        flush.fill_(1.0)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
-        ms.append(e0.elapsed_time(e1))
-    ms.sort()
-    return 1e3 * ms[len(ms) // 2]
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(n):
+            flush.fill_(1.0)
+            fn()
+        torch.cuda.synchronize()
+    tot = sum(e.time_range.end - e.time_range.start for e in prof.events()
+              if e.device_type == torch.autograd.DeviceType.CUDA and "FillFunctor" not in e.name)
+    return tot / n
 
 
 spec, cm = ops.stft_compress(y, win, hop, 256, 0.5)
 T = spec.shape[2]
-bands = [(4, 8, 5), (6, 16, 3), (4, 32, 1)]  # (N, ctr, df): 256 bins
+bands = [(8, 4, 3), (3, 32, 1), (2, 64, 1)]  # (N, ctr, df) of the S recipe: 256 bins
 projs = [torch.randn(T, B * n, 2 * c * d, device=dev) for n, c, d in bands]
 Ns, ctrs, dfs = ([b[i] for b in bands] for i in range(3))
 print("stft_compress            %7.1f us" % timed(lambda: ops.stft_compress(y, win, hop, 256, 0.5)))
