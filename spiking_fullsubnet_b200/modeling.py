@@ -1775,9 +1775,22 @@ class Separator(_StreamingPipeline, _GraphedNetwork, nn.Module):
         fb_act = r1[0][3]
         if self.num_repeats * fb_act.shape[2] < F - 1:
             raise ValueError("full-band output does not cover the spectrum")
-        for d in p2:
-            d["div"] = _utterance_divisor(ops.subband_features(cm, fb_act, d["N"], d["lo"], d["ctr"], d["nbr"]), B,
-                                          self.norm_type)
+        # the bands' divisors on forked streams: each is a gather + a reduction well below the HBM rate on its own, and
+        # the sub-band pipeline cannot start before the last of them (same kernels and reductions: identical values)
+        main = torch.cuda.current_stream(dev)
+        streams = _band_streams(dev, len(p2), tag="surface_b_div")
+        fork = torch.cuda.Event()
+        fork.record(main)
+        for d, st in zip(p2, streams):
+            st.wait_event(fork)
+            with torch.cuda.stream(st):
+                gathered = ops.subband_features(cm, fb_act, d["N"], d["lo"], d["ctr"], d["nbr"])
+                d["div"] = _utterance_divisor(gathered, B, self.norm_type)
+                done = torch.cuda.Event()
+                done.record(st)
+            main.wait_event(done)
+            if not torch.cuda.is_current_stream_capturing():
+                d["div"].record_stream(main)
         r2 = self._stream_run(p2, cm, fb_act=fb_act, tag="b2")
         return [r[3] for r in r2], r1[0][1], [r[1] for r in r2]
 
