@@ -186,6 +186,34 @@ __global__ void __launch_bounds__(256) k_overlap_add(const float* __restrict__ f
   y[idx] = acc / env;
 }
 
+// the same, four consecutive samples per thread (hop, n_fft / 2 and length multiples of 4: every load and the store are
+// 16-byte accesses; the four samples share their covering frames)
+__global__ void __launch_bounds__(256) k_overlap_add4(const float* __restrict__ frames, const float* __restrict__ window,
+                                                      float* __restrict__ y, int B, int T, int n_fft, int hop, int length) {
+  const int s = (blockIdx.x * blockDim.x + threadIdx.x) * 4, b = blockIdx.y;
+  if (s >= length) return;
+  float4* out = reinterpret_cast<float4*>(y + (size_t)b * length + s);
+  const int j = s + n_fft / 2;  // position in the centre-padded signal
+  if (j >= n_fft + hop * (T - 1)) {  // past the last frame (the signal's end is a multiple of 4 as well)
+    *out = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  int t_hi = j / hop;
+  if (t_hi > T - 1) t_hi = T - 1;
+  int t_lo = (j - n_fft + hop) / hop;  // smallest t with t*hop + n_fft > j
+  if (j - n_fft + 1 <= 0) t_lo = 0;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), env = acc;
+  const float* fb = frames + (size_t)b * T * n_fft;
+  for (int t = t_lo; t <= t_hi; ++t) {
+    const int pos = j - t * hop;
+    const float4 w = *reinterpret_cast<const float4*>(window + pos);
+    const float4 f = *reinterpret_cast<const float4*>(fb + (size_t)t * n_fft + pos);
+    acc.x = fmaf(f.x, w.x, acc.x); acc.y = fmaf(f.y, w.y, acc.y); acc.z = fmaf(f.z, w.z, acc.z); acc.w = fmaf(f.w, w.w, acc.w);
+    env.x = fmaf(w.x, w.x, env.x); env.y = fmaf(w.y, w.y, env.y); env.z = fmaf(w.z, w.z, env.z); env.w = fmaf(w.w, w.w, env.w);
+  }
+  *out = make_float4(acc.x / env.x, acc.y / env.y, acc.z / env.z, acc.w / env.w);
+}
+
 // y [B, L] -> frames [B, T, n_fft]: the analysis half of torch.stft(center=True, pad_mode="constant") in front of the
 // real FFT (audio_feature.py:236-294): zero padding of n_fft/2 samples on both sides, framing at `hop`, analysis window.
 // One float4 per thread; hop and n_fft are multiples of 4 and y is 16-byte aligned per row when L % 4 == 0, else scalar.
@@ -305,6 +333,15 @@ extern "C" int gsn_overlap_add(const float* frames, const float* window, float* 
   GSN_REQUIRE(frames && window && y, "gsn_overlap_add: null pointer");
   GSN_REQUIRE(B > 0 && T > 0 && n_fft > 0 && hop > 0 && hop <= n_fft && length > 0, "gsn_overlap_add: bad shape");
   GSN_REQUIRE(B <= 65535, "gsn_overlap_add: B=%d > 65535", B);
+  const bool vec4 = ((hop | (n_fft / 2) | length) & 3) == 0 &&
+                    ((reinterpret_cast<uintptr_t>(frames) | reinterpret_cast<uintptr_t>(window) |
+                      reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  if (vec4) {
+    gsn::k_overlap_add4<<<dim3((length / 4 + 255) / 256, B), 256, 0, gsn::as_stream(stream)>>>(frames, window, y, B, T, n_fft,
+                                                                                            hop, length);
+    GSN_LAUNCH_CHECK("k_overlap_add4");
+    return GSN_OK;
+  }
   gsn::k_overlap_add<<<dim3((length + 255) / 256, B), 256, 0, gsn::as_stream(stream)>>>(frames, window, y, B, T, n_fft, hop,
                                                                                      length);
   GSN_LAUNCH_CHECK("k_overlap_add");

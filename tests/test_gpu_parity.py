@@ -776,7 +776,8 @@ def test_deepfilter_spec_matches_the_reference_formula(B, N, ctr, df, S, lo, F, 
     assert torch.equal(out_tm[:, :, lo:], out[:, :, lo:])
 
 
-@pytest.mark.parametrize("B,n_fft,hop,L", [(3, 512, 128, 16000), (2, 64, 16, 528), (1, 512, 128, 64000), (2, 512, 128, 1000)])
+@pytest.mark.parametrize("B,n_fft,hop,L", [(3, 512, 128, 16000), (2, 64, 16, 528), (1, 512, 128, 64000), (2, 512, 128, 1000),
+                                           (2, 512, 128, 1001), (2, 64, 16, 531)])
 def test_fused_istft_matches_torch_istft(B, n_fft, hop, L):
     """cuFFT inverse real FFT + gsn_overlap_add against torch.istft (audio_feature.py:297-347)."""
     from spiking_fullsubnet_b200.modeling import _istft_fused
