@@ -678,20 +678,40 @@ class _GraphedNetwork:
         key = ("network", tuple(mag.shape), mag.dtype, mag.device.index)
         entry = graphs.get(key)
         if entry is None:
-            static_in = torch.empty_like(mag)  # keeps the strides (a complex STFT may be time-major, ops._spec_layout)
+            # keeps the strides of a complex STFT (it may be time-major, ops._spec_layout); a real magnitude is made
+            # contiguous by every schedule before it is compressed
+            static_in = torch.empty_like(mag) if mag.is_complex() else torch.empty(mag.shape, dtype=mag.dtype, device=mag.device)
             static_in.copy_(mag)
             with torch.no_grad():
                 self._network(static_in)  # warm-up outside the capture (lazy CUDA initialisation)
                 torch.cuda.synchronize(mag.device)
+                # The compression of the input (the first kernel of every schedule) stays outside the graph and runs on
+                # the caller's tensor in front of each replay: no copy of the input into a static buffer.  `hook`
+                # collects what ops.compress_mag was asked for during the capture.
+                hook = {"args": None, "cm": None, "bad": False}
+                if os.environ.get("GSN_GRAPH_INPUT_COPY", "0") != "1":
+                    static_in._gsn_cm_capture = hook
                 graph = torch.cuda.CUDAGraph()
                 n0 = ops.LAUNCHES[0]
                 with torch.cuda.graph(graph):
                     static_out = self._network_sched(static_in)
-                self.graph_launches = ops.LAUNCHES[0] - n0  # kernels of this library inside one replay
-            entry = graphs[key] = (graph, static_in, static_out)
-        graph, static_in, static_out = entry
+                if hasattr(static_in, "_gsn_cm_capture"):
+                    del static_in._gsn_cm_capture
+                if hook["bad"]:  # not a schedule the shortcut knows: capture again with the compression inside
+                    hook = {"args": None, "cm": None, "bad": False}
+                    graph = torch.cuda.CUDAGraph()
+                    n0 = ops.LAUNCHES[0]
+                    with torch.cuda.graph(graph):
+                        static_out = self._network_sched(static_in)
+                eager_cm = hook["args"] is not None
+                self.graph_launches = ops.LAUNCHES[0] - n0 + int(eager_cm)  # kernels of this library per step
+            entry = graphs[key] = (graph, static_in, static_out, hook if eager_cm else None)
+        graph, static_in, static_out, hook = entry
         self.refresh_folded_bn()
-        static_in.copy_(mag)
+        if hook is not None:
+            ops.compress_mag(mag if mag.is_complex() else mag.contiguous(), hook["args"][0], hook["args"][1], out=hook["cm"])
+        else:
+            static_in.copy_(mag)
         graph.replay()
         return static_out
 

@@ -66,25 +66,42 @@ def _spec_layout(z, what):
     raise ValueError(f"{what}: spectrum must be contiguous as [.., F, T] or as [.., T, F]")
 
 
-def compress_mag(mag, f_keep, fdrc):
+def compress_mag(mag, f_keep, fdrc, out=None):
     """mag [B,F,T] (or the complex STFT itself, in either layout of `_spec_layout`) -> cm [T,B,f_keep] = |.|**fdrc
-    (MSF:434-436, time-major)."""
-    if mag.is_complex():
-        pre = getattr(mag, "_gsn_cm", None)  # gsn_stft_compress already produced it (modeling._stft_fused)
-        if pre is not None and pre[0] == int(f_keep) and pre[1] == float(fdrc):
+    (MSF:434-436, time-major).  `out`: write into this [T,B,f_keep] buffer."""
+    pre = getattr(mag, "_gsn_cm", None)  # gsn_stft_compress already produced it (modeling._stft_fused)
+    if pre is not None and pre[0] == int(f_keep) and pre[1] == float(fdrc):
+        if out is None:
             return pre[2]
+        out.copy_(pre[2])
+        return out
+    B, F, T = mag.shape
+    hook = getattr(mag, "_gsn_cm_capture", None)
+    if hook is not None:
+        # modeling._GraphedNetwork.network is capturing its graph on this (static) tensor: the compression stays OUTSIDE
+        # the graph -- it runs eagerly on the caller's tensor in front of every replay, into the buffer handed out here,
+        # so the caller's input is never copied into a static buffer first
+        args = (int(f_keep), float(fdrc))
+        if hook["args"] is None:
+            hook["args"] = args
+            hook["cm"] = torch.empty((T, B, f_keep), device=mag.device, dtype=torch.float32)
+        if hook["args"] == args:
+            return hook["cm"]
+        hook["bad"] = True  # a second, different compression of the same input: not a schedule this shortcut knows
+    if out is not None and (out.shape != (T, B, f_keep) or out.dtype != torch.float32 or not out.is_contiguous()
+                            or out.device != mag.device):
+        raise ValueError("compress_mag: out must be a contiguous float32 [T,B,f_keep] tensor on the input's device")
+    if mag.is_complex():
         tm = _spec_layout(mag, "compress_mag")
         lib = _lib.load()
         _bind(mag.device)
         st = torch.cuda.current_stream(mag.device).cuda_stream
-        B, F, T = mag.shape
-        cm = torch.empty((T, B, f_keep), device=mag.device, dtype=torch.float32)
+        cm = out if out is not None else torch.empty((T, B, f_keep), device=mag.device, dtype=torch.float32)
         _lib.check(lib.gsn_compress_spec(mag.data_ptr(), _ptr(cm), B, F, f_keep, T, float(fdrc), tm, st))
         LAUNCHES[0] += 1
         return cm
     lib, st = _prep(mag)
-    B, F, T = mag.shape
-    cm = torch.empty((T, B, f_keep), device=mag.device, dtype=torch.float32)
+    cm = out if out is not None else torch.empty((T, B, f_keep), device=mag.device, dtype=torch.float32)
     _lib.check(lib.gsn_compress_mag(_ptr(mag), _ptr(cm), B, F, f_keep, T, float(fdrc), st))
     LAUNCHES[0] += 1
     return cm

@@ -926,6 +926,31 @@ def test_forward_with_the_fused_fft_kernels_equals_its_parts():
     assert y0.shape == y.shape and torch.isfinite(y0).all()
 
 
+@pytest.mark.parametrize("streaming", [False, True])
+def test_graph_replay_compresses_the_callers_tensor(streaming):
+    """network() in graph mode keeps the input compression outside the captured graph (it runs on the caller's tensor in
+    front of every replay, no copy into a static input): replays on DIFFERENT tensors, real magnitudes and complex
+    spectra of either layout, must equal the eager results on those tensors."""
+    cfg = synth.CONFIGS["S"]
+    m = _model(cfg, synth.make_params(cfg, 5))
+    if streaming:
+        m.enable_streaming(True)
+    window = torch.hann_window(512, device=DEV)
+    specs = [torch.stft(_t(synth.make_wave(2, 8000, seed)), 512, 128, 512, window=window, return_complex=True,
+                        pad_mode="constant") for seed in (3, 4, 5)]
+    inputs = [specs[0].abs().contiguous(), specs[1].abs().contiguous(), specs[2], specs[1].contiguous(), specs[0]]
+    with torch.no_grad():
+        m.enable_cuda_graph(False)
+        want = [[p.clone() for p in m.network(x)[0]] for x in inputs]
+        m.enable_cuda_graph(True, frame_chunks=4)
+        for _ in range(2):
+            for x, w in zip(inputs, want):
+                got = m.network(x)[0]
+                for a, b in zip(got, w):
+                    assert torch.equal(a, b)
+    assert m.graph_launches > 0
+
+
 def test_loss_terms_on_the_gpu_match_reference_values_and_gradient():
     """Row f3 on the device the training step runs on: freq_MAE / mag_MAE / SISNRLoss and the recipe's combined loss
     (audiozen/loss.py:138-190, 11-40; recipes/.../trainer.py:33-37) against values and the waveform gradient the
