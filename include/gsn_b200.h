@@ -72,6 +72,11 @@ GSN_API int gsn_compress_mag(const float* mag, float* cm, int B, int F, int f_ke
 GSN_API int gsn_subband_features(const float* cm, int f_cm, const float* fb, int f_fb, float* x, int T, int B,
                          int N, int lo, int ctr, int nbr, const float* ln_weight, const float* ln_bias,
                          float ln_eps, gsn_stream_t stream);
+/* rowsum[t, b*N + n] = sum over j of the UN-normalised gathered features above (no x written): what surface B's laplace
+ * norms reduce (model_low_freq.py:146-171: mean over an utterance; model_low_freq_count_time.py:173-204: running mean of a
+ * row) before gsn_xplanes_stream gathers the same features again and divides by the result.  rowsum [T, B*N].        */
+GSN_API int gsn_subband_rowsums(const float* cm, int f_cm, const float* fb, int f_fb, float* rowsum, int T, int B, int N,
+                                int lo, int ctr, int nbr, gsn_stream_t stream);
 
 /* ---- dense fp32 linear (input-to-hidden product ESN:141, proj MSF:118) -------------------------
  * out[M, N] = a[M, K] @ w[N, K]^T + bias[N]   (bias may be NULL).  fp32 FMA, k ascending.

@@ -28,6 +28,7 @@ SIGNATURES = {
     "gsn_device_info": (_i, [C.POINTER(_i)] * 4),
     "gsn_compress_mag": (_i, [_p, _p, _i, _i, _i, _i, _f, _p]),
     "gsn_subband_features": (_i, [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p, _p, _f, _p]),
+    "gsn_subband_rowsums": (_i, [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p]),
     "gsn_linear_f32": (_i, [_p, _p, _p, _p, _p, _i, _i64, _i, _i, _p]),
     "gsn_linear_spikes": (_i, [_p, _p, _p, _p, _p, _i, _i64, _i, _i, _i, _p]),
     "gsn_layer_recurrence_workspace_bytes": (_sz, [_i, _i, _i, _i]),

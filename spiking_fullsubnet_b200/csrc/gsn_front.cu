@@ -115,6 +115,46 @@ __global__ void __launch_bounds__(256) k_subband_features(
   }
 }
 
+// rowsum[t, r] = sum over the K gathered features of row r at frame t -- k_subband_features without the LayerNorm and
+// WITHOUT writing x: all that surface B's laplace norms need of the gathered input (model_low_freq.py:146-171: its mean
+// over an utterance; model_low_freq_count_time.py:173-204: the running mean of a row) before the streaming front end
+// gathers it again on the fly.  One warp per (t, row), lanes stride over the features, shuffle reduction.
+__global__ void __launch_bounds__(256) k_subband_rowsums(const float* __restrict__ cm, int f_cm,
+                                                         const float* __restrict__ fb, int f_fb,
+                                                         float* __restrict__ rowsum, int T, int B, int N, int lo, int ctr,
+                                                         int nbr) {
+  const int lane = threadIdx.x & 31;
+  const int k_noisy = ctr + 2 * nbr;
+  const int K = k_noisy + (fb ? ctr : 0);
+  // one warp per (t, b) FRAME: its N rows one after the other (the frame's spectrum and full-band rows stay in L1), 32-bit
+  // index arithmetic, no per-element modulo
+  const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (unsigned fr = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; fr < (unsigned)(T * B); fr += nwarps) {
+    const float* cm_row = cm + (size_t)fr * f_cm;
+    const float* fb_row = fb ? fb + (size_t)fr * f_fb : nullptr;
+    for (int n = 0; n < N; ++n) {
+      const int base = lo + n * ctr;
+      const int fb0 = fb ? base % f_fb : 0;
+      float sum = 0.f;
+      for (int j = lane; j < K; j += 32) {
+        if (j < k_noisy) {
+          int q = base - nbr + j;
+          q = q < 0 ? -q : q;
+          q = q > f_cm - 1 ? 2 * (f_cm - 1) - q : q;
+          sum += cm_row[q];
+        } else {
+          int q = fb0 + j - k_noisy;
+          while (q >= f_fb) q -= f_fb;
+          sum += fb_row[q];
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      if (lane == 0) rowsum[(size_t)fr * N + n] = sum;  // row r = b*N + n of frame t: (t*B + b)*N + n
+    }
+  }
+}
+
 // thread per (b, s, n, fc, t): t fastest so spectrogram reads/writes are coalesced
 __global__ void __launch_bounds__(256) k_deepfilter_band(
     const float* __restrict__ proj, const float* __restrict__ sre, const float* __restrict__ sim,
@@ -195,6 +235,25 @@ extern "C" int gsn_subband_features(const float* cm, int f_cm, const float* fb, 
   else if (K <= 256) launch(gsn::k_subband_features<8>);
   else launch(gsn::k_subband_features<gsn::kMaxPerLane>);
   GSN_LAUNCH_CHECK("k_subband_features");
+  return GSN_OK;
+}
+
+extern "C" int gsn_subband_rowsums(const float* cm, int f_cm, const float* fb, int f_fb, float* rowsum, int T, int B,
+                                   int N, int lo, int ctr, int nbr, gsn_stream_t stream) {
+  GSN_REQUIRE(cm && rowsum, "gsn_subband_rowsums: null pointer");
+  GSN_REQUIRE(T > 0 && B > 0 && N > 0 && ctr > 0 && nbr >= 0 && lo >= 0, "gsn_subband_rowsums: bad shape");
+  GSN_REQUIRE(lo + N * ctr <= f_cm, "gsn_subband_rowsums: band [%d,%d) leaves the %d-bin spectrum", lo, lo + N * ctr,
+              f_cm);
+  GSN_REQUIRE(nbr < f_cm, "gsn_subband_rowsums: nbr=%d too large", nbr);
+  GSN_REQUIRE(lo == 0 || lo - nbr >= 0, "gsn_subband_rowsums: lower neighbourhood out of range");
+  GSN_REQUIRE(lo + N * ctr == f_cm || lo + N * ctr + nbr <= f_cm, "gsn_subband_rowsums: upper neighbourhood out of range");
+  GSN_REQUIRE(!fb || f_fb > 0, "gsn_subband_rowsums: f_fb");
+  GSN_REQUIRE((long long)T * B < 2147483647LL, "gsn_subband_rowsums: too many frames");
+  long long blocks = ((long long)T * B + 7) / 8;  // a warp per (t, b) frame
+  if (blocks > 148 * 16) blocks = 148 * 16;  // grid-stride
+  gsn::k_subband_rowsums<<<(unsigned)blocks, 256, 0, gsn::as_stream(stream)>>>(cm, f_cm, fb, f_fb, rowsum, T, B, N, lo, ctr,
+                                                                               nbr);
+  GSN_LAUNCH_CHECK("k_subband_rowsums");
   return GSN_OK;
 }
 

@@ -1623,6 +1623,22 @@ def _utterance_divisor(x, B, norm_type):
     return None
 
 
+def _stream_divisor(cm, fb_act, N, lo, ctr, nbr, B, norm_type):
+    """`_utterance_divisor` of the gathered input of one model WITHOUT materialising the gather: gsn_subband_rowsums
+    leaves one sum per (frame, row), the rest is a reduction over T x R numbers.  (Summation order differs from
+    `_utterance_divisor`'s: the last bit of the divisor may.)"""
+    rs = ops.subband_rowsums(cm, fb_act, N, lo, ctr, nbr)                              # [T, B*N]
+    T = rs.shape[0]
+    K = ctr + 2 * nbr + (ctr if fb_act is not None else 0)
+    if norm_type == "offline_laplace_norm":
+        return (rs.sum(dim=0).view(B, N).sum(dim=1) / float(T * N * K) + EPSILON).contiguous()
+    if norm_type == "cumulative_laplace_norm":
+        cum = torch.cumsum(rs, dim=0)
+        count = torch.arange(K, K * T + 1, K, dtype=rs.dtype, device=rs.device).view(T, 1)
+        return (cum / count + EPSILON).contiguous()
+    return None
+
+
 class _FreezeSubbandModel(nn.Module):
     def __init__(self, freq_cutoffs, sb_num_center_freqs, sb_num_neighbor_freqs, fb_num_center_freqs,
                  fb_num_neighbor_freqs, sb_df_orders, sequence_model, hidden_size, activate_function=False,
@@ -1790,13 +1806,13 @@ class Separator(_StreamingPipeline, _GraphedNetwork, nn.Module):
         dev = mag.device
         ops.stream_preload(dev)
         cm = ops.compress_mag(mag if mag.is_complex() else mag.contiguous(), F - 1, self.fdrc)
-        p1[0]["div"] = _utterance_divisor(ops.subband_features(cm, None, 1, 0, self.fb_freqs, 0), B, self.norm_type)
+        p1[0]["div"] = _stream_divisor(cm, None, 1, 0, self.fb_freqs, 0, B, self.norm_type)
         r1 = self._stream_run(p1, cm, tag="b1")
         fb_act = r1[0][3]
         if self.num_repeats * fb_act.shape[2] < F - 1:
             raise ValueError("full-band output does not cover the spectrum")
-        # the bands' divisors on forked streams: each is a gather + a reduction well below the HBM rate on its own, and
-        # the sub-band pipeline cannot start before the last of them (same kernels and reductions: identical values)
+        # the bands' divisors on forked streams (row sums of the gathered input + a small reduction each): the sub-band
+        # pipeline cannot start before the last of them
         main = torch.cuda.current_stream(dev)
         streams = _band_streams(dev, len(p2), tag="surface_b_div")
         fork = torch.cuda.Event()
@@ -1804,8 +1820,7 @@ class Separator(_StreamingPipeline, _GraphedNetwork, nn.Module):
         for d, st in zip(p2, streams):
             st.wait_event(fork)
             with torch.cuda.stream(st):
-                gathered = ops.subband_features(cm, fb_act, d["N"], d["lo"], d["ctr"], d["nbr"])
-                d["div"] = _utterance_divisor(gathered, B, self.norm_type)
+                d["div"] = _stream_divisor(cm, fb_act, d["N"], d["lo"], d["ctr"], d["nbr"], B, self.norm_type)
                 done = torch.cuda.Event()
                 done.record(st)
             main.wait_event(done)

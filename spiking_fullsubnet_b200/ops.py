@@ -253,6 +253,17 @@ def subband_features(cm, fb, N, lo, ctr, nbr, ln_weight=None, ln_bias=None, eps=
     return x
 
 
+def subband_rowsums(cm, fb, N, lo, ctr, nbr):
+    """Row sums [T, B*N] of the gathered (un-normalised) features `subband_features` would write, without writing them."""
+    lib, st = _prep(cm, fb)
+    T, B, f_cm = cm.shape
+    f_fb = fb.shape[2] if fb is not None else 0
+    rs = torch.empty((T, B * N), device=cm.device, dtype=torch.float32)
+    _lib.check(lib.gsn_subband_rowsums(_ptr(cm), f_cm, _ptr(fb), f_fb, _ptr(rs), T, B, N, lo, ctr, nbr, st))
+    LAUNCHES[0] += 1
+    return rs
+
+
 TC_TRAIN = [True]   # training forward on tcgen05 where supported (False: fp32 CUDA-core kernel)
 TC_LINEAR = [True]  # spike-input linears on tcgen05 (set False to force the fp32 CUDA-core kernel)
 

@@ -459,3 +459,25 @@ def test_streaming_surface_b_vs_golden(name, graph):
             assert _rel(coefs[i].cpu().numpy(), g[f"coef{i}"]) < 1e-3
         assert _rel(enh_y.cpu().numpy(), g["enh_y"]) < 1e-3
         assert _rel(enh_mag.cpu().numpy(), g["enh_mag"]) < 1e-3
+
+
+@pytest.mark.parametrize("N,lo,ctr,nbr,with_fb", [(8, 0, 4, 15, True), (3, 32, 32, 15, True), (2, 128, 64, 15, True), (1, 0, 64, 0, False)])
+def test_subband_rowsums_and_stream_divisors(N, lo, ctr, nbr, with_fb):
+    """gsn_subband_rowsums (surface B's laplace-norm statistics without materialising the gathered input) against the
+    gather itself, and the streaming divisors against the eager path's torch reductions (model_low_freq.py:146-171,
+    model_low_freq_count_time.py:173-204): equal to fp32 summation order."""
+    from spiking_fullsubnet_b200 import modeling
+    T, B = 77, 3
+    rs = np.random.RandomState(N * 100 + ctr)
+    cm = _t(np.abs(rs.standard_normal((T, B, 256))).astype(np.float32))
+    fb = _t(np.abs(rs.standard_normal((T, B, 64))).astype(np.float32)) if with_fb else None
+    x = ops.subband_features(cm, fb, N, lo, ctr, nbr)
+    got = ops.subband_rowsums(cm, fb, N, lo, ctr, nbr)
+    want = x.double().sum(dim=2)
+    assert got.shape == (T, B * N)
+    assert float((got.double() - want).abs().max()) <= 2e-6 * float(want.abs().max())
+    for norm in ("offline_laplace_norm", "cumulative_laplace_norm"):
+        a = modeling._stream_divisor(cm, fb, N, lo, ctr, nbr, B, norm)
+        b = modeling._utterance_divisor(x, B, norm)
+        assert a.shape == b.shape
+        assert float(((a - b).abs() / b.abs()).max()) <= 2e-6
