@@ -663,9 +663,26 @@ class _GraphedNetwork:
         for c in cells:
             c.folded_bn()
 
+    def _warn_cell_hooks(self):
+        """The reference's debug mode (audiozen/trainer.py:354-356, DebugUnderflowOverflow) hooks every sub-module; the
+        frame loop lives inside the kernels here, so `GSUCell.forward` / `GSULayer.forward` are never called per frame
+        and their hooks cannot fire.  Say so once instead of letting a debugging session believe it saw every frame; the
+        per-layer spike traces are in the returned `all_layer_outputs`, hooks on the top-level module do fire."""
+        if self.__dict__.get("_cell_hooks_checked"):
+            return
+        self.__dict__["_cell_hooks_checked"] = True
+        hooked = [n for n, m in self.named_modules()
+                  if isinstance(m, (GSUCell, GSULayer, StackedGSU)) and (m._forward_hooks or m._forward_pre_hooks)]
+        if hooked:
+            import warnings
+            warnings.warn(f"spiking_fullsubnet_b200: forward hooks on {len(hooked)} GSN sub-modules (e.g. {hooked[0]!r}) are "
+                          "not called: the per-frame loop runs inside the CUDA kernels.  Hook the top-level module, or "
+                          "read the per-layer traces the model returns.", stacklevel=3)
+
     def network(self, mag):
         if not mag.is_cuda:
             raise RuntimeError("spiking_fullsubnet_b200 has no CPU path: move the model and input to CUDA")
+        self._warn_cell_hooks()
         if torch.cuda.is_current_stream_capturing():
             return self._network_sched(mag) if self.use_cuda_graph else self._network(mag)
         if not self.use_cuda_graph:
@@ -1385,6 +1402,7 @@ class SpikingFullSubNet(_StreamingPipeline, _GraphedNetwork, nn.Module):
         if not input.is_cuda:
             raise RuntimeError("spiking_fullsubnet_b200 has no CPU path: move the model and input to CUDA")
         if _needs_autograd(self):
+            self._warn_cell_hooks()
             from . import training
             return training.spiking_fullsubnet_forward(self, input)
         if not self.use_cuda_graph or torch.cuda.is_current_stream_capturing():
@@ -1492,6 +1510,7 @@ class CirmGSN(_GraphedNetwork, nn.Module):
         if not input.is_cuda:
             raise RuntimeError("spiking_fullsubnet_b200 has no CPU path: move the model and input to CUDA")
         if _needs_autograd(self):
+            self._warn_cell_hooks()
             from . import training
             return training.cirm_gsn_forward(self, input)
         B, L = input.shape
@@ -1845,6 +1864,7 @@ class Separator(_StreamingPipeline, _GraphedNetwork, nn.Module):
         if not noisy_y.is_cuda:
             raise RuntimeError("spiking_fullsubnet_b200 has no CPU path: move the model and input to CUDA")
         if _needs_autograd(self):
+            self._warn_cell_hooks()
             from . import training
             return training.separator_forward(self, noisy_y)
         B, L = noisy_y.shape

@@ -159,3 +159,25 @@ def test_spike_bits_layout_helpers_on_cpu():
     from spiking_fullsubnet_b200 import ops
     for H, W in [(16, 1), (32, 1), (33, 2), (160, 5), (240, 8), (320, 10)]:
         assert tuple(ops.spike_bits_buffer((7, 3), H, "cpu").shape) == (7, 3, W)
+
+
+def test_hooks_on_gsn_submodules_are_reported_once():
+    """The reference's debug mode hooks every sub-module (audiozen/trainer.py:354-356); the fused kernels never call
+    GSUCell.forward per frame, so the model says so (once) instead of silently skipping the hooks."""
+    import warnings
+    import torch
+    from oracle import synth
+    from spiking_fullsubnet_b200 import SpikingFullSubNet
+    m = SpikingFullSubNet(**synth.tiny_cfg())
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        m._warn_cell_hooks()
+    assert not w
+    del m.__dict__["_cell_hooks_checked"]
+    cell = next(mod for mod in m.modules() if type(mod).__name__ == "GSUCell")
+    cell.register_forward_hook(lambda mod, inp, out: None)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        m._warn_cell_hooks()
+        m._warn_cell_hooks()
+    assert len(w) == 1 and "forward hooks" in str(w[0].message)
