@@ -96,10 +96,11 @@ __device__ __forceinline__ void fft_tables(float2* tw, float2* w256) {
 
 // |z| as torch.abs of a complex number gives it (hypotf), without hypotf's scaling on the common path: when x^2 + y^2
 // neither overflows nor loses bits to underflow, sqrt(fma(x, x, y*y)) is within one ulp of it
+__device__ __noinline__ float cabs_slow(float x, float y) { return hypotf(x, y); }  // (one copy: code size)
 __device__ __forceinline__ float cabs_fast(float2 z) {
   const float v = fmaf(z.x, z.x, z.y * z.y);
   if (v > 1e-30f && v < 1e30f) return sqrtf(v);
-  return hypotf(z.x, z.y);
+  return cabs_slow(z.x, z.y);
 }
 __device__ __forceinline__ float compress_abs(float2 z, float fdrc, int mode) {
   const float v = cabs_fast(z);
@@ -107,9 +108,10 @@ __device__ __forceinline__ float compress_abs(float2 z, float fdrc, int mode) {
 }
 
 // y [B,L] -> spec [B,T,257] complex, cm [T,B,Fk] (NULL: not wanted)
+template <bool PAIRS>
 __global__ void __launch_bounds__(FFT_THREADS, 8) k_stft512(const float* __restrict__ y, const float* __restrict__ window,
                                                          float2* __restrict__ spec, float* __restrict__ cm, int B, int L,
-                                                         int T, int hop, int Fk, float fdrc, int mode, int pairs) {
+                                                         int T, int hop, int Fk, float fdrc, int mode) {
   __shared__ float2 tw[FFT_M + 1], w256[256];
   __shared__ float2 win[FFT_M];
   __shared__ float2 sm[FFT_FPB][FFT_SM];
@@ -132,7 +134,7 @@ __global__ void __launch_bounds__(FFT_THREADS, 8) k_stft512(const float* __restr
       const int n = 16 * n1 + j, p = s0 + 2 * n;
       float2 x = make_float2(0.f, 0.f);
       if (valid) {
-        if (pairs) {  // L, hop even and y 8-byte aligned: both samples of a pair are in range or neither is
+        if (PAIRS) {  // L, hop even and y 8-byte aligned: both samples of a pair are in range or neither is
           if (p >= 0 && p < L) x = *reinterpret_cast<const float2*>(yb + p);
         } else {
           if (p >= 0 && p < L) x.x = yb[p];
@@ -149,10 +151,10 @@ __global__ void __launch_bounds__(FFT_THREADS, 8) k_stft512(const float* __restr
     if (valid) {
       float2* srow = spec + (size_t)fr * F;
       float* crow = cm != nullptr ? cm + ((size_t)t * B + b) * Fk : nullptr;
-#pragma unroll
+#pragma unroll 4  // (rolled: fully unrolled, this step made the kernel 4 096 instructions -- instruction-cache misses)
       for (int k2 = 0; k2 < 16; ++k2) {
         const int k = j + 16 * k2;
-        const float2 zk = v[pos16(k2)], zm = s[(FFT_M - k) & (FFT_M - 1)];
+        const float2 zk = s[k], zm = s[(FFT_M - k) & (FFT_M - 1)];
         // E = (Z[k] + conj Z[M-k]) / 2 (even samples' DFT), O = -i (Z[k] - conj Z[M-k]) / 2 (odd samples' DFT)
         const float2 e = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
         const float2 o = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
@@ -210,43 +212,51 @@ __global__ void __launch_bounds__(FFT_THREADS, 8) k_irfft512(const float2* __res
           const float* __restrict__ prow = bands.proj[i] + ((size_t)t * B + b) * (size_t)N * (size_t)(2 * ctr * df);
           const float2* __restrict__ xs0 = spec + ((ptrdiff_t)fr - (df - 1)) * F + lo;  // tap d reads frame t - (df-1) + d
           const int d0 = t < df - 1 ? df - 1 - t : 0;  // taps that reach in front of the first frame are skipped
-          for (int q0 = j; q0 < W; q0 += 64) {  // four bins per thread at a time: their loads are in flight together
-            float2 x[4];
+          // one bin: (n, fc) of band bin q, its df taps
+          auto bin = [&](int q) {
+            int n, fc;
+            if (shift >= 0) { n = q >> shift; fc = q & (ctr - 1); } else { n = q / ctr; fc = q - n * ctr; }
+            const float* pr = prow + (size_t)n * (2 * ctr * df);
+            float yr = 0.f, yi = 0.f;
+            for (int d = d0; d < df; ++d) {
+              const float cr = layout == 0 ? pr[fc * df + d] : pr[d * ctr + fc];
+              const float ci = layout == 0 ? pr[(ctr + fc) * df + d] : pr[(df + d) * ctr + fc];
+              const float2 z = xs0[(ptrdiff_t)d * F + q];
+              yr += z.x * cr - z.y * ci;
+              yi += z.x * ci + z.y * cr;
+            }
+            return make_float2(yr, yi);
+          };
+          auto put = [&](int q, float2 x) {
+            const int k = lo + q;
+            if (mrow != nullptr) mrow[k] = cabs_fast(x);  // enh_mag, MSF:472
+            if (erow != nullptr) erow[k] = x;
+            if (k == 0 || k == FFT_M) x.y = 0.f;  // a C2R transform ignores the imaginary parts of DC and Nyquist
+            s[k] = x;
+          };
+          if (df == 1 && shift >= 0) {
+            // most bins of every recipe: one tap, four bins per thread at a time so that their loads are in flight together
+            for (int q0 = j; q0 < W; q0 += 64) {
+              float2 x[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int q = q0 + 16 * u;
-              x[u] = make_float2(0.f, 0.f);
-              if (q < W) {
-                int n, fc;
-                if (shift >= 0) { n = q >> shift; fc = q & (ctr - 1); } else { n = q / ctr; fc = q - n * ctr; }
-                const float* pr = prow + (size_t)n * (2 * ctr * df);
-                if (df == 1) {  // most bins of every recipe
+              for (int u = 0; u < 4; ++u) {
+                const int q = q0 + 16 * u;
+                x[u] = make_float2(0.f, 0.f);
+                if (q < W) {
+                  const float* pr = prow + (size_t)(q >> shift) * (2 * ctr);
+                  const int fc = q & (ctr - 1);
                   const float cr = pr[fc], ci = pr[ctr + fc];
                   const float2 z = xs0[q];
                   x[u] = make_float2(z.x * cr - z.y * ci, z.x * ci + z.y * cr);
-                } else {
-                  float yr = 0.f, yi = 0.f;
-                  for (int d = d0; d < df; ++d) {
-                    const float cr = layout == 0 ? pr[fc * df + d] : pr[d * ctr + fc];
-                    const float ci = layout == 0 ? pr[(ctr + fc) * df + d] : pr[(df + d) * ctr + fc];
-                    const float2 z = xs0[(ptrdiff_t)d * F + q];
-                    yr += z.x * cr - z.y * ci;
-                    yi += z.x * ci + z.y * cr;
-                  }
-                  x[u] = make_float2(yr, yi);
                 }
               }
-            }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int q = q0 + 16 * u, k = lo + q;
-              if (q < W) {
-                if (mrow != nullptr) mrow[k] = cabs_fast(x[u]);  // enh_mag, MSF:472
-                if (erow != nullptr) erow[k] = x[u];
-                if (k == 0 || k == FFT_M) x[u].y = 0.f;  // a C2R transform ignores the imaginary parts of DC and Nyquist
-                s[k] = x[u];
-              }
+              for (int u = 0; u < 4; ++u)
+                if (q0 + 16 * u < W) put(q0 + 16 * u, x[u]);
             }
+          } else {
+#pragma unroll 1
+            for (int q = j; q < W; q += 16) put(q, bin(q));
           }
         }
       }
@@ -315,8 +325,12 @@ extern "C" int gsn_stft_compress(const float* y, const float* window, float* spe
               "gsn_stft_compress: window and spectrum must be 8-byte aligned");
   const int mode = fdrc == 0.5f ? 0 : (fdrc == 1.0f ? 1 : 2);
   const int pairs = ((L | hop) & 1) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0;
-  gsn::k_stft512<<<gsn::fft_grid(B * T), gsn::FFT_THREADS, 0, gsn::as_stream(stream)>>>(
-      y, window, reinterpret_cast<float2*>(spec_ri), cm, B, L, T, hop, f_keep, fdrc, mode, pairs);
+  if (pairs)
+    gsn::k_stft512<true><<<gsn::fft_grid(B * T), gsn::FFT_THREADS, 0, gsn::as_stream(stream)>>>(
+        y, window, reinterpret_cast<float2*>(spec_ri), cm, B, L, T, hop, f_keep, fdrc, mode);
+  else
+    gsn::k_stft512<false><<<gsn::fft_grid(B * T), gsn::FFT_THREADS, 0, gsn::as_stream(stream)>>>(
+        y, window, reinterpret_cast<float2*>(spec_ri), cm, B, L, T, hop, f_keep, fdrc, mode);
   GSN_LAUNCH_CHECK("k_stft512");
   return GSN_OK;
 }
